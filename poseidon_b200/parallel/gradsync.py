@@ -1,0 +1,344 @@
+"""DWBP scheduler + the library-based (baseline) communication backends.
+
+Distributed wait-free backprop in this framework: every learnable layer is a *bucket*; the
+moment autograd has produced all gradients of a bucket (post-accumulate-grad hooks — the
+equivalent of "layer i's Backward returned" in the reference's hand-rolled backward loop)
+the bucket is handed to a backend which reduces it across ranks and applies the optimizer
+step on a communication stream while backprop continues through the lower layers.  The
+next forward of layer ℓ waits only on ℓ's own bucket event, not on a global barrier.
+
+Backends in this file (the product's fused NVLink kernels live in ``fused.py``):
+  * ``LocalBackend``      – world_size 1: optimizer step only.
+  * ``TorchDistBackend``  – NCCL (GPU baseline) / gloo (CPU tests): per-bucket all-reduce from
+                            the hooks + unfused step.  "The baseline, not the product."
+  * ``SSPBackend``        – bounded-staleness async SGD (Bösen SSP semantics): apply own update
+                            now, fold in the other workers' summed updates ≤ s clocks later.
+
+reference: src/caffe/solver.cpp:405-451 (ForwardBackward/DWBP), :455-473 (ThreadSyncWithPS),
+:534-540 (JoinSyncThreads), :815-892 (SGD ComputeUpdateValue), blob.cpp:208-248.
+"""
+from __future__ import annotations
+
+import logging
+from collections import deque
+from typing import Callable, Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from ..ops import reference as R
+
+log = logging.getLogger("poseidon_b200")
+
+SGD, NESTEROV, ADAGRAD = 0, 1, 2
+
+
+class Hyper:
+    """Per-iteration optimizer hyper-parameters (global part)."""
+
+    def __init__(self, solver_type=SGD, momentum=0.0, weight_decay=0.0, l1=False, delta=1e-8):
+        self.solver_type = solver_type
+        self.momentum = momentum
+        self.weight_decay = weight_decay
+        self.l1 = l1
+        self.delta = delta
+        self.lr = 0.0
+
+
+class Bucket:
+    def __init__(self, bid, layer_idx, layer_name, layer):
+        self.id, self.layer_idx, self.layer_name, self.layer = bid, layer_idx, layer_name, layer
+        self.params: List[torch.nn.Parameter] = []
+        self.lr_mult: List[float] = []
+        self.decay_mult: List[float] = []
+        self.history: List[torch.Tensor] = []
+        self.pending = 0
+        self.mode = "dense"          # "dense" | "sfb"
+        self.event = None            # CUDA event recorded after this bucket's update
+        self.numel = 0
+
+
+def build_buckets(net) -> List[Bucket]:
+    """One bucket per layer that owns learnable blobs (CONV/IP weight+bias ≙ the reference's
+    two PS tables per layer: src/caffe/caffe_engine.cpp:79-128)."""
+    by_layer: Dict[int, Bucket] = {}
+    buckets: List[Bucket] = []
+    for p, li, lr, wd in zip(net.params, net.param_layer_idx, net.params_lr, net.params_weight_decay):
+        if not p.requires_grad:
+            continue
+        b = by_layer.get(li)
+        if b is None:
+            b = Bucket(len(buckets), li, net.layer_names[li], net.layers[li])
+            by_layer[li] = b
+            buckets.append(b)
+        b.params.append(p)
+        b.lr_mult.append(lr)
+        b.decay_mult.append(wd)
+        b.history.append(torch.zeros_like(p))
+        b.numel += p.numel()
+    return buckets
+
+
+def apply_rule(hyper: Hyper, w, g, h, lr_mult, decay_mult, decay_scale=1.0):
+    """One optimizer step on a single tensor (torch ops; the oracle for the fused kernels)."""
+    lr = hyper.lr * lr_mult
+    wd = hyper.weight_decay * decay_mult * decay_scale
+    with torch.no_grad():
+        if hyper.solver_type == SGD:
+            R.sgd_step(w, g, h, lr, hyper.momentum, wd, hyper.l1)
+        elif hyper.solver_type == NESTEROV:
+            R.nesterov_step(w, g, h, lr, hyper.momentum, wd, hyper.l1)
+        else:
+            R.adagrad_step(w, g, h, lr, hyper.delta, wd, hyper.l1)
+
+
+def compute_update(hyper: Hyper, w, g, h, lr_mult, decay_mult):
+    """Return the step Δ (so that w_new = w − Δ) and advance the history, without touching w."""
+    lr = hyper.lr * lr_mult
+    wd = hyper.weight_decay * decay_mult
+    with torch.no_grad():
+        if wd:
+            g = g + wd * (torch.sign(w) if hyper.l1 else w)
+        if hyper.solver_type == SGD:
+            h.mul_(hyper.momentum).add_(g, alpha=lr)
+            return h.clone()
+        if hyper.solver_type == NESTEROV:
+            h_old = h.clone()
+            h.mul_(hyper.momentum).add_(g, alpha=lr)
+            return (1 + hyper.momentum) * h - hyper.momentum * h_old
+        h.add_(g * g)
+        return lr * g / (h.sqrt() + hyper.delta)
+
+
+class Backend:
+    name = "base"
+    uses_comm_stream = False
+
+    def setup(self, sync: "GradSync"):
+        self.sync = sync
+
+    def launch(self, bucket: Bucket):
+        raise NotImplementedError
+
+    def finish_iteration(self):
+        pass
+
+    def bytes_on_wire(self) -> Dict[str, int]:
+        return {}
+
+
+class LocalBackend(Backend):
+    name = "local"
+
+    def launch(self, bucket):
+        hy = self.sync.hyper
+        for p, h, lm, dm in zip(bucket.params, bucket.history, bucket.lr_mult, bucket.decay_mult):
+            apply_rule(hy, p.data, p.grad, h, lm, dm)
+
+
+class TorchDistBackend(Backend):
+    """Per-bucket ``all_reduce`` (NCCL on GPUs, gloo on CPU) launched from the backward hooks
+    on a side stream, followed by an unfused step.  ``reduce='sum'`` reproduces the reference's
+    summed-update semantics (effective LR ∝ #workers); weight decay is scaled by
+    world_size so the result equals the PS's sum of per-worker updates under BSP."""
+    name = "torchdist"
+
+    def __init__(self, reduce="sum"):
+        self.reduce = reduce
+        self.dense_bytes = 0
+
+    def setup(self, sync):
+        super().setup(sync)
+        dev = sync.rank_ctx.device
+        self.cuda = dev.type == "cuda"
+        self.uses_comm_stream = self.cuda
+        self.stream = torch.cuda.Stream(device=dev, priority=-1) if self.cuda else None
+
+    def _reduce_and_step(self, bucket):
+        hy = self.sync.hyper
+        ws = self.sync.rank_ctx.world_size
+        # SFB weights already hold the global gradient (reconstructed from factors)
+        red = [p for p in bucket.params if not getattr(p, "_grad_is_global", False)]
+        grads = {}
+        if red:
+            flat = torch.cat([p.grad.reshape(-1) for p in red]) if len(red) > 1 else red[0].grad.reshape(-1)
+            dist.all_reduce(flat)
+            self.dense_bytes += flat.numel() * flat.element_size()
+            off = 0
+            for p in red:
+                grads[id(p)] = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+        for p, h, lm, dm in zip(bucket.params, bucket.history, bucket.lr_mult, bucket.decay_mult):
+            g = grads.get(id(p), p.grad)
+            if self.reduce == "mean":
+                g = g / ws
+            apply_rule(hy, p.data, g, h, lm, dm, decay_scale=float(ws) if self.reduce == "sum" else 1.0)
+
+    def launch(self, bucket):
+        if not self.cuda:
+            self._reduce_and_step(bucket)
+            return
+        cur = torch.cuda.current_stream()
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            for p in bucket.params:
+                p.grad.record_stream(self.stream)
+            self._reduce_and_step(bucket)
+            if bucket.event is None:
+                bucket.event = torch.cuda.Event()
+            bucket.event.record(self.stream)
+
+    def bytes_on_wire(self):
+        return {"dense_allreduce_bytes": self.dense_bytes}
+
+
+class SSPBackend(Backend):
+    """Stale-synchronous-parallel async SGD without a server.
+
+    Worker p at clock c computes its own step Δ_p(c) (own momentum history, as in the
+    reference), applies it locally at once (read-my-writes) and starts an asynchronous
+    all-reduce of Δ(c).  The summed remote part Σ_{q≠p} Δ_q(c) is folded into the weights as
+    soon as the collective finishes, and *must* have been folded in before clock c+s+1 starts —
+    Bösen's guarantee that a reader at clock c sees all updates with clock ≤ c−s−1.
+    ``staleness=0`` degenerates to BSP with summed per-worker updates (SSPPush, s=0).
+
+    reference: ps/src/petuum_ps/consistency/ssp_consistency_controller.cpp:37-161,
+    ssp_push_consistency_controller.cpp:70-115, SURVEY Appendix B "Consistency contract"."""
+    name = "ssp"
+
+    def __init__(self, staleness=0, delay_hook: Optional[Callable[[int], None]] = None):
+        self.staleness = int(staleness)
+        self.inflight: deque = deque()     # (clock, [(param, delta_sum, own, work)])
+        self.clock = 0
+        self.delay_hook = delay_hook       # fault/delay injection for tests
+        self.max_observed_lag = 0
+        self.wire_bytes = 0
+
+    def setup(self, sync):
+        super().setup(sync)
+        self.cur: List = []
+
+    def launch(self, bucket):
+        hy = self.sync.hyper
+        for p, h, lm, dm in zip(bucket.params, bucket.history, bucket.lr_mult, bucket.decay_mult):
+            delta = compute_update(hy, p.data, p.grad, h, lm, dm)
+            with torch.no_grad():
+                p.data.sub_(delta)                       # read-my-writes
+            total = delta.clone()
+            work = dist.all_reduce(total, async_op=True) if self.sync.rank_ctx.distributed else None
+            self.wire_bytes += total.numel() * total.element_size()
+            self.cur.append((p, total, delta, work))
+
+    def _fold(self, entry):
+        for p, total, own, work in entry:
+            if work is not None:
+                work.wait()
+            with torch.no_grad():
+                p.data.sub_(total - own)
+
+    def finish_iteration(self):
+        if self.delay_hook is not None:
+            self.delay_hook(self.clock)
+        self.inflight.append((self.clock, self.cur))
+        self.cur = []
+        self.clock += 1
+        # fold in everything that has already completed (opportunistic freshness) ...
+        while self.inflight:
+            clk, entry = self.inflight[0]
+            done = all(w is None or w.is_completed() for (_, _, _, w) in entry)
+            must = clk <= self.clock - 1 - self.staleness
+            if not (done or must):
+                break
+            self.max_observed_lag = max(self.max_observed_lag, self.clock - 1 - clk)
+            self._fold(entry)
+            self.inflight.popleft()
+
+    def drain(self):
+        while self.inflight:
+            _, entry = self.inflight.popleft()
+            self._fold(entry)
+
+    def bytes_on_wire(self):
+        return {"ssp_delta_bytes": self.wire_bytes}
+
+
+class GradSync:
+    """Hooks autograd to the backend (DWBP) and tracks per-bucket completion events."""
+
+    def __init__(self, net, rank_ctx, hyper: Hyper, backend: Backend):
+        self.net, self.rank_ctx, self.hyper, self.backend = net, rank_ctx, hyper, backend
+        self.buckets = build_buckets(net)
+        self.bucket_of: Dict[int, Bucket] = {}
+        self._handles = []
+        self.launch_order: List[int] = []
+        for b in self.buckets:
+            for p in b.params:
+                self.bucket_of[id(p)] = b
+        backend.setup(self)
+        self.attach()
+
+    def attach(self):
+        for b in self.buckets:
+            for p in b.params:
+                self._handles.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        if self.backend.uses_comm_stream:
+            for b in self.buckets:
+                self._handles.append(b.layer.register_forward_pre_hook(self._make_wait(b)))
+
+    def detach(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+    def _make_wait(self, bucket):
+        def wait(module, args):
+            if bucket.event is not None:
+                torch.cuda.current_stream().wait_event(bucket.event)
+        return wait
+
+    def begin_iteration(self, lr: float):
+        self.hyper.lr = lr
+        self.launch_order = []
+        for b in self.buckets:
+            b.pending = len(b.params)
+
+    def _on_grad(self, p):
+        b = self.bucket_of[id(p)]
+        b.pending -= 1
+        if b.pending == 0:
+            self.launch_order.append(b.id)
+            self.backend.launch(b)
+            for q in b.params:
+                q.grad = None
+
+    def finish_iteration(self):
+        """Launch buckets whose grads never materialised this step (unused layers) — none in
+        practice — and let the backend close the clock.  Does *not* host-sync."""
+        self.backend.finish_iteration()
+
+    def wait_all(self):
+        """JoinSyncThreads equivalent (stream-level, no host sync)."""
+        if self.backend.uses_comm_stream:
+            cur = torch.cuda.current_stream()
+            for b in self.buckets:
+                if b.event is not None:
+                    cur.wait_event(b.event)
+
+    # ---- optimizer state for .solverstate ------------------------------------------------
+    def history_tensors(self) -> List[torch.Tensor]:
+        out = []
+        by_param = {}
+        for b in self.buckets:
+            for p, h in zip(b.params, b.history):
+                by_param[id(p)] = h
+        for p in self.net.params:
+            out.append(by_param.get(id(p), torch.zeros_like(p)))
+        return out
+
+    def load_history(self, tensors: List[torch.Tensor]):
+        hs = self.history_tensors()
+        if len(tensors) != len(hs):
+            raise ValueError("Incorrect length of history blobs.")
+        for h, t in zip(hs, tensors):
+            with torch.no_grad():
+                h.copy_(t.reshape(h.shape))

@@ -1,0 +1,124 @@
+"""Sufficient-factor broadcasting (SFB / "SVB") for fully-connected layers.
+
+For an InnerProduct weight W (N×K) the dense gradient of a batch of M samples is
+ΔW = uᵀ·v with u = ∂L/∂y (M×N) and v = x (M×K).  Instead of all-reducing the N×K matrix,
+every rank broadcasts its (u, v) and reconstructs ΔW_total = Σ_p u_pᵀ v_p = U_allᵀ·V_all
+locally — one GEMM over the gathered P·M rows, then ONE optimizer step (the mathematically
+clean version; the reference re-applies momentum/decay once per received factor).
+
+This file holds the library-based implementation (``all_gather`` + cuBLAS GEMM) used by the
+baseline engine and by the CPU/gloo tests, plus the cost-model hybrid chooser that decides
+per layer between SFB and dense all-reduce (absent from the reference, which applies SFB to
+every IP weight whenever ``--svb`` is on: tools/caffe_main.cpp:149-151, solver.cpp:434-436).
+The fused NVLink-multicast + tcgen05 kernel version lives in ``fused.py`` / ``csrc/comm``.
+
+reference: src/caffe/solver.cpp:477-531 (ThreadSyncWithSVB), src/caffe/svb_worker.cpp:125-167,
+src/caffe/layers/inner_product_layer.cu:55-64 (ComputeGradientFromSV_gpu),
+include/caffe/sufficient_vector.hpp:17-50.
+"""
+from __future__ import annotations
+
+import logging
+from typing import Dict
+
+import torch
+import torch.distributed as dist
+
+log = logging.getLogger("poseidon_b200")
+
+
+def sfb_wins(M: int, N: int, K: int, P: int) -> bool:
+    """Per-GPU ingress bytes: SFB (P−1)·M·(N+K) vs two-shot dense all-reduce (1+1/P)·N·K."""
+    return (P - 1) * M * (N + K) < (1.0 + 1.0 / P) * N * K
+
+
+def sfb_bytes(M: int, N: int, K: int, P: int, elem: int = 4) -> Dict[str, int]:
+    return {
+        "sfb_egress": M * (N + K) * elem,
+        "sfb_ingress": (P - 1) * M * (N + K) * elem,
+        "dense_each_way": int((1.0 + 1.0 / P) * N * K * elem),
+    }
+
+
+class SFBStats:
+    def __init__(self):
+        self.sfb_bytes = 0
+        self.dense_equiv_bytes = 0
+        self.layers: Dict[str, str] = {}
+
+
+class _SFBLinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, relu, world, layer_name, stats):
+        x2 = x.reshape(x.shape[0], -1)
+        y = torch.nn.functional.linear(x2, w.to(x2.dtype), None if b is None else b.to(x2.dtype))
+        if relu:
+            y = torch.relu(y)
+        ctx.save_for_backward(x2, w, y if relu else None)
+        ctx.relu, ctx.has_bias, ctx.world = relu, b is not None, world
+        ctx.x_shape, ctx.stats = x.shape, stats
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, y = ctx.saved_tensors
+        if ctx.relu:
+            dy = dy * (y > 0).to(dy.dtype)
+        dy = dy.contiguous()
+        dx = (dy @ w.to(dy.dtype)).reshape(ctx.x_shape) if ctx.needs_input_grad[0] else None
+        db = dy.sum(0).to(torch.float32) if ctx.has_bias else None
+        # --- sufficient-factor exchange: all-gather u and v, reconstruct the global ΔW ---
+        P = ctx.world
+        M, N = dy.shape
+        K = x2.shape[1]
+        fac = torch.cat([dy.reshape(-1), x2.reshape(-1).to(dy.dtype)])
+        gathered = torch.empty(P * fac.numel(), dtype=fac.dtype, device=fac.device)
+        dist.all_gather_into_tensor(gathered, fac)
+        gathered = gathered.view(P, fac.numel())
+        U = gathered[:, : M * N].reshape(P * M, N)
+        V = gathered[:, M * N:].reshape(P * M, K)
+        dw = (U.t() @ V).to(torch.float32)
+        st = ctx.stats
+        st.sfb_bytes += fac.numel() * fac.element_size()
+        st.dense_equiv_bytes += N * K * 4
+        return dx, dw, db, None, None, None, None
+
+
+class SFBHandle:
+    """Attached to an InnerProduct layer as ``layer.sfb``; the op engines route the layer's
+    forward through it so that backward exchanges factors instead of a dense gradient."""
+
+    def __init__(self, world: int, stats: SFBStats):
+        self.world, self.stats = world, stats
+
+    def apply(self, layer, x, w, b, relu):
+        return _SFBLinear.apply(x, w, b, relu, self.world, layer.layer_name, self.stats)
+
+
+def enable_sfb(net, sync, rank_ctx, mode: str = "auto") -> SFBStats:
+    """Mark IP weights for SFB. ``mode``: "all" (reference behaviour), "auto" (cost model),
+    "none".  SFB weights carry an already-global gradient, so the dense backend must skip
+    their all-reduce (bias still goes dense, as in the reference: solver.cpp:441-443)."""
+    stats = SFBStats()
+    if mode == "none" or not rank_ctx.distributed:
+        return stats
+    P = rank_ctx.world_size
+    for li, (name, layer) in enumerate(zip(net.layer_names, net.layers)):
+        if layer.type_name != "INNER_PRODUCT" or not layer.weight.requires_grad:
+            continue
+        N, K = layer.weight.shape
+        M = net.blob_shapes[net.bottom_names[li][0]][0]
+        use = mode == "all" or sfb_wins(M, N, K, P)
+        stats.layers[name] = "sfb" if use else "dense"
+        if use:
+            layer.sfb = SFBHandle(P, stats)
+            layer.weight._grad_is_global = True
+            b = sync.bucket_of.get(id(layer.weight))
+            if b is not None:
+                b.mode = "sfb"
+        if rank_ctx.is_root:
+            by = sfb_bytes(M, N, K, P)
+            log.info("SFB chooser: layer %s (M=%d N=%d K=%d P=%d): %s  [sfb ingress %.1f MB vs dense %.1f MB]",
+                     name, M, N, K, P, stats.layers[name], by["sfb_ingress"] / 1e6, by["dense_each_way"] / 1e6)
+    sync.sfb_stats = stats
+    return stats
