@@ -1,0 +1,221 @@
+// Host side of the tcgen05 GEMM family: tensor-map encoding, template dispatch, torch op registration.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/library.h>
+#include <torch/types.h>
+
+#include "umma_gemm.cuh"
+
+namespace psd {
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn get_encode_fn() {
+  static EncodeFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    TORCH_CHECK(e == cudaSuccess && qres == cudaDriverEntryPointSuccess && ptr != nullptr,
+                "cuTensorMapEncodeTiled not available from the driver");
+    fn = reinterpret_cast<EncodeFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows `ld` elements apart, 128B swizzle.
+void encode_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld,
+                         int box_inner, int box_outer) {
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
+  TORCH_CHECK((ld * 2) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes (ld=", ld, ")");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                               box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TORCH_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed: ", static_cast<int>(r), " inner=", inner,
+              " outer=", outer, " ld=", ld);
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static void launch(const TmapSet& tm, const GemmParams& p, int grid, cudaStream_t stream) {
+  auto kern = umma_gemm_kernel<BN, A_MN, B_MN, EPI>;
+  constexpr int smem = GemmSmem<BN>::kTotal;
+  static bool configured = false;
+  if (!configured) {
+    C10_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  kern<<<grid, kNumThreads, smem, stream>>>(tm, p);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+static void dispatch_bn(int bn, const TmapSet& tm, const GemmParams& p, int grid, cudaStream_t s) {
+  switch (bn) {
+    case 64: launch<64, A_MN, B_MN, EPI>(tm, p, grid, s); break;
+    case 128: launch<128, A_MN, B_MN, EPI>(tm, p, grid, s); break;
+    case 256: launch<256, A_MN, B_MN, EPI>(tm, p, grid, s); break;
+    default: TORCH_CHECK(false, "unsupported BLOCK_N ", bn);
+  }
+}
+
+int pick_bn(int64_t M, int64_t N, int sms) {
+  // Largest N tile that still yields at least ~one wave of CTAs; small N never pays for a wide tile.
+  const int64_t mb = (M + BLOCK_M - 1) / BLOCK_M;
+  for (int bn : {256, 128}) {
+    if (N >= bn && mb * ((N + bn - 1) / bn) >= sms) return bn;
+  }
+  if (N > 64 && mb * ((N + 127) / 128) * 2 >= sms) return 128;
+  return N > 64 ? 128 : 64;
+}
+
+// The one entry point.  Operands are described by raw device pointers so that peer (symmetric-memory)
+// buffers can be passed exactly like local ones.
+//   a_ptrs[i] : A of source i.  a_mn=false: [M, K] row-major (ld = lda) ; a_mn=true: [K, M] row-major.
+//   b_ptrs[i] : B of source i, same convention with N.
+//   K         : reduction length per source.
+void gemm_launch(const std::vector<int64_t>& a_ptrs, bool a_mn, int64_t lda, const std::vector<int64_t>& b_ptrs,
+                 bool b_mn, int64_t ldb, int64_t M, int64_t N, int64_t K, int epi, GemmParams p, int bn,
+                 int max_ctas, cudaStream_t stream) {
+  const int nsrc = static_cast<int>(a_ptrs.size());
+  TORCH_CHECK(nsrc >= 1 && nsrc <= kMaxSrc && b_ptrs.size() == a_ptrs.size(), "1..8 sources expected");
+  const auto* prop = at::cuda::getCurrentDeviceProperties();
+  const int sms = prop->multiProcessorCount;
+  if (bn <= 0) bn = pick_bn(M, N, sms);
+  TmapSet tm;
+  for (int s = 0; s < nsrc; ++s) {
+    if (!a_mn) encode_tmap_bf16_2d(&tm.a[s], reinterpret_cast<void*>(a_ptrs[s]), K, M, lda, BLOCK_K, BLOCK_M);
+    else       encode_tmap_bf16_2d(&tm.a[s], reinterpret_cast<void*>(a_ptrs[s]), M, K, lda, 64, BLOCK_K);
+    if (!b_mn) encode_tmap_bf16_2d(&tm.b[s], reinterpret_cast<void*>(b_ptrs[s]), K, N, ldb, BLOCK_K, bn);
+    else       encode_tmap_bf16_2d(&tm.b[s], reinterpret_cast<void*>(b_ptrs[s]), N, K, ldb, 64, BLOCK_K);
+  }
+  p.M = static_cast<int>(M);
+  p.N = static_cast<int>(N);
+  p.kb_per_src = static_cast<int>((K + BLOCK_K - 1) / BLOCK_K);
+  p.num_src = nsrc;
+  if (p.split_k < 1) p.split_k = 1;
+  p.split_k = std::min(p.split_k, p.kb_per_src * nsrc);
+  const int64_t tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + bn - 1) / bn) * p.split_k;
+  int grid = static_cast<int>(std::min<int64_t>(tiles, max_ctas > 0 ? max_ctas : sms));
+  if (!a_mn && !b_mn) {
+    if (epi == EPI_BF16) dispatch_bn<false, false, EPI_BF16>(bn, tm, p, grid, stream);
+    else if (epi == EPI_F32) dispatch_bn<false, false, EPI_F32>(bn, tm, p, grid, stream);
+    else TORCH_CHECK(false, "EPI_SGD requires MN-major operands");
+  } else if (!a_mn && b_mn) {
+    TORCH_CHECK(epi == EPI_BF16, "K-major x MN-major supports the bf16 epilogue only");
+    dispatch_bn<false, true, EPI_BF16>(bn, tm, p, grid, stream);
+  } else if (a_mn && b_mn) {
+    if (epi == EPI_F32) dispatch_bn<true, true, EPI_F32>(bn, tm, p, grid, stream);
+    else if (epi == EPI_SGD) dispatch_bn<true, true, EPI_SGD>(bn, tm, p, grid, stream);
+    else TORCH_CHECK(false, "MN-major x MN-major supports fp32 / SGD epilogues");
+  } else {
+    TORCH_CHECK(false, "MN-major A with K-major B is not instantiated");
+  }
+}
+
+// ------------------------------------------------------------------------------------ torch ops
+static const void* opt_ptr(const c10::optional<at::Tensor>& t) { return t.has_value() ? t->data_ptr() : nullptr; }
+
+// C[M,N] bf16 = act(alpha * A·Bᵀ + bias) (optionally masked).  a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N]).
+at::Tensor gemm_bf16(const at::Tensor& a, bool a_mn, const at::Tensor& b, bool b_mn,
+                     const c10::optional<at::Tensor>& bias, bool relu, double slope,
+                     const c10::optional<at::Tensor>& mask, c10::optional<at::Tensor> out, int64_t bn) {
+  TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && a.stride(1) == 1 && b.stride(1) == 1);
+  c10::cuda::CUDAGuard guard(a.device());
+  const int64_t M = a_mn ? a.size(1) : a.size(0), K = a_mn ? a.size(0) : a.size(1);
+  const int64_t N = b_mn ? b.size(1) : b.size(0);
+  TORCH_CHECK((b_mn ? b.size(0) : b.size(1)) == K, "K mismatch");
+  at::Tensor c = out.has_value() ? *out : at::empty({M, N}, a.options());
+  TORCH_CHECK(c.scalar_type() == at::kBFloat16 && c.size(0) == M && c.size(1) == N && c.stride(1) == 1);
+  GemmParams p{};
+  p.c_bf16 = reinterpret_cast<__nv_bfloat16*>(c.data_ptr());
+  p.ldc = c.stride(0);
+  p.bias = reinterpret_cast<const float*>(opt_ptr(bias));
+  if (bias.has_value()) TORCH_CHECK(bias->scalar_type() == at::kFloat && bias->numel() == N);
+  p.mask = reinterpret_cast<const __nv_bfloat16*>(opt_ptr(mask));
+  if (mask.has_value()) TORCH_CHECK(mask->scalar_type() == at::kBFloat16 && mask->stride(0) == p.ldc);
+  p.relu = relu;
+  p.relu_slope = static_cast<float>(slope);
+  p.alpha = 1.f;
+  p.split_k = 1;
+  gemm_launch({reinterpret_cast<int64_t>(a.data_ptr())}, a_mn, a.stride(0),
+              {reinterpret_cast<int64_t>(b.data_ptr())}, b_mn, b.stride(0), M, N, K, EPI_BF16, p,
+              static_cast<int>(bn), 0, at::cuda::getCurrentCUDAStream());
+  return c;
+}
+
+// out[M,N] fp32 (+)= alpha * Aᵀ-style product; split_k>1 accumulates atomically (out must be pre-zeroed
+// or hold the value to accumulate onto).
+void gemm_f32(const at::Tensor& a, bool a_mn, const at::Tensor& b, bool b_mn, at::Tensor out, double alpha,
+              bool accumulate, int64_t split_k, int64_t bn) {
+  TORCH_CHECK(a.is_cuda() && a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && a.stride(1) == 1 && b.stride(1) == 1);
+  TORCH_CHECK(out.scalar_type() == at::kFloat && out.dim() == 2 && out.stride(1) == 1);
+  c10::cuda::CUDAGuard guard(a.device());
+  const int64_t M = a_mn ? a.size(1) : a.size(0), K = a_mn ? a.size(0) : a.size(1);
+  const int64_t N = b_mn ? b.size(1) : b.size(0);
+  TORCH_CHECK((b_mn ? b.size(0) : b.size(1)) == K && out.size(0) == M && out.size(1) == N, "shape mismatch");
+  GemmParams p{};
+  p.c_f32 = out.data_ptr<float>();
+  p.ldc = out.stride(0);
+  p.alpha = static_cast<float>(alpha);
+  p.split_k = static_cast<int>(split_k);
+  p.atomic = (accumulate || split_k > 1) ? 1 : 0;
+  gemm_launch({reinterpret_cast<int64_t>(a.data_ptr())}, a_mn, a.stride(0),
+              {reinterpret_cast<int64_t>(b.data_ptr())}, b_mn, b.stride(0), M, N, K, EPI_F32, p,
+              static_cast<int>(bn), 0, at::cuda::getCurrentCUDAStream());
+}
+
+// The sufficient-factor outer product with the optimizer fused into the epilogue:
+//   ΔW[N,K] = alpha * Σ_src U_srcᵀ[N,Mb] · V_src[Mb,K];   (W, H, Wb) <- step(W, H, ΔW)   in place.
+// u_ptrs / v_ptrs are device addresses (local or NVLink-peer-mapped) of [Mb, N] / [Mb, K] bf16 buffers.
+// With one source this is the local weight-gradient + update kernel (no dense dW is ever materialised).
+void sfb_outer_sgd(std::vector<int64_t> u_ptrs, std::vector<int64_t> v_ptrs, int64_t Mb, int64_t N, int64_t K,
+                   at::Tensor w, at::Tensor h, c10::optional<at::Tensor> wb, double alpha, double lr,
+                   double momentum, double decay, int64_t rule, bool l1, double delta,
+                   const c10::optional<at::Tensor>& flags, int64_t epoch, int64_t src_rot, int64_t bn,
+                   int64_t max_ctas) {
+  TORCH_CHECK(w.is_cuda() && w.scalar_type() == at::kFloat && h.scalar_type() == at::kFloat);
+  TORCH_CHECK(w.numel() == N * K && h.numel() == N * K && w.is_contiguous() && h.is_contiguous());
+  c10::cuda::CUDAGuard guard(w.device());
+  GemmParams p{};
+  p.w = w.data_ptr<float>();
+  p.h = h.data_ptr<float>();
+  p.wb = wb.has_value() ? reinterpret_cast<__nv_bfloat16*>(wb->data_ptr()) : nullptr;
+  p.ldc = K;
+  p.alpha = static_cast<float>(alpha);
+  p.lr = static_cast<float>(lr);
+  p.momentum = static_cast<float>(momentum);
+  p.decay = static_cast<float>(decay);
+  p.rule = static_cast<int>(rule);
+  p.l1 = l1;
+  p.delta = static_cast<float>(delta);
+  p.split_k = 1;
+  p.src_rot = static_cast<int>(src_rot);
+  if (flags.has_value()) {
+    TORCH_CHECK(flags->scalar_type() == at::kInt && flags->numel() >= static_cast<int64_t>(u_ptrs.size()));
+    p.flags = reinterpret_cast<const uint32_t*>(flags->data_ptr());
+    p.epoch = static_cast<uint32_t>(epoch);
+  }
+  // A = Uᵀ : MN-major with "M" = N_out ; B = Vᵀ... : MN-major with "N" = K_in ; reduction = Mb rows.
+  gemm_launch(u_ptrs, true, N, v_ptrs, true, K, N, K, Mb, EPI_SGD, p, static_cast<int>(bn),
+              static_cast<int>(max_ctas), at::cuda::getCurrentCUDAStream());
+}
+
+}  // namespace psd
+
+TORCH_LIBRARY_FRAGMENT(poseidon, m) {
+  m.def("gemm_bf16(Tensor a, bool a_mn, Tensor b, bool b_mn, Tensor? bias, bool relu, float slope, Tensor? mask, "
+        "Tensor? out, int bn) -> Tensor", &psd::gemm_bf16);
+  m.def("gemm_f32(Tensor a, bool a_mn, Tensor b, bool b_mn, Tensor(a!) out, float alpha, bool accumulate, "
+        "int split_k, int bn) -> ()", &psd::gemm_f32);
+  m.def("sfb_outer_sgd(int[] u_ptrs, int[] v_ptrs, int Mb, int N, int K, Tensor(a!) w, Tensor(b!) h, "
+        "Tensor(c!)? wb, float alpha, float lr, float momentum, float decay, int rule, bool l1, float delta, "
+        "Tensor? flags, int epoch, int src_rot, int bn, int max_ctas) -> ()", &psd::sfb_outer_sgd);
+}

@@ -1,0 +1,360 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a:
+//
+//     D[M,N] (+)= sum_{src} sum_k A_src[M,k] * B_src[N,k]       bf16 x bf16 -> fp32 (TMEM)
+//
+// * operands staged by TMA into 128B-swizzled shared memory, 64-wide K blocks, N-stage mbarrier ring
+// * one elected thread issues tcgen05.mma (UMMA 128 x BN x 16), accumulators double-buffered in TMEM so
+//   the epilogue of tile i overlaps the main loop of tile i+1
+// * either operand may be K-major ([rows][K]) or MN-major ([K][rows]) — the latter is what makes the
+//   weight-gradient / sufficient-factor outer product  dW = Uᵀ·V  a plain TMA GEMM with no transposes
+// * the reduction may span several *sources* (one tensor map per source): for SFB the sources are the
+//   peers' symmetric (u, v) buffers read over NVLink, gated by per-peer epoch flags
+// * A may instead be produced by gather warps (implicit-GEMM convolution, see conv_gather.cuh)
+// * fused epilogues: bias + ReLU (+ mask) -> bf16 ; fp32 store / atomic split-K ; in-place SGD update
+//
+// Replaces the reference's cublasSgemm call sites (src/caffe/util/math_functions.cu:15-45) used by
+// InnerProduct fwd/bwd (layers/inner_product_layer.cu:13-52), the per-image conv GEMMs
+// (layers/conv_layer.cu:23-119) and ComputeGradientFromSV_gpu (layers/inner_product_layer.cu:55-64).
+#pragma once
+#include "sm100_prims.cuh"
+
+namespace psd {
+
+constexpr int kMaxSrc = 8;
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int kNumThreads = 256;          // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+constexpr int kEpiWarp0 = 4;
+
+enum EpiMode : int { EPI_BF16 = 0, EPI_F32 = 1, EPI_SGD = 2 };
+
+struct TmapSet {
+  CUtensorMap a[kMaxSrc];
+  CUtensorMap b[kMaxSrc];
+};
+
+struct GemmParams {
+  int M, N;              // output extent
+  int kb_per_src;        // number of 64-wide k blocks per source
+  int num_src;
+  int split_k;           // >1: partial sums accumulated with atomics (EPI_F32 only)
+  int src_rot;           // first source to visit (own rank for SFB: local data needs no flag wait)
+  // --- epilogue operands
+  __nv_bfloat16* c_bf16; // EPI_BF16 output [M, ldc]
+  float* c_f32;          // EPI_F32 output [M, ldc]
+  long ldc;
+  const float* bias;     // optional, per output column (N)
+  const __nv_bfloat16* mask;  // optional [M, ldc]: zero the output where mask <= 0 (fused ReLU backward)
+  int relu;              // EPI_BF16: apply max(0, x) (negative_slope below)
+  float relu_slope;
+  int atomic;            // EPI_F32: atomicAdd instead of store
+  float alpha;           // scale applied to the accumulator
+  // --- EPI_SGD: W[M,N] fp32 master, H history, Wb bf16 shadow, in place
+  float* w;
+  float* h;
+  __nv_bfloat16* wb;
+  float lr, momentum, decay;
+  int rule;              // 0 SGD, 1 Nesterov, 2 AdaGrad
+  int l1;
+  float delta;
+  // --- peer gating (SFB): flag[src] must reach `epoch` before src's tiles are read
+  const uint32_t* flags;
+  uint32_t epoch;
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;     // 16 KB
+  static constexpr int kBBytes = BN * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kBarBytes = 1024;
+  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // +1024 alignment slack
+};
+
+__device__ __forceinline__ float sgd_apply(float acc, float& w, float& h, const GemmParams& p) {
+  float g = acc;
+  if (p.decay != 0.f) g += p.decay * (p.l1 ? (w > 0.f ? 1.f : (w < 0.f ? -1.f : 0.f)) : w);
+  float step;
+  if (p.rule == 0) {
+    h = p.lr * g + p.momentum * h;
+    step = h;
+  } else if (p.rule == 1) {
+    float h_old = h;
+    h = p.lr * g + p.momentum * h;
+    step = (1.f + p.momentum) * h - p.momentum * h_old;
+  } else {
+    h = h + g * g;
+    step = p.lr * g / (sqrtf(h) + p.delta);
+  }
+  w -= step;
+  return w;
+}
+
+// Epilogue for 32 consecutive columns of one output row held in registers.
+template <int EPI>
+__device__ __forceinline__ void epilogue_row32(const GemmParams& p, const uint32_t (&r)[32], int row, int col0) {
+  if (row >= p.M || col0 >= p.N) return;
+  const int ncols = min(32, p.N - col0);
+  const long off = static_cast<long>(row) * p.ldc + col0;
+  if constexpr (EPI == EPI_BF16) {
+    const bool vec_ok = (ncols == 32) && ((off & 7) == 0);
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = __uint_as_float(r[j]) * p.alpha;
+      if (p.bias != nullptr && j < ncols) x += __ldg(p.bias + col0 + j);
+      if (p.relu) x = x > 0.f ? x : x * p.relu_slope;
+      v[j] = x;
+    }
+    if (p.mask != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols && !(__bfloat162float(p.mask[off + j]) > 0.f)) v[j] *= p.relu_slope;
+    }
+    if (vec_ok) {
+      uint4* dst = reinterpret_cast<uint4*>(p.c_bf16 + off);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        __nv_bfloat162 b0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]);
+        __nv_bfloat162 b1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
+        __nv_bfloat162 b3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&b0);
+        u.y = *reinterpret_cast<uint32_t*>(&b1);
+        u.z = *reinterpret_cast<uint32_t*>(&b2);
+        u.w = *reinterpret_cast<uint32_t*>(&b3);
+        dst[q] = u;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) p.c_bf16[off + j] = __float2bfloat16(v[j]);
+    }
+  } else if constexpr (EPI == EPI_F32) {
+    float* dst = p.c_f32 + off;
+    if (p.atomic) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) atomicAdd(dst + j, __uint_as_float(r[j]) * p.alpha);
+    } else if (ncols == 32 && (off & 3) == 0) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 f = make_float4(__uint_as_float(r[4 * q]) * p.alpha, __uint_as_float(r[4 * q + 1]) * p.alpha,
+                               __uint_as_float(r[4 * q + 2]) * p.alpha, __uint_as_float(r[4 * q + 3]) * p.alpha);
+        reinterpret_cast<float4*>(dst)[q] = f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) dst[j] = __uint_as_float(r[j]) * p.alpha;
+    }
+  } else {  // EPI_SGD: W, H updated in place, bf16 shadow refreshed
+    float* w = p.w + off;
+    float* h = p.h + off;
+    if (ncols == 32 && (off & 7) == 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 w0 = reinterpret_cast<float4*>(w)[2 * q], w1 = reinterpret_cast<float4*>(w)[2 * q + 1];
+        float4 h0 = reinterpret_cast<float4*>(h)[2 * q], h1 = reinterpret_cast<float4*>(h)[2 * q + 1];
+        float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sgd_apply(__uint_as_float(r[8 * q + j]) * p.alpha, wv[j], hv[j], p);
+        reinterpret_cast<float4*>(w)[2 * q] = make_float4(wv[0], wv[1], wv[2], wv[3]);
+        reinterpret_cast<float4*>(w)[2 * q + 1] = make_float4(wv[4], wv[5], wv[6], wv[7]);
+        reinterpret_cast<float4*>(h)[2 * q] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+        reinterpret_cast<float4*>(h)[2 * q + 1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
+        if (p.wb != nullptr) {
+          __nv_bfloat162 b0 = __floats2bfloat162_rn(wv[0], wv[1]), b1 = __floats2bfloat162_rn(wv[2], wv[3]);
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(wv[4], wv[5]), b3 = __floats2bfloat162_rn(wv[6], wv[7]);
+          uint4 u;
+          u.x = *reinterpret_cast<uint32_t*>(&b0);
+          u.y = *reinterpret_cast<uint32_t*>(&b1);
+          u.z = *reinterpret_cast<uint32_t*>(&b2);
+          u.w = *reinterpret_cast<uint32_t*>(&b3);
+          reinterpret_cast<uint4*>(p.wb + off)[q] = u;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) {
+          float wv = w[j], hv = h[j];
+          sgd_apply(__uint_as_float(r[j]) * p.alpha, wv, hv, p);
+          w[j] = wv;
+          h[j] = hv;
+          if (p.wb != nullptr) p.wb[off + j] = __float2bfloat16(wv);
+        }
+    }
+  }
+}
+
+// Producer policy: both operands via TMA.
+template <int BN, bool A_MN, bool B_MN>
+struct TmaProducer {
+  __device__ static void load_stage(const TmapSet& tm, int src, int kb, int m_blk, int n_blk, uint8_t* sa,
+                                    uint8_t* sb, uint64_t* full) {
+    const int k0 = kb * BLOCK_K;
+    if constexpr (!A_MN) {
+      tma_load_2d(sa, &tm.a[src], full, k0, m_blk * BLOCK_M);
+    } else {
+#pragma unroll
+      for (int c = 0; c < BLOCK_M / 64; ++c) tma_load_2d(sa + c * 8192, &tm.a[src], full, m_blk * BLOCK_M + 64 * c, k0);
+    }
+    if constexpr (!B_MN) {
+      tma_load_2d(sb, &tm.b[src], full, k0, n_blk * BN);
+    } else {
+#pragma unroll
+      for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &tm.b[src], full, n_blk * BN + 64 * c, k0);
+    }
+  }
+};
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(kNumThreads, 1)
+umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p) {
+  using S = GemmSmem<BN>;
+  constexpr int kStages = S::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bar_base = smem + kStages * S::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int n_blocks = (p.N + BN - 1) / BN;
+  const int total_kb = p.kb_per_src * p.num_src;
+  const int num_tiles = m_blocks * n_blocks * p.split_k;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.num_src; ++s) {
+      tma_prefetch_desc(&tm.a[s]);
+      tma_prefetch_desc(&tm.b[s]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);   // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % m_blocks;
+        const int rest = tile / m_blocks;
+        const int n_blk = rest % n_blocks;
+        const int split = rest / n_blocks;
+        const int g0 = static_cast<int>(static_cast<long>(total_kb) * split / p.split_k);
+        const int g1 = static_cast<int>(static_cast<long>(total_kb) * (split + 1) / p.split_k);
+        int last_src = -1;
+        for (int g = g0; g < g1; ++g) {
+          int src = g / p.kb_per_src;
+          const int kb = g - src * p.kb_per_src;
+          src = (src + p.src_rot) % p.num_src;
+          if (p.flags != nullptr && src != last_src) {
+            wait_flag_ge(p.flags + src, p.epoch);
+            last_src = src;
+          }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+          uint8_t* sa = smem + stage * S::kStageBytes;
+          TmaProducer<BN, A_MN, B_MN>::load_stage(tm, src, kb, m_blk, n_blk, sa, sa + S::kABytes, &full_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int rest = tile / m_blocks;
+        const int split = rest / n_blocks;
+        const int g0 = static_cast<int>(static_cast<long>(total_kb) * split / p.split_k);
+        const int g1 = static_cast<int>(static_cast<long>(total_kb) * (split + 1) / p.split_k);
+        const int as = it & 1;
+        mbar_wait(&tmem_empty[as], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int g = g0; g < g1; ++g) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * S::kStageBytes);
+          const uint32_t b_addr = a_addr + S::kABytes;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = A_MN ? make_smem_desc(a_addr + k * (UMMA_K * 128), 8192, 1024)
+                                     : make_smem_desc(a_addr + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc(b_addr + k * (UMMA_K * 128), 8192, 1024)
+                                     : make_smem_desc(b_addr + k * (UMMA_K * 2), 16, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (g > g0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);               // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue warps: TMEM -> registers -> global =====================
+    const int q = warp - kEpiWarp0;               // TMEM lane quadrant == warp_id % 4
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile % m_blocks;
+      const int n_blk = (tile / m_blocks) % n_blocks;
+      const int as = it & 1;
+      mbar_wait(&tmem_full[as], (it >> 1) & 1);
+      tc_fence_after();
+      const int row = m_blk * BLOCK_M + q * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, r);
+        tmem_ld_wait();
+        epilogue_row32<EPI>(p, r, row, n_blk * BN + c * 32);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+}  // namespace psd
