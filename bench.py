@@ -1,0 +1,227 @@
+#!/usr/bin/env python
+"""Headline benchmark: training throughput (images/sec, whole job) of the flagship models.
+
+Contract (see the task statement): ``python bench.py --gpus N --steps K --warmup W`` — for N > 1 it is
+launched under ``torch.distributed.run`` (one rank per GPU, NCCL for bootstrap only).  Prints ONE JSON
+line on rank 0.  ``--impl reference`` reports why the unmodified reference cannot run here.
+
+What is timed
+-------------
+* ``value``      : K optimizer steps (forward + backward + DWBP/SFB communication + weight update) with the
+                   input batch already resident on the device (the data layer's transform kernel still runs);
+                   CUDA events on the compute stream, barrier + synchronize on both sides, max over ranks.
+* ``e2e.value``  : the same K steps through the public API (``Solver.step``) with, every step, the raw uint8
+                   batch copied host->device from pinned memory and the loss read back device->host.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+BASELINE_IMG_S_PER_GPU = 133.0   # derived 1.07 k img/s on 8 x K20 (AlexNet) — the only citeable figure
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="alexnet", choices=["alexnet", "caffenet", "googlenet", "vgg16"])
+    ap.add_argument("--engine", default="sm100", choices=["sm100", "torch"])
+    ap.add_argument("--comm", default="auto")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the reference prototxt's)")
+    ap.add_argument("--svb", type=int, default=1)
+    ap.add_argument("--sfb-mode", default="auto")
+    ap.add_argument("--staleness", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--vendor-dtype", default="bf16", choices=["bf16", "fp32"])
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def reference_unavailable():
+    why = ("petuum/poseidon cannot be built offline: needs the un-vendored petuum/third_party bundle (zmq, glog, gflags, "
+           "leveldb, lmdb, hdf5, opencv, protobuf-dev), cuDNN R2/R3 APIs removed since cuDNN 8, and sm_20..sm_50 "
+           "gencodes rejected by nvcc 12.9; `pip install /root/reference` has no setup.py/pyproject (see DESIGN.md)")
+    print(json.dumps({"impl": "reference", "unavailable": why}))
+
+
+def build_solver(args, rank_ctx, device_resident: bool):
+    import torch
+    from poseidon_b200 import get_solver
+    from poseidon_b200.models import zoo
+    kw = {}
+    if args.batch:
+        kw["batch"] = args.batch
+    net = zoo.get_model(args.model, **kw)
+    sp = zoo.get_solver_param(args.model, net=net, display=0, snapshot=0, snapshot_after_train=False,
+                              test_interval=0, max_iter=10 ** 9, random_seed=1234)
+    sp.clear("test_iter")
+    dtype = None
+    if args.engine == "torch":
+        dtype = torch.bfloat16 if args.vendor_dtype == "bf16" else torch.float32
+    solver = get_solver(sp, rank_ctx=rank_ctx, engine=args.engine, comm=args.comm, svb=bool(args.svb),
+                        sfb_mode=args.sfb_mode, staleness=args.staleness, dtype=dtype)
+    for dl in solver.net.data_layers():
+        dl.device_resident = device_resident
+    return solver
+
+
+def timed_steps(solver, rank_ctx, steps, read_loss: bool):
+    import torch
+    dev = rank_ctx.device
+    rank_ctx.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    last = None
+    for _ in range(steps):
+        solver.step(1)
+        if read_loss:
+            last = float(solver.last_loss)      # device -> host read of the step's result
+    solver.sync.wait_all()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    rank_ctx.barrier()
+    ms = e0.elapsed_time(e1)
+    return rank_ctx.max_over_ranks(ms), last
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_unavailable()
+        return 0
+    import torch
+    from poseidon_b200 import init_rank_context
+    from poseidon_b200.ops import sm100 as _sm  # noqa: F401
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        # convenience: re-launch ourselves under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), __file__] + sys.argv[1:]
+        return subprocess.call(cmd)
+    rc = init_rank_context()
+    if rc.device.type != "cuda":
+        print(json.dumps({"error": "bench.py needs a CUDA device"}))
+        return 1
+    torch.backends.cudnn.benchmark = True
+    if args.engine == "torch":
+        torch.backends.cuda.matmul.allow_tf32 = args.vendor_dtype != "fp32"
+        torch.backends.cudnn.allow_tf32 = args.vendor_dtype != "fp32"
+
+    from poseidon_b200.ops import counting
+    # ---------------- device-resident-input measurement (kernel + comm + update time)
+    solver = build_solver(args, rc, device_resident=True)
+    batch = solver.net.blob_shapes[solver.net.top_names[0][0]][0]
+    for _ in range(args.warmup):
+        solver.step(1)
+    solver.sync.wait_all()
+    sampler = ClockSampler(rc.device.index)
+    if rc.is_root:
+        sampler.start()
+    counting.reset()
+    ms, _ = timed_steps(solver, rc, args.steps, read_loss=False)
+    launches = counting.total()
+    clocks = sampler.stop() if rc.is_root else None
+    value = batch * world * args.steps / (ms / 1e3)
+    wire = solver.sync.backend.bytes_on_wire() if hasattr(solver.sync.backend, "bytes_on_wire") else {}
+    sfb_layers = getattr(getattr(solver.sync.backend, "sfb_stats", None), "layers", {})
+    # ---------------- end-to-end through the public API: pinned H2D of every batch + D2H of every loss
+    e2e = None
+    if not args.no_e2e:
+        for dl in solver.net.data_layers():
+            dl.device_resident = False
+        for _ in range(max(3, args.warmup)):
+            solver.step(1)
+            float(solver.last_loss)
+        ms2, _ = timed_steps(solver, rc, args.steps, read_loss=True)
+        h2d = sum(getattr(dl.prefetch, "h2d_bytes", 0) for dl in solver.net.data_layers() if getattr(dl, "prefetch", None))
+        e2e = {"value": batch * world * args.steps / (ms2 / 1e3), "unit": "images/sec", "ms_per_step": ms2 / args.steps,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4}
+    solver.close()
+    if rc.is_root:
+        shape = solver.net.blob_shapes[solver.net.top_names[0][0]]
+        out = {
+            "metric": f"{args.model}_train_images_per_sec", "value": value, "unit": "images/sec", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": value / (BASELINE_IMG_S_PER_GPU * world) if args.model == "alexnet" else None,
+            "dtype": "bf16" if (args.engine == "sm100" or args.vendor_dtype == "bf16") else "fp32",
+            "data": "synthetic (random uint8 images, random-init weights)",
+            "config": {"model": args.model, "global_batch": batch * world, "per_gpu_batch": batch,
+                       "input": list(shape[1:]), "seq_len": None,
+                       "parallelism": f"dp{world}" + ("+dwbp" if world > 1 else "") +
+                                      ("+sfb" if any(v == "sfb" for v in sfb_layers.values()) and world > 1 else ""),
+                       "engine": args.engine, "comm": solver.comm_name, "solver": "SGD momentum 0.9 wd 5e-4 (reference solver.prototxt)",
+                       "l2": "per-step working set (weights+history+grads+activations) >> 126 MB L2; inputs rotate over 4 batches",
+                       "sfb_layers": sfb_layers, "wire_bytes_total": wire,
+                       "baseline_ref": "133 img/s per K20 derived in BASELINE.md §1 (reference publishes no img/s)"},
+            "clocks": clocks, "gpu_launches": launches, "impl": "ours",
+        }
+        if e2e is not None:
+            out["e2e"] = e2e
+        print(json.dumps(out))
+    rc.shutdown()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

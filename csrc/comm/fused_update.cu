@@ -1,0 +1,319 @@
+// Fused gradient all-reduce + optimizer step over NVLink peer memory — the replacement for the whole
+// Bösen push/pull path (worker D2H -> oplog -> ZeroMQ -> server add -> ServerPushRow -> H2D).
+//
+//   world == 1 : fused_update         W,H (+bf16 shadow) <- step(W, H, G)      one pass, all rules
+//   world  > 1 : allreduce_sgd        every rank owns 1/P of each bucket ("two-shot"):
+//        phase 0  signal "my gradients for epoch e are in my symmetric G buffer", wait for all peers
+//        phase 1  g = sum_p G_p[slice]  (P2P vector loads, or one multimem.ld_reduce through the NVSwitch)
+//                 apply weight decay + momentum/Nesterov/AdaGrad on the owned slice (history is sharded)
+//                 store the new fp32 weights (+ bf16 shadow) into EVERY rank's W (P2P stores / multimem.st)
+//        phase 2  last CTA: signal "slice written / done reading", wait for all peers
+//      small buckets use the one-shot variant (every rank reduces the full bucket, no weight broadcast).
+//   No NCCL call, no host round trip, one kernel per bucket launched from the backward hooks (DWBP).
+//
+// reference: src/caffe/solver.cpp:455-473 (ThreadSyncWithPS), :815-892 (ComputeUpdateValue: 4-5 cuBLAS L1
+// passes per blob), src/caffe/blob.cpp:208-286 (UpdatePSTable / SyncWithPSTable via host memory).
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/library.h>
+#include <torch/types.h>
+
+#include "../gemm/sm100_prims.cuh"
+
+namespace psd {
+
+constexpr int kMaxRanks = 8;
+
+struct UpdateHyper {
+  float lr, momentum, decay, delta, gscale;
+  int rule, l1;
+};
+
+__device__ __forceinline__ float step_rule(float g, float& w, float& h, const UpdateHyper& p) {
+  g *= p.gscale;
+  if (p.decay != 0.f) g += p.decay * (p.l1 ? (w > 0.f ? 1.f : (w < 0.f ? -1.f : 0.f)) : w);
+  float step;
+  if (p.rule == 0) {
+    h = p.lr * g + p.momentum * h;
+    step = h;
+  } else if (p.rule == 1) {
+    const float h_old = h;
+    h = p.lr * g + p.momentum * h;
+    step = (1.f + p.momentum) * h - p.momentum * h_old;
+  } else {
+    h = h + g * g;
+    step = p.lr * g / (sqrtf(h) + p.delta);
+  }
+  w -= step;
+  return w;
+}
+
+__device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  return u;
+}
+
+// ------------------------------------------------------------------------------------ single GPU
+__global__ void __launch_bounds__(256)
+fused_update_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ h, __nv_bfloat16* __restrict__ wb,
+                    long n, UpdateHyper hp) {
+  const long n4 = n >> 2;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    float4 wv = reinterpret_cast<float4*>(w)[i], hv = reinterpret_cast<float4*>(h)[i];
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    step_rule(gv.x, wv.x, hv.x, hp);
+    step_rule(gv.y, wv.y, hv.y, hp);
+    step_rule(gv.z, wv.z, hv.z, hp);
+    step_rule(gv.w, wv.w, hv.w, hp);
+    reinterpret_cast<float4*>(w)[i] = wv;
+    reinterpret_cast<float4*>(h)[i] = hv;
+    if (wb != nullptr) reinterpret_cast<uint2*>(wb)[i] = pack_bf16x4(wv);
+  }
+  // tail
+  for (long i = (n4 << 2) + blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    float wv = w[i], hv = h[i];
+    step_rule(g[i], wv, hv, hp);
+    w[i] = wv;
+    h[i] = hv;
+    if (wb != nullptr) wb[i] = __float2bfloat16(wv);
+  }
+}
+
+static UpdateHyper make_hyper(double lr, double momentum, double decay, int64_t rule, bool l1, double delta, double gscale) {
+  UpdateHyper hp;
+  hp.lr = static_cast<float>(lr);
+  hp.momentum = static_cast<float>(momentum);
+  hp.decay = static_cast<float>(decay);
+  hp.delta = static_cast<float>(delta);
+  hp.gscale = static_cast<float>(gscale);
+  hp.rule = static_cast<int>(rule);
+  hp.l1 = l1;
+  return hp;
+}
+
+static bool same_dense_layout(const at::Tensor& a, const at::Tensor& b) {
+  return a.numel() == b.numel() && a.strides() == b.strides() && a.sizes() == b.sizes();
+}
+
+// W, G, H: fp32 tensors with identical (dense) layout; wb: optional bf16 shadow in the same storage order.
+void fused_update(at::Tensor w, const at::Tensor& g, at::Tensor h, c10::optional<at::Tensor> wb, double lr, double momentum,
+                  double decay, int64_t rule, bool l1, double delta, double gscale) {
+  TORCH_CHECK(w.is_cuda() && w.scalar_type() == at::kFloat && g.scalar_type() == at::kFloat && h.scalar_type() == at::kFloat);
+  TORCH_CHECK(same_dense_layout(w, g) && same_dense_layout(w, h), "fused_update: W, G, H must share one dense layout");
+  TORCH_CHECK(w.is_non_overlapping_and_dense(), "fused_update: dense tensors expected");
+  c10::cuda::CUDAGuard guard(w.device());
+  const long n = w.numel();
+  __nv_bfloat16* wbp = nullptr;
+  if (wb.has_value()) {
+    TORCH_CHECK(wb->scalar_type() == at::kBFloat16 && wb->numel() == n && wb->is_non_overlapping_and_dense());
+    wbp = reinterpret_cast<__nv_bfloat16*>(wb->data_ptr());
+  }
+  const bool aligned = (reinterpret_cast<uintptr_t>(w.data_ptr()) | reinterpret_cast<uintptr_t>(g.data_ptr()) |
+                        reinterpret_cast<uintptr_t>(h.data_ptr())) % 16 == 0 &&
+                       (wbp == nullptr || reinterpret_cast<uintptr_t>(wbp) % 8 == 0);
+  TORCH_CHECK(aligned, "fused_update: 16-byte aligned buffers expected");
+  const int grid = static_cast<int>(std::max<long>(1, std::min<long>((n / 4 + 255) / 256, 148 * 8)));
+  fused_update_kernel<<<grid, 256, 0, at::cuda::getCurrentCUDAStream()>>>(
+      w.data_ptr<float>(), g.data_ptr<float>(), h.data_ptr<float>(), wbp, n,
+      make_hyper(lr, momentum, decay, rule, l1, delta, gscale));
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------ multi GPU
+struct PeerPtrs {
+  const float* g[kMaxRanks];      // every rank's gradient bucket (symmetric)
+  float* w[kMaxRanks];            // every rank's fp32 master weights for this bucket (symmetric)
+  __nv_bfloat16* wb[kMaxRanks];   // every rank's bf16 shadow (may be null)
+  uint32_t* flags[kMaxRanks];     // every rank's flag block for this bucket: [2][kMaxRanks] u32
+  const float* g_mc;              // multicast (NVLS) address of the gradient bucket, or null
+  float* w_mc;                    // multicast address of the weights, or null
+};
+
+__device__ __forceinline__ float4 multimem_ld_reduce_f32x4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_f32x4(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+// Cross-rank barrier on this bucket's flag block.  phase 0/1 use separate words so epochs never alias.
+__device__ __forceinline__ void peer_barrier(const PeerPtrs& pp, int rank, int world, int phase, uint32_t epoch) {
+  if (threadIdx.x < world) {
+    // tell peer t that `rank` reached `epoch`
+    st_release_sys(pp.flags[threadIdx.x] + phase * kMaxRanks + rank, epoch);
+  }
+  if (threadIdx.x < world) wait_flag_ge(pp.flags[rank] + phase * kMaxRanks + threadIdx.x, epoch);
+  __syncthreads();
+}
+
+template <bool ONE_SHOT>
+__global__ void __launch_bounds__(512)
+allreduce_sgd_kernel(PeerPtrs pp, float* __restrict__ h, long n, int rank, int world, uint32_t epoch, UpdateHyper hp,
+                     unsigned int* __restrict__ done_counter) {
+  // ---- phase 0: all ranks' gradients for this epoch are in place
+  peer_barrier(pp, rank, world, 0, epoch);
+
+  const long n4 = n >> 2;           // buckets are padded to multiples of 4 floats by the arena
+  long lo = 0, hi = n4;
+  if (!ONE_SHOT) {
+    const long per = (n4 + world - 1) / world;
+    lo = min(n4, per * rank);
+    hi = min(n4, lo + per);
+  }
+  for (long i = lo + blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < hi;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    float4 gv;
+    if (pp.g_mc != nullptr) {
+      gv = multimem_ld_reduce_f32x4(pp.g_mc + 4 * i);
+    } else {
+      gv = reinterpret_cast<const float4*>(pp.g[rank])[i];
+#pragma unroll 1
+      for (int q = 1; q < world; ++q) {
+        const int p = (rank + q) % world;           // stagger peers so links are used evenly
+        const float4 t = reinterpret_cast<const float4*>(pp.g[p])[i];
+        gv.x += t.x; gv.y += t.y; gv.z += t.z; gv.w += t.w;
+      }
+    }
+    float4 wv = reinterpret_cast<float4*>(pp.w[rank])[i];
+    float4 hv = reinterpret_cast<float4*>(h)[i];
+    step_rule(gv.x, wv.x, hv.x, hp);
+    step_rule(gv.y, wv.y, hv.y, hp);
+    step_rule(gv.z, wv.z, hv.z, hp);
+    step_rule(gv.w, wv.w, hv.w, hp);
+    reinterpret_cast<float4*>(h)[i] = hv;
+    if (ONE_SHOT) {
+      reinterpret_cast<float4*>(pp.w[rank])[i] = wv;
+      if (pp.wb[rank] != nullptr) reinterpret_cast<uint2*>(pp.wb[rank])[i] = pack_bf16x4(wv);
+    } else {
+      const uint2 b = pack_bf16x4(wv);
+      if (pp.w_mc != nullptr) {
+        multimem_st_f32x4(pp.w_mc + 4 * i, wv);
+      } else {
+#pragma unroll 1
+        for (int q = 0; q < world; ++q) reinterpret_cast<float4*>(pp.w[(rank + q) % world])[i] = wv;
+      }
+#pragma unroll 1
+      for (int q = 0; q < world; ++q) {
+        const int p = (rank + q) % world;
+        if (pp.wb[p] != nullptr) reinterpret_cast<uint2*>(pp.wb[p])[i] = b;
+      }
+    }
+  }
+  // ---- phase 1: everyone finished reading my G and (two-shot) writing my W
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last) {
+    if (threadIdx.x == 0) *done_counter = 0;       // ready for the next launch on this stream
+    peer_barrier(pp, rank, world, 1, epoch);
+  }
+}
+
+// g_ptrs / w_ptrs / wb_ptrs / flag_ptrs: per-rank device addresses of this bucket inside each rank's symmetric arena.
+void allreduce_sgd(std::vector<int64_t> g_ptrs, std::vector<int64_t> w_ptrs, std::vector<int64_t> wb_ptrs,
+                   std::vector<int64_t> flag_ptrs, int64_t g_mc, int64_t w_mc, at::Tensor h, int64_t n, int64_t rank,
+                   int64_t epoch, bool one_shot, at::Tensor done_counter, double lr, double momentum, double decay,
+                   int64_t rule, bool l1, double delta, double gscale, int64_t max_ctas) {
+  const int world = static_cast<int>(g_ptrs.size());
+  TORCH_CHECK(world >= 1 && world <= kMaxRanks && w_ptrs.size() == g_ptrs.size() && flag_ptrs.size() == g_ptrs.size());
+  TORCH_CHECK(h.is_cuda() && h.scalar_type() == at::kFloat && h.numel() >= n && n % 4 == 0);
+  TORCH_CHECK(done_counter.scalar_type() == at::kInt && done_counter.numel() >= 1);
+  c10::cuda::CUDAGuard guard(h.device());
+  PeerPtrs pp{};
+  for (int p = 0; p < world; ++p) {
+    pp.g[p] = reinterpret_cast<const float*>(g_ptrs[p]);
+    pp.w[p] = reinterpret_cast<float*>(w_ptrs[p]);
+    pp.wb[p] = wb_ptrs.empty() ? nullptr : reinterpret_cast<__nv_bfloat16*>(wb_ptrs[p]);
+    pp.flags[p] = reinterpret_cast<uint32_t*>(flag_ptrs[p]);
+  }
+  pp.g_mc = reinterpret_cast<const float*>(g_mc);
+  pp.w_mc = reinterpret_cast<float*>(w_mc);
+  UpdateHyper hp = make_hyper(lr, momentum, decay, rule, l1, delta, gscale);
+  const long work4 = one_shot ? n / 4 : (n / 4 + world - 1) / world;
+  int grid = static_cast<int>(std::max<long>(1, std::min<long>((work4 + 511) / 512, max_ctas > 0 ? max_ctas : 64)));
+  auto stream = at::cuda::getCurrentCUDAStream();
+  auto* dc = reinterpret_cast<unsigned int*>(done_counter.data_ptr());
+  if (one_shot)
+    allreduce_sgd_kernel<true><<<grid, 512, 0, stream>>>(pp, h.data_ptr<float>(), n, static_cast<int>(rank), world,
+                                                         static_cast<uint32_t>(epoch), hp, dc);
+  else
+    allreduce_sgd_kernel<false><<<grid, 512, 0, stream>>>(pp, h.data_ptr<float>(), n, static_cast<int>(rank), world,
+                                                          static_cast<uint32_t>(epoch), hp, dc);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+// Publish a payload (sufficient factors) into EVERY rank's arena at the same offset — one multimem.st through
+// the NVSwitch when a multicast mapping exists, P2P stores otherwise — then (optionally) raise this rank's
+// epoch flag on every peer.  The payload crosses NVLink exactly once per peer; consumers read it locally.
+__global__ void __launch_bounds__(512)
+peer_push_kernel(const uint4* __restrict__ src, PeerPtrs dst, uint4* __restrict__ dst_mc, long n16, int rank, int world,
+                 int slot, uint32_t epoch, int signal, unsigned int* __restrict__ done_counter) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n16; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const uint4 v = src[i];
+    if (dst_mc != nullptr) {
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_mc + i),
+                   "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                   : "memory");
+    } else {
+#pragma unroll 1
+      for (int q = 0; q < world; ++q) reinterpret_cast<uint4*>(dst.w[(rank + q) % world])[i] = v;
+    }
+  }
+  if (!signal) return;
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last) {
+    if (threadIdx.x == 0) *done_counter = 0;
+    __threadfence_system();
+    if (threadIdx.x < world) st_release_sys(dst.flags[threadIdx.x] + slot * kMaxRanks + rank, epoch);
+  }
+}
+
+// src: dense tensor (nbytes % 16 == 0).  dst_ptrs[p]: destination address inside rank p's arena.
+void peer_push(const at::Tensor& src, std::vector<int64_t> dst_ptrs, int64_t dst_mc, std::vector<int64_t> flag_ptrs,
+               int64_t rank, int64_t slot, int64_t epoch, bool signal, at::Tensor done_counter) {
+  const int world = static_cast<int>(dst_ptrs.size());
+  TORCH_CHECK(world >= 1 && world <= kMaxRanks && src.is_cuda() && src.is_contiguous());
+  const long nbytes = src.numel() * src.element_size();
+  TORCH_CHECK(nbytes % 16 == 0 && reinterpret_cast<uintptr_t>(src.data_ptr()) % 16 == 0, "peer_push: 16-byte granularity");
+  c10::cuda::CUDAGuard guard(src.device());
+  PeerPtrs pp{};
+  for (int p = 0; p < world; ++p) {
+    pp.w[p] = reinterpret_cast<float*>(dst_ptrs[p]);
+    pp.flags[p] = signal ? reinterpret_cast<uint32_t*>(flag_ptrs[p]) : nullptr;
+  }
+  const long n16 = nbytes / 16;
+  const int grid = static_cast<int>(std::max<long>(1, std::min<long>((n16 + 511) / 512, 32)));
+  peer_push_kernel<<<grid, 512, 0, at::cuda::getCurrentCUDAStream()>>>(
+      reinterpret_cast<const uint4*>(src.data_ptr()), pp, reinterpret_cast<uint4*>(dst_mc), n16, static_cast<int>(rank), world,
+      static_cast<int>(slot), static_cast<uint32_t>(epoch), signal ? 1 : 0,
+      reinterpret_cast<unsigned int*>(done_counter.data_ptr()));
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+}  // namespace psd
+
+TORCH_LIBRARY_FRAGMENT(poseidon, m) {
+  m.def("fused_update(Tensor(a!) w, Tensor g, Tensor(b!) h, Tensor(c!)? wb, float lr, float momentum, float decay, int rule, "
+        "bool l1, float delta, float gscale) -> ()", &psd::fused_update);
+  m.def("allreduce_sgd(int[] g_ptrs, int[] w_ptrs, int[] wb_ptrs, int[] flag_ptrs, int g_mc, int w_mc, Tensor(a!) h, int n, "
+        "int rank, int epoch, bool one_shot, Tensor(b!) done_counter, float lr, float momentum, float decay, int rule, "
+        "bool l1, float delta, float gscale, int max_ctas) -> ()", &psd::allreduce_sgd);
+  m.def("peer_push(Tensor src, int[] dst_ptrs, int dst_mc, int[] flag_ptrs, int rank, int slot, int epoch, bool signal, "
+        "Tensor(a!) done_counter) -> ()", &psd::peer_push);
+}

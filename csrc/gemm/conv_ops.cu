@@ -1,0 +1,252 @@
+// Implicit-GEMM convolution on the tcgen05 GEMM core: fprop, dgrad (stride 1), wgrad (split-K fp32 atomics).
+//
+// Layouts (sm100 engine): activations NHWC bf16 (pixel pitch may exceed C for channel-slice views);
+// weights fp32 master + bf16 shadow as [Cout][R][S][Cg] ("KRSC", K-major rows of length R*S*Cg), or
+// [Cout][R][Lp] for first layers in ROW mode (see conv_gather.cuh).
+//
+// reference semantics: src/caffe/layers/conv_layer.cpp:114-155 (output size, groups),
+// conv_layer.cu:13-44 (fprop + bias), :48-119 (bias / weight / data gradients).
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/library.h>
+#include <torch/types.h>
+
+#include "../ops/nhwc_common.cuh"
+#include "umma_gemm.cuh"
+
+namespace psd {
+
+void encode_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner,
+                         int box_outer);
+
+template <int BN, bool A_MN, bool B_MN, int EPI, int GATHER>
+static void launch_conv(const TmapSet& tm, const GemmParams& p, const ConvGeom& cg, int grid, cudaStream_t stream) {
+  auto kern = umma_gemm_kernel<BN, A_MN, B_MN, EPI, GATHER>;
+  constexpr int smem = GemmSmem<BN>::kTotal;
+  static bool configured = false;
+  if (!configured) {
+    C10_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  kern<<<grid, kNumThreads + kGatherThreads, smem, stream>>>(tm, p, cg);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+struct ConvDesc {
+  int R, S, sh, sw, ph, pw, groups;
+  int mode;      // 0 TAP, 1 ROW
+};
+
+static ConvGeom make_geom(const at::Tensor& x, const NhwcView& xv, int c_off, int Cg, int OH, int OW, const ConvDesc& d,
+                          bool dgrad) {
+  ConvGeom g{};
+  g.x = reinterpret_cast<const __nv_bfloat16*>(x.data_ptr()) + c_off;
+  g.N = xv.N; g.H = xv.H; g.W = xv.W;
+  g.pitch = xv.pitch;
+  g.Cg = Cg;
+  g.OH = OH; g.OW = OW;
+  g.R = d.R; g.S = d.S;
+  g.sh = dgrad ? 1 : d.sh; g.sw = dgrad ? 1 : d.sw;
+  g.off_h = dgrad ? d.ph : -d.ph;
+  g.off_w = dgrad ? d.pw : -d.pw;
+  g.dr = dgrad ? -1 : 1;
+  g.mode = d.mode;
+  g.L = d.S * Cg;
+  g.Lp = (g.L + 7) / 8 * 8;
+  g.K = d.mode == 1 ? d.R * g.Lp : d.R * d.S * Cg;
+  g.M = static_cast<long>(xv.N) * OH * OW;
+  if (d.mode == 1) {
+    TORCH_CHECK(xv.pitch == Cg, "ROW-mode conv needs a dense input (pitch == channels)");
+    TORCH_CHECK(d.ph == 0 && d.pw == 0, "ROW-mode conv expects a pre-padded input");
+    TORCH_CHECK((d.sw * Cg) % 8 == 0 && (xv.W * Cg) % 8 == 0, "ROW-mode conv: 16-byte alignment of kernel rows");
+  } else {
+    TORCH_CHECK(Cg % 8 == 0 && xv.pitch % 8 == 0 && c_off % 8 == 0, "TAP-mode conv: channels must be multiples of 8");
+  }
+  return g;
+}
+
+static int pick_conv_bn(int64_t n_cols) { return n_cols > 128 ? 256 : (n_cols > 64 ? 128 : 64); }
+
+// y[N, Cout, OH, OW] (NHWC bf16) = act(conv(x, w) + bias).  wb: [Cout, Kw] bf16 (Kw = R*S*Cg or R*Lp).
+at::Tensor conv_fprop(const at::Tensor& x, const at::Tensor& wb, const c10::optional<at::Tensor>& bias, at::IntArrayRef kernel,
+                      at::IntArrayRef stride, at::IntArrayRef pad, int64_t groups, int64_t mode, int64_t OH, int64_t OW,
+                      bool relu, double slope, c10::optional<at::Tensor> out) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && wb.scalar_type() == at::kBFloat16 && wb.dim() == 2);
+  c10::cuda::CUDAGuard guard(x.device());
+  NhwcView xv = nhwc_view(x);
+  ConvDesc d{static_cast<int>(kernel[0]), static_cast<int>(kernel[1]), static_cast<int>(stride[0]), static_cast<int>(stride[1]),
+             static_cast<int>(pad[0]), static_cast<int>(pad[1]), static_cast<int>(groups), static_cast<int>(mode)};
+  const int Cout = wb.size(0), Cout_g = Cout / groups, Cg = xv.C / groups;
+  at::Tensor y = out.has_value() ? *out : empty_nhwc(xv.N, Cout, OH, OW, x.options());
+  NhwcView yv = nhwc_view(y);
+  TORCH_CHECK(yv.C == Cout && yv.H == OH && yv.W == OW && yv.N == xv.N, "conv_fprop: bad output tensor");
+  auto stream = at::cuda::getCurrentCUDAStream();
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  for (int gidx = 0; gidx < groups; ++gidx) {
+    ConvGeom cg = make_geom(x, xv, gidx * Cg, Cg, OH, OW, d, false);
+    TORCH_CHECK(wb.size(1) == cg.K, "conv_fprop: weight K ", wb.size(1), " != expected ", cg.K);
+    const int bn = pick_conv_bn(Cout_g);
+    TmapSet tm;
+    const __nv_bfloat16* wptr = reinterpret_cast<const __nv_bfloat16*>(wb.data_ptr()) + static_cast<long>(gidx) * Cout_g * cg.K;
+    encode_tmap_bf16_2d(&tm.b[0], wptr, cg.K, Cout_g, cg.K, BLOCK_K, bn);
+    tm.a[0] = tm.b[0];
+    GemmParams p{};
+    p.M = static_cast<int>(cg.M);
+    p.N = Cout_g;
+    p.kb_per_src = (cg.K + BLOCK_K - 1) / BLOCK_K;
+    p.num_src = 1;
+    p.split_k = 1;
+    p.c_bf16 = reinterpret_cast<__nv_bfloat16*>(y.data_ptr()) + gidx * Cout_g;
+    p.ldc = yv.pitch;
+    p.bias = bias.has_value() ? bias->data_ptr<float>() + gidx * Cout_g : nullptr;
+    p.relu = relu;
+    p.relu_slope = static_cast<float>(slope);
+    p.alpha = 1.f;
+    const long tiles = ((cg.M + BLOCK_M - 1) / BLOCK_M) * ((Cout_g + bn - 1) / bn);
+    const int grid = static_cast<int>(std::min<long>(tiles, sms));
+    switch (bn) {
+      case 64: launch_conv<64, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
+      case 128: launch_conv<128, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
+      default: launch_conv<256, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
+    }
+  }
+  return y;
+}
+
+// dx[N, Cin, H, W] = conv_transpose(dy, w) for stride-1 convolutions; wt: [groups*Cg, R*S*Cout_g] bf16
+// (per group: rows = input channel, K = (r, s, co)).  Optional mask = forward output of the producer layer
+// (fused ReLU backward: dx is zeroed / scaled by slope where mask <= 0).
+at::Tensor conv_dgrad(const at::Tensor& dy, const at::Tensor& wt, at::IntArrayRef kernel, at::IntArrayRef pad, int64_t groups,
+                      int64_t H, int64_t W, const c10::optional<at::Tensor>& mask, double slope) {
+  TORCH_CHECK(dy.is_cuda() && dy.scalar_type() == at::kBFloat16 && wt.scalar_type() == at::kBFloat16 && wt.dim() == 2);
+  c10::cuda::CUDAGuard guard(dy.device());
+  NhwcView dv = nhwc_view(dy);
+  ConvDesc d{static_cast<int>(kernel[0]), static_cast<int>(kernel[1]), 1, 1, static_cast<int>(pad[0]), static_cast<int>(pad[1]),
+             static_cast<int>(groups), 0};
+  const int Cin = wt.size(0), Cg = Cin / groups, Cout_g = dv.C / groups;
+  at::Tensor dx = empty_nhwc(dv.N, Cin, H, W, dy.options());
+  NhwcView xv = nhwc_view(dx);
+  auto stream = at::cuda::getCurrentCUDAStream();
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  long mask_pitch = 0;
+  if (mask.has_value()) {
+    NhwcView mv = nhwc_view(*mask);
+    TORCH_CHECK(mv.C == Cin && mv.H == H && mv.W == W && mv.pitch == xv.pitch, "conv_dgrad: mask must match dx layout");
+    mask_pitch = mv.pitch;
+  }
+  for (int gidx = 0; gidx < groups; ++gidx) {
+    ConvGeom cg = make_geom(dy, dv, gidx * Cout_g, Cout_g, H, W, d, true);
+    TORCH_CHECK(wt.size(1) == cg.K, "conv_dgrad: packed weight K mismatch");
+    const int bn = pick_conv_bn(Cg);
+    TmapSet tm;
+    const __nv_bfloat16* wptr = reinterpret_cast<const __nv_bfloat16*>(wt.data_ptr()) + static_cast<long>(gidx) * Cg * cg.K;
+    encode_tmap_bf16_2d(&tm.b[0], wptr, cg.K, Cg, cg.K, BLOCK_K, bn);
+    tm.a[0] = tm.b[0];
+    GemmParams p{};
+    p.M = static_cast<int>(cg.M);
+    p.N = Cg;
+    p.kb_per_src = (cg.K + BLOCK_K - 1) / BLOCK_K;
+    p.num_src = 1;
+    p.split_k = 1;
+    p.c_bf16 = reinterpret_cast<__nv_bfloat16*>(dx.data_ptr()) + gidx * Cg;
+    p.ldc = xv.pitch;
+    p.mask = mask.has_value() ? reinterpret_cast<const __nv_bfloat16*>(mask->data_ptr()) + gidx * Cg : nullptr;
+    p.relu_slope = static_cast<float>(slope);
+    p.alpha = 1.f;
+    (void)mask_pitch;
+    const long tiles = ((cg.M + BLOCK_M - 1) / BLOCK_M) * ((Cg + bn - 1) / bn);
+    const int grid = static_cast<int>(std::min<long>(tiles, sms));
+    switch (bn) {
+      case 64: launch_conv<64, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
+      case 128: launch_conv<128, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
+      default: launch_conv<256, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
+    }
+  }
+  return dx;
+}
+
+// dw[Cout, Kw] fp32 += alpha * dYᵀ · im2col(x)   (atomic split-K over the N*OH*OW reduction; dw pre-zeroed
+// unless accumulating into an existing gradient).
+void conv_wgrad(const at::Tensor& x, const at::Tensor& dy, at::Tensor dw, at::IntArrayRef kernel, at::IntArrayRef stride,
+                at::IntArrayRef pad, int64_t groups, int64_t mode, double alpha) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && dy.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(dw.scalar_type() == at::kFloat && dw.dim() == 2 && dw.is_contiguous());
+  c10::cuda::CUDAGuard guard(x.device());
+  NhwcView xv = nhwc_view(x), dv = nhwc_view(dy);
+  ConvDesc d{static_cast<int>(kernel[0]), static_cast<int>(kernel[1]), static_cast<int>(stride[0]), static_cast<int>(stride[1]),
+             static_cast<int>(pad[0]), static_cast<int>(pad[1]), static_cast<int>(groups), static_cast<int>(mode)};
+  const int Cout = dv.C, Cout_g = Cout / groups, Cg = xv.C / groups;
+  TORCH_CHECK(dv.pitch % 8 == 0 && Cout_g % 8 == 0, "conv_wgrad: output channels must be multiples of 8");
+  auto stream = at::cuda::getCurrentCUDAStream();
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  for (int gidx = 0; gidx < groups; ++gidx) {
+    ConvGeom cg = make_geom(x, xv, gidx * Cg, Cg, dv.H, dv.W, d, false);
+    TORCH_CHECK(dw.size(0) == Cout && dw.size(1) == cg.K, "conv_wgrad: dw shape mismatch");
+    const int bn = cg.K > 128 ? 256 : (cg.K > 64 ? 128 : 64);
+    TmapSet tm;
+    // A = dYᵀ: MN-major, inner = Cout_g channels of this group, outer = M pixels, pitch = dy pixel pitch
+    const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(dy.data_ptr()) + gidx * Cout_g;
+    encode_tmap_bf16_2d(&tm.a[0], dyp, Cout_g, cg.M, dv.pitch, 64, BLOCK_K);
+    tm.b[0] = tm.a[0];
+    GemmParams p{};
+    p.M = Cout_g;
+    p.N = cg.K;
+    p.kb_per_src = static_cast<int>((cg.M + BLOCK_K - 1) / BLOCK_K);
+    p.num_src = 1;
+    const long tiles = ((Cout_g + BLOCK_M - 1) / BLOCK_M) * ((cg.K + bn - 1) / bn);
+    long split = std::max<long>(1, (2L * sms + tiles - 1) / tiles);
+    split = std::min<long>(split, std::max<long>(1, p.kb_per_src / 8));
+    p.split_k = static_cast<int>(split);
+    p.c_f32 = dw.data_ptr<float>() + static_cast<long>(gidx) * Cout_g * cg.K;
+    p.ldc = cg.K;
+    p.atomic = 1;
+    p.alpha = static_cast<float>(alpha);
+    const int grid = static_cast<int>(std::min<long>(tiles * split, sms));
+    switch (bn) {
+      case 64: launch_conv<64, true, true, EPI_F32, GATHER_B>(tm, p, cg, grid, stream); break;
+      case 128: launch_conv<128, true, true, EPI_F32, GATHER_B>(tm, p, cg, grid, stream); break;
+      default: launch_conv<256, true, true, EPI_F32, GATHER_B>(tm, p, cg, grid, stream); break;
+    }
+  }
+}
+
+// Pack the dgrad operand from the fp32 master weights: w [Cout][R][S][Cg] -> wt [groups][Cg][R][S][Cout_g] bf16.
+__global__ void pack_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wt, int Cout, int RS, int Cg,
+                                  int groups) {
+  const int Cout_g = Cout / groups;
+  const long total = static_cast<long>(Cout) * RS * Cg;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    // i indexes wt: (((g*Cg + ci)*RS + tap)*Cout_g + co)
+    const int co = static_cast<int>(i % Cout_g);
+    long t = i / Cout_g;
+    const int tap = static_cast<int>(t % RS); t /= RS;
+    const int ci = static_cast<int>(t % Cg);
+    const int g = static_cast<int>(t / Cg);
+    wt[i] = __float2bfloat16(w[((static_cast<long>(g) * Cout_g + co) * RS + tap) * Cg + ci]);
+  }
+}
+
+at::Tensor conv_pack_dgrad(const at::Tensor& w, int64_t Cout, int64_t RS, int64_t Cg, int64_t groups,
+                           c10::optional<at::Tensor> out) {
+  TORCH_CHECK(w.is_cuda() && w.scalar_type() == at::kFloat && w.numel() == Cout * RS * Cg);
+  c10::cuda::CUDAGuard guard(w.device());
+  at::Tensor wt = out.has_value() ? *out : at::empty({groups * Cg, RS * (Cout / groups)}, w.options().dtype(at::kBFloat16));
+  const long total = Cout * RS * Cg;
+  pack_dgrad_kernel<<<grid_for(total, 256), 256, 0, at::cuda::getCurrentCUDAStream()>>>(
+      w.data_ptr<float>(), reinterpret_cast<__nv_bfloat16*>(wt.data_ptr()), Cout, RS, Cg, groups);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  return wt;
+}
+
+}  // namespace psd
+
+TORCH_LIBRARY_FRAGMENT(poseidon, m) {
+  m.def("conv_fprop(Tensor x, Tensor wb, Tensor? bias, int[] kernel, int[] stride, int[] pad, int groups, int mode, "
+        "int OH, int OW, bool relu, float slope, Tensor? out) -> Tensor", &psd::conv_fprop);
+  m.def("conv_dgrad(Tensor dy, Tensor wt, int[] kernel, int[] pad, int groups, int H, int W, Tensor? mask, float slope) "
+        "-> Tensor", &psd::conv_dgrad);
+  m.def("conv_wgrad(Tensor x, Tensor dy, Tensor(a!) dw, int[] kernel, int[] stride, int[] pad, int groups, int mode, "
+        "float alpha) -> ()", &psd::conv_wgrad);
+  m.def("conv_pack_dgrad(Tensor w, int Cout, int RS, int Cg, int groups, Tensor? out) -> Tensor", &psd::conv_pack_dgrad);
+}

@@ -50,7 +50,7 @@ static void launch(const TmapSet& tm, const GemmParams& p, int grid, cudaStream_
     C10_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  kern<<<grid, kNumThreads, smem, stream>>>(tm, p);
+  kern<<<grid, kNumThreads, smem, stream>>>(tm, p, ConvGeom{});
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 

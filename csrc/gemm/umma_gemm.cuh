@@ -17,6 +17,7 @@
 // (layers/conv_layer.cu:23-119) and ComputeGradientFromSV_gpu (layers/inner_product_layer.cu:55-64).
 #pragma once
 #include "sm100_prims.cuh"
+#include "conv_gather.cuh"
 
 namespace psd {
 
@@ -26,6 +27,10 @@ constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
 constexpr int kNumThreads = 256;          // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
 constexpr int kEpiWarp0 = 4;
+constexpr int kGatherWarp0 = 8;           // conv kernels: warps 8-11 gather the implicit-im2col operand
+constexpr int kGatherThreads = 128;
+constexpr int kGatherLag = 2;             // cp.async groups kept in flight per gather thread
+enum GatherMode : int { GATHER_NONE = 0, GATHER_A = 1, GATHER_B = 2 };
 
 enum EpiMode : int { EPI_BF16 = 0, EPI_F32 = 1, EPI_SGD = 2 };
 
@@ -195,8 +200,7 @@ __device__ __forceinline__ void epilogue_row32(const GemmParams& p, const uint32
 // Producer policy: both operands via TMA.
 template <int BN, bool A_MN, bool B_MN>
 struct TmaProducer {
-  __device__ static void load_stage(const TmapSet& tm, int src, int kb, int m_blk, int n_blk, uint8_t* sa,
-                                    uint8_t* sb, uint64_t* full) {
+  __device__ static void load_a(const TmapSet& tm, int src, int kb, int m_blk, uint8_t* sa, uint64_t* full) {
     const int k0 = kb * BLOCK_K;
     if constexpr (!A_MN) {
       tma_load_2d(sa, &tm.a[src], full, k0, m_blk * BLOCK_M);
@@ -204,6 +208,9 @@ struct TmaProducer {
 #pragma unroll
       for (int c = 0; c < BLOCK_M / 64; ++c) tma_load_2d(sa + c * 8192, &tm.a[src], full, m_blk * BLOCK_M + 64 * c, k0);
     }
+  }
+  __device__ static void load_b(const TmapSet& tm, int src, int kb, int n_blk, uint8_t* sb, uint64_t* full) {
+    const int k0 = kb * BLOCK_K;
     if constexpr (!B_MN) {
       tma_load_2d(sb, &tm.b[src], full, k0, n_blk * BN);
     } else {
@@ -211,11 +218,18 @@ struct TmaProducer {
       for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &tm.b[src], full, n_blk * BN + 64 * c, k0);
     }
   }
+  __device__ static void load_stage(const TmapSet& tm, int src, int kb, int m_blk, int n_blk, uint8_t* sa,
+                                    uint8_t* sb, uint64_t* full) {
+    load_a(tm, src, kb, m_blk, sa, full);
+    load_b(tm, src, kb, n_blk, sb, full);
+  }
 };
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
-__global__ void __launch_bounds__(kNumThreads, 1)
-umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p) {
+template <int BN, bool A_MN, bool B_MN, int EPI, int GATHER = GATHER_NONE>
+__global__ void __launch_bounds__(kNumThreads + (GATHER != GATHER_NONE ? kGatherThreads : 0), 1)
+umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const ConvGeom cg) {
+  static_assert(GATHER != GATHER_A || !A_MN, "gathered A is produced K-major");
+  static_assert(GATHER != GATHER_B || B_MN, "gathered B is produced MN-major");
   using S = GemmSmem<BN>;
   constexpr int kStages = S::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -243,7 +257,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p) {
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 1 + (GATHER != GATHER_NONE ? kGatherThreads : 0));
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -283,9 +297,17 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p) {
             last_src = src;
           }
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
           uint8_t* sa = smem + stage * S::kStageBytes;
-          TmaProducer<BN, A_MN, B_MN>::load_stage(tm, src, kb, m_blk, n_blk, sa, sa + S::kABytes, &full_bar[stage]);
+          if constexpr (GATHER == GATHER_NONE) {
+            mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+            TmaProducer<BN, A_MN, B_MN>::load_stage(tm, src, kb, m_blk, n_blk, sa, sa + S::kABytes, &full_bar[stage]);
+          } else if constexpr (GATHER == GATHER_A) {
+            mbar_arrive_expect_tx(&full_bar[stage], S::kBBytes);
+            TmaProducer<BN, A_MN, B_MN>::load_b(tm, src, kb, n_blk, sa + S::kABytes, &full_bar[stage]);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], S::kABytes);
+            TmaProducer<BN, A_MN, B_MN>::load_a(tm, src, kb, m_blk, sa, &full_bar[stage]);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -325,7 +347,57 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p) {
         umma_commit(&tmem_full[as]);               // accumulator complete -> epilogue
       }
     }
-  } else if (warp >= kEpiWarp0) {
+  } else if (GATHER != GATHER_NONE && warp >= kGatherWarp0) {
+    // ===================== gather producers: implicit im2col -> swizzled smem via cp.async =====================
+    const int gt = threadIdx.x - kGatherWarp0 * 32;      // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    int issued = 0;                                       // k-blocks issued so far (continuous across tiles)
+    int sig_stage = 0;                                    // next stage to signal
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % m_blocks;
+      const int rest = tile / m_blocks;
+      const int n_blk = rest % n_blocks;
+      const int split = rest / n_blocks;
+      const int g0 = static_cast<int>(static_cast<long>(total_kb) * split / p.split_k);
+      const int g1 = static_cast<int>(static_cast<long>(total_kb) * (split + 1) / p.split_k);
+      for (int g = g0; g < g1; ++g) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * S::kStageBytes;
+        if constexpr (GATHER == GATHER_A) {
+          // A tile: 128 rows (m) x 64 k, row = gt
+          gather_row(cg, smem_u32(sa) + gt * 128, gt, static_cast<long>(m_blk) * BLOCK_M + gt, g * BLOCK_K);
+        } else {
+          // B tile (MN-major): BN/64 chunks of [64 reduction rows (m)][64 k-columns]; reduction index = g
+          constexpr int kChunks = BN / 64;
+          const uint32_t sb = smem_u32(sa) + S::kABytes;
+#pragma unroll
+          for (int i = gt; i < kChunks * 64; i += kGatherThreads) {
+            const int chunk = i >> 6, r = i & 63;
+            gather_row(cg, sb + chunk * 8192 + r * 128, r, static_cast<long>(g) * BLOCK_K + r,
+                       n_blk * BN + chunk * 64);
+          }
+        }
+        cp_async_commit();
+        ++issued;
+        if (issued > kGatherLag) {
+          cp_async_wait<kGatherLag>();
+          fence_proxy_async_smem();
+          mbar_arrive(&full_bar[sig_stage]);
+          if (++sig_stage == kStages) sig_stage = 0;
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+    // drain
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    const int pending = issued < kGatherLag ? issued : kGatherLag;
+    for (int i = 0; i < pending; ++i) {
+      mbar_arrive(&full_bar[sig_stage]);
+      if (++sig_stage == kStages) sig_stage = 0;
+    }
+  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
     // ===================== epilogue warps: TMEM -> registers -> global =====================
     const int q = warp - kEpiWarp0;               // TMEM lane quadrant == warp_id % 4
     int it = 0;

@@ -14,9 +14,9 @@ template <typename TIn, int CP>
 __global__ void __launch_bounds__(256)
 transform_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const int* __restrict__ h_off,
                  const int* __restrict__ w_off, const uint8_t* __restrict__ flip, const float* __restrict__ mean,
-                 int mean_mode, float scale, int N, int C, int H, int W, int OH, int OW, int opad) {
+                 int mean_mode, float scale, int N, int C, int H, int W, int OH, int OW, int opad, int wextra) {
   const long total = static_cast<long>(N) * OH * OW;
-  const int OHp = OH + 2 * opad, OWp = OW + 2 * opad;
+  const int OHp = OH + 2 * opad, OWp = OW + 2 * opad + wextra;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
     const int ow = static_cast<int>(i % OW);
@@ -56,15 +56,14 @@ transform_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, con
 // x: [N,C,H,W] uint8|float32 contiguous -> [N, Cp, OH+2opad, OW+2opad] bf16 channels-last (border zero).
 at::Tensor transform_nhwc(const at::Tensor& x, const at::Tensor& h_off, const at::Tensor& w_off, const at::Tensor& flip,
                           const c10::optional<at::Tensor>& mean, double scale, int64_t OH, int64_t OW, int64_t cp,
-                          int64_t opad) {
+                          int64_t opad, int64_t wextra) {
   TORCH_CHECK(x.is_cuda() && x.dim() == 4 && x.is_contiguous());
   TORCH_CHECK(h_off.scalar_type() == at::kInt && w_off.scalar_type() == at::kInt && flip.scalar_type() == at::kByte);
   c10::cuda::CUDAGuard guard(x.device());
   const int N = x.size(0), C = x.size(1), H = x.size(2), W = x.size(3);
   TORCH_CHECK(C <= cp && (cp == 4 || cp == 8), "transform: channel padding must be 4 or 8");
-  at::Tensor out = opad > 0 ? at::zeros({N, cp, OH + 2 * opad, OW + 2 * opad},
-                                        x.options().dtype(at::kBFloat16).memory_format(at::MemoryFormat::ChannelsLast))
-                            : empty_nhwc(N, cp, OH, OW, x.options().dtype(at::kBFloat16));
+  at::Tensor out = empty_nhwc(N, cp, OH + 2 * opad, OW + 2 * opad + wextra, x.options().dtype(at::kBFloat16));
+  if (opad > 0 || wextra > 0) out.zero_();      // (at::zeros ignores the channels-last request)
   int mean_mode = 0;
   const float* mp = nullptr;
   if (mean.has_value()) {
@@ -79,7 +78,7 @@ at::Tensor transform_nhwc(const at::Tensor& x, const at::Tensor& h_off, const at
 #define PSD_XF(T, CPV)                                                                                          \
   transform_kernel<T, CPV><<<grid_for(total, 256), 256, 0, stream>>>(                                         \
       x.data_ptr<T>(), op, h_off.data_ptr<int>(), w_off.data_ptr<int>(), flip.data_ptr<uint8_t>(), mp, mean_mode, \
-      static_cast<float>(scale), N, C, H, W, OH, OW, opad)
+      static_cast<float>(scale), N, C, H, W, OH, OW, opad, wextra)
   if (x.scalar_type() == at::kByte) {
     if (cp == 4) PSD_XF(uint8_t, 4); else PSD_XF(uint8_t, 8);
   } else {
@@ -228,7 +227,7 @@ void colsum(const at::Tensor& dy, int64_t rows, int64_t C, int64_t ld, at::Tenso
 
 TORCH_LIBRARY_FRAGMENT(poseidon, m) {
   m.def("transform_nhwc(Tensor x, Tensor h_off, Tensor w_off, Tensor flip, Tensor? mean, float scale, int OH, int OW, "
-        "int cp, int opad) -> Tensor", &psd::transform_nhwc);
+        "int cp, int opad, int wextra) -> Tensor", &psd::transform_nhwc);
   m.def("relu_fwd(Tensor x, float slope) -> Tensor", &psd::relu_fwd);
   m.def("relu_bwd(Tensor y, Tensor dy, float slope) -> Tensor", &psd::relu_bwd);
   m.def("dropout_apply(Tensor x, float ratio, int seed) -> Tensor", &psd::dropout_apply);

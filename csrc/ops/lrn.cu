@@ -28,7 +28,8 @@ lrn_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict_
   float* sr = sm + pix_per_cta * CP;     // bwd: r = dy * x * scale^(-beta-1)   [pix][CP]
   const int c8 = C / 8;
   for (long p0 = static_cast<long>(blockIdx.x) * pix_per_cta; p0 < npix; p0 += static_cast<long>(gridDim.x) * pix_per_cta) {
-    const int np = static_cast<int>(min<long>(pix_per_cta, npix - p0));
+    const long rem = npix - p0;
+    const int np = rem < pix_per_cta ? static_cast<int>(rem) : pix_per_cta;
     // stage x (optionally with a fused ReLU on the way in)
     for (int i = threadIdx.x; i < np * c8; i += blockDim.x) {
       const int p = i / c8, v = i - p * c8;

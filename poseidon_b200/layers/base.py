@@ -112,6 +112,30 @@ class Layer(nn.Module):
         s = tuple(self.blobs[idx].shape)
         return (1,) * (4 - len(s)) + s
 
+    # ---- checkpoint views: engines may store a blob in a permuted physical order -------------------
+    def export_blob(self, idx: int, tensor=None):
+        """Blob ``idx`` (or a same-shaped companion tensor such as its momentum history) as a numpy array in
+        Caffe's canonical element order and 4-D shape."""
+        t = (self.blobs[idx] if tensor is None else tensor).detach().float()
+        perm = getattr(self, "_k_perm", None)
+        if perm is not None and idx == 0:
+            c, h, w = perm
+            t = t.reshape(t.shape[0], h, w, c).permute(0, 3, 1, 2)
+        shape = getattr(self, "_caffe_shapes", {}).get(idx) or self.caffe_blob_shape(idx)
+        return t.cpu().contiguous().numpy().reshape(shape)
+
+    def import_blob(self, idx: int, array, tensor=None):
+        """Inverse of :meth:`export_blob` (in-place copy into the blob / companion tensor)."""
+        dst = self.blobs[idx] if tensor is None else tensor
+        src = torch.from_numpy(array.copy()).float()
+        perm = getattr(self, "_k_perm", None)
+        with torch.no_grad():
+            if perm is not None and idx == 0:
+                c, h, w = perm
+                n = dst.shape[0]
+                src = src.reshape(n, c, h, w).permute(0, 2, 3, 1).reshape(n, -1)
+            dst.copy_(src.reshape(dst.shape).to(dst.device))
+
     def extra_repr(self):
         return f"name={self.layer_name!r}, type={self.type_name}"
 

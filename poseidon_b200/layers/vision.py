@@ -28,6 +28,7 @@ class ConvolutionLayer(Layer):
         self.num_output = int(cp.num_output)
         self.bias_term = bool(cp.bias_term)
         n, c, h, w = bottom_shapes[0]
+        self.in_hw = (h, w)
         for s in bottom_shapes[1:]:
             if tuple(s) != tuple(bottom_shapes[0]):
                 raise ValueError("all conv bottoms must have the same shape")
@@ -78,7 +79,7 @@ class PoolingLayer(Layer):
             if self.n_tops == 2:
                 y, mask = k.max_pool(x, self.kernel, self.stride, self.pad, return_mask=True)
                 return y, mask
-            return (k.max_pool(x, self.kernel, self.stride, self.pad),)
+            return (k.max_pool(x, self.kernel, self.stride, self.pad, **getattr(self, "engine_kw", {})),)
         if self.method == "AVE":
             return (k.ave_pool(x, self.kernel, self.stride, self.pad),)
         return (k.stochastic_pool(x, self.kernel, self.stride, self.ctx.train),)
@@ -103,7 +104,7 @@ class LRNLayer(Layer):
     def forward(self, x):
         k = ops.get(self.ctx)
         if self.region == "ACROSS_CHANNELS":
-            return (k.lrn_across(x, self.size, self.alpha, self.beta),)
+            return (k.lrn_across(x, self.size, self.alpha, self.beta, **getattr(self, "engine_kw", {})),)
         return (k.lrn_within(x, self.size, self.alpha, self.beta),)
 
 

@@ -122,6 +122,7 @@ class Net(nn.Module):
         self.param_display_names: List[str] = []
         self.param_layer_idx: List[int] = []
         self.param_is_owner: List[bool] = []
+        self.param_owner: List[tuple] = []     # (layer, blob index) owning each entry of self.params
         named: Dict[str, int] = {}
         for li, lp in enumerate(pd.layers):
             layer = create_layer(lp, self.ctx)
@@ -177,6 +178,7 @@ class Net(nn.Module):
                 if lr == 0.0:
                     p.requires_grad_(False)
                 idx = len(self.params)
+                self.param_owner.append((layer, j))
                 self.params.append(p)
                 self.params_lr.append(lr)
                 self.params_weight_decay.append(wd)
@@ -202,6 +204,10 @@ class Net(nn.Module):
         self.blobs: Dict[str, torch.Tensor] = {}
         self.force_backward = bool(pd.force_backward)
         self.debug_info = False
+        self.skip_layer = [False] * len(self.layers)
+        if self.ctx.engine == "sm100" and self.ctx.device.type == "cuda":
+            from .fusion import plan_sm100
+            plan_sm100(self)
 
     def _consumed_later(self, blob: str) -> bool:
         last_prod = max(i for i, tn in enumerate(self.top_names) if blob in tn)
@@ -224,6 +230,8 @@ class Net(nn.Module):
         end = len(self.layers) - 1 if end is None else end
         loss = None
         for i in range(start, end + 1):
+            if self.skip_layer[i]:
+                continue                      # fused into the producer's epilogue (in-place layer: blob unchanged)
             layer = self.layers[i]
             ins = [blobs[b] for b in self.bottom_names[i]]
             outs = layer(*ins)
@@ -285,9 +293,13 @@ class Net(nn.Module):
                 raise ValueError(f"Incompatible number of blobs for layer {name}")
             for a_dst, a_src in zip(layer.blob_names, src.blob_names):
                 ps, pd_ = getattr(src, a_src), getattr(layer, a_dst)
-                if tuple(ps.shape) != tuple(pd_.shape):
+                if ps.numel() != pd_.numel():
                     raise ValueError(f"Cannot share layer {name}: shape mismatch")
                 setattr(layer, a_dst, ps)
+            if getattr(src, "_sm100", None) is not None:
+                layer._sm100 = src._sm100            # one set of bf16 operands per weight
+                if hasattr(src, "_k_perm"):
+                    layer._k_perm = src._k_perm
         self._reindex_params()
 
     def _reindex_params(self):
@@ -320,8 +332,10 @@ class Net(nn.Module):
                 got = (blob.num, blob.channels, blob.height, blob.width)
                 if got != want:
                     raise ValueError(f"layer {slp.name} blob {j}: shape mismatch {got} vs {want}")
-                with torch.no_grad():
-                    p.copy_(torch.from_numpy(np.asarray(blob.data, dtype=np.float32).reshape(tuple(p.shape)).copy()))
+                layer.import_blob(j, np.asarray(blob.data, dtype=np.float32))
+            st = getattr(layer, "_sm100", None)
+            if st is not None:
+                st.mark_updated()
             loaded.append(slp.name)
         return loaded
 
@@ -337,10 +351,8 @@ class Net(nn.Module):
             nl = lp.copy()
             nl.clear("blobs")
             for j, p in enumerate(layer.blobs):
-                diff = p.grad.detach().float().cpu().numpy() if (write_diff and p.grad is not None) else None
-                b = P.array_to_blob(p.detach().float().cpu().numpy().reshape(layer.caffe_blob_shape(j)),
-                                    diff=diff)
-                nl.blobs.append(b)
+                diff = layer.export_blob(j, p.grad) if (write_diff and p.grad is not None) else None
+                nl.blobs.append(P.array_to_blob(layer.export_blob(j), diff=diff))
             out.layers.append(nl)
         return out
 

@@ -1,0 +1,538 @@
+"""The sm100 engine: every hot op runs a hand-written sm_100a kernel from ``csrc/``.
+
+Conventions
+-----------
+* activations: bf16, logical NCHW with channels-last (NHWC) memory; channel counts multiples of 8
+  (first-layer images are padded to 4 channels and spatially pre-padded by the transform kernel);
+* learnable blobs: fp32 master (``nn.Parameter``; conv weights physically [Cout][R][S][Cg]) plus a
+  bf16 shadow that the fused optimizer kernels refresh in place;
+* backward is explicit (``torch.autograd.Function``) so that weight gradients land where the DWBP /
+  SFB engines want them and ReLU masks are applied inside the neighbouring kernels' epilogues.
+
+Nothing here silently falls back to a library kernel for the ops the engine claims (conv, inner product,
+LRN, pooling, softmax-loss, dropout, transform): unsupported shapes raise, except where noted as
+``torch_engine`` delegation for cold ops (within-channel LRN, stochastic pooling, ...).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import reference as R
+from . import torch_engine as TE
+from .build import load_extension
+
+_ops = None
+
+
+def K():
+    """torch.ops.poseidon, loading the in-tree extension on first use (fails loudly if absent)."""
+    global _ops
+    if _ops is None:
+        load_extension()
+        from .counting import CountingOps
+        _ops = CountingOps(torch.ops.poseidon)
+    return _ops
+
+
+CL = torch.channels_last
+
+
+def to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
+    if x.dtype != torch.bfloat16:
+        x = x.to(torch.bfloat16)
+    if x.dim() == 4 and not (x.stride(1) == 1 or x.shape[1] == 1):
+        x = x.contiguous(memory_format=CL)
+    elif x.dim() == 4 and x.shape[1] == 1 and not x.is_contiguous(memory_format=CL):
+        x = x.contiguous(memory_format=CL)
+    return x
+
+
+def _dense_pitch_ok(x: torch.Tensor) -> bool:
+    """NHWC tensor whose only irregularity may be a pixel pitch > C (channel-slice view)."""
+    if x.dim() != 4 or x.stride(1) != 1:
+        return False
+    n, c, h, w = x.shape
+    pitch = x.stride(3) if w > 1 else (x.stride(2) if h > 1 else (x.stride(0) if n > 1 else c))
+    return (h == 1 or w == 1 or x.stride(2) == pitch * w) and (n == 1 or x.stride(0) == pitch * w * h) and pitch % 8 == 0
+
+
+def as_kernel_input(x: torch.Tensor) -> torch.Tensor:
+    x = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+    if x.dim() == 4 and _dense_pitch_ok(x):
+        return x
+    return x.contiguous(memory_format=CL) if x.dim() == 4 else x.contiguous()
+
+
+# =====================================================================================================
+# Convolution
+# =====================================================================================================
+class ConvState:
+    """Per-layer engine state: operand layouts + bf16 shadows, refreshed lazily by weight version."""
+
+    def __init__(self, layer, cin_logical: int):
+        self.layer = layer
+        self.groups = layer.group
+        self.R, self.S = layer.kernel
+        self.Cout = layer.num_output
+        cg = cin_logical // self.groups
+        self.row_mode = cg % 8 != 0
+        if self.row_mode:
+            if self.groups != 1 or cin_logical > 4:
+                raise ValueError(f"sm100 conv '{layer.layer_name}': input channels {cin_logical} (group "
+                                 f"{self.groups}) must be a multiple of 8 or <= 4 (first layer)")
+            self.Cp = 4
+            self.L = self.S * self.Cp
+            self.Lp = (self.L + 7) // 8 * 8
+            self.Kw = self.R * self.Lp
+            if (layer.stride[1] * self.Cp) % 8:
+                raise ValueError("sm100 first-layer conv needs an even horizontal stride")
+        else:
+            self.Cp = cin_logical
+            self.Kw = self.R * self.S * cg
+        self.cg = self.Cp // self.groups
+        self.cin_logical = cin_logical
+        self.wb: Optional[torch.Tensor] = None
+        self.wt: Optional[torch.Tensor] = None
+        self.dirty_wb = True               # bf16 fprop/wgrad operand is stale w.r.t. the fp32 master
+        self.dirty_wt = True               # packed dgrad operand is stale
+        self.arena_shadow = False          # wb lives in the symmetric arena and is refreshed by the update kernels
+        self.need_dgrad = True
+        self.consumer_masks = False        # a downstream kernel applies this layer's ReLU mask
+        self.mask_input = False            # this layer's dgrad applies the producer's ReLU mask
+        w = layer.weight
+        if not self.row_mode and not w.data.is_contiguous(memory_format=CL):
+            w.data = w.data.contiguous(memory_format=CL)
+
+    # physical [Cout, Kw] fp32 view of the master weight (TAP mode only)
+    def w2d(self) -> torch.Tensor:
+        w = self.layer.weight.data
+        return w.permute(0, 2, 3, 1).reshape(self.Cout, self.Kw)
+
+    def mark_updated(self, keep_wb: bool = False):
+        """The fp32 master changed (optimizer step / weight load)."""
+        self.dirty_wt = True
+        if not keep_wb and not self.arena_shadow:
+            self.dirty_wb = True
+
+    def shadow(self) -> torch.Tensor:
+        if self.wb is not None and not self.dirty_wb:
+            return self.wb
+        w = self.layer.weight
+        with torch.no_grad():
+            if self.row_mode:
+                t = w.data.permute(0, 2, 3, 1)                                    # Cout,R,S,C
+                t = torch.nn.functional.pad(t, (0, self.Cp - self.cin_logical))  # -> Cp
+                t = t.reshape(self.Cout, self.R, self.L)
+                src = torch.nn.functional.pad(t, (0, self.Lp - self.L)).reshape(self.Cout, self.Kw)
+            else:
+                src = self.w2d()
+            if self.wb is None:
+                self.wb = src.to(torch.bfloat16).contiguous()
+            else:
+                self.wb.copy_(src)
+        self.dirty_wb = False
+        return self.wb
+
+    def dgrad_pack(self) -> torch.Tensor:
+        if self.wt is not None and not self.dirty_wt:
+            return self.wt
+        self.wt = K().conv_pack_dgrad(self.w2d().reshape(-1), self.Cout, self.R * self.S, self.cg, self.groups, self.wt)
+        self.dirty_wt = False
+        return self.wt
+
+    def grad_from_dw(self, dw: torch.Tensor) -> torch.Tensor:
+        """[Cout, Kw] fp32 -> gradient tensor with the master weight's logical shape."""
+        if self.row_mode:
+            g = dw.view(self.Cout, self.R, self.Lp)[:, :, : self.L].reshape(self.Cout, self.R, self.S, self.Cp)
+            return g[..., : self.cin_logical].permute(0, 3, 1, 2).contiguous()
+        return dw.view(self.Cout, self.R, self.S, self.cg).permute(0, 3, 1, 2)   # channels-last strided view
+
+
+def conv_state(layer, cin_logical) -> ConvState:
+    st = getattr(layer, "_sm100", None)
+    if st is None:
+        st = ConvState(layer, cin_logical)
+        layer._sm100 = st
+    return st
+
+
+def prepare_first_layer_input(x: torch.Tensor, st: ConvState, pad, in_hw) -> torch.Tensor:
+    """Bring the first-layer input into the padded NHWC4 layout ROW-mode conv consumes: channels padded to
+    Cp, spatially pre-padded by the conv's own padding, physical width rounded up to even (16-byte rows).
+    The data layers emit this layout straight from the transform kernel; anything else is converted here."""
+    h, w = in_hw
+    wp = w + 2 * pad[1]
+    extra = wp % 2
+    if (x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[1] == st.Cp and x.shape[2] == h + 2 * pad[0]
+            and x.shape[3] == wp + extra and x.is_contiguous(memory_format=CL)):
+        return x
+    n, c = x.shape[:2]
+    if x.shape[2] != h or x.shape[3] != w:
+        raise ValueError(f"first-layer conv: unexpected input shape {tuple(x.shape)} for logical {h}x{w}")
+    t = torch.nn.functional.pad(x.float(), (pad[1], pad[1] + extra, pad[0], pad[0], 0, st.Cp - c))
+    return t.to(torch.bfloat16).contiguous(memory_format=CL)
+
+
+class _ConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, layer, relu_slope):
+        st: ConvState = layer._sm100
+        k = K()
+        stride, pad = layer.stride, layer.pad
+        if st.row_mode:
+            h, w = layer.in_hw
+            xin = prepare_first_layer_input(x, st, pad, (h, w))
+            conv_pad = (0, 0)
+        else:
+            xin = as_kernel_input(x)
+            h, w = xin.shape[2], xin.shape[3]
+            conv_pad = pad
+        oh = (h + 2 * pad[0] - st.R) // stride[0] + 1
+        ow = (w + 2 * pad[1] - st.S) // stride[1] + 1
+        relu = relu_slope is not None
+        y = k.conv_fprop(xin, st.shadow(), bias, [st.R, st.S], list(stride), list(conv_pad), st.groups,
+                         1 if st.row_mode else 0, oh, ow, relu, float(relu_slope or 0.0), None)
+        ctx.layer, ctx.relu_slope, ctx.conv_pad = layer, relu_slope, conv_pad
+        ctx.in_shape = tuple(x.shape)
+        ctx.save_for_backward(xin, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        layer = ctx.layer
+        st: ConvState = layer._sm100
+        k = K()
+        xin, y = ctx.saved_tensors
+        dy = as_kernel_input(dy)
+        if y is not None and not st.consumer_masks:
+            dy = k.relu_bwd(y, dy.contiguous(memory_format=CL), float(ctx.relu_slope))
+        stride = layer.stride
+        dw = db = dx = None
+        if ctx.needs_input_grad[1]:
+            sink = getattr(layer, "_grad_sink", None)
+            dw2 = sink.weight_buffer(layer, st) if sink is not None else \
+                torch.zeros(st.Cout, st.Kw, device=dy.device, dtype=torch.float32)
+            k.conv_wgrad(xin, dy, dw2, [st.R, st.S], list(stride), list(ctx.conv_pad), st.groups,
+                         1 if st.row_mode else 0, 1.0)
+            dw = st.grad_from_dw(dw2)
+        if layer.bias_term and ctx.needs_input_grad[2]:
+            db = torch.empty(st.Cout, device=dy.device, dtype=torch.float32)
+            pitch = dy.stride(3) if dy.shape[3] > 1 else (dy.stride(2) if dy.shape[2] > 1 else dy.stride(0))
+            k.colsum(dy, dy.shape[0] * dy.shape[2] * dy.shape[3], st.Cout, pitch, db, 1.0, False)
+        if ctx.needs_input_grad[0]:
+            if st.row_mode or stride != (1, 1):
+                raise NotImplementedError(f"sm100 conv '{layer.layer_name}': data gradient is implemented for "
+                                          "stride-1 convolutions (first / strided layers never need it in the "
+                                          "supported model families)")
+            mask = xin if st.mask_input else None
+            dx = k.conv_dgrad(dy, st.dgrad_pack(), [st.R, st.S], list(layer.pad), st.groups, xin.shape[2],
+                              xin.shape[3], mask, 0.0)
+        return dx, dw, db, None, None
+
+
+def conv2d(x, w, b, stride, pad, groups, relu_slope=None, layer=None):
+    if layer is None or not x.is_cuda:
+        return TE.conv2d(x, w, b, stride, pad, groups, relu_slope, layer)
+    conv_state(layer, w.shape[1] * groups)
+    return _ConvFn.apply(x, w, b, layer, relu_slope)
+
+
+# =====================================================================================================
+# Inner product
+# =====================================================================================================
+class IPState:
+    def __init__(self, layer, bottom_shape):
+        self.layer = layer
+        self.N, self.K = layer.weight.shape
+        self.wb: Optional[torch.Tensor] = None
+        self.dirty_wb = True
+        self.arena_shadow = False
+        self.perm = None
+        if len(bottom_shape) == 4 and bottom_shape[2] * bottom_shape[3] > 1:
+            # activations are NHWC: store the weight with K ordered (h, w, c) so flatten is free
+            c, h, w = bottom_shape[1:]
+            self.perm = (c, h, w)
+            with torch.no_grad():
+                wd = layer.weight.data
+                layer.weight.data = wd.view(self.N, c, h, w).permute(0, 2, 3, 1).reshape(self.N, self.K).contiguous()
+            layer._k_perm = self.perm
+        if self.K % 8:
+            raise ValueError(f"sm100 inner product '{layer.layer_name}': K={self.K} must be a multiple of 8")
+
+    def mark_updated(self, keep_wb: bool = False):
+        if not keep_wb and not self.arena_shadow:
+            self.dirty_wb = True
+
+    def shadow(self) -> torch.Tensor:
+        if self.wb is not None and not self.dirty_wb:
+            return self.wb
+        w = self.layer.weight
+        with torch.no_grad():
+            if self.wb is None:
+                self.wb = w.data.to(torch.bfloat16)
+            else:
+                self.wb.copy_(w.data)
+        self.dirty_wb = False
+        return self.wb
+
+
+def _flatten_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """(N,C,H,W) channels-last -> (N, H*W*C) bf16 row-major without a copy when dense."""
+    x = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+    if x.dim() == 2:
+        return x.contiguous()
+    if x.shape[2] * x.shape[3] == 1:
+        return x.reshape(x.shape[0], -1).contiguous()
+    if not x.is_contiguous(memory_format=CL):
+        x = x.contiguous(memory_format=CL)
+    return x.permute(0, 2, 3, 1).reshape(x.shape[0], -1)
+
+
+class _IPFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, layer, relu):
+        st: IPState = layer._sm100
+        k = K()
+        x2 = _flatten_nhwc(x)
+        n_pad = (st.N + 7) // 8 * 8
+        if n_pad != st.N:
+            out = torch.empty(x2.shape[0], n_pad, device=x.device, dtype=torch.bfloat16)[:, : st.N]
+        else:
+            out = None
+        y = k.gemm_bf16(x2, False, st.shadow(), False, bias, bool(relu), 0.0, None, out, 0)
+        ctx.layer, ctx.relu = layer, relu
+        ctx.x_shape = tuple(x.shape)
+        ctx.save_for_backward(x2, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        layer = ctx.layer
+        st: IPState = layer._sm100
+        k = K()
+        x2, y = ctx.saved_tensors
+        dy = dy if dy.dtype == torch.bfloat16 else dy.to(torch.bfloat16)
+        n_pad = (st.N + 7) // 8 * 8
+        if dy.stride(1) != 1 or dy.stride(0) % 8 or (y is not None):
+            buf = torch.empty(dy.shape[0], n_pad, device=dy.device, dtype=torch.bfloat16)
+            if n_pad != st.N:
+                buf[:, st.N:].zero_()
+            d2 = buf[:, : st.N]
+            if y is not None:
+                d2.copy_(dy * (y > 0))
+            else:
+                d2.copy_(dy)
+            dy = d2
+        dw = db = dx = None
+        if ctx.needs_input_grad[0]:
+            # dX[M, K] = dY[M, N] · W[N, K]   (W row-major is the MN-major B operand).  Must be issued before the
+            # fused SFB kernel below, which rewrites W / its bf16 shadow in place.
+            dx2 = k.gemm_bf16(dy, False, st.shadow(), True, None, False, 0.0, None, None, 0)
+            xs = ctx.x_shape
+            if len(xs) == 4 and xs[2] * xs[3] > 1:
+                dx = dx2.view(xs[0], xs[2], xs[3], xs[1]).permute(0, 3, 1, 2)
+            else:
+                dx = dx2.view(xs)
+        if layer.bias_term and ctx.needs_input_grad[2]:
+            db = dy.float().sum(0)
+        sfb = getattr(layer, "sfb", None)
+        if ctx.needs_input_grad[1]:
+            if sfb is not None:
+                dw = sfb.exchange_and_update(layer, dy, x2)     # fused path: returns None (W updated in place)
+            else:
+                sink = getattr(layer, "_grad_sink", None)
+                dw = sink.weight_buffer(layer, st) if sink is not None else \
+                    torch.empty(st.N, st.K, device=dy.device, dtype=torch.float32)
+                k.gemm_f32(dy, True, x2, True, dw, 1.0, False, 1, 0)
+        return dx, dw, db, None, None
+
+
+def inner_product(x, w, b, relu=False, layer=None):
+    if layer is None or not x.is_cuda:
+        return TE.inner_product(x, w, b, relu, layer)
+    if getattr(layer, "_sm100", None) is None:
+        layer._sm100 = IPState(layer, tuple(x.shape))
+    return _IPFn.apply(x, w, b, layer, relu)
+
+
+# =====================================================================================================
+# LRN / pooling / ReLU / dropout / softmax-loss / concat / transform
+# =====================================================================================================
+class _LRNFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, size, alpha, beta, mask_input):
+        x = as_kernel_input(x).contiguous(memory_format=CL)
+        ctx.save_for_backward(x)
+        ctx.args = (size, alpha, beta, mask_input)
+        return K().lrn_fwd(x, size, alpha, beta, False)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        size, alpha, beta, mask_input = ctx.args
+        dy = as_kernel_input(dy)
+        return K().lrn_bwd(x, dy, size, alpha, beta, bool(mask_input)), None, None, None, None
+
+
+def lrn_across(x, size, alpha, beta, mask_input=False):
+    if not x.is_cuda or x.shape[1] % 8:
+        return R.lrn_across(x, size, alpha, beta)
+    return _LRNFn.apply(x, size, alpha, beta, mask_input)
+
+
+lrn_within = R.lrn_within
+stochastic_pool = R.stochastic_pool
+
+
+class _PoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, is_max, kernel, stride, pad, mask_input):
+        x = as_kernel_input(x)
+        oh = R.pool_out_size(x.shape[2], kernel[0], stride[0], pad[0])
+        ow = R.pool_out_size(x.shape[3], kernel[1], stride[1], pad[1])
+        y, idx = K().pool_fwd(x, is_max, list(kernel), list(stride), list(pad), oh, ow, bool(ctx.needs_input_grad[0]))
+        ctx.save_for_backward(idx, y if mask_input else None)
+        ctx.args = (is_max, tuple(x.shape[2:]), kernel, stride, pad)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        idx, y = ctx.saved_tensors
+        is_max, in_hw, kernel, stride, pad = ctx.args
+        dy = as_kernel_input(dy)
+        if y is not None:
+            dy = dy * (y > 0)        # producer's ReLU mask, evaluated on the (small) pooled tensor
+        dx = K().pool_bwd(dy, idx, is_max, list(in_hw), list(kernel), list(stride), list(pad))
+        return dx, None, None, None, None, None
+
+
+def max_pool(x, kernel, stride, pad, return_mask=False, mask_input=False):
+    if return_mask or not x.is_cuda or x.shape[1] % 8:
+        return R.max_pool(x, kernel, stride, pad, return_mask)
+    return _PoolFn.apply(x, True, tuple(kernel), tuple(stride), tuple(pad), mask_input)
+
+
+def ave_pool(x, kernel, stride, pad, mask_input=False):
+    if not x.is_cuda or x.shape[1] % 8:
+        return R.ave_pool(x, kernel, stride, pad)
+    return _PoolFn.apply(x, False, tuple(kernel), tuple(stride), tuple(pad), False)
+
+
+class _ReLUFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, slope):
+        y = K().relu_fwd(x, slope)
+        ctx.save_for_backward(y)
+        ctx.slope = slope
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = dy if dy.dtype == torch.bfloat16 else dy.to(torch.bfloat16)
+        if dy.stride() != y.stride():
+            dy = dy.contiguous(memory_format=CL) if y.dim() == 4 and y.is_contiguous(memory_format=CL) else dy.contiguous()
+        return K().relu_bwd(y, dy, ctx.slope), None
+
+
+def relu(x, negative_slope=0.0):
+    dense = x.is_contiguous() or (x.dim() == 4 and x.is_contiguous(memory_format=CL))
+    if not x.is_cuda or x.dtype != torch.bfloat16 or x.numel() % 8 or not dense:
+        return R.relu(x, negative_slope)
+    return _ReLUFn.apply(x, float(negative_slope))
+
+
+_dropout_counter = [0]
+
+
+class _DropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ratio, seed):
+        ctx.ratio, ctx.seed = ratio, seed
+        return K().dropout_apply(x, ratio, seed)
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy if dy.dtype == torch.bfloat16 else dy.to(torch.bfloat16)
+        dy = dy if (dy.is_contiguous() or (dy.dim() == 4 and dy.is_contiguous(memory_format=CL))) else dy.contiguous()
+        return K().dropout_apply(dy, ctx.ratio, ctx.seed), None, None
+
+
+def dropout(x, ratio, train):
+    if not train:
+        return x
+    dense = x.is_contiguous() or (x.dim() == 4 and x.is_contiguous(memory_format=CL))
+    if not x.is_cuda or x.dtype != torch.bfloat16 or x.numel() % 8 or not dense:
+        return R.dropout(x, ratio, train)
+    _dropout_counter[0] += 1
+    seed = (torch.initial_seed() * 1000003 + _dropout_counter[0] * 7919) & 0x7FFFFFFFFFFFFFFF
+    return _DropoutFn.apply(x, float(ratio), int(seed))
+
+
+class _SoftmaxLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, label, want_prob):
+        x2 = x.reshape(x.shape[0], -1)
+        if x2.stride(1) != 1:
+            x2 = x2.contiguous()
+        lab = label.reshape(-1).float().contiguous()
+        loss, dx, prob = K().softmax_xent(x2, lab, 1.0, True, bool(want_prob))
+        ctx.save_for_backward(dx)
+        ctx.x_shape = tuple(x.shape)
+        ctx.mark_non_differentiable(prob)
+        return loss.reshape(()), prob
+
+    @staticmethod
+    def backward(ctx, dloss, _dprob):
+        (dx,) = ctx.saved_tensors
+        g = dx * dloss.to(dx.dtype)
+        return g.view(ctx.x_shape), None, None
+
+
+def softmax_loss(x, label, return_prob=False):
+    spatial = x.dim() == 4 and x.shape[2] * x.shape[3] > 1
+    if not x.is_cuda or spatial:
+        return R.softmax_loss(x, label, return_prob)
+    loss, prob = _SoftmaxLossFn.apply(x, label, return_prob)
+    if return_prob:
+        return loss, prob.view(x.shape[0], -1, 1, 1)
+    return loss
+
+
+softmax = R.softmax
+
+
+def concat(xs, dim):
+    return torch.cat([x if x.dtype == xs[0].dtype else x.to(xs[0].dtype) for x in xs], dim=dim)
+
+
+def transform(transformer, x, out_dtype, first_conv=None):
+    """uint8/float NCHW batch -> bf16 NHWC in one kernel (crop / mirror / mean / scale / channel pad)."""
+    if not x.is_cuda or out_dtype != torch.bfloat16:
+        return TE.transform(transformer, x, out_dtype)
+    n, c, h, w = x.shape
+    oh, ow = transformer.out_hw(h, w)
+    h_off, w_off, flip = transformer.draw(n, h, w)
+    dev = x.device
+    mean = None
+    if transformer.mean is not None:
+        mean = transformer.mean.to(dev).float().contiguous()
+    elif transformer.mean_values is not None:
+        mv = transformer.mean_values.to(dev).float()
+        mean = (mv.expand(c) if mv.numel() == 1 else mv).contiguous()
+    cp = 4 if c <= 4 else 8
+    if c > 8:
+        return TE.transform(transformer, x, out_dtype).contiguous(memory_format=CL)
+    if first_conv is None or getattr(first_conv, "_sm100", None) is None or not first_conv._sm100.row_mode:
+        # generic consumer: logical (N,C,oh,ow) bf16 channels-last
+        return TE.transform(transformer, x, out_dtype).contiguous(memory_format=CL)
+    opad = first_conv.pad
+    if opad[0] != opad[1]:
+        return TE.transform(transformer, x, out_dtype).contiguous(memory_format=CL)
+    xin = x if x.dtype in (torch.uint8, torch.float32) else x.float()
+    wextra = (ow + 2 * opad[1]) % 2      # even physical width => every image row starts 16-byte aligned
+    return K().transform_nhwc(xin.contiguous(), h_off.to(dev, torch.int32), w_off.to(dev, torch.int32),
+                              flip.to(dev, torch.uint8), mean, float(transformer.scale), oh, ow, cp, opad[0], wextra)

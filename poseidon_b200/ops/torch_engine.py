@@ -38,5 +38,8 @@ def concat(xs, dim):
     return torch.cat(list(xs), dim=dim)
 
 
-def transform(transformer, x, out_dtype):
-    return transformer(x, out_dtype)
+def transform(transformer, x, out_dtype, first_conv=None):
+    y = transformer(x, out_dtype)
+    if y.is_cuda and out_dtype != torch.float32:
+        y = y.contiguous(memory_format=torch.channels_last)     # cuDNN's tensor-core friendly layout
+    return y

@@ -1,0 +1,434 @@
+"""The product's communication backend: fused NVLink kernels, no NCCL on the hot path.
+
+* ``SymmetricArena`` — one symmetric-memory allocation per rank (CUDA VMM, peer-mapped on every rank
+  and bound to an NVLS multicast object; handles come from ``torch.distributed._symmetric_memory``,
+  which is bootstrap plumbing only).  It holds, at identical offsets on every rank: the gradient
+  staging buffer G, the fp32 master weights W, the bf16 shadow weights Wb, the sufficient-factor
+  staging ring (u, v per SFB layer, double-buffered by step parity) and the epoch-flag blocks.
+  This replaces the Bösen PS tables + process/thread caches (reference: src/caffe/blob.cpp:58-83,
+  ps/src/petuum_ps/client/client_table.cpp:26-158, ps/src/petuum_ps/server/server_table.cpp).
+* ``FusedBackend`` — per-bucket ``allreduce_sgd`` kernel (two-shot, history sharded across ranks;
+  one-shot for small buckets) launched from the DWBP hooks on a high-priority stream.
+* ``FusedSFB`` — sufficient-factor broadcasting: u, v are published in the arena, peers are signalled
+  with release flags, and ONE tcgen05 kernel pulls every peer's factors over NVLink with TMA and
+  accumulates Σ_p u_pᵀ v_p in TMEM with the optimizer step fused into its epilogue — no dense ΔW ever
+  exists, locally or on the wire.  With one rank it degenerates to the fused wgrad+update kernel.
+
+reference: src/caffe/solver.cpp:455-531 (ThreadSyncWithPS / ThreadSyncWithSVB),
+src/caffe/svb_worker.cpp:19-179, ps/src/petuum_ps/thread/ssp_push_bg_worker.cpp:12-68.
+"""
+from __future__ import annotations
+
+import logging
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from ..ops import sm100
+from .gradsync import Backend, Bucket
+from .sfb import SFBStats, sfb_bytes, sfb_wins
+
+log = logging.getLogger("poseidon_b200")
+
+K_MAX_RANKS = 8
+_ALIGN = 256          # bytes; every arena segment starts on this boundary
+
+
+def _round_up(x, a):
+    return (x + a - 1) // a * a
+
+
+class SymmetricArena:
+    def __init__(self, nbytes: int, rank_ctx):
+        import torch.distributed._symmetric_memory as symm
+        self.rank, self.world = rank_ctx.rank, rank_ctx.world_size
+        self.device = rank_ctx.device
+        nbytes = _round_up(nbytes, 2 << 20)
+        self.buf = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.hdl = symm.rendezvous(self.buf, dist.group.WORLD.group_name)
+        self.buf.zero_()
+        self.base_ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        mc = getattr(self.hdl, "multicast_ptr", 0) or 0
+        self.multicast_ptr = int(mc)
+        self.offset = 0
+        self.nbytes = nbytes
+        torch.cuda.synchronize(self.device)
+        dist.barrier(device_ids=[self.device.index])
+
+    def carve(self, nbytes: int) -> int:
+        off = self.offset
+        self.offset = _round_up(off + nbytes, _ALIGN)
+        if self.offset > self.nbytes:
+            raise RuntimeError("symmetric arena exhausted")
+        return off
+
+    def view(self, off: int, shape, dtype) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= s
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        return self.buf[off:off + nbytes].view(dtype).view(*shape)
+
+    def peer_ptrs(self, off: int) -> List[int]:
+        return [b + off for b in self.base_ptrs]
+
+    def mc_ptr(self, off: int) -> int:
+        return self.multicast_ptr + off if self.multicast_ptr else 0
+
+
+class _Seg:
+    __slots__ = ("param", "numel", "g_off", "w_off", "wb_off", "hist")
+
+
+class FusedBackend(Backend):
+    name = "fused"
+
+    def __init__(self, svb: bool = False, sfb_mode: str = "auto", grad_reduce: str = "sum",
+                 one_shot_bytes: int = 256 * 1024, use_multimem: bool = True):
+        self.svb, self.sfb_mode, self.reduce = svb, sfb_mode, grad_reduce
+        self.one_shot_bytes = one_shot_bytes
+        self.use_multimem = use_multimem
+        self.arena: Optional[SymmetricArena] = None
+        self.epoch = 0
+        self.dense_bytes = 0
+        self.sfb_stats = SFBStats()
+        self.launches = 0
+
+    # ------------------------------------------------------------------------------ setup
+    def setup(self, sync):
+        super().setup(sync)
+        rc = sync.rank_ctx
+        self.world, self.rank, self.device = rc.world_size, rc.rank, rc.device
+        self.uses_comm_stream = self.world > 1
+        self.stream = torch.cuda.Stream(device=self.device, priority=-1) if self.world > 1 else None
+        self.k = sm100.K()
+        net = sync.net
+        # engine state for every learnable layer must exist before we re-home weights
+        self._ensure_layer_states(net)
+        self.sfb_layers: Dict[int, "FusedSFB"] = {}
+        self._choose_sfb(net, sync)
+        if self.world > 1:
+            self._build_arena(net, sync)
+        self.done_counter = torch.zeros(4, dtype=torch.int32, device=self.device)
+
+    def _ensure_layer_states(self, net):
+        for li, layer in enumerate(net.layers):
+            if layer.type_name == "CONVOLUTION" and getattr(layer, "_sm100", None) is None:
+                cin = net.blob_shapes[net.bottom_names[li][0]][1]
+                sm100.conv_state(layer, cin)
+            elif layer.type_name == "INNER_PRODUCT" and getattr(layer, "_sm100", None) is None:
+                layer._sm100 = sm100.IPState(layer, tuple(net.blob_shapes[net.bottom_names[li][0]]))
+
+    def _choose_sfb(self, net, sync):
+        """Per-layer SFB-vs-dense decision.  world==1: every IP weight takes the fused wgrad+update kernel
+        (same kernel, one source).  world>1 with --svb: cost model (auto) or every IP layer (all)."""
+        P = self.world
+        for li, (name, layer) in enumerate(zip(net.layer_names, net.layers)):
+            if layer.type_name != "INNER_PRODUCT" or not layer.weight.requires_grad:
+                continue
+            N, Kd = layer.weight.shape
+            M = net.blob_shapes[net.bottom_names[li][0]][0]
+            ok_shape = (N % 8 == 0 and Kd % 8 == 0)
+            if P == 1:
+                use = ok_shape
+            elif not self.svb or self.sfb_mode == "none":
+                use = False
+            else:
+                use = ok_shape and (self.sfb_mode == "all" or sfb_wins(M, N, Kd, P))
+            self.sfb_stats.layers[name] = "sfb" if use else "dense"
+            if P > 1 and sync.rank_ctx.is_root:
+                by = sfb_bytes(M, N, Kd, P, 2)
+                log.info("SFB chooser: %s (M=%d N=%d K=%d P=%d) -> %s  [sfb ingress %.1f MB vs dense %.1f MB]",
+                         name, M, N, Kd, P, self.sfb_stats.layers[name], by["sfb_ingress"] / 1e6,
+                         by["dense_each_way"] * 2 / 1e6)
+            if use:
+                h = FusedSFB(self, layer, li, M, N, Kd)
+                layer.sfb = h
+                self.sfb_layers[li] = h
+                b = sync.bucket_of.get(id(layer.weight))
+                if b is not None:
+                    b.mode = "sfb"
+                    h.bucket = b
+                    h.param_idx = [id(q) for q in b.params].index(id(layer.weight))
+                    b.self_updating.add(id(layer.weight))
+
+    def _build_arena(self, net, sync):
+        segs: List[_Seg] = []
+        total = 0
+        n_flag_blocks = len(sync.buckets) + len(self.sfb_layers) + 4
+        for b in sync.buckets:
+            for p in b.params:
+                n4 = _round_up(p.numel(), 4)
+                total += _round_up(n4 * 4, _ALIGN) * 2 + _round_up(n4 * 2, _ALIGN)
+        for h in self.sfb_layers.values():
+            total += h.arena_bytes(self.world)
+        total += n_flag_blocks * _ALIGN * 2 + (1 << 20)
+        self.arena = SymmetricArena(total, sync.rank_ctx)
+        ar = self.arena
+        self.flag_off = ar.carve(n_flag_blocks * _ALIGN)
+        self._next_flag = 0
+        self.seg_of: Dict[int, _Seg] = {}
+        for b in sync.buckets:
+            b.flag_off = self._alloc_flag_block()
+            b.segs = []
+            for p, hist in zip(b.params, b.history):
+                s = _Seg()
+                s.param, s.numel = p, _round_up(p.numel(), 4)
+                s.g_off = ar.carve(s.numel * 4)
+                s.w_off = ar.carve(s.numel * 4)
+                s.wb_off = ar.carve(s.numel * 2)
+                s.hist = hist
+                # re-home the fp32 master into the arena, keeping shape/strides
+                wflat = ar.view(s.w_off, (s.numel,), torch.float32)
+                src = p.data
+                stor = src.as_strided((src.numel(),), (1,)) if src.is_non_overlapping_and_dense() else src.reshape(-1)
+                if not src.is_non_overlapping_and_dense():
+                    raise RuntimeError("parameters must be dense")
+                wflat[: src.numel()].copy_(_storage_order_flat(src))
+                p.data = torch.as_strided(wflat, src.shape, src.stride())
+                del stor
+                # history must share the master's storage order
+                hflat = torch.zeros(s.numel, dtype=torch.float32, device=self.device)
+                hflat[: hist.numel()].copy_(_storage_order_flat(hist))
+                s.hist = hflat
+                b.history[b.params.index(p)] = torch.as_strided(hflat, src.shape, src.stride())
+                self.seg_of[id(p)] = s
+                b.segs.append(s)
+                self._bind_shadow(p, s)
+        for h in self.sfb_layers.values():
+            h.alloc(ar, self._alloc_flag_block())
+        for layer in net.layers:
+            st = getattr(layer, "_sm100", None)
+            if st is not None and not getattr(st, "row_mode", False) and id(layer.weight) in self.seg_of:
+                layer._grad_sink = self
+        torch.cuda.synchronize(self.device)
+        dist.barrier(device_ids=[self.device.index])
+        self.refresh_shadows()
+
+    def weight_buffer(self, layer, st) -> torch.Tensor:
+        """Gradient sink: the layer's wgrad kernel accumulates straight into the symmetric G arena (the segment
+        is zeroed by the previous step's all-reduce launch)."""
+        seg = self.seg_of[id(layer.weight)]
+        shape = (st.Cout, st.Kw) if isinstance(st, sm100.ConvState) else (st.N, st.K)
+        return self.arena.view(seg.g_off, (seg.numel,), torch.float32)[: layer.weight.numel()].view(*shape)
+
+    def _alloc_flag_block(self) -> int:
+        off = self.flag_off + self._next_flag * _ALIGN
+        self._next_flag += 1
+        return off
+
+    def _bind_shadow(self, p, seg):
+        """Point the layer's bf16 operand at the arena shadow so the update kernels refresh it in place."""
+        layer = self._layer_of(p)
+        st = getattr(layer, "_sm100", None)
+        if st is None or p is not layer.weight:
+            return
+        if isinstance(st, sm100.ConvState) and st.row_mode:
+            return                                  # packed first-layer operand is derived lazily
+        shape = (st.Cout, st.Kw) if isinstance(st, sm100.ConvState) else (st.N, st.K)
+        st.wb = self.arena.view(seg.wb_off, (seg.numel,), torch.bfloat16)[: p.numel()].view(*shape)
+        st.arena_shadow = True
+
+    def _layer_of(self, p):
+        b = self.sync.bucket_of[id(p)]
+        return b.layer
+
+    def refresh_shadows(self):
+        """fp32 master -> bf16 operands for every layer (after init / weight load)."""
+        for layer in self.sync.net.layers:
+            st = getattr(layer, "_sm100", None)
+            if st is None:
+                continue
+            st.mark_updated()
+            if getattr(st, "arena_shadow", False):
+                with torch.no_grad():
+                    st.wb.copy_(_storage_order_flat(layer.weight.data).view(st.wb.shape))
+                st.dirty_wb = False
+
+    # ------------------------------------------------------------------------------ per-bucket launch
+    def _hyper_args(self, lm, dm):
+        hy = self.sync.hyper
+        ws = self.world
+        decay = hy.weight_decay * dm * (ws if self.reduce == "sum" else 1.0)
+        gscale = 1.0 if self.reduce == "sum" else 1.0 / ws
+        return (hy.lr * lm, hy.momentum, decay, hy.solver_type, hy.l1, hy.delta, gscale)
+
+    def launch(self, bucket: Bucket):
+        if self.world == 1:
+            self._launch_local(bucket)
+        else:
+            self._launch_peer(bucket)
+        st = getattr(bucket.layer, "_sm100", None)
+        if st is not None:
+            st.mark_updated()
+
+    def _launch_local(self, bucket):
+        for p, h, lm, dm in zip(bucket.params, bucket.history, bucket.lr_mult, bucket.decay_mult):
+            if p.grad is None:
+                continue                            # weight already stepped inside the fused SFB/wgrad kernel
+            st = getattr(bucket.layer, "_sm100", None)
+            wb = None
+            if st is not None and p is bucket.layer.weight and st.wb is not None and not getattr(st, "row_mode", False):
+                wb = st.wb
+            g = p.grad
+            if g.stride() != p.data.stride():
+                g = g.contiguous(memory_format=torch.channels_last) if p.dim() == 4 and \
+                    p.data.is_contiguous(memory_format=torch.channels_last) else g.contiguous()
+            lr, mom, decay, rule, l1, delta, gscale = self._hyper_args(lm, dm)
+            self.k.fused_update(p.data, g, h, wb, lr, mom, decay, rule, l1, delta, gscale)
+            self.launches += 1
+            if wb is not None:
+                st.dirty_wb = False
+
+    def _launch_peer(self, bucket):
+        ar = self.arena
+        cur = torch.cuda.current_stream()
+        # stage gradients that were not produced directly inside the arena (biases, first-layer weights)
+        for p, seg in zip(bucket.params, bucket.segs):
+            if p.grad is None:
+                continue
+            gview = torch.as_strided(ar.view(seg.g_off, (seg.numel,), torch.float32), p.shape, p.data.stride())
+            if p.grad.data_ptr() != gview.data_ptr():
+                gview.copy_(p.grad)
+        self.stream.wait_stream(cur)
+        self.epoch_of_bucket = self.epoch + 1
+        with torch.cuda.stream(self.stream):
+            for p, seg, lm, dm in zip(bucket.params, bucket.segs, bucket.lr_mult, bucket.decay_mult):
+                if p.grad is None:
+                    continue
+                n = seg.numel
+                one_shot = n * 4 <= self.one_shot_bytes
+                lr, mom, decay, rule, l1, delta, gscale = self._hyper_args(lm, dm)
+                use_mc = self.use_multimem and ar.multicast_ptr != 0
+                self.k.allreduce_sgd(ar.peer_ptrs(seg.g_off), ar.peer_ptrs(seg.w_off), ar.peer_ptrs(seg.wb_off),
+                                     ar.peer_ptrs(bucket.flag_off + 64 * bucket.params.index(p)),
+                                     ar.mc_ptr(seg.g_off) if use_mc else 0,
+                                     ar.mc_ptr(seg.w_off) if (use_mc and not one_shot) else 0,
+                                     seg.hist, n, self.rank, self.epoch + 1, one_shot, self.done_counter,
+                                     lr, mom, decay, rule, l1, delta, gscale, 64)
+                ar.view(seg.g_off, (n,), torch.float32).zero_()
+                self.launches += 2
+                self.dense_bytes += n * 4
+            if bucket.event is None:
+                bucket.event = torch.cuda.Event()
+            bucket.event.record(self.stream)
+
+    def finish_iteration(self):
+        self.epoch += 1
+
+    def bytes_on_wire(self):
+        return {"dense_allreduce_bytes": self.dense_bytes, "sfb_bytes": self.sfb_stats.sfb_bytes,
+                "sfb_dense_equiv_bytes": self.sfb_stats.dense_equiv_bytes}
+
+    # optimizer-state plumbing for snapshots: history of a two-shot bucket is sharded by rank
+    def gather_history(self):
+        if self.world == 1:
+            return
+        for b in self.sync.buckets:
+            for seg in getattr(b, "segs", []):
+                n = seg.numel
+                if n * 4 <= self.one_shot_bytes:
+                    continue
+                per = ((n // 4 + self.world - 1) // self.world) * 4
+                padded = torch.zeros(per * self.world, dtype=torch.float32, device=self.device)
+                lo = min(n, per * self.rank)
+                hi = min(n, lo + per)
+                mine = torch.zeros(per, dtype=torch.float32, device=self.device)
+                mine[: hi - lo] = seg.hist[lo:hi]
+                dist.all_gather_into_tensor(padded, mine)
+                seg.hist.copy_(padded[:n])
+
+
+def _storage_order_flat(t: torch.Tensor) -> torch.Tensor:
+    """1-D view of a dense tensor in storage order."""
+    return t.as_strided((t.numel(),), (1,))
+
+
+class FusedSFB:
+    """Per-layer sufficient-factor exchange + fused outer-product/optimizer kernel.
+
+    Staging layout (per step parity) inside every rank's arena:  U[P][M][N], V[P][M][K] bf16.  Rank r
+    *pushes* its factors into slot r of every rank (one NVSwitch-multicast store stream, or P2P stores),
+    raises its epoch flag on every peer, and the tcgen05 kernel walks the P slots as P reduction sources,
+    waiting on slot p's flag right before its first TMA load of that slot — so the outer product of the
+    factors that have already landed overlaps the arrival of the rest.  All ranks reduce in the same slot
+    order, so replicas stay bit-identical."""
+
+    def __init__(self, backend: FusedBackend, layer, layer_idx, M, N, Kd):
+        self.be, self.layer, self.layer_idx = backend, layer, layer_idx
+        self.M, self.N, self.K = M, N, Kd
+        self.bucket = None
+        self.param_idx = 0
+        self.u_off = self.v_off = None
+        self.flag_off = None
+        self.local_flags = None
+        self.event = None
+
+    def arena_bytes(self, world):
+        return 2 * world * (_round_up(self.M * self.N * 2, _ALIGN) + _round_up(self.M * self.K * 2, _ALIGN))
+
+    def alloc(self, arena: SymmetricArena, flag_off: int):
+        P = arena.world
+        self.u_slot = _round_up(self.M * self.N * 2, _ALIGN)
+        self.v_slot = _round_up(self.M * self.K * 2, _ALIGN)
+        self.u_off = [arena.carve(P * self.u_slot) for _ in range(2)]
+        self.v_off = [arena.carve(P * self.v_slot) for _ in range(2)]
+        self.flag_off = flag_off
+        # flag block: [slot][rank] u32; slots 2/3 = SFB parity 0/1 (slots 0/1 belong to the all-reduce barriers)
+        self.local_flags = [arena.view(flag_off + (2 + par) * K_MAX_RANKS * 4, (K_MAX_RANKS,), torch.int32)
+                            for par in range(2)]
+
+    def exchange_and_update(self, layer, dy: torch.Tensor, x2: torch.Tensor):
+        """Called from the IP backward with u = dY [M,N] and v = X [M,K] (bf16).  Steps W, H and the bf16
+        shadow in place; returns None (no dense gradient exists, locally or on the wire)."""
+        be = self.be
+        k = be.k
+        b = self.bucket
+        st = layer._sm100
+        lm, dm = b.lr_mult[self.param_idx], b.decay_mult[self.param_idx]
+        lr, mom, decay, rule, l1, delta, gscale = be._hyper_args(lm, dm)
+        w = layer.weight.data
+        h = b.history[self.param_idx]
+        if st.wb is None or st.dirty_wb:
+            st.shadow()
+        dy = dy.contiguous()
+        x2 = x2.contiguous()
+        M = dy.shape[0]
+        if be.world == 1:
+            k.sfb_outer_sgd([dy.data_ptr()], [x2.data_ptr()], M, self.N, self.K, w, h, st.wb, gscale, lr, mom, decay,
+                            rule, l1, delta, None, 0, 0, 0, 0)
+            be.launches += 1
+            st.mark_updated(keep_wb=True)
+            be.sfb_stats.dense_equiv_bytes += self.N * self.K * 4
+            return None
+        ar = be.arena
+        P = be.world
+        par = be.epoch & 1
+        epoch = be.epoch + 1
+        cur = torch.cuda.current_stream()
+        be.stream.wait_stream(cur)
+        with torch.cuda.stream(be.stream):
+            dy.record_stream(be.stream)
+            x2.record_stream(be.stream)
+            mc = be.use_multimem and ar.multicast_ptr != 0
+            u_dst = self.u_off[par] + be.rank * self.u_slot
+            v_dst = self.v_off[par] + be.rank * self.v_slot
+            k.peer_push(dy, ar.peer_ptrs(u_dst), ar.mc_ptr(u_dst) if mc else 0, ar.peer_ptrs(self.flag_off), be.rank,
+                        2 + par, epoch, False, be.done_counter[1:2])
+            k.peer_push(x2, ar.peer_ptrs(v_dst), ar.mc_ptr(v_dst) if mc else 0, ar.peer_ptrs(self.flag_off), be.rank,
+                        2 + par, epoch, True, be.done_counter[1:2])
+            base = ar.base_ptrs[be.rank]
+            u_ptrs = [base + self.u_off[par] + p * self.u_slot for p in range(P)]
+            v_ptrs = [base + self.v_off[par] + p * self.v_slot for p in range(P)]
+            k.sfb_outer_sgd(u_ptrs, v_ptrs, M, self.N, self.K, w, h, st.wb, gscale, lr, mom, decay, rule, l1, delta,
+                            self.local_flags[par], epoch, 0, 0, 0)
+            be.launches += 3
+            if self.event is None:
+                self.event = torch.cuda.Event()
+            self.event.record(be.stream)
+        st.mark_updated(keep_wb=True)
+        be.sfb_stats.sfb_bytes += M * (self.N + self.K) * 2
+        be.sfb_stats.dense_equiv_bytes += self.N * self.K * 4
+        self.bucket.sfb_event = self.event      # the layer's next forward also waits for this kernel
+        return None

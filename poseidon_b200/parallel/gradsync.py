@@ -55,6 +55,8 @@ class Bucket:
         self.pending = 0
         self.mode = "dense"          # "dense" | "sfb"
         self.event = None            # CUDA event recorded after this bucket's update
+        self.sfb_event = None        # ... and after the fused SFB kernel of an IP weight
+        self.self_updating = set()   # ids of params stepped inside their layer's backward (no .grad appears)
         self.numel = 0
 
 
@@ -294,13 +296,15 @@ class GradSync:
         def wait(module, args):
             if bucket.event is not None:
                 torch.cuda.current_stream().wait_event(bucket.event)
+            if bucket.sfb_event is not None:
+                torch.cuda.current_stream().wait_event(bucket.sfb_event)
         return wait
 
     def begin_iteration(self, lr: float):
         self.hyper.lr = lr
         self.launch_order = []
         for b in self.buckets:
-            b.pending = len(b.params)
+            b.pending = len(b.params) - len(b.self_updating)
 
     def _on_grad(self, p):
         b = self.bucket_of[id(p)]
@@ -323,6 +327,8 @@ class GradSync:
             for b in self.buckets:
                 if b.event is not None:
                     cur.wait_event(b.event)
+                if b.sfb_event is not None:
+                    cur.wait_event(b.sfb_event)
 
     # ---- optimizer state for .solverstate ------------------------------------------------
     def history_tensors(self) -> List[torch.Tensor]:

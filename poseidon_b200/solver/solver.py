@@ -72,7 +72,15 @@ class Solver:
             param = P.read_solver(param)
         self.param = param
         self.model_dir = model_dir
-        self.rank_ctx = rank_ctx if rank_ctx is not None else RankContext()
+        if rank_ctx is None:
+            use_cuda = torch.cuda.is_available() and param.enum_name("solver_mode") != "CPU"
+            if use_cuda:
+                ids = [int(x) for x in str(param.device_id or "0").split(",") if x.strip() != ""]
+                rank_ctx = RankContext(device=f"cuda:{ids[0] if ids else 0}")
+                torch.cuda.set_device(rank_ctx.device)
+            else:
+                rank_ctx = RankContext()
+        self.rank_ctx = rank_ctx
         self.engine = engine
         self.staleness = int(staleness)
         self.svb = bool(svb)
@@ -214,10 +222,12 @@ class Solver:
             else:
                 comm = "nccl"
         self.comm_name = comm
-        if self.engine == "sm100":
-            from ..parallel.fused import FusedGradSync
-            return FusedGradSync(self.net, rc, self.hyper, comm=comm, svb=self.svb, staleness=self.staleness,
-                                 grad_reduce=grad_reduce, sfb_mode=sfb_mode)
+        if self.engine == "sm100" and comm in ("fused", "local"):
+            if self.device.type != "cuda":
+                raise RuntimeError("the sm100 engine needs a CUDA device (B200)")
+            from ..parallel.fused import FusedBackend
+            self.comm_name = "fused"
+            return GradSync(self.net, rc, self.hyper, FusedBackend(self.svb, sfb_mode, grad_reduce))
         if comm == "local":
             backend = LocalBackend()
         elif comm in ("nccl", "gloo", "torchdist"):
@@ -254,7 +264,7 @@ class Solver:
         self.sync.finish_iteration()
         if self.net.debug_info:
             self.net.backward_debug()
-        self.last_loss = loss
+        self.last_loss = None if loss is None else loss.detach()
         if display:
             self._display(loss, outputs, lr)
         self.iter += 1
@@ -425,8 +435,10 @@ class Solver:
             P.write_binary(model_file, netp)
         if self.rank_ctx.is_root or per_rank:
             st = P.SolverState(iter=self.iter, learned_net=model_file)
-            for h, p in zip(self.sync.history_tensors(), self.net.params):
-                st.history.append(P.array_to_blob(h.detach().float().cpu().numpy()))
+            if hasattr(self.sync.backend, "gather_history"):
+                self.sync.backend.gather_history()
+            for h, (layer, j) in zip(self.sync.history_tensors(), self.net.param_owner):
+                st.history.append(P.array_to_blob(layer.export_blob(j, h)))
             fn = state_file + (f".{self.rank_ctx.rank}.0" if per_rank else "")
             log.info("Snapshotting solver state to %s", fn)
             P.write_binary(fn, st)
@@ -452,8 +464,11 @@ class Solver:
                 self.sync.weights_changed()
         self.iter = int(st.iter)
         self._start_iter = self.iter
-        hist = [torch.from_numpy(P.blob_to_array(b).copy()) for b in st.history]
-        self.sync.load_history([h.to(self.device) for h in hist])
+        hs = self.sync.history_tensors()
+        if len(st.history) != len(hs):
+            raise ValueError("Incorrect length of history blobs.")
+        for b, h, (layer, j) in zip(st.history, hs, self.net.param_owner):
+            layer.import_blob(j, np.asarray(b.data, dtype=np.float32), tensor=h)
         if self.rank_ctx.is_root:
             log.info("Restored solver state from %s (iter %d)", fn, self.iter)
 

@@ -1,0 +1,65 @@
+"""Whole-net checks of the sm100 engine against the fp32 torch engine on identical data/weights."""
+import pytest
+import torch
+
+from smallnet import feed, make_data, small_net, small_solver_param
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(engine, steps, solver_type="SGD", momentum=0.9):
+    from poseidon_b200 import get_solver
+    net = small_net(batch=16)
+    sp = small_solver_param(net, max_iter=steps, solver_type=solver_type, momentum=momentum)
+    s = get_solver(sp, engine=engine, dtype=torch.float32 if engine == "torch" else None)
+    x, y = make_data(16 * steps)
+    feed(s, x, y)
+    losses = []
+    for _ in range(steps):
+        s.step(1)
+        losses.append(float(s.last_loss))
+    torch.cuda.synchronize()
+    weights = {n: l.export_blob(j) for n, l in zip(s.net.layer_names, s.net.layers) for j in range(len(l.blobs))
+               if j == 0}
+    s.close()
+    return losses, weights
+
+
+@pytest.mark.parametrize("solver_type,momentum", [("SGD", 0.9), ("NESTEROV", 0.9), ("ADAGRAD", 0.0)])
+def test_sm100_matches_fp32_engine(ext, solver_type, momentum):
+    steps = 4
+    l_ref, w_ref = _run("torch", steps, solver_type, momentum)
+    l_sm, w_sm = _run("sm100", steps, solver_type, momentum)
+    for a, b in zip(l_ref, l_sm):
+        assert abs(a - b) < 0.05 * max(1.0, abs(a)), (l_ref, l_sm)
+    import numpy as np
+    for name in w_ref:
+        d = np.abs(w_ref[name] - w_sm[name]).max()
+        m = np.abs(w_ref[name]).max()
+        tol = 0.25 if solver_type == "ADAGRAD" else 0.05      # AdaGrad's first steps amplify bf16 noise
+        assert d <= tol * m + 1e-3, f"{name}: max diff {d} vs {m}"
+
+
+def test_smoke_entry(ext):
+    import __graft_entry__ as g
+    g.smoke()
+
+
+def test_snapshot_roundtrip_sm100(ext, tmp_path):
+    from poseidon_b200 import get_solver
+    net = small_net(batch=16)
+    sp = small_solver_param(net, max_iter=2)
+    sp.snapshot_prefix = str(tmp_path / "small")
+    s = get_solver(sp, engine="sm100")
+    x, y = make_data(64)
+    feed(s, x, y)
+    s.step(2)
+    s.snapshot()
+    ref = {n: l.export_blob(0) for n, l in zip(s.net.layer_names, s.net.layers) if len(l.blobs)}
+    s2 = get_solver(sp, engine="torch", dtype=torch.float32)
+    s2.restore(str(tmp_path / "small_iter_2.solverstate"))
+    import numpy as np
+    for n, l in zip(s2.net.layer_names, s2.net.layers):
+        if len(l.blobs):
+            assert np.allclose(l.export_blob(0), ref[n], atol=1e-6), n
+    assert s2.iter == 2
