@@ -37,7 +37,7 @@ class DataTransformer:
                 logging.getLogger("poseidon_b200").warning(
                     "mean_file %s not found; using zero mean", path)
         if len(tp.mean_value):
-            if self.mean is not None:
+            if tp.has("mean_file"):
                 raise ValueError("Cannot specify mean_file and mean_value at the same time")
             self.mean_values = torch.tensor(list(tp.mean_value), dtype=torch.float32, device=self.device)
         self.gen = torch.Generator(device="cpu")

@@ -1,0 +1,37 @@
+"""partition_data: round-robin split of a record DB into N shards ``<db>_0 .. <db>_{N-1}`` — the layout the
+DATA layer expects when ``shared_file_system`` is false (each client opens ``source_<client_id>``).
+
+    python -m poseidon_b200.tools.partition_data --num_partitions N DB_PATH
+reference: tools/partition_data.cpp:30 (flags), :87-112 (round-robin copy), :120.
+"""
+from __future__ import annotations
+
+import argparse
+import sys
+
+from ..data.db import RecordWriter, open_db
+
+
+def partition(db_path: str, n: int):
+    db = open_db(db_path)
+    writers = [RecordWriter(f"{db_path}_{k}") for k in range(n)]
+    for i in range(len(db)):
+        writers[i % n].put(db.key(i), db.value(i))
+    for w in writers:
+        w.close()
+    return [w.path for w in writers]
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("db")
+    ap.add_argument("--num_partitions", type=int, required=True)
+    ap.add_argument("--backend", default="pdb")
+    args = ap.parse_args(argv)
+    for p in partition(args.db, args.num_partitions):
+        print(p)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,93 @@
+"""Multi-process data-parallel semantics on CPU (gloo, world_size 2): summed-update all-reduce, library SFB,
+SSP bounded staleness — checked against single-process training on the concatenated batch."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def launch(world, out, extra, device="cpu", timeout=300):
+    port = _free_port()
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), OMP_NUM_THREADS="2")
+        cmd = [sys.executable, os.path.join(HERE, "dist_worker.py"), "--out", out] + extra
+        if device:
+            cmd += ["--device", device]
+        procs.append(subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    for p in procs:
+        try:
+            o, _ = p.communicate(timeout=timeout)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        outs.append(o)
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o[-3000:]
+    return [dict(np.load(f"{out}.{r}.npz")) for r in range(world)]
+
+
+def _weights(d):
+    return {k: v for k, v in d.items() if "." in k and not k.startswith("wire_")}
+
+
+def _assert_close(a, b, tol=2e-5):
+    for k in _weights(a):
+        assert np.allclose(a[k], b[k], atol=tol, rtol=1e-4), (k, np.abs(a[k] - b[k]).max())
+
+
+@pytest.fixture(scope="module")
+def single(tmp_path_factory):
+    """1 process, batch 2M, lr x2  ==  2 workers with summed updates (reference semantics)."""
+    out = str(tmp_path_factory.mktemp("single") / "w")
+    return launch(1, out, ["--batch", "16", "--base_lr", "0.02"])[0]
+
+
+def test_dense_allreduce_sum_semantics(tmp_path, single):
+    res = launch(2, str(tmp_path / "w"), ["--batch", "8", "--comm", "gloo"])
+    _assert_close(res[0], res[1], 1e-7)           # replicas identical
+    _assert_close(res[0], single)
+    assert int(res[0]["wire_dense_allreduce_bytes"]) > 0
+
+
+def test_grad_reduce_mean_equals_large_batch(tmp_path):
+    ref = launch(1, str(tmp_path / "s"), ["--batch", "16", "--base_lr", "0.01"])[0]
+    res = launch(2, str(tmp_path / "w"), ["--batch", "8", "--comm", "gloo", "--grad_reduce", "mean"])
+    _assert_close(res[0], ref)
+
+
+def test_sufficient_factor_broadcast_equals_dense(tmp_path, single):
+    res = launch(2, str(tmp_path / "w"), ["--batch", "8", "--comm", "gloo", "--svb", "1", "--sfb_mode", "all"])
+    _assert_close(res[0], res[1], 1e-6)
+    _assert_close(res[0], single, 5e-5)
+
+
+def test_ssp_staleness_zero_is_bsp_with_summed_updates(tmp_path, single):
+    res = launch(2, str(tmp_path / "w"), ["--batch", "8", "--comm", "ssp", "--staleness", "0"])
+    _assert_close(res[0], res[1], 1e-6)
+    _assert_close(res[0], single, 5e-5)
+
+
+def test_ssp_bounded_staleness_converges_to_same_table(tmp_path):
+    res = launch(2, str(tmp_path / "w"), ["--batch", "8", "--comm", "ssp", "--staleness", "2", "--steps", "6",
+                                            "--delay_rank", "1"])
+    # every update is applied exactly once everywhere: after the final drain all replicas hold the same table
+    _assert_close(res[0], res[1], 1e-5)
+    assert int(res[0]["max_lag"]) <= 2 and int(res[1]["max_lag"]) <= 2
+    assert np.isfinite(res[0]["loss"])
