@@ -7,8 +7,15 @@
 //   TAP : C_g % 8 == 0.  A 16-byte chunk is 8 channels of one tap; per-tap bounds checks.
 //   ROW : first layers (C padded to 4): the S*C elements of one kernel row are contiguous in memory, so
 //         K is organised as [R][Lp] (Lp = S*C rounded up to 8; the pad multiplies zero weights).
-// The same routine feeds fprop (A operand, K-major: 128 rows x 64 k), dgrad (gathers dY with mirrored
-// taps) and wgrad (B operand, MN-major: 64 reduction rows x 64 k-columns per chunk).
+//
+// Thread mapping (coalescing): thread t owns chunk column j = t & 7 and rows (t >> 3) + 16*i.  A warp-level
+// cp.async therefore covers 4 rows x 128 contiguous bytes (4-8 L1 wavefronts) instead of 32 scattered 16-byte
+// pieces (32 wavefronts) — the difference between a gather-bound and an MMA-bound main loop.  The k -> (r,s,c)
+// split is per thread per k-block (same for all its rows); the m -> (n,oh,ow) split uses precomputed magic
+// multipliers.
+//
+// The same routine feeds fprop (A operand, K-major: 128 rows x 64 k), dgrad (gathers dY with mirrored taps)
+// and wgrad (B operand, MN-major: 64 reduction rows x 64 k-columns per chunk).
 //
 // Replaces im2col_gpu_kernel/col2im_gpu_kernel + per-image cublasSgemm loops
 // (reference: src/caffe/util/im2col.cu:12-132, src/caffe/layers/conv_layer.cu:13-119).
@@ -16,6 +23,26 @@
 #include "sm100_prims.cuh"
 
 namespace psd {
+
+struct FastDiv {
+  uint32_t mul, shift, d;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  // exact for all 32-bit n when computed with a 64-bit product (n < 2^31 here)
+  FastDiv f;
+  f.d = d;
+  if (d == 1) { f.mul = 0; f.shift = 0; return f; }
+  uint32_t s = 0;
+  while ((1ull << s) < d) ++s;
+  f.shift = s;
+  f.mul = static_cast<uint32_t>(((1ull << (32 + s)) + d - 1) / d - (1ull << 32));
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  if (f.d == 1) return n;
+  const uint32_t hi = __umulhi(n, f.mul);
+  return (hi + ((n - hi) >> 1)) >> (f.shift - 1);
+}
 
 struct ConvGeom {
   const __nv_bfloat16* x;   // gathered tensor (activations for fprop/wgrad, dY for dgrad), group offset applied
@@ -30,56 +57,70 @@ struct ConvGeom {
   int L, Lp;                // ROW: valid / padded elements per kernel row
   int K;                    // total reduction length (multiple of 8)
   long M;                   // N*OH*OW
+  FastDiv div_ow, div_ohow, div_cg, div_s, div_lp;
 };
 
-// Fill `nrows` rows x 64 k-elements (128 B each, swizzled) at smem `dst` for rows m0.. and k-range k0..k0+63.
-// Called by 128 threads with (row, chunk-group) assignment passed in: thread handles row `row` (< nrows)
-// and all 8 chunks of it.
-__device__ __forceinline__ void gather_row(const ConvGeom& g, uint32_t dst_row_addr, int row_in_tile, long m, int k0) {
-  const uint32_t sw = static_cast<uint32_t>(row_in_tile & 7);
-  if (m >= g.M) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) cp_async_16(dst_row_addr + ((j ^ sw) << 4), g.x, 0);
-    return;
-  }
-  const int ow = static_cast<int>(m % g.OW);
-  const long t = m / g.OW;
-  const int oh = static_cast<int>(t % g.OH);
-  const int n = static_cast<int>(t / g.OH);
-  const int ih0 = oh * g.sh + g.off_h, iw0 = ow * g.sw + g.off_w;
-  const __nv_bfloat16* img = g.x + static_cast<long>(n) * g.H * g.W * g.pitch;
+// Per-thread, per-k-block decode of this thread's chunk column.
+struct ChunkTap {
+  int r, s, c;      // TAP: tap row / col / first channel ; ROW: r = kernel row, c = element offset in the padded row
+  bool in_k;
+};
+__device__ __forceinline__ ChunkTap decode_chunk(const ConvGeom& g, int k) {
+  ChunkTap t;
+  t.in_k = k < g.K;
   if (g.mode == 0) {
-    int tap = k0 / g.Cg;
-    int c = k0 - tap * g.Cg;
-    int r = tap / g.S;
-    int s = tap - r * g.S;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int ih = ih0 + r * g.dr, iw = iw0 + s * g.dr;
-      const bool ok = (k0 + j * 8 < g.K) && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W;
-      const __nv_bfloat16* src = ok ? img + (static_cast<long>(ih) * g.W + iw) * g.pitch + c : g.x;
-      cp_async_16(dst_row_addr + ((j ^ sw) << 4), src, ok ? 16u : 0u);
-      c += 8;
-      if (c >= g.Cg) { c = 0; if (++s == g.S) { s = 0; ++r; } }
-    }
+    const uint32_t tap = fdiv(static_cast<uint32_t>(k), g.div_cg);
+    t.c = k - static_cast<int>(tap) * g.Cg;
+    t.r = static_cast<int>(fdiv(tap, g.div_s));
+    t.s = static_cast<int>(tap) - t.r * g.S;
   } else {
-    int r = k0 / g.Lp;
-    int e = k0 - r * g.Lp;          // element offset inside the padded kernel row
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int ih = ih0 + r;
-      // elements [e, e+8) of the row starting at pixel iw0; valid while e < L and inside the image row
-      int valid = 0;
-      if (k0 + j * 8 < g.K && ih >= 0 && ih < g.H) {
-        const int row_elems = (g.W - iw0) * g.Cg;            // elements left in this image row
-        const int lim = min(g.L, row_elems);
-        valid = max(0, min(8, lim - e));
+    t.r = static_cast<int>(fdiv(static_cast<uint32_t>(k), g.div_lp));
+    t.c = k - t.r * g.Lp;
+    t.s = 0;
+  }
+  return t;
+}
+
+// Copy this thread's 16-byte chunk of row m (or zeros) to `dst`.
+__device__ __forceinline__ void gather_chunk(const ConvGeom& g, uint32_t dst, long m, const ChunkTap& t) {
+  const __nv_bfloat16* src = g.x;
+  uint32_t bytes = 0;
+  if (t.in_k && m < g.M) {
+    const uint32_t mm = static_cast<uint32_t>(m);
+    const uint32_t n = fdiv(mm, g.div_ohow);
+    const uint32_t rem = mm - n * static_cast<uint32_t>(g.OH * g.OW);
+    const uint32_t oh = fdiv(rem, g.div_ow);
+    const uint32_t ow = rem - oh * static_cast<uint32_t>(g.OW);
+    const int ih = static_cast<int>(oh) * g.sh + g.off_h + t.r * g.dr;
+    if (g.mode == 0) {
+      const int iw = static_cast<int>(ow) * g.sw + g.off_w + t.s * g.dr;
+      if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) {
+        src = g.x + ((static_cast<long>(n) * g.H + ih) * g.W + iw) * g.pitch + t.c;
+        bytes = 16;
       }
-      const __nv_bfloat16* src = valid > 0 ? img + (static_cast<long>(ih) * g.W + iw0) * g.pitch + e : g.x;
-      cp_async_16(dst_row_addr + ((j ^ sw) << 4), src, static_cast<uint32_t>(valid * 2));
-      e += 8;
-      if (e >= g.Lp) { e = 0; ++r; }
+    } else {
+      const int iw0 = static_cast<int>(ow) * g.sw + g.off_w;
+      if (ih >= 0 && ih < g.H) {
+        const int lim = min(g.L, (g.W - iw0) * g.Cg);     // valid elements of this kernel row inside the image row
+        const int valid = max(0, min(8, lim - t.c));
+        if (valid > 0) {
+          src = g.x + ((static_cast<long>(n) * g.H + ih) * g.W + iw0) * g.pitch + t.c;
+          bytes = static_cast<uint32_t>(valid * 2);
+        }
+      }
     }
+  }
+  cp_async_16(dst, src, bytes);
+}
+
+// Fill `nrows` (multiple of 16) rows x 64 k-elements at smem `tile` (rows of 128 B, swizzled) for rows m0.. and
+// k-range k0..k0+63.  Called by all 128 gather threads (gt = 0..127).
+__device__ __forceinline__ void gather_tile(const ConvGeom& g, uint32_t tile, int nrows, long m0, int k0, int gt) {
+  const int j = gt & 7;
+  const ChunkTap t = decode_chunk(g, k0 + j * 8);
+#pragma unroll 4
+  for (int r = gt >> 3; r < nrows; r += 16) {
+    gather_chunk(g, tile + r * 128 + ((j ^ (r & 7)) << 4), m0 + r, t);
   }
 }
 

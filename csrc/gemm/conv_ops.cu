@@ -55,6 +55,12 @@ static ConvGeom make_geom(const at::Tensor& x, const NhwcView& xv, int c_off, in
   g.Lp = (g.L + 7) / 8 * 8;
   g.K = d.mode == 1 ? d.R * g.Lp : d.R * d.S * Cg;
   g.M = static_cast<long>(xv.N) * OH * OW;
+  TORCH_CHECK(g.M < (1L << 31), "conv: N*OH*OW must fit in 31 bits");
+  g.div_ow = make_fastdiv(OW);
+  g.div_ohow = make_fastdiv(static_cast<uint32_t>(OH) * OW);
+  g.div_cg = make_fastdiv(Cg);
+  g.div_s = make_fastdiv(d.S);
+  g.div_lp = make_fastdiv(g.Lp);
   if (d.mode == 1) {
     TORCH_CHECK(xv.pitch == Cg, "ROW-mode conv needs a dense input (pitch == channels)");
     TORCH_CHECK(d.ph == 0 && d.pw == 0, "ROW-mode conv expects a pre-padded input");

@@ -75,7 +75,8 @@ struct GemmSmem {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int kBarBytes = 1024;
-  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // +1024 alignment slack
+  static constexpr int kEpiStageBytes = 4 * 32 * 33 * 4;    // per epilogue warp: 32x32 fp32 transpose tile (+1 pad)
+  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + kEpiStageBytes + 1024;  // +1024 alignment slack
 };
 
 __device__ __forceinline__ float sgd_apply(float acc, float& w, float& h, const GemmParams& p) {
@@ -97,104 +98,73 @@ __device__ __forceinline__ float sgd_apply(float acc, float& w, float& h, const 
   return w;
 }
 
-// Epilogue for 32 consecutive columns of one output row held in registers.
+// Epilogue of one 32x32 accumulator sub-tile.  `r` holds, per lane, 32 consecutive columns of ONE row
+// (tcgen05.ld 32x32b layout).  The sub-tile is transposed through a per-warp padded smem tile so that every
+// global access of the warp is row-contiguous (64-128 B segments) instead of 32 scattered pieces.
 template <int EPI>
-__device__ __forceinline__ void epilogue_row32(const GemmParams& p, const uint32_t (&r)[32], int row, int col0) {
-  if (row >= p.M || col0 >= p.N) return;
+__device__ __forceinline__ void epilogue_tile32(const GemmParams& p, const uint32_t (&r)[32], float* stage, int lane,
+                                                int row0, int col0) {
+  if (row0 >= p.M || col0 >= p.N) return;          // warp-uniform
+#pragma unroll
+  for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(r[j]) * p.alpha;
+  __syncwarp();
+  const int nrows = min(32, p.M - row0);
   const int ncols = min(32, p.N - col0);
-  const long off = static_cast<long>(row) * p.ldc + col0;
   if constexpr (EPI == EPI_BF16) {
-    const bool vec_ok = (ncols == 32) && ((off & 7) == 0);
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float x = __uint_as_float(r[j]) * p.alpha;
-      if (p.bias != nullptr && j < ncols) x += __ldg(p.bias + col0 + j);
-      if (p.relu) x = x > 0.f ? x : x * p.relu_slope;
-      v[j] = x;
+    // two rows per pass: lanes 0-15 -> row 2i, lanes 16-31 -> row 2i+1, each lane a column pair
+    const int half = lane >> 4, cp = (lane & 15) * 2;
+    const bool c0 = cp < ncols, c1 = cp + 1 < ncols;
+    float b0 = 0.f, b1 = 0.f;
+    if (p.bias != nullptr) {
+      if (c0) b0 = __ldg(p.bias + col0 + cp);
+      if (c1) b1 = __ldg(p.bias + col0 + cp + 1);
     }
-    if (p.mask != nullptr) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols && !(__bfloat162float(p.mask[off + j]) > 0.f)) v[j] *= p.relu_slope;
-    }
-    if (vec_ok) {
-      uint4* dst = reinterpret_cast<uint4*>(p.c_bf16 + off);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        __nv_bfloat162 b0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]);
-        __nv_bfloat162 b1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
-        __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
-        __nv_bfloat162 b3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
-        uint4 u;
-        u.x = *reinterpret_cast<uint32_t*>(&b0);
-        u.y = *reinterpret_cast<uint32_t*>(&b1);
-        u.z = *reinterpret_cast<uint32_t*>(&b2);
-        u.w = *reinterpret_cast<uint32_t*>(&b3);
-        dst[q] = u;
+    const bool pair_ok = c1 && ((p.ldc & 1) == 0) && (((col0 + cp) & 1) == 0);
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const int rr = 2 * i + half;
+      if (rr >= nrows) continue;
+      float x0 = stage[rr * 33 + cp] + b0, x1 = stage[rr * 33 + cp + 1] + b1;
+      if (p.relu) {
+        x0 = x0 > 0.f ? x0 : x0 * p.relu_slope;
+        x1 = x1 > 0.f ? x1 : x1 * p.relu_slope;
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols) p.c_bf16[off + j] = __float2bfloat16(v[j]);
+      const long off = static_cast<long>(row0 + rr) * p.ldc + col0 + cp;
+      if (p.mask != nullptr) {
+        if (c0 && !(__bfloat162float(p.mask[off]) > 0.f)) x0 *= p.relu_slope;
+        if (c1 && !(__bfloat162float(p.mask[off + 1]) > 0.f)) x1 *= p.relu_slope;
+      }
+      if (pair_ok) {
+        *reinterpret_cast<__nv_bfloat162*>(p.c_bf16 + off) = __floats2bfloat162_rn(x0, x1);
+      } else {
+        if (c0) p.c_bf16[off] = __float2bfloat16(x0);
+        if (c1) p.c_bf16[off + 1] = __float2bfloat16(x1);
+      }
     }
   } else if constexpr (EPI == EPI_F32) {
-    float* dst = p.c_f32 + off;
-    if (p.atomic) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols) atomicAdd(dst + j, __uint_as_float(r[j]) * p.alpha);
-    } else if (ncols == 32 && (off & 3) == 0) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float4 f = make_float4(__uint_as_float(r[4 * q]) * p.alpha, __uint_as_float(r[4 * q + 1]) * p.alpha,
-                               __uint_as_float(r[4 * q + 2]) * p.alpha, __uint_as_float(r[4 * q + 3]) * p.alpha);
-        reinterpret_cast<float4*>(dst)[q] = f;
+    if (lane < ncols) {
+#pragma unroll 4
+      for (int rr = 0; rr < nrows; ++rr) {
+        float* dst = p.c_f32 + static_cast<long>(row0 + rr) * p.ldc + col0 + lane;
+        const float v = stage[rr * 33 + lane];
+        if (p.atomic) atomicAdd(dst, v);
+        else *dst = v;
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols) dst[j] = __uint_as_float(r[j]) * p.alpha;
     }
-  } else {  // EPI_SGD: W, H updated in place, bf16 shadow refreshed
-    float* w = p.w + off;
-    float* h = p.h + off;
-    if (ncols == 32 && (off & 7) == 0) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float4 w0 = reinterpret_cast<float4*>(w)[2 * q], w1 = reinterpret_cast<float4*>(w)[2 * q + 1];
-        float4 h0 = reinterpret_cast<float4*>(h)[2 * q], h1 = reinterpret_cast<float4*>(h)[2 * q + 1];
-        float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-        float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sgd_apply(__uint_as_float(r[8 * q + j]) * p.alpha, wv[j], hv[j], p);
-        reinterpret_cast<float4*>(w)[2 * q] = make_float4(wv[0], wv[1], wv[2], wv[3]);
-        reinterpret_cast<float4*>(w)[2 * q + 1] = make_float4(wv[4], wv[5], wv[6], wv[7]);
-        reinterpret_cast<float4*>(h)[2 * q] = make_float4(hv[0], hv[1], hv[2], hv[3]);
-        reinterpret_cast<float4*>(h)[2 * q + 1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
-        if (p.wb != nullptr) {
-          __nv_bfloat162 b0 = __floats2bfloat162_rn(wv[0], wv[1]), b1 = __floats2bfloat162_rn(wv[2], wv[3]);
-          __nv_bfloat162 b2 = __floats2bfloat162_rn(wv[4], wv[5]), b3 = __floats2bfloat162_rn(wv[6], wv[7]);
-          uint4 u;
-          u.x = *reinterpret_cast<uint32_t*>(&b0);
-          u.y = *reinterpret_cast<uint32_t*>(&b1);
-          u.z = *reinterpret_cast<uint32_t*>(&b2);
-          u.w = *reinterpret_cast<uint32_t*>(&b3);
-          reinterpret_cast<uint4*>(p.wb + off)[q] = u;
-        }
+  } else {  // EPI_SGD: W, H stepped in place (coalesced 128 B rows), bf16 shadow refreshed
+    if (lane < ncols) {
+#pragma unroll 2
+      for (int rr = 0; rr < nrows; ++rr) {
+        const long off = static_cast<long>(row0 + rr) * p.ldc + col0 + lane;
+        float wv = p.w[off], hv = p.h[off];
+        sgd_apply(stage[rr * 33 + lane], wv, hv, p);
+        p.w[off] = wv;
+        p.h[off] = hv;
+        if (p.wb != nullptr) p.wb[off] = __float2bfloat16(wv);
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols) {
-          float wv = w[j], hv = h[j];
-          sgd_apply(__uint_as_float(r[j]) * p.alpha, wv, hv, p);
-          w[j] = wv;
-          h[j] = hv;
-          if (p.wb != nullptr) p.wb[off + j] = __float2bfloat16(wv);
-        }
     }
   }
+  __syncwarp();
 }
 
 // Producer policy: both operands via TMA.
@@ -240,6 +210,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* epi_stage = reinterpret_cast<float*>(bar_base + S::kBarBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -365,18 +336,15 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * S::kStageBytes;
         if constexpr (GATHER == GATHER_A) {
-          // A tile: 128 rows (m) x 64 k, row = gt
-          gather_row(cg, smem_u32(sa) + gt * 128, gt, static_cast<long>(m_blk) * BLOCK_M + gt, g * BLOCK_K);
+          // A tile: 128 rows (m) x 64 k
+          gather_tile(cg, smem_u32(sa), BLOCK_M, static_cast<long>(m_blk) * BLOCK_M, g * BLOCK_K, gt);
         } else {
           // B tile (MN-major): BN/64 chunks of [64 reduction rows (m)][64 k-columns]; reduction index = g
           constexpr int kChunks = BN / 64;
           const uint32_t sb = smem_u32(sa) + S::kABytes;
 #pragma unroll
-          for (int i = gt; i < kChunks * 64; i += kGatherThreads) {
-            const int chunk = i >> 6, r = i & 63;
-            gather_row(cg, sb + chunk * 8192 + r * 128, r, static_cast<long>(g) * BLOCK_K + r,
-                       n_blk * BN + chunk * 64);
-          }
+          for (int c = 0; c < kChunks; ++c)
+            gather_tile(cg, sb + c * 8192, 64, static_cast<long>(g) * BLOCK_K, n_blk * BN + c * 64, gt);
         }
         cp_async_commit();
         ++issued;
@@ -407,13 +375,13 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
       const int as = it & 1;
       mbar_wait(&tmem_full[as], (it >> 1) & 1);
       tc_fence_after();
-      const int row = m_blk * BLOCK_M + q * 32 + lane;
+      const int row0 = m_blk * BLOCK_M + q * 32;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, r);
         tmem_ld_wait();
-        epilogue_row32<EPI>(p, r, row, n_blk * BN + c * 32);
+        epilogue_tile32<EPI>(p, r, epi_stage + q * (32 * 33), lane, row0, n_blk * BN + c * 32);
       }
       tc_fence_before();
       __syncwarp();

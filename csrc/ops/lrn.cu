@@ -117,6 +117,100 @@ lrn_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict_
   }
 }
 
+// Register/L1 variant for the usual small windows (local_size <= 9): each thread owns 8 channels of one pixel and
+// reads the neighbouring 16-byte vectors directly (they are L1 hits: the same lines are being read by the
+// adjacent threads), so there is no shared-memory staging, no bank conflicts and DRAM sees every byte once.
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+lrn_reg_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ out,
+               long npix, int C, long xpitch, long dpitch, long opitch, int size, float alpha_over_n, float beta,
+               int mask_relu) {
+  const int c8 = C / 8;
+  const int pre = (size - 1) / 2;
+  const long total = npix * c8;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long p = i / c8;
+    const int v = static_cast<int>(i - p * c8);
+    float xw[24];                                 // channels [8v-8, 8v+16)
+    {
+      const __nv_bfloat16* xp = x + p * xpitch + v * 8;
+      float t[8];
+      if (v > 0) { unpack8(ld8(xp - 8), t); } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xw[j] = t[j];
+      unpack8(ld8(xp), t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xw[8 + j] = t[j];
+      if (v + 1 < c8) { unpack8(ld8(xp + 8), t); } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xw[16 + j] = t[j];
+    }
+    float o[8];
+    if constexpr (!BWD) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float acc = 0.f;
+        for (int k = -pre; k <= pre; ++k) { const float a = xw[8 + j + k]; acc += a * a; }
+        o[j] = xw[8 + j] * exp2f(-beta * log2f(1.f + alpha_over_n * acc));
+      }
+    } else {
+      float dw[24];
+      {
+        const __nv_bfloat16* dp = dy + p * dpitch + v * 8;
+        float t[8];
+        if (v > 0) { unpack8(ld8(dp - 8), t); } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dw[j] = t[j];
+        unpack8(ld8(dp), t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dw[8 + j] = t[j];
+        if (v + 1 < c8) { unpack8(ld8(dp + 8), t); } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dw[16 + j] = t[j];
+      }
+      // r_c = dy_c * x_c * scale_c^(-beta-1) for c in [8v-pre, 8v+7+pre]; keep log2(scale) of the centre 8
+      float rr[16], l2s[8];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int jj = q - 4;                       // channel offset relative to 8v, covers [-4, 11]
+        float acc = 0.f;
+        for (int k = -pre; k <= pre; ++k) {
+          const int idx = 8 + jj + k;
+          const float a = (idx >= 0 && idx < 24) ? xw[idx] : 0.f;
+          acc += a * a;
+        }
+        const float ls = log2f(1.f + alpha_over_n * acc);
+        rr[q] = dw[8 + jj] * xw[8 + jj] * exp2f((-beta - 1.f) * ls);
+        if (jj >= 0 && jj < 8) l2s[jj] = ls;
+      }
+      const float ratio = 2.f * alpha_over_n * beta;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float racc = 0.f;
+        for (int k = -pre; k <= pre; ++k) racc += rr[4 + j + k];
+        const float xc = xw[8 + j];
+        float g = dw[8 + j] * exp2f(-beta * l2s[j]) - ratio * xc * racc;
+        if (mask_relu && !(xc > 0.f)) g = 0.f;
+        o[j] = g;
+      }
+    }
+    st8(out + p * opitch + v * 8, pack8(o));
+  }
+}
+
 static void lrn_launch(bool bwd, const at::Tensor& x, const at::Tensor* dy, at::Tensor& out, int64_t size, double alpha,
                        double beta, bool fuse_relu) {
   TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16, "lrn: bf16 CUDA tensor expected");
@@ -140,6 +234,18 @@ static void lrn_launch(bool bwd, const at::Tensor& x, const at::Tensor* dy, at::
   }
   auto xp = reinterpret_cast<const __nv_bfloat16*>(x.data_ptr());
   auto op = reinterpret_cast<__nv_bfloat16*>(out.data_ptr());
+  if (size <= 9) {
+    const long total = npix * (v.C / 8);
+    const int g2 = grid_for(total, 256, 148 * 32);
+    if (bwd)
+      lrn_reg_kernel<true><<<g2, 256, 0, stream>>>(xp, dyp, op, npix, v.C, v.pitch, dpitch, o.pitch, static_cast<int>(size),
+                                                   static_cast<float>(alpha / size), static_cast<float>(beta), fuse_relu);
+    else
+      lrn_reg_kernel<false><<<g2, 256, 0, stream>>>(xp, nullptr, op, npix, v.C, v.pitch, 0, o.pitch, static_cast<int>(size),
+                                                    static_cast<float>(alpha / size), static_cast<float>(beta), fuse_relu);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    return;
+  }
   if (bwd) {
     C10_CUDA_CHECK(cudaFuncSetAttribute(lrn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     lrn_kernel<true><<<grid, kLrnThreads, smem, stream>>>(xp, dyp, op, npix, v.C, v.pitch, dpitch, o.pitch,

@@ -45,8 +45,13 @@ class SymmetricArena:
         self.rank, self.world = rank_ctx.rank, rank_ctx.world_size
         self.device = rank_ctx.device
         nbytes = _round_up(nbytes, 2 << 20)
+        group_name = dist.group.WORLD.group_name
+        try:
+            symm.enable_symm_mem_for_group(group_name)      # required on some builds, deprecated no-op on others
+        except Exception:
+            pass
         self.buf = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
-        self.hdl = symm.rendezvous(self.buf, dist.group.WORLD.group_name)
+        self.hdl = symm.rendezvous(self.buf, group_name)
         self.buf.zero_()
         self.base_ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         mc = getattr(self.hdl, "multicast_ptr", 0) or 0

@@ -40,6 +40,65 @@ def sfb_bytes(M: int, N: int, K: int, P: int, elem: int = 4) -> Dict[str, int]:
     }
 
 
+class SufficientVector:
+    """(u, v) factor pair of one layer with SVProto (de)serialisation — the unit the reference ships between
+    machines (include/caffe/sufficient_vector.hpp:17-50, src/caffe/proto/caffe.proto:6-10)."""
+
+    def __init__(self, a: torch.Tensor, b: torch.Tensor, layer_id: int = 0):
+        self.a, self.b, self.layer_id = a, b, layer_id
+
+    def to_proto(self):
+        from .. import proto as P
+        m = P.SVProto(layer_id=self.layer_id)
+        m.a = self.a.detach().float().reshape(-1).cpu().numpy()
+        m.b = self.b.detach().float().reshape(-1).cpu().numpy()
+        return m
+
+    @classmethod
+    def from_proto(cls, m, a_shape, b_shape, device="cpu"):
+        import numpy as np
+        a = torch.from_numpy(np.asarray(m.a, dtype=np.float32).reshape(a_shape).copy()).to(device)
+        b = torch.from_numpy(np.asarray(m.b, dtype=np.float32).reshape(b_shape).copy()).to(device)
+        return cls(a, b, int(m.layer_id or 0))
+
+    def gradient(self) -> torch.Tensor:
+        """ΔW = aᵀ·b  (reference: inner_product_layer.cu:55-64 ComputeGradientFromSV_gpu)."""
+        return self.a.t() @ self.b
+
+
+class SufficientVectorQueue:
+    """FIFO whose head is retired only after ``max_read_count`` readers have fetched it — the host-side queue of
+    the reference (include/caffe/sufficient_vector_queue.hpp:17-35).  The fused engine replaces it with the
+    double-buffered slot ring in the symmetric arena; this class serves the library path and tools."""
+
+    def __init__(self, max_read_count: int):
+        import threading
+        self.max_read_count = max_read_count
+        self.q = []
+        self.read_count = 0
+        self.lock = threading.Lock()
+
+    def add(self, sv: SufficientVector):
+        with self.lock:
+            self.q.append(sv)
+
+    def get(self):
+        """Non-blocking: returns the head (shared) or None; the head is popped after max_read_count reads."""
+        with self.lock:
+            if not self.q:
+                return None
+            sv = self.q[0]
+            self.read_count += 1
+            if self.read_count >= self.max_read_count:
+                self.q.pop(0)
+                self.read_count = 0
+            return sv
+
+    def __len__(self):
+        with self.lock:
+            return len(self.q)
+
+
 class SFBStats:
     def __init__(self):
         self.sfb_bytes = 0
