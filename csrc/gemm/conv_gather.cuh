@@ -81,47 +81,51 @@ __device__ __forceinline__ ChunkTap decode_chunk(const ConvGeom& g, int k) {
   return t;
 }
 
-// Copy this thread's 16-byte chunk of row m (or zeros) to `dst`.
-__device__ __forceinline__ void gather_chunk(const ConvGeom& g, uint32_t dst, long m, const ChunkTap& t) {
+// Per-thread decoded row position m -> (image base, ih0, iw0); computed once per tile (fprop / dgrad: the rows of
+// a tile do not change along K) or once per k-block (wgrad: the reduction runs over m).
+struct RowPos {
+  long base;        // element offset of image n
+  int ih0, iw0;     // input coordinates of tap (0,0)
+  int lim;          // ROW mode: valid elements of a kernel row inside the image row; TAP: unused
+  bool valid;
+};
+__device__ __forceinline__ RowPos decode_row(const ConvGeom& g, long m) {
+  RowPos p;
+  p.valid = m < g.M;
+  const uint32_t mm = p.valid ? static_cast<uint32_t>(m) : 0u;
+  const uint32_t n = fdiv(mm, g.div_ohow);
+  const uint32_t rem = mm - n * static_cast<uint32_t>(g.OH * g.OW);
+  const uint32_t oh = fdiv(rem, g.div_ow);
+  const uint32_t ow = rem - oh * static_cast<uint32_t>(g.OW);
+  p.base = static_cast<long>(n) * g.H * g.W * g.pitch;
+  p.ih0 = static_cast<int>(oh) * g.sh + g.off_h;
+  p.iw0 = static_cast<int>(ow) * g.sw + g.off_w;
+  p.lim = min(g.L, (g.W - p.iw0) * g.Cg);
+  return p;
+}
+
+// Copy this thread's 16-byte chunk of the row at `pos` (or zeros) to `dst`: no divisions on this path.
+__device__ __forceinline__ void gather_chunk(const ConvGeom& g, uint32_t dst, const RowPos& pos, const ChunkTap& t) {
   const __nv_bfloat16* src = g.x;
   uint32_t bytes = 0;
-  if (t.in_k && m < g.M) {
-    const uint32_t mm = static_cast<uint32_t>(m);
-    const uint32_t n = fdiv(mm, g.div_ohow);
-    const uint32_t rem = mm - n * static_cast<uint32_t>(g.OH * g.OW);
-    const uint32_t oh = fdiv(rem, g.div_ow);
-    const uint32_t ow = rem - oh * static_cast<uint32_t>(g.OW);
-    const int ih = static_cast<int>(oh) * g.sh + g.off_h + t.r * g.dr;
-    if (g.mode == 0) {
-      const int iw = static_cast<int>(ow) * g.sw + g.off_w + t.s * g.dr;
-      if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) {
-        src = g.x + ((static_cast<long>(n) * g.H + ih) * g.W + iw) * g.pitch + t.c;
-        bytes = 16;
-      }
-    } else {
-      const int iw0 = static_cast<int>(ow) * g.sw + g.off_w;
-      if (ih >= 0 && ih < g.H) {
-        const int lim = min(g.L, (g.W - iw0) * g.Cg);     // valid elements of this kernel row inside the image row
-        const int valid = max(0, min(8, lim - t.c));
-        if (valid > 0) {
-          src = g.x + ((static_cast<long>(n) * g.H + ih) * g.W + iw0) * g.pitch + t.c;
-          bytes = static_cast<uint32_t>(valid * 2);
-        }
+  const int ih = pos.ih0 + t.r * g.dr;
+  if (g.mode == 0) {
+    const int iw = pos.iw0 + t.s * g.dr;
+    if (pos.valid && t.in_k && static_cast<unsigned>(ih) < static_cast<unsigned>(g.H) &&
+        static_cast<unsigned>(iw) < static_cast<unsigned>(g.W)) {
+      src = g.x + pos.base + (static_cast<long>(ih) * g.W + iw) * g.pitch + t.c;
+      bytes = 16;
+    }
+  } else {
+    if (pos.valid && t.in_k && static_cast<unsigned>(ih) < static_cast<unsigned>(g.H)) {
+      const int valid = max(0, min(8, pos.lim - t.c));
+      if (valid > 0) {
+        src = g.x + pos.base + (static_cast<long>(ih) * g.W + pos.iw0) * g.pitch + t.c;
+        bytes = static_cast<uint32_t>(valid * 2);
       }
     }
   }
   cp_async_16(dst, src, bytes);
-}
-
-// Fill `nrows` (multiple of 16) rows x 64 k-elements at smem `tile` (rows of 128 B, swizzled) for rows m0.. and
-// k-range k0..k0+63.  Called by all 128 gather threads (gt = 0..127).
-__device__ __forceinline__ void gather_tile(const ConvGeom& g, uint32_t tile, int nrows, long m0, int k0, int gt) {
-  const int j = gt & 7;
-  const ChunkTap t = decode_chunk(g, k0 + j * 8);
-#pragma unroll 4
-  for (int r = gt >> 3; r < nrows; r += 16) {
-    gather_chunk(g, tile + r * 128 + ((j ^ (r & 7)) << 4), m0 + r, t);
-  }
 }
 
 }  // namespace psd

@@ -65,13 +65,13 @@ static void dispatch_bn(int bn, const TmapSet& tm, const GemmParams& p, int grid
 }
 
 int pick_bn(int64_t M, int64_t N, int sms) {
-  // Largest N tile that still yields at least ~one wave of CTAs; small N never pays for a wide tile.
+  // Largest N tile that still fills the machine; when even BN=64 cannot, take the tile that launches most CTAs
+  // (small-M GEMMs such as the FC forward are bandwidth/latency bound: more CTAs = more TMA streams in flight).
   const int64_t mb = (M + BLOCK_M - 1) / BLOCK_M;
-  for (int bn : {256, 128}) {
+  for (int bn : {256, 128, 64}) {
     if (N >= bn && mb * ((N + bn - 1) / bn) >= sms) return bn;
   }
-  if (N > 64 && mb * ((N + 127) / 128) * 2 >= sms) return 128;
-  return N > 64 ? 128 : 64;
+  return N > 128 ? 64 : (N > 64 ? 128 : 64);
 }
 
 // The one entry point.  Operands are described by raw device pointers so that peer (symmetric-memory)

@@ -99,6 +99,11 @@ __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc,
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes)
                : "memory");
 }
+// The mbarrier receives one arrival from this thread once all of the thread's prior cp.async copies have
+// landed (the barrier's expected count must include it: .noinc) — no wait_group, no stall in the producer.
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

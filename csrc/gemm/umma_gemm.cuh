@@ -25,10 +25,11 @@ constexpr int kMaxSrc = 8;
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int kNumThreads = 256;          // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+constexpr int kEpiWarps = 8;              // two warps per TMEM lane quadrant, alternating 32-column chunks
+constexpr int kNumThreads = 128 + 32 * kEpiWarps;   // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-11 epilogue
 constexpr int kEpiWarp0 = 4;
-constexpr int kGatherWarp0 = 8;           // conv kernels: warps 8-11 gather the implicit-im2col operand
-constexpr int kGatherThreads = 128;
+constexpr int kGatherWarp0 = kEpiWarp0 + kEpiWarps;  // conv kernels: 8 more warps gather the implicit-im2col operand
+constexpr int kGatherThreads = 256;          // 8 warps: the producers are instruction-latency bound, not bandwidth bound
 constexpr int kGatherLag = 2;             // cp.async groups kept in flight per gather thread
 enum GatherMode : int { GATHER_NONE = 0, GATHER_A = 1, GATHER_B = 2 };
 
@@ -74,8 +75,8 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
-  static constexpr int kBarBytes = 1024;
-  static constexpr int kEpiStageBytes = 4 * 32 * 33 * 4;    // per epilogue warp: 32x32 fp32 transpose tile (+1 pad)
+  static constexpr int kBarBytes = 256;
+  static constexpr int kEpiStageBytes = kEpiWarps * 32 * 33 * 4;    // per epilogue warp: 32x32 fp32 transpose tile (+1 pad)
   static constexpr int kTotal = kStages * kStageBytes + kBarBytes + kEpiStageBytes + 1024;  // +1024 alignment slack
 };
 
@@ -120,7 +121,26 @@ __device__ __forceinline__ void epilogue_tile32(const GemmParams& p, const uint3
       if (c1) b1 = __ldg(p.bias + col0 + cp + 1);
     }
     const bool pair_ok = c1 && ((p.ldc & 1) == 0) && (((col0 + cp) & 1) == 0);
-#pragma unroll 4
+    // fused ReLU-backward mask: issue all 16 loads of this lane up front (they are independent), then combine
+    uint32_t mk[16];
+    if (p.mask != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int rr = 2 * i + half;
+        const long off = static_cast<long>(row0 + rr) * p.ldc + col0 + cp;
+        uint32_t v = 0x3f803f80u;                                      // (1.0, 1.0): keep
+        if (rr < nrows) {
+          if (pair_ok) v = *reinterpret_cast<const uint32_t*>(p.mask + off);
+          else {
+            const uint32_t lo = c0 ? __bfloat16_as_ushort(p.mask[off]) : 0x3f80u;
+            const uint32_t hi = c1 ? __bfloat16_as_ushort(p.mask[off + 1]) : 0x3f80u;
+            v = lo | (hi << 16);
+          }
+        }
+        mk[i] = v;
+      }
+    }
+#pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int rr = 2 * i + half;
       if (rr >= nrows) continue;
@@ -131,8 +151,9 @@ __device__ __forceinline__ void epilogue_tile32(const GemmParams& p, const uint3
       }
       const long off = static_cast<long>(row0 + rr) * p.ldc + col0 + cp;
       if (p.mask != nullptr) {
-        if (c0 && !(__bfloat162float(p.mask[off]) > 0.f)) x0 *= p.relu_slope;
-        if (c1 && !(__bfloat162float(p.mask[off + 1]) > 0.f)) x1 *= p.relu_slope;
+        const float m0 = __uint_as_float(mk[i] << 16), m1 = __uint_as_float(mk[i] & 0xffff0000u);
+        if (!(m0 > 0.f)) x0 *= p.relu_slope;
+        if (!(m1 > 0.f)) x1 *= p.relu_slope;
       }
       if (pair_ok) {
         *reinterpret_cast<__nv_bfloat162*>(p.c_bf16 + off) = __floats2bfloat162_rn(x0, x1);
@@ -153,14 +174,26 @@ __device__ __forceinline__ void epilogue_tile32(const GemmParams& p, const uint3
     }
   } else {  // EPI_SGD: W, H stepped in place (coalesced 128 B rows), bf16 shadow refreshed
     if (lane < ncols) {
-#pragma unroll 2
-      for (int rr = 0; rr < nrows; ++rr) {
-        const long off = static_cast<long>(row0 + rr) * p.ldc + col0 + lane;
-        float wv = p.w[off], hv = p.h[off];
-        sgd_apply(stage[rr * 33 + lane], wv, hv, p);
-        p.w[off] = wv;
-        p.h[off] = hv;
-        if (p.wb != nullptr) p.wb[off] = __float2bfloat16(wv);
+#pragma unroll 1
+      for (int r0 = 0; r0 < nrows; r0 += 16) {
+        float wv[16], hv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {                // 32 independent 128-byte row loads in flight per warp
+          const long off = static_cast<long>(row0 + r0 + j) * p.ldc + col0 + lane;
+          const bool ok = r0 + j < nrows;
+          wv[j] = ok ? p.w[off] : 0.f;
+          hv[j] = ok ? p.h[off] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (r0 + j < nrows) {
+            const long off = static_cast<long>(row0 + r0 + j) * p.ldc + col0 + lane;
+            sgd_apply(stage[(r0 + j) * 33 + lane], wv[j], hv[j], p);
+            p.w[off] = wv[j];
+            p.h[off] = hv[j];
+            if (p.wb != nullptr) p.wb[off] = __float2bfloat16(wv[j]);
+          }
+        }
       }
     }
   }
@@ -233,7 +266,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);   // one arrive per epilogue warp
+      mbar_init(&tmem_empty[s], kEpiWarps);   // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -320,11 +353,12 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
     }
   } else if (GATHER != GATHER_NONE && warp >= kGatherWarp0) {
     // ===================== gather producers: implicit im2col -> swizzled smem via cp.async =====================
-    const int gt = threadIdx.x - kGatherWarp0 * 32;      // 0..127
+    const int gt = threadIdx.x - kGatherWarp0 * 32;      // 0..kGatherThreads-1
+    const int j = gt & 7;                                 // this thread's 16-byte chunk column
+    const int rg = gt >> 3;                               // first row; further rows every kGatherThreads/8
+    constexpr int kRowStep = kGatherThreads / 8;
     int stage = 0;
     uint32_t phase = 0;
-    int issued = 0;                                       // k-blocks issued so far (continuous across tiles)
-    int sig_stage = 0;                                    // next stage to signal
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile % m_blocks;
       const int rest = tile / m_blocks;
@@ -332,42 +366,57 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
       const int split = rest / n_blocks;
       const int g0 = static_cast<int>(static_cast<long>(total_kb) * split / p.split_k);
       const int g1 = static_cast<int>(static_cast<long>(total_kb) * (split + 1) / p.split_k);
-      for (int g = g0; g < g1; ++g) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * S::kStageBytes;
-        if constexpr (GATHER == GATHER_A) {
-          // A tile: 128 rows (m) x 64 k
-          gather_tile(cg, smem_u32(sa), BLOCK_M, static_cast<long>(m_blk) * BLOCK_M, g * BLOCK_K, gt);
-        } else {
-          // B tile (MN-major): BN/64 chunks of [64 reduction rows (m)][64 k-columns]; reduction index = g
-          constexpr int kChunks = BN / 64;
-          const uint32_t sb = smem_u32(sa) + S::kABytes;
+      if constexpr (GATHER == GATHER_A) {
+        // rows of the A tile are fixed along K: decode them once per tile
+        constexpr int kRows = BLOCK_M / kRowStep;
+        RowPos pos[kRows];
 #pragma unroll
-          for (int c = 0; c < kChunks; ++c)
-            gather_tile(cg, sb + c * 8192, 64, static_cast<long>(g) * BLOCK_K, n_blk * BN + c * 64, gt);
+        for (int i = 0; i < kRows; ++i) pos[i] = decode_row(cg, static_cast<long>(m_blk) * BLOCK_M + rg + i * kRowStep);
+        for (int g = g0; g < g1; ++g) {
+          const ChunkTap t = decode_chunk(cg, g * BLOCK_K + j * 8);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+#pragma unroll
+          for (int i = 0; i < kRows; ++i) {
+            const int r = rg + i * kRowStep;
+            gather_chunk(cg, sa + r * 128 + ((j ^ (r & 7)) << 4), pos[i], t);
+          }
+          cp_async_mbar_arrive_noinc(&full_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        cp_async_commit();
-        ++issued;
-        if (issued > kGatherLag) {
-          cp_async_wait<kGatherLag>();
-          fence_proxy_async_smem();
-          mbar_arrive(&full_bar[sig_stage]);
-          if (++sig_stage == kStages) sig_stage = 0;
+      } else {
+        // B tile (MN-major): BN/64 chunk-columns of [64 reduction rows (m)][64 k-columns]; the k-columns are
+        // fixed per tile (decode the taps once), the rows advance with the reduction index g
+        constexpr int kChunks = BN / 64;
+        constexpr int kRows = 64 / kRowStep;
+        ChunkTap taps[kChunks];
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) taps[c] = decode_chunk(cg, n_blk * BN + c * 64 + j * 8);
+        for (int g = g0; g < g1; ++g) {
+          RowPos pos[kRows];
+#pragma unroll
+          for (int i = 0; i < kRows; ++i) pos[i] = decode_row(cg, static_cast<long>(g) * BLOCK_K + rg + i * kRowStep);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const uint32_t sb = smem_u32(smem + stage * S::kStageBytes) + S::kABytes;
+#pragma unroll
+          for (int c = 0; c < kChunks; ++c) {
+#pragma unroll
+            for (int i = 0; i < kRows; ++i) {
+              const int r = rg + i * kRowStep;
+              gather_chunk(cg, sb + c * 8192 + r * 128 + ((j ^ (r & 7)) << 4), pos[i], taps[c]);
+            }
+          }
+          cp_async_mbar_arrive_noinc(&full_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
-    // drain
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    const int pending = issued < kGatherLag ? issued : kGatherLag;
-    for (int i = 0; i < pending; ++i) {
-      mbar_arrive(&full_bar[sig_stage]);
-      if (++sig_stage == kStages) sig_stage = 0;
-    }
-  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
     // ===================== epilogue warps: TMEM -> registers -> global =====================
-    const int q = warp - kEpiWarp0;               // TMEM lane quadrant == warp_id % 4
+    const int e = warp - kEpiWarp0;
+    const int q = e & 3;                          // TMEM lane quadrant == warp_id % 4
+    const int half = e >> 2;                      // which of the two warps of this quadrant
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile % m_blocks;
@@ -377,11 +426,11 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
       tc_fence_after();
       const int row0 = m_blk * BLOCK_M + q * 32;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += kEpiWarps / 4) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, r);
         tmem_ld_wait();
-        epilogue_tile32<EPI>(p, r, epi_stage + q * (32 * 33), lane, row0, n_blk * BN + c * 32);
+        epilogue_tile32<EPI>(p, r, epi_stage + e * (32 * 33), lane, row0, n_blk * BN + c * 32);
       }
       tc_fence_before();
       __syncwarp();

@@ -10,45 +10,58 @@ namespace psd {
 
 // ------------------------------------------------------------------ data transform
 // out[n, oh+opad, ow+opad, 0..Cp) = (x[n, c, h_off+oh, w_off+(flip ? OW-1-ow : ow)] - mean) * scale, channels >= C zero.
-template <typename TIn, int CP>
+// Each thread produces PX consecutive output pixels of one row: PX*C independent loads in flight, and the PX
+// packed pixels leave as one or two 16-byte stores.
+template <typename TIn, int CP, int PX>
 __global__ void __launch_bounds__(256)
 transform_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const int* __restrict__ h_off,
                  const int* __restrict__ w_off, const uint8_t* __restrict__ flip, const float* __restrict__ mean,
                  int mean_mode, float scale, int N, int C, int H, int W, int OH, int OW, int opad, int wextra) {
-  const long total = static_cast<long>(N) * OH * OW;
+  const int OWG = (OW + PX - 1) / PX;
+  const long total = static_cast<long>(N) * OH * OWG;
   const int OHp = OH + 2 * opad, OWp = OW + 2 * opad + wextra;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int ow = static_cast<int>(i % OW);
-    const int oh = static_cast<int>((i / OW) % OH);
-    const int n = static_cast<int>(i / (static_cast<long>(OW) * OH));
+    const int owg = static_cast<int>(i % OWG);
+    const int oh = static_cast<int>((i / OWG) % OH);
+    const int n = static_cast<int>(i / (static_cast<long>(OWG) * OH));
     const int h = h_off[n] + oh;
-    const int w = w_off[n] + (flip[n] ? (OW - 1 - ow) : ow);
-    float v[CP];
+    const int wo = w_off[n];
+    const bool fl = flip[n] != 0;
+    float v[PX][CP];
 #pragma unroll
-    for (int c = 0; c < CP; ++c) {
-      float f = 0.f;
-      if (c < C) {
-        const long src = ((static_cast<long>(n) * C + c) * H + h) * W + w;
-        f = static_cast<float>(x[src]);
-        if (mean_mode == 1) f -= mean[c];
-        else if (mean_mode == 2) f -= mean[(static_cast<long>(c) * H + h) * W + w];
-        f *= scale;
+    for (int q = 0; q < PX; ++q) {
+      const int ow = owg * PX + q;
+      const int w = wo + (fl ? (OW - 1 - ow) : ow);
+#pragma unroll
+      for (int c = 0; c < CP; ++c) {
+        float f = 0.f;
+        if (c < C && ow < OW) {
+          const long src = ((static_cast<long>(n) * C + c) * H + h) * W + w;
+          f = static_cast<float>(x[src]);
+          if (mean_mode == 1) f -= mean[c];
+          else if (mean_mode == 2) f -= mean[(static_cast<long>(c) * H + h) * W + w];
+          f *= scale;
+        }
+        v[q][c] = f;
       }
-      v[c] = f;
     }
-    __nv_bfloat16* o = out + ((static_cast<long>(n) * OHp + oh + opad) * OWp + ow + opad) * CP;
-    if constexpr (CP == 4) {
-      __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
-      uint2 u;
-      u.x = *reinterpret_cast<uint32_t*>(&a);
-      u.y = *reinterpret_cast<uint32_t*>(&b);
-      *reinterpret_cast<uint2*>(o) = u;
-    } else {
-      float f8[8];
+    __nv_bfloat16* o = out + ((static_cast<long>(n) * OHp + oh + opad) * OWp + owg * PX + opad) * CP;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) f8[c] = v[c];
-      st8(o, pack8(f8));
+    for (int q = 0; q < PX; ++q) {
+      if (owg * PX + q >= OW) break;
+      if constexpr (CP == 4) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[q][0], v[q][1]), b = __floats2bfloat162_rn(v[q][2], v[q][3]);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&a);
+        u.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(o + q * CP) = u;
+      } else {
+        float f8[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) f8[c] = v[q][c];
+        st8(o + q * CP, pack8(f8));
+      }
     }
   }
 }
@@ -73,10 +86,11 @@ at::Tensor transform_nhwc(const at::Tensor& x, const at::Tensor& h_off, const at
     if (mean_mode == 2) TORCH_CHECK(mean->numel() == static_cast<int64_t>(C) * H * W, "mean image shape mismatch");
   }
   auto stream = at::cuda::getCurrentCUDAStream();
-  const long total = static_cast<long>(N) * OH * OW;
+  constexpr int kPx = 4;
+  const long total = static_cast<long>(N) * OH * ((OW + kPx - 1) / kPx);
   auto op = reinterpret_cast<__nv_bfloat16*>(out.data_ptr());
 #define PSD_XF(T, CPV)                                                                                          \
-  transform_kernel<T, CPV><<<grid_for(total, 256), 256, 0, stream>>>(                                         \
+  transform_kernel<T, CPV, kPx><<<grid_for(total, 256, 148 * 32), 256, 0, stream>>>(                                         \
       x.data_ptr<T>(), op, h_off.data_ptr<int>(), w_off.data_ptr<int>(), flip.data_ptr<uint8_t>(), mp, mean_mode, \
       static_cast<float>(scale), N, C, H, W, OH, OW, opad, wextra)
   if (x.scalar_type() == at::kByte) {

@@ -120,13 +120,13 @@ lrn_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict_
 // Register/L1 variant for the usual small windows (local_size <= 9): each thread owns 8 channels of one pixel and
 // reads the neighbouring 16-byte vectors directly (they are L1 hits: the same lines are being read by the
 // adjacent threads), so there is no shared-memory staging, no bank conflicts and DRAM sees every byte once.
-template <bool BWD>
+template <bool BWD, int PRE>
 __global__ void __launch_bounds__(256)
 lrn_reg_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ out,
                long npix, int C, long xpitch, long dpitch, long opitch, int size, float alpha_over_n, float beta,
                int mask_relu) {
   const int c8 = C / 8;
-  const int pre = (size - 1) / 2;
+  constexpr int pre = PRE;             // compile-time window: all register-array indices below are static
   const long total = npix * c8;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -157,6 +157,7 @@ lrn_reg_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float acc = 0.f;
+#pragma unroll
         for (int k = -pre; k <= pre; ++k) { const float a = xw[8 + j + k]; acc += a * a; }
         o[j] = xw[8 + j] * exp2f(-beta * log2f(1.f + alpha_over_n * acc));
       }
@@ -187,9 +188,10 @@ lrn_reg_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
       for (int q = 0; q < 16; ++q) {
         const int jj = q - 4;                       // channel offset relative to 8v, covers [-4, 11]
         float acc = 0.f;
+#pragma unroll
         for (int k = -pre; k <= pre; ++k) {
           const int idx = 8 + jj + k;
-          const float a = (idx >= 0 && idx < 24) ? xw[idx] : 0.f;
+          const float a = (idx >= 0 && idx < 24) ? xw[idx < 0 ? 0 : (idx > 23 ? 23 : idx)] : 0.f;
           acc += a * a;
         }
         const float ls = log2f(1.f + alpha_over_n * acc);
@@ -200,6 +202,7 @@ lrn_reg_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float racc = 0.f;
+#pragma unroll
         for (int k = -pre; k <= pre; ++k) racc += rr[4 + j + k];
         const float xc = xw[8 + j];
         float g = dw[8 + j] * exp2f(-beta * l2s[j]) - ratio * xc * racc;
@@ -237,12 +240,20 @@ static void lrn_launch(bool bwd, const at::Tensor& x, const at::Tensor* dy, at::
   if (size <= 9) {
     const long total = npix * (v.C / 8);
     const int g2 = grid_for(total, 256, 148 * 32);
-    if (bwd)
-      lrn_reg_kernel<true><<<g2, 256, 0, stream>>>(xp, dyp, op, npix, v.C, v.pitch, dpitch, o.pitch, static_cast<int>(size),
-                                                   static_cast<float>(alpha / size), static_cast<float>(beta), fuse_relu);
-    else
-      lrn_reg_kernel<false><<<g2, 256, 0, stream>>>(xp, nullptr, op, npix, v.C, v.pitch, 0, o.pitch, static_cast<int>(size),
-                                                    static_cast<float>(alpha / size), static_cast<float>(beta), fuse_relu);
+    const float aon = static_cast<float>(alpha / size), bt = static_cast<float>(beta);
+#define PSD_LRN(PRE)                                                                                                   \
+  if (bwd) lrn_reg_kernel<true, PRE><<<g2, 256, 0, stream>>>(xp, dyp, op, npix, v.C, v.pitch, dpitch, o.pitch,          \
+                                                              static_cast<int>(size), aon, bt, fuse_relu);             \
+  else lrn_reg_kernel<false, PRE><<<g2, 256, 0, stream>>>(xp, nullptr, op, npix, v.C, v.pitch, 0, o.pitch,              \
+                                                           static_cast<int>(size), aon, bt, fuse_relu)
+    switch ((size - 1) / 2) {
+      case 0: PSD_LRN(0); break;
+      case 1: PSD_LRN(1); break;
+      case 2: PSD_LRN(2); break;
+      case 3: PSD_LRN(3); break;
+      default: PSD_LRN(4); break;
+    }
+#undef PSD_LRN
     C10_CUDA_KERNEL_LAUNCH_CHECK();
     return;
   }

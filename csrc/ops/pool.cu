@@ -16,7 +16,8 @@ struct PoolGeom {
   long xpitch, ypitch;   // pixel pitches of the input-side and output-side tensors
 };
 
-template <bool MAXP>
+// KT > 0: compile-time square window (fully unrolled, all window loads issued before use); KT == 0: generic.
+template <bool MAXP, int KT>
 __global__ void __launch_bounds__(256)
 pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx,
                 PoolGeom g) {
@@ -38,17 +39,45 @@ pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc[j] = MAXP ? -3.402823466e38f : 0.f; best[j] = 0; }
     const __nv_bfloat16* xb = x + (static_cast<long>(n) * g.H * g.W) * g.xpitch + v * 8;
-    for (int h = h0; h < he; ++h) {
-      for (int w = w0; w < we; ++w) {
+    if constexpr (KT > 0) {
+      bf16x8 win[KT * KT];
+      bool ok[KT * KT];
+#pragma unroll
+      for (int dh = 0; dh < KT; ++dh) {
+#pragma unroll
+        for (int dw = 0; dw < KT; ++dw) {
+          const int h = hs + dh, w = ws + dw;
+          ok[dh * KT + dw] = h >= 0 && h < g.H && w >= 0 && w < g.W;
+          if (ok[dh * KT + dw]) win[dh * KT + dw] = ld8(xb + (static_cast<long>(h) * g.W + w) * g.xpitch);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < KT * KT; ++t) {
+        if (!ok[t]) continue;
         float f[8];
-        unpack8(ld8(xb + (static_cast<long>(h) * g.W + w) * g.xpitch), f);
-        const int tap = (h - hs) * g.kw + (w - ws);
+        unpack8(win[t], f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if (MAXP) {
-            if (f[j] > acc[j]) { acc[j] = f[j]; best[j] = tap; }
+            if (f[j] > acc[j]) { acc[j] = f[j]; best[j] = t; }
           } else {
             acc[j] += f[j];
+          }
+        }
+      }
+    } else {
+      for (int h = h0; h < he; ++h) {
+        for (int w = w0; w < we; ++w) {
+          float f[8];
+          unpack8(ld8(xb + (static_cast<long>(h) * g.W + w) * g.xpitch), f);
+          const int tap = (h - hs) * g.kw + (w - ws);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (MAXP) {
+              if (f[j] > acc[j]) { acc[j] = f[j]; best[j] = tap; }
+            } else {
+              acc[j] += f[j];
+            }
           }
         }
       }
@@ -69,7 +98,9 @@ pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
   }
 }
 
-template <bool MAXP>
+// NC > 0: at most NC x NC output windows cover an input pixel (NC = ceil(k / stride)), loops unrolled with
+// predicates so every dy / index load is in flight before the accumulation; NC == 0: generic.
+template <bool MAXP, int NC>
 __global__ void __launch_bounds__(256)
 pool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx, __nv_bfloat16* __restrict__ dx,
                 PoolGeom g) {
@@ -91,25 +122,57 @@ pool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict_
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int oh = oh0; oh < oh1; ++oh) {
-      for (int ow = ow0; ow < ow1; ++ow) {
-        const long opix = (static_cast<long>(n) * g.OH + oh) * g.OW + ow;
-        float d[8];
-        unpack8(ld8(dy + opix * g.ypitch + v * 8), d);
-        const int hs = oh * g.sh - g.ph, ws = ow * g.sw - g.pw;
-        if (MAXP) {
-          const int tap = (h - hs) * g.kw + (w - ws);
-          const uint2 pk = *reinterpret_cast<const uint2*>(idx + opix * g.C + v * 8);
+    auto accumulate = [&](int oh, int ow, const bf16x8& dv, const uint2& pk) {
+      float d[8];
+      unpack8(dv, d);
+      const int hs = oh * g.sh - g.ph, ws = ow * g.sw - g.pw;
+      if (MAXP) {
+        const int tap = (h - hs) * g.kw + (w - ws);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int b = ((j < 4 ? pk.x : pk.y) >> (8 * (j & 3))) & 0xff;
-            if (b == tap) acc[j] += d[j];
+        for (int j = 0; j < 8; ++j) {
+          const int b = ((j < 4 ? pk.x : pk.y) >> (8 * (j & 3))) & 0xff;
+          if (b == tap) acc[j] += d[j];
+        }
+      } else {
+        const int he_pad = min(hs + g.kh, g.H + g.ph), we_pad = min(ws + g.kw, g.W + g.pw);
+        const float inv = 1.f / static_cast<float>((he_pad - hs) * (we_pad - ws));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += d[j] * inv;
+      }
+    };
+    if constexpr (NC > 0) {
+      bf16x8 dv[NC * NC];
+      uint2 pk[NC * NC];
+      bool ok[NC * NC];
+#pragma unroll
+      for (int a = 0; a < NC; ++a) {
+#pragma unroll
+        for (int b = 0; b < NC; ++b) {
+          const int oh = oh0 + a, ow = ow0 + b;
+          const int t = a * NC + b;
+          ok[t] = oh < oh1 && ow < ow1;
+          pk[t] = make_uint2(0, 0);
+          if (ok[t]) {
+            const long opix = (static_cast<long>(n) * g.OH + oh) * g.OW + ow;
+            dv[t] = ld8(dy + opix * g.ypitch + v * 8);
+            if (MAXP) pk[t] = *reinterpret_cast<const uint2*>(idx + opix * g.C + v * 8);
           }
-        } else {
-          const int he_pad = min(hs + g.kh, g.H + g.ph), we_pad = min(ws + g.kw, g.W + g.pw);
-          const float inv = 1.f / static_cast<float>((he_pad - hs) * (we_pad - ws));
+        }
+      }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] += d[j] * inv;
+      for (int a = 0; a < NC; ++a) {
+#pragma unroll
+        for (int b = 0; b < NC; ++b)
+          if (ok[a * NC + b]) accumulate(oh0 + a, ow0 + b, dv[a * NC + b], pk[a * NC + b]);
+      }
+    } else {
+      for (int oh = oh0; oh < oh1; ++oh) {
+        for (int ow = ow0; ow < ow1; ++ow) {
+          const long opix = (static_cast<long>(n) * g.OH + oh) * g.OW + ow;
+          const bf16x8 dv = ld8(dy + opix * g.ypitch + v * 8);
+          uint2 pk = make_uint2(0, 0);
+          if (MAXP) pk = *reinterpret_cast<const uint2*>(idx + opix * g.C + v * 8);
+          accumulate(oh, ow, dv, pk);
         }
       }
     }
@@ -142,10 +205,13 @@ std::tuple<at::Tensor, at::Tensor> pool_fwd(const at::Tensor& x, bool is_max, at
   auto stream = at::cuda::getCurrentCUDAStream();
   auto xp = reinterpret_cast<const __nv_bfloat16*>(x.data_ptr());
   auto yp = reinterpret_cast<__nv_bfloat16*>(y.data_ptr());
-  if (is_max)
-    pool_fwd_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(xp, yp, idx.defined() ? idx.data_ptr<uint8_t>() : nullptr, g);
-  else
-    pool_fwd_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(xp, yp, nullptr, g);
+  uint8_t* ip = idx.defined() ? idx.data_ptr<uint8_t>() : nullptr;
+  const int grid = grid_for(total, 256, 148 * 32);
+  const int kt = (g.kh == g.kw && (g.kh == 2 || g.kh == 3)) ? g.kh : 0;
+#define PSD_PF(MX, KT) pool_fwd_kernel<MX, KT><<<grid, 256, 0, stream>>>(xp, yp, MX ? ip : nullptr, g)
+  if (is_max) { if (kt == 3) PSD_PF(true, 3); else if (kt == 2) PSD_PF(true, 2); else PSD_PF(true, 0); }
+  else        { if (kt == 3) PSD_PF(false, 3); else if (kt == 2) PSD_PF(false, 2); else PSD_PF(false, 0); }
+#undef PSD_PF
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   return {y, idx.defined() ? idx : at::empty({0}, x.options().dtype(at::kByte))};
 }
@@ -163,12 +229,18 @@ at::Tensor pool_bwd(const at::Tensor& dy, const at::Tensor& idx, bool is_max, at
   auto stream = at::cuda::getCurrentCUDAStream();
   auto dyp = reinterpret_cast<const __nv_bfloat16*>(dy.data_ptr());
   auto dxp = reinterpret_cast<__nv_bfloat16*>(dx.data_ptr());
+  const int grid = grid_for(total, 256, 148 * 32);
+  const int ncand = std::max((g.kh + g.sh - 1) / g.sh, (g.kw + g.sw - 1) / g.sw);
+  const int nc = ncand <= 3 ? ncand : 0;
+  const uint8_t* ip = nullptr;
   if (is_max) {
     TORCH_CHECK(idx.numel() == dy.numel(), "pool_bwd: index tensor missing");
-    pool_bwd_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(dyp, idx.data_ptr<uint8_t>(), dxp, g);
-  } else {
-    pool_bwd_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(dyp, nullptr, dxp, g);
+    ip = idx.data_ptr<uint8_t>();
   }
+#define PSD_PB(MX, NCV) pool_bwd_kernel<MX, NCV><<<grid, 256, 0, stream>>>(dyp, ip, dxp, g)
+  if (is_max) { if (nc == 1) PSD_PB(true, 1); else if (nc == 2) PSD_PB(true, 2); else if (nc == 3) PSD_PB(true, 3); else PSD_PB(true, 0); }
+  else        { if (nc == 1) PSD_PB(false, 1); else if (nc == 2) PSD_PB(false, 2); else if (nc == 3) PSD_PB(false, 3); else PSD_PB(false, 0); }
+#undef PSD_PB
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   return dx;
 }
