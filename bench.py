@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--sfb-mode", default="auto")
     ap.add_argument("--staleness", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--graph", type=int, default=-1, help="CUDA-graph the step (default: on for 1-GPU sm100)")
     ap.add_argument("--vendor-dtype", default="bf16", choices=["bf16", "fp32"])
     return ap.parse_args()
 
@@ -172,6 +173,9 @@ def main():
     # ---------------- device-resident-input measurement (kernel + comm + update time)
     solver = build_solver(args, rc, device_resident=True)
     batch = solver.net.blob_shapes[solver.net.top_names[0][0]][0]
+    use_graph = (args.graph == 1) or (args.graph < 0 and args.engine == "sm100" and world == 1)
+    if use_graph:
+        solver.enable_cuda_graph(warmup=2)
     for _ in range(args.warmup):
         solver.step(1)
     solver.sync.wait_all()
@@ -180,7 +184,7 @@ def main():
         sampler.start()
     counting.reset()
     ms, _ = timed_steps(solver, rc, args.steps, read_loss=False)
-    launches = counting.total()
+    launches = counting.total() + (args.steps * getattr(solver, 'graph_launches', 0) if use_graph else 0)
     clocks = sampler.stop() if rc.is_root else None
     value = batch * world * args.steps / (ms / 1e3)
     wire = solver.sync.backend.bytes_on_wire() if hasattr(solver.sync.backend, "bytes_on_wire") else {}
@@ -210,7 +214,7 @@ def main():
                        "input": list(shape[1:]), "seq_len": None,
                        "parallelism": f"dp{world}" + ("+dwbp" if world > 1 else "") +
                                       ("+sfb" if any(v == "sfb" for v in sfb_layers.values()) and world > 1 else ""),
-                       "engine": args.engine, "comm": solver.comm_name, "solver": "SGD momentum 0.9 wd 5e-4 (reference solver.prototxt)",
+                       "engine": args.engine, "comm": solver.comm_name, "cuda_graph": bool(use_graph), "solver": "SGD momentum 0.9 wd 5e-4 (reference solver.prototxt)",
                        "l2": "per-step working set (weights+history+grads+activations) >> 126 MB L2; inputs rotate over 4 batches",
                        "sfb_layers": sfb_layers, "wire_bytes_total": wire,
                        "baseline_ref": "133 img/s per K20 derived in BASELINE.md §1 (reference publishes no img/s)"},

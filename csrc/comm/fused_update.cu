@@ -59,7 +59,8 @@ __device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
 // ------------------------------------------------------------------------------------ single GPU
 __global__ void __launch_bounds__(256)
 fused_update_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ h, __nv_bfloat16* __restrict__ wb,
-                    long n, UpdateHyper hp) {
+                    long n, UpdateHyper hp, const float* __restrict__ lr_dev) {
+  if (lr_dev != nullptr) hp.lr *= __ldg(lr_dev);     // global learning rate lives on the device (CUDA-graph replay safe)
   const long n4 = n >> 2;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<long>(gridDim.x) * blockDim.x) {
     float4 wv = reinterpret_cast<float4*>(w)[i], hv = reinterpret_cast<float4*>(h)[i];
@@ -100,7 +101,7 @@ static bool same_dense_layout(const at::Tensor& a, const at::Tensor& b) {
 
 // W, G, H: fp32 tensors with identical (dense) layout; wb: optional bf16 shadow in the same storage order.
 void fused_update(at::Tensor w, const at::Tensor& g, at::Tensor h, c10::optional<at::Tensor> wb, double lr, double momentum,
-                  double decay, int64_t rule, bool l1, double delta, double gscale) {
+                  double decay, int64_t rule, bool l1, double delta, double gscale, const c10::optional<at::Tensor>& lr_dev) {
   TORCH_CHECK(w.is_cuda() && w.scalar_type() == at::kFloat && g.scalar_type() == at::kFloat && h.scalar_type() == at::kFloat);
   TORCH_CHECK(same_dense_layout(w, g) && same_dense_layout(w, h), "fused_update: W, G, H must share one dense layout");
   TORCH_CHECK(w.is_non_overlapping_and_dense(), "fused_update: dense tensors expected");
@@ -118,7 +119,7 @@ void fused_update(at::Tensor w, const at::Tensor& g, at::Tensor h, c10::optional
   const int grid = static_cast<int>(std::max<long>(1, std::min<long>((n / 4 + 255) / 256, 148 * 8)));
   fused_update_kernel<<<grid, 256, 0, at::cuda::getCurrentCUDAStream()>>>(
       w.data_ptr<float>(), g.data_ptr<float>(), h.data_ptr<float>(), wbp, n,
-      make_hyper(lr, momentum, decay, rule, l1, delta, gscale));
+      make_hyper(lr, momentum, decay, rule, l1, delta, gscale), lr_dev.has_value() ? lr_dev->data_ptr<float>() : nullptr);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
@@ -159,7 +160,8 @@ __device__ __forceinline__ void peer_barrier(const PeerPtrs& pp, int rank, int w
 template <bool ONE_SHOT>
 __global__ void __launch_bounds__(512)
 allreduce_sgd_kernel(PeerPtrs pp, float* __restrict__ h, long n, int rank, int world, uint32_t epoch, UpdateHyper hp,
-                     unsigned int* __restrict__ done_counter) {
+                     unsigned int* __restrict__ done_counter, const float* __restrict__ lr_dev) {
+  if (lr_dev != nullptr) hp.lr *= __ldg(lr_dev);
   // ---- phase 0: all ranks' gradients for this epoch are in place
   peer_barrier(pp, rank, world, 0, epoch);
 
@@ -225,8 +227,10 @@ allreduce_sgd_kernel(PeerPtrs pp, float* __restrict__ h, long n, int rank, int w
 void allreduce_sgd(std::vector<int64_t> g_ptrs, std::vector<int64_t> w_ptrs, std::vector<int64_t> wb_ptrs,
                    std::vector<int64_t> flag_ptrs, int64_t g_mc, int64_t w_mc, at::Tensor h, int64_t n, int64_t rank,
                    int64_t epoch, bool one_shot, at::Tensor done_counter, double lr, double momentum, double decay,
-                   int64_t rule, bool l1, double delta, double gscale, int64_t max_ctas) {
+                   int64_t rule, bool l1, double delta, double gscale, int64_t max_ctas,
+                   const c10::optional<at::Tensor>& lr_dev) {
   const int world = static_cast<int>(g_ptrs.size());
+  const float* lrp = lr_dev.has_value() ? lr_dev->data_ptr<float>() : nullptr;
   TORCH_CHECK(world >= 1 && world <= kMaxRanks && w_ptrs.size() == g_ptrs.size() && flag_ptrs.size() == g_ptrs.size());
   TORCH_CHECK(h.is_cuda() && h.scalar_type() == at::kFloat && h.numel() >= n && n % 4 == 0);
   TORCH_CHECK(done_counter.scalar_type() == at::kInt && done_counter.numel() >= 1);
@@ -247,10 +251,10 @@ void allreduce_sgd(std::vector<int64_t> g_ptrs, std::vector<int64_t> w_ptrs, std
   auto* dc = reinterpret_cast<unsigned int*>(done_counter.data_ptr());
   if (one_shot)
     allreduce_sgd_kernel<true><<<grid, 512, 0, stream>>>(pp, h.data_ptr<float>(), n, static_cast<int>(rank), world,
-                                                         static_cast<uint32_t>(epoch), hp, dc);
+                                                         static_cast<uint32_t>(epoch), hp, dc, lrp);
   else
     allreduce_sgd_kernel<false><<<grid, 512, 0, stream>>>(pp, h.data_ptr<float>(), n, static_cast<int>(rank), world,
-                                                          static_cast<uint32_t>(epoch), hp, dc);
+                                                          static_cast<uint32_t>(epoch), hp, dc, lrp);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
@@ -310,10 +314,10 @@ void peer_push(const at::Tensor& src, std::vector<int64_t> dst_ptrs, int64_t dst
 
 TORCH_LIBRARY_FRAGMENT(poseidon, m) {
   m.def("fused_update(Tensor(a!) w, Tensor g, Tensor(b!) h, Tensor(c!)? wb, float lr, float momentum, float decay, int rule, "
-        "bool l1, float delta, float gscale) -> ()", &psd::fused_update);
+        "bool l1, float delta, float gscale, Tensor? lr_dev) -> ()", &psd::fused_update);
   m.def("allreduce_sgd(int[] g_ptrs, int[] w_ptrs, int[] wb_ptrs, int[] flag_ptrs, int g_mc, int w_mc, Tensor(a!) h, int n, "
         "int rank, int epoch, bool one_shot, Tensor(b!) done_counter, float lr, float momentum, float decay, int rule, "
-        "bool l1, float delta, float gscale, int max_ctas) -> ()", &psd::allreduce_sgd);
+        "bool l1, float delta, float gscale, int max_ctas, Tensor? lr_dev) -> ()", &psd::allreduce_sgd);
   m.def("peer_push(Tensor src, int[] dst_ptrs, int dst_mc, int[] flag_ptrs, int rank, int slot, int epoch, bool signal, "
         "Tensor(a!) done_counter) -> ()", &psd::peer_push);
 }

@@ -180,7 +180,7 @@ void sfb_outer_sgd(std::vector<int64_t> u_ptrs, std::vector<int64_t> v_ptrs, int
                    at::Tensor w, at::Tensor h, c10::optional<at::Tensor> wb, double alpha, double lr,
                    double momentum, double decay, int64_t rule, bool l1, double delta,
                    const c10::optional<at::Tensor>& flags, int64_t epoch, int64_t src_rot, int64_t bn,
-                   int64_t max_ctas) {
+                   int64_t max_ctas, const c10::optional<at::Tensor>& lr_dev) {
   TORCH_CHECK(w.is_cuda() && w.scalar_type() == at::kFloat && h.scalar_type() == at::kFloat);
   TORCH_CHECK(w.numel() == N * K && h.numel() == N * K && w.is_contiguous() && h.is_contiguous());
   c10::cuda::CUDAGuard guard(w.device());
@@ -191,6 +191,7 @@ void sfb_outer_sgd(std::vector<int64_t> u_ptrs, std::vector<int64_t> v_ptrs, int
   p.ldc = K;
   p.alpha = static_cast<float>(alpha);
   p.lr = static_cast<float>(lr);
+  p.lr_dev = lr_dev.has_value() ? lr_dev->data_ptr<float>() : nullptr;
   p.momentum = static_cast<float>(momentum);
   p.decay = static_cast<float>(decay);
   p.rule = static_cast<int>(rule);
@@ -217,5 +218,5 @@ TORCH_LIBRARY_FRAGMENT(poseidon, m) {
         "int split_k, int bn) -> ()", &psd::gemm_f32);
   m.def("sfb_outer_sgd(int[] u_ptrs, int[] v_ptrs, int Mb, int N, int K, Tensor(a!) w, Tensor(b!) h, "
         "Tensor(c!)? wb, float alpha, float lr, float momentum, float decay, int rule, bool l1, float delta, "
-        "Tensor? flags, int epoch, int src_rot, int bn, int max_ctas) -> ()", &psd::sfb_outer_sgd);
+        "Tensor? flags, int epoch, int src_rot, int bn, int max_ctas, Tensor? lr_dev) -> ()", &psd::sfb_outer_sgd);
 }

@@ -61,6 +61,7 @@ struct GemmParams {
   float* h;
   __nv_bfloat16* wb;
   float lr, momentum, decay;
+  const float* lr_dev;   // optional device-resident global learning rate (multiplies lr)
   int rule;              // 0 SGD, 1 Nesterov, 2 AdaGrad
   int l1;
   float delta;
@@ -80,20 +81,20 @@ struct GemmSmem {
   static constexpr int kTotal = kStages * kStageBytes + kBarBytes + kEpiStageBytes + 1024;  // +1024 alignment slack
 };
 
-__device__ __forceinline__ float sgd_apply(float acc, float& w, float& h, const GemmParams& p) {
+__device__ __forceinline__ float sgd_apply(float acc, float& w, float& h, const GemmParams& p, float lr) {
   float g = acc;
   if (p.decay != 0.f) g += p.decay * (p.l1 ? (w > 0.f ? 1.f : (w < 0.f ? -1.f : 0.f)) : w);
   float step;
   if (p.rule == 0) {
-    h = p.lr * g + p.momentum * h;
+    h = lr * g + p.momentum * h;
     step = h;
   } else if (p.rule == 1) {
     float h_old = h;
-    h = p.lr * g + p.momentum * h;
+    h = lr * g + p.momentum * h;
     step = (1.f + p.momentum) * h - p.momentum * h_old;
   } else {
     h = h + g * g;
-    step = p.lr * g / (sqrtf(h) + p.delta);
+    step = lr * g / (sqrtf(h) + p.delta);
   }
   w -= step;
   return w;
@@ -173,6 +174,7 @@ __device__ __forceinline__ void epilogue_tile32(const GemmParams& p, const uint3
       }
     }
   } else {  // EPI_SGD: W, H stepped in place (coalesced 128 B rows), bf16 shadow refreshed
+    const float lr_eff = p.lr_dev != nullptr ? p.lr * __ldg(p.lr_dev) : p.lr;
     if (lane < ncols) {
 #pragma unroll 1
       for (int r0 = 0; r0 < nrows; r0 += 16) {
@@ -188,7 +190,7 @@ __device__ __forceinline__ void epilogue_tile32(const GemmParams& p, const uint3
         for (int j = 0; j < 16; ++j) {
           if (r0 + j < nrows) {
             const long off = static_cast<long>(row0 + r0 + j) * p.ldc + col0 + lane;
-            sgd_apply(stage[(r0 + j) * 33 + lane], wv[j], hv[j], p);
+            sgd_apply(stage[(r0 + j) * 33 + lane], wv[j], hv[j], p, lr_eff);
             p.w[off] = wv[j];
             p.h[off] = hv[j];
             if (p.wb != nullptr) p.wb[off] = __float2bfloat16(wv[j]);

@@ -163,7 +163,12 @@ __device__ __forceinline__ uint32_t mix32(uint32_t a, uint32_t b) {
 }
 // keep iff hash > threshold, threshold = UINT_MAX * ratio (same test as the reference's uint mask).
 __global__ void dropout_kernel(const bf16x8* __restrict__ x, bf16x8* __restrict__ y, long n8, uint32_t seed_lo, uint32_t seed_hi,
-                               uint32_t threshold, float scale) {
+                               uint32_t threshold, float scale, const long long* __restrict__ seed_dev) {
+  if (seed_dev != nullptr) {                       // per-iteration counter kept on the device (CUDA-graph replay safe)
+    const unsigned long long s = static_cast<unsigned long long>(*seed_dev) * 0x9E3779B97F4A7C15ull;
+    seed_lo ^= static_cast<uint32_t>(s);
+    seed_hi ^= static_cast<uint32_t>(s >> 32);
+  }
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<long>(gridDim.x) * blockDim.x) {
     float f[8];
     unpack8(x[i], f);
@@ -177,7 +182,7 @@ __global__ void dropout_kernel(const bf16x8* __restrict__ x, bf16x8* __restrict_
   }
 }
 // forward and backward are the same map applied to x resp. dy.
-at::Tensor dropout_apply(const at::Tensor& x, double ratio, int64_t seed) {
+at::Tensor dropout_apply(const at::Tensor& x, double ratio, int64_t seed, const c10::optional<at::Tensor>& seed_dev) {
   check_dense8(x);
   c10::cuda::CUDAGuard guard(x.device());
   at::Tensor y = at::empty_like(x);
@@ -186,7 +191,8 @@ at::Tensor dropout_apply(const at::Tensor& x, double ratio, int64_t seed) {
   dropout_kernel<<<grid_for(n8, 256), 256, 0, at::cuda::getCurrentCUDAStream()>>>(
       reinterpret_cast<const bf16x8*>(x.data_ptr()), reinterpret_cast<bf16x8*>(y.data_ptr()), n8,
       static_cast<uint32_t>(seed), static_cast<uint32_t>(static_cast<uint64_t>(seed) >> 32), thr,
-      static_cast<float>(1.0 / (1.0 - ratio)));
+      static_cast<float>(1.0 / (1.0 - ratio)),
+      seed_dev.has_value() ? reinterpret_cast<const long long*>(seed_dev->data_ptr<int64_t>()) : nullptr);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   return y;
 }
@@ -244,6 +250,6 @@ TORCH_LIBRARY_FRAGMENT(poseidon, m) {
         "int cp, int opad, int wextra) -> Tensor", &psd::transform_nhwc);
   m.def("relu_fwd(Tensor x, float slope) -> Tensor", &psd::relu_fwd);
   m.def("relu_bwd(Tensor y, Tensor dy, float slope) -> Tensor", &psd::relu_bwd);
-  m.def("dropout_apply(Tensor x, float ratio, int seed) -> Tensor", &psd::dropout_apply);
+  m.def("dropout_apply(Tensor x, float ratio, int seed, Tensor? seed_dev) -> Tensor", &psd::dropout_apply);
   m.def("colsum(Tensor dy, int rows, int C, int ld, Tensor(a!) out, float alpha, bool accumulate) -> ()", &psd::colsum);
 }

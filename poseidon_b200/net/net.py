@@ -221,7 +221,7 @@ class Net(nn.Module):
                 end: Optional[int] = None, keep_blobs: bool = True):
         """Run layers [start, end]; returns (loss, {output blob name: tensor}).
         reference: src/caffe/net.cpp:709-750 (ForwardFromTo / ForwardPrefilled)."""
-        blobs = self.blobs if (start > 0 and self.blobs) else {}
+        blobs = dict(self.blobs) if (start > 0 and self.blobs) else {}
         if inputs:
             blobs.update(inputs)
         for n in self.input_names:
@@ -275,6 +275,22 @@ class Net(nn.Module):
 
     def data_layers(self):
         return [l for l in self.layers if getattr(l, "is_data", False)]
+
+    def num_leading_data_layers(self) -> int:
+        n = 0
+        for l in self.layers:
+            if not getattr(l, "is_data", False):
+                break
+            n += 1
+        return n
+
+    def forward_data(self) -> Dict[str, torch.Tensor]:
+        """Run only the leading data layers; returns their top blobs."""
+        out = {}
+        for i in range(self.num_leading_data_layers()):
+            for t, o in zip(self.top_names[i], self.layers[i]()):
+                out[t] = o
+        return out
 
     def close(self):
         for l in self.layers:

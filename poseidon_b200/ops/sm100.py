@@ -446,19 +446,34 @@ def relu(x, negative_slope=0.0):
 
 
 _dropout_counter = [0]
+_iter_seed: dict = {}          # device -> int64[1] iteration counter mixed into every dropout mask
+
+
+def iteration_seed(device) -> torch.Tensor:
+    t = _iter_seed.get(device)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int64, device=device)
+        _iter_seed[device] = t
+    return t
+
+
+def bump_iteration_seed(device):
+    """Advance the on-device iteration counter (called once per training step; capturable in a CUDA graph)."""
+    iteration_seed(device).add_(1)
 
 
 class _DropoutFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, ratio, seed):
         ctx.ratio, ctx.seed = ratio, seed
-        return K().dropout_apply(x, ratio, seed)
+        ctx.seed_t = iteration_seed(x.device)
+        return K().dropout_apply(x, ratio, seed, ctx.seed_t)
 
     @staticmethod
     def backward(ctx, dy):
         dy = dy if dy.dtype == torch.bfloat16 else dy.to(torch.bfloat16)
         dy = dy if (dy.is_contiguous() or (dy.dim() == 4 and dy.is_contiguous(memory_format=CL))) else dy.contiguous()
-        return K().dropout_apply(dy, ctx.ratio, ctx.seed), None, None
+        return K().dropout_apply(dy, ctx.ratio, ctx.seed, ctx.seed_t), None, None
 
 
 def dropout(x, ratio, train):
@@ -467,7 +482,7 @@ def dropout(x, ratio, train):
     dense = x.is_contiguous() or (x.dim() == 4 and x.is_contiguous(memory_format=CL))
     if not x.is_cuda or x.dtype != torch.bfloat16 or x.numel() % 8 or not dense:
         return R.dropout(x, ratio, train)
-    _dropout_counter[0] += 1
+    _dropout_counter[0] += 1          # distinct per call site within an iteration (a constant under graph replay)
     seed = (torch.initial_seed() * 1000003 + _dropout_counter[0] * 7919) & 0x7FFFFFFFFFFFFFFF
     return _DropoutFn.apply(x, float(ratio), int(seed))
 

@@ -116,6 +116,7 @@ class FusedBackend(Backend):
         if self.world > 1:
             self._build_arena(net, sync)
         self.done_counter = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self.lr_t = torch.zeros(1, dtype=torch.float32, device=self.device)     # global lr, read by the kernels
 
     def _ensure_layer_states(self, net):
         for li, layer in enumerate(net.layers):
@@ -252,12 +253,17 @@ class FusedBackend(Backend):
                 st.dirty_wb = False
 
     # ------------------------------------------------------------------------------ per-bucket launch
+    def set_lr(self, lr: float):
+        """The global learning rate is a device scalar so that captured CUDA graphs see per-step changes."""
+        self.lr_t.fill_(float(lr))
+
     def _hyper_args(self, lm, dm):
         hy = self.sync.hyper
         ws = self.world
         decay = hy.weight_decay * dm * (ws if self.reduce == "sum" else 1.0)
         gscale = 1.0 if self.reduce == "sum" else 1.0 / ws
-        return (hy.lr * lm, hy.momentum, decay, hy.solver_type, hy.l1, hy.delta, gscale)
+        # lr here is only the per-blob multiplier; the kernels multiply by lr_t[0]
+        return (lm, hy.momentum, decay, hy.solver_type, hy.l1, hy.delta, gscale)
 
     def launch(self, bucket: Bucket):
         if self.world == 1:
@@ -281,7 +287,7 @@ class FusedBackend(Backend):
                 g = g.contiguous(memory_format=torch.channels_last) if p.dim() == 4 and \
                     p.data.is_contiguous(memory_format=torch.channels_last) else g.contiguous()
             lr, mom, decay, rule, l1, delta, gscale = self._hyper_args(lm, dm)
-            self.k.fused_update(p.data, g, h, wb, lr, mom, decay, rule, l1, delta, gscale)
+            self.k.fused_update(p.data, g, h, wb, lr, mom, decay, rule, l1, delta, gscale, self.lr_t)
             self.launches += 1
             if wb is not None:
                 st.dirty_wb = False
@@ -311,7 +317,7 @@ class FusedBackend(Backend):
                                      ar.mc_ptr(seg.g_off) if use_mc else 0,
                                      ar.mc_ptr(seg.w_off) if (use_mc and not one_shot) else 0,
                                      seg.hist, n, self.rank, self.epoch + 1, one_shot, self.done_counter,
-                                     lr, mom, decay, rule, l1, delta, gscale, 64)
+                                     lr, mom, decay, rule, l1, delta, gscale, 64, self.lr_t)
                 ar.view(seg.g_off, (n,), torch.float32).zero_()
                 self.launches += 2
                 self.dense_bytes += n * 4
@@ -402,7 +408,7 @@ class FusedSFB:
         M = dy.shape[0]
         if be.world == 1:
             k.sfb_outer_sgd([dy.data_ptr()], [x2.data_ptr()], M, self.N, self.K, w, h, st.wb, gscale, lr, mom, decay,
-                            rule, l1, delta, None, 0, 0, 0, 0)
+                            rule, l1, delta, None, 0, 0, 0, 0, be.lr_t)
             be.launches += 1
             st.mark_updated(keep_wb=True)
             be.sfb_stats.dense_equiv_bytes += self.N * self.K * 4
@@ -427,7 +433,7 @@ class FusedSFB:
             u_ptrs = [base + self.u_off[par] + p * self.u_slot for p in range(P)]
             v_ptrs = [base + self.v_off[par] + p * self.v_slot for p in range(P)]
             k.sfb_outer_sgd(u_ptrs, v_ptrs, M, self.N, self.K, w, h, st.wb, gscale, lr, mom, decay, rule, l1, delta,
-                            self.local_flags[par], epoch, 0, 0, 0)
+                            self.local_flags[par], epoch, 0, 0, 0, be.lr_t)
             be.launches += 3
             if self.event is None:
                 self.event = torch.cuda.Event()

@@ -302,6 +302,8 @@ class GradSync:
 
     def begin_iteration(self, lr: float):
         self.hyper.lr = lr
+        if hasattr(self.backend, "set_lr"):
+            self.backend.set_lr(lr)
         self.launch_order = []
         for b in self.buckets:
             b.pending = len(b.params) - len(b.self_updating)

@@ -251,12 +251,67 @@ class Solver:
         for _ in range(iters):
             self._train_iteration()
 
+    # ---- CUDA-graph execution: the whole step (forward, backward, DWBP hooks, fused updates) is one graph ----
+    def enable_cuda_graph(self, warmup: int = 3):
+        """Capture forward+backward+update of everything after the data layers into a CUDA graph and replay it
+        every iteration (launch-bound nets such as GoogLeNet at batch 32).  The data layers stay eager and feed
+        static input tensors; the learning rate and the dropout iteration counter live in device memory so replays
+        see fresh values.  Single-GPU sm100 engine only (the multi-GPU epoch flags are kernel arguments)."""
+        if self.engine != "sm100" or self.rank_ctx.distributed or self.device.type != "cuda":
+            raise RuntimeError("CUDA-graph steps need the sm100 engine on one GPU")
+        from ..ops import sm100
+        for _ in range(warmup):
+            self._train_iteration()
+        net = self.net
+        k = net.num_leading_data_layers()
+        torch.cuda.synchronize(self.device)
+        self._g_inputs = {n: t.clone() for n, t in net.forward_data().items()}
+        self._g_first = k
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        self.sync.begin_iteration(learning_rate(self.param, self.iter))
+        graph = torch.cuda.CUDAGraph()
+        from ..ops import counting
+        n0 = counting.total()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                sm100.bump_iteration_seed(self.device)
+                loss, outs = net.forward(self._g_inputs, start=k)
+                loss.backward()
+                self.sync.finish_iteration()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph_launches = counting.total() - n0          # kernels of ours inside one replay
+        self._graph, self._g_loss, self._g_outs = graph, loss.detach(), {n: o.detach() for n, o in outs.items()}
+        self.iter += 1           # the capture pass executed one real step
+        return graph
+
+    def _graph_iteration(self):
+        sp = self.param
+        display = bool(sp.display) and self.iter % sp.display == 0
+        lr = learning_rate(sp, self.iter)
+        fresh = self.net.forward_data()
+        for n, t in fresh.items():
+            self._g_inputs[n].copy_(t, non_blocking=True)
+        if hasattr(self.sync.backend, "set_lr"):
+            self.sync.backend.set_lr(lr)
+        self._graph.replay()
+        self.last_loss = self._g_loss
+        if display:
+            self._display(self._g_loss, self._g_outs, lr)
+        self.iter += 1
+        STATS.count("iterations")
+
     def _train_iteration(self):
+        if getattr(self, "_graph", None) is not None:
+            return self._graph_iteration()
         sp = self.param
         display = bool(sp.display) and self.iter % sp.display == 0
         self.net.debug_info = display and bool(sp.debug_info)
         lr = learning_rate(sp, self.iter)
         self.sync.begin_iteration(lr)
+        if self.engine == "sm100" and self.device.type == "cuda":
+            from ..ops import sm100
+            sm100.bump_iteration_seed(self.device)
         with STATS.timer("forward_backward"):
             loss, outputs = self.net.forward()
             if loss is not None and loss.requires_grad:

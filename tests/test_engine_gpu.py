@@ -65,3 +65,48 @@ def test_snapshot_roundtrip_sm100(ext, tmp_path):
         if len(l.blobs):
             assert np.allclose(l.export_blob(0), ref[n], atol=1e-6), n
     assert s2.iter == 2
+
+
+def test_cuda_graph_step_matches_eager(ext):
+    """The captured step (forward+backward+fused updates as one CUDA graph) follows the eager trajectory."""
+    from poseidon_b200 import get_solver
+
+    def run(graph):
+        net = small_net(batch=16)
+        sp = small_solver_param(net, max_iter=8)
+        s = get_solver(sp, engine="sm100")
+        x, y = make_data(16 * 8)
+        feed(s, x, y)
+        if graph:
+            s.enable_cuda_graph(warmup=2)          # 2 eager + 1 captured step
+            s.step(5)
+        else:
+            s.step(8)
+        torch.cuda.synchronize()
+        out = {n: l.export_blob(0) for n, l in zip(s.net.layer_names, s.net.layers) if len(l.blobs)}
+        loss = float(s.last_loss)
+        s.close()
+        return out, loss
+
+    import numpy as np
+    w_e, l_e = run(False)
+    w_g, l_g = run(True)
+    assert abs(l_e - l_g) < 0.05 * max(1.0, abs(l_e)), (l_e, l_g)
+    for n in w_e:
+        d = np.abs(w_e[n] - w_g[n]).max()
+        assert d <= 0.02 * np.abs(w_e[n]).max() + 1e-4, (n, d)
+
+
+def test_googlenet_small_batch_step(ext):
+    """GoogLeNet (59 conv, 9 concat, 3 losses) trains on the sm100 engine."""
+    from poseidon_b200 import get_solver
+    from poseidon_b200.models import zoo
+    net = zoo.googlenet(batch=4, test_batch=4)
+    sp = zoo.get_solver_param("googlenet", net=net, display=0, snapshot=0, snapshot_after_train=False, test_interval=0,
+                              max_iter=2, random_seed=3)
+    sp.clear("test_iter")
+    s = get_solver(sp, engine="sm100")
+    s.step(2)
+    loss = float(s.last_loss)
+    assert loss == loss and 5 < loss < 20, loss      # ~ (0.3+0.3+1) * ln(1000) = 11
+    s.close()

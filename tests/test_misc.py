@@ -1,0 +1,78 @@
+"""Smaller API-parity pieces: split insertion, flag context, sufficient-vector containers, SFB cost model."""
+import numpy as np
+import torch
+
+from poseidon_b200 import Net
+from poseidon_b200 import proto as P
+from poseidon_b200.proto import parse_text
+
+
+def test_insert_splits_names_and_equivalence():
+    from poseidon_b200.net.insert_splits import insert_splits
+    txt = '''input: "x" input_dim: 2 input_dim: 3 input_dim: 1 input_dim: 1
+    layers { name: "a" type: POWER bottom: "x" top: "a" power_param { scale: 2 } }
+    layers { name: "b" type: RELU bottom: "a" top: "b" }
+    layers { name: "c" type: SIGMOID bottom: "a" top: "c" }
+    layers { name: "e" type: ELTWISE bottom: "b" bottom: "c" top: "e" }'''
+    p = parse_text(txt, P.NetParameter)
+    o = insert_splits(p)
+    names = [l.name for l in o.layers]
+    assert names == ["a", "a_a_0_split", "b", "c", "e"]
+    assert list(o.layers[1].top) == ["a_a_0_split_0", "a_a_0_split_1"]
+    x = torch.randn(2, 3, 1, 1)
+    _, o1 = Net(p).forward({"x": x})
+    _, o2 = Net(o).forward({"x": x})
+    assert torch.allclose(o1["e"], o2["e"])
+
+
+def test_context_flag_store():
+    from poseidon_b200.utils.context import Context
+    c = Context().load({"num_table_threads": 5, "svb": "true", "table_staleness": 2, "lr": "0.5", "none": None})
+    assert c.get_int32("table_staleness") == 2 and c.get_bool("svb") and c.get_double("lr") == 0.5
+    assert c.get_int32("num_app_threads") == 4
+    assert Context.parse_int_list("0,1, 3") == [0, 1, 3]
+    assert Context.get_instance() is Context.get_instance()
+
+
+def test_sufficient_vector_roundtrip_and_queue():
+    from poseidon_b200.parallel.sfb import SufficientVector, SufficientVectorQueue, sfb_bytes, sfb_wins
+    a, b = torch.randn(4, 3), torch.randn(4, 5)
+    sv = SufficientVector(a, b, layer_id=7)
+    raw = sv.to_proto().SerializeToString()
+    sv2 = SufficientVector.from_proto(P.SVProto.FromString(raw), (4, 3), (4, 5))
+    assert sv2.layer_id == 7 and torch.allclose(sv2.gradient(), a.t() @ b, atol=1e-6)
+    q = SufficientVectorQueue(max_read_count=2)
+    q.add(sv)
+    assert q.get() is sv and len(q) == 1      # first reader: still queued
+    assert q.get() is sv and len(q) == 0      # second reader retires it
+    assert q.get() is None
+    # cost model: AlexNet b=256, P=8
+    assert sfb_wins(256, 4096, 9216, 8) and sfb_wins(256, 4096, 4096, 8) and not sfb_wins(256, 1000, 4096, 8)
+    assert sfb_wins(64, 4096, 25088, 8)                             # VGG-16 fc6
+    by = sfb_bytes(256, 4096, 9216, 8, 4)
+    assert by["sfb_egress"] == 256 * (4096 + 9216) * 4
+
+
+def test_stats_and_timer(tmp_path):
+    from poseidon_b200.utils.stats import Stats
+    from poseidon_b200.utils.timer import Timer
+    st = Stats()
+    with st.timer("x"):
+        pass
+    st.count("n", 3)
+    st.set("bytes", {"a": 1})
+    st.dump_yaml(str(tmp_path / "s.yaml"))
+    import yaml
+    d = yaml.safe_load((tmp_path / "s.yaml").read_text())
+    assert d["counters"]["n"] == 3 and d["timer_calls"]["x"] == 1
+    t = Timer("cpu")
+    t.start()
+    t.stop()
+    assert t.milliseconds() >= 0
+
+
+def test_hostfile_parser(tmp_path):
+    from poseidon_b200.parallel.context import parse_hostfile
+    f = tmp_path / "hosts"
+    f.write_text("# comment\n1 10.0.0.2 9999\n0 127.0.0.1 9999\n")
+    assert parse_hostfile(str(f)) == [(0, "127.0.0.1", 9999), (1, "10.0.0.2", 9999)]

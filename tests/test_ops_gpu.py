@@ -84,6 +84,12 @@ def test_dropout_statistics_and_backward(ext):
     assert torch.equal(x.grad, y.detach())          # same mask, same scale
     y2 = sm100.dropout(x, 0.5, True)
     assert not torch.equal(y2, y)                    # fresh mask every call
+    sm100.bump_iteration_seed(x.device)              # ... and every iteration (device-side counter)
+    from poseidon_b200.ops.sm100 import _DropoutFn
+    a = _DropoutFn.apply(x, 0.5, 123)
+    sm100.bump_iteration_seed(x.device)
+    b = _DropoutFn.apply(x, 0.5, 123)
+    assert not torch.equal(a, b)
 
 
 def test_colsum(ext):
