@@ -95,8 +95,13 @@ static UpdateHyper make_hyper(double lr, double momentum, double decay, int64_t 
   return hp;
 }
 
+// Same element order in memory: equal sizes, and equal strides on every dimension that has extent > 1
+// (size-1 dimensions carry arbitrary strides, e.g. 1x1 convolution weights in channels-last form).
 static bool same_dense_layout(const at::Tensor& a, const at::Tensor& b) {
-  return a.numel() == b.numel() && a.strides() == b.strides() && a.sizes() == b.sizes();
+  if (a.numel() != b.numel() || a.sizes() != b.sizes()) return false;
+  for (int64_t d = 0; d < a.dim(); ++d)
+    if (a.size(d) > 1 && a.stride(d) != b.stride(d)) return false;
+  return true;
 }
 
 // W, G, H: fp32 tensors with identical (dense) layout; wb: optional bf16 shadow in the same storage order.

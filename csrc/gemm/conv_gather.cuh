@@ -60,72 +60,93 @@ struct ConvGeom {
   FastDiv div_ow, div_ohow, div_cg, div_s, div_lp;
 };
 
-// Per-thread, per-k-block decode of this thread's chunk column.
-struct ChunkTap {
-  int r, s, c;      // TAP: tap row / col / first channel ; ROW: r = kernel row, c = element offset in the padded row
-  bool in_k;
+// Per-thread decoded row position m -> pointer to tap (0,0) + its input coordinates; computed once per tile
+// (fprop / dgrad: the rows of a tile do not change along K) or once per k-block (wgrad: the reduction runs over m).
+struct RowPos {
+  const __nv_bfloat16* p00;   // address of input element (n, ih0, iw0, 0) — may point outside the image (never dereferenced then)
+  int ih0, iw0;               // input coordinates of tap (0,0); ih0 = INT_MIN/2 marks an invalid (out-of-range) row
+  int lim;                    // ROW mode: valid elements of a kernel row inside the image row
 };
-__device__ __forceinline__ ChunkTap decode_chunk(const ConvGeom& g, int k) {
-  ChunkTap t;
-  t.in_k = k < g.K;
-  if (g.mode == 0) {
-    const uint32_t tap = fdiv(static_cast<uint32_t>(k), g.div_cg);
-    t.c = k - static_cast<int>(tap) * g.Cg;
-    t.r = static_cast<int>(fdiv(tap, g.div_s));
-    t.s = static_cast<int>(tap) - t.r * g.S;
-  } else {
-    t.r = static_cast<int>(fdiv(static_cast<uint32_t>(k), g.div_lp));
-    t.c = k - t.r * g.Lp;
-    t.s = 0;
-  }
-  return t;
+
+// The geometry fields the inner loops need, hoisted into registers once per role (the asm memory clobbers of
+// cp.async would otherwise make the compiler re-read the kernel-parameter bank on every use).
+struct GatherRegs {
+  const __nv_bfloat16* x;
+  int H, W, S, dr, Cg, Lp, K, OHOW, OW, sh, sw, off_h, off_w, L, mode;
+  long pitch, img;            // pixel pitch, elements per image
+  long M;
+  int row_step;               // elements between consecutive input rows (W * pitch)
+  FastDiv div_ow, div_ohow, div_cg, div_s, div_lp;
+};
+__device__ __forceinline__ GatherRegs load_gather_regs(const ConvGeom& g) {
+  GatherRegs r;
+  r.x = g.x; r.H = g.H; r.W = g.W; r.S = g.S; r.dr = g.dr; r.Cg = g.Cg; r.Lp = g.Lp; r.K = g.K;
+  r.OHOW = g.OH * g.OW; r.OW = g.OW; r.sh = g.sh; r.sw = g.sw; r.off_h = g.off_h; r.off_w = g.off_w; r.L = g.L;
+  r.mode = g.mode; r.pitch = g.pitch; r.img = static_cast<long>(g.H) * g.W * g.pitch; r.M = g.M;
+  r.row_step = static_cast<int>(g.W * g.pitch);
+  r.div_ow = g.div_ow; r.div_ohow = g.div_ohow; r.div_cg = g.div_cg; r.div_s = g.div_s; r.div_lp = g.div_lp;
+  return r;
 }
 
-// Per-thread decoded row position m -> (image base, ih0, iw0); computed once per tile (fprop / dgrad: the rows of
-// a tile do not change along K) or once per k-block (wgrad: the reduction runs over m).
-struct RowPos {
-  long base;        // element offset of image n
-  int ih0, iw0;     // input coordinates of tap (0,0)
-  int lim;          // ROW mode: valid elements of a kernel row inside the image row; TAP: unused
-  bool valid;
-};
-__device__ __forceinline__ RowPos decode_row(const ConvGeom& g, long m) {
+__device__ __forceinline__ RowPos decode_row(const GatherRegs& g, long m) {
   RowPos p;
-  p.valid = m < g.M;
-  const uint32_t mm = p.valid ? static_cast<uint32_t>(m) : 0u;
+  if (m >= g.M) {
+    p.p00 = g.x; p.ih0 = -(1 << 29); p.iw0 = -(1 << 29); p.lim = 0;
+    return p;
+  }
+  const uint32_t mm = static_cast<uint32_t>(m);
   const uint32_t n = fdiv(mm, g.div_ohow);
-  const uint32_t rem = mm - n * static_cast<uint32_t>(g.OH * g.OW);
+  const uint32_t rem = mm - n * static_cast<uint32_t>(g.OHOW);
   const uint32_t oh = fdiv(rem, g.div_ow);
   const uint32_t ow = rem - oh * static_cast<uint32_t>(g.OW);
-  p.base = static_cast<long>(n) * g.H * g.W * g.pitch;
   p.ih0 = static_cast<int>(oh) * g.sh + g.off_h;
   p.iw0 = static_cast<int>(ow) * g.sw + g.off_w;
+  p.p00 = g.x + static_cast<long>(n) * g.img + static_cast<long>(p.ih0) * g.row_step + static_cast<long>(p.iw0) * g.pitch;
   p.lim = min(g.L, (g.W - p.iw0) * g.Cg);
   return p;
 }
 
-// Copy this thread's 16-byte chunk of the row at `pos` (or zeros) to `dst`: no divisions on this path.
-__device__ __forceinline__ void gather_chunk(const ConvGeom& g, uint32_t dst, const RowPos& pos, const ChunkTap& t) {
-  const __nv_bfloat16* src = g.x;
-  uint32_t bytes = 0;
-  const int ih = pos.ih0 + t.r * g.dr;
+// Per-thread, per-k-block chunk decode with everything the row loop needs precomputed.
+struct ChunkOff {
+  int dh, dw;        // tap displacement in input rows / columns (already multiplied by the direction)
+  int off;           // element offset from the row's p00 to this chunk
+  int c;             // ROW mode: element offset inside the padded kernel row
+  bool in_k;
+};
+__device__ __forceinline__ ChunkOff decode_chunk_off(const GatherRegs& g, int k) {
+  ChunkOff t;
+  t.in_k = k < g.K;
   if (g.mode == 0) {
-    const int iw = pos.iw0 + t.s * g.dr;
-    if (pos.valid && t.in_k && static_cast<unsigned>(ih) < static_cast<unsigned>(g.H) &&
-        static_cast<unsigned>(iw) < static_cast<unsigned>(g.W)) {
-      src = g.x + pos.base + (static_cast<long>(ih) * g.W + iw) * g.pitch + t.c;
-      bytes = 16;
-    }
+    const uint32_t tap = fdiv(static_cast<uint32_t>(k), g.div_cg);
+    const int c = k - static_cast<int>(tap) * g.Cg;
+    const int r = static_cast<int>(fdiv(tap, g.div_s));
+    const int s = static_cast<int>(tap) - r * g.S;
+    t.dh = r * g.dr;
+    t.dw = s * g.dr;
+    t.off = t.dh * g.row_step + t.dw * static_cast<int>(g.pitch) + c;
+    t.c = c;
   } else {
-    if (pos.valid && t.in_k && static_cast<unsigned>(ih) < static_cast<unsigned>(g.H)) {
-      const int valid = max(0, min(8, pos.lim - t.c));
-      if (valid > 0) {
-        src = g.x + pos.base + (static_cast<long>(ih) * g.W + pos.iw0) * g.pitch + t.c;
-        bytes = static_cast<uint32_t>(valid * 2);
-      }
-    }
+    const int r = static_cast<int>(fdiv(static_cast<uint32_t>(k), g.div_lp));
+    t.c = k - r * g.Lp;
+    t.dh = r;
+    t.dw = 0;
+    t.off = r * g.row_step + t.c;
   }
-  cp_async_16(dst, src, bytes);
+  return t;
+}
+
+// One 16-byte chunk of one row: ~8 integer instructions + the cp.async.
+__device__ __forceinline__ void gather_chunk_tap(const GatherRegs& g, uint32_t dst, const RowPos& pos, const ChunkOff& t) {
+  const int ih = pos.ih0 + t.dh, iw = pos.iw0 + t.dw;
+  const bool ok = t.in_k && static_cast<unsigned>(ih) < static_cast<unsigned>(g.H) &&
+                  static_cast<unsigned>(iw) < static_cast<unsigned>(g.W);
+  cp_async_16(dst, ok ? pos.p00 + t.off : g.x, ok ? 16u : 0u);
+}
+__device__ __forceinline__ void gather_chunk_row(const GatherRegs& g, uint32_t dst, const RowPos& pos, const ChunkOff& t) {
+  const int ih = pos.ih0 + t.dh;
+  int valid = min(8, pos.lim - t.c);
+  if (!(t.in_k && static_cast<unsigned>(ih) < static_cast<unsigned>(g.H)) || valid < 0) valid = 0;
+  cp_async_16(dst, valid > 0 ? pos.p00 + t.off : g.x, static_cast<uint32_t>(valid * 2));
 }
 
 }  // namespace psd

@@ -198,12 +198,27 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
 __device__ __forceinline__ void red_add_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#ifndef PSD_PEER_TIMEOUT_NS
+#define PSD_PEER_TIMEOUT_NS 180000000000ull   // 3 minutes: ranks may be skewed by start-up work; a dead peer traps
+#endif
+// Wait until *p >= want (wrap-safe).  Time-bounded so that a lost peer becomes a trap (the watchdog), not a hang.
 __device__ __forceinline__ void wait_flag_ge(const uint32_t* p, uint32_t want) {
   uint32_t spins = 0;
+  unsigned long long t0 = 0;
   while (static_cast<int32_t>(ld_acquire_sys(p) - want) < 0) {
-    if (++spins > PSD_SPIN_LIMIT) {
-      printf("psd: peer flag timeout block %d (have %u want %u)\n", blockIdx.x, ld_acquire_sys(p), want);
-      __trap();
+    if ((++spins & 0x3ff) == 0) {
+      const unsigned long long now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > PSD_PEER_TIMEOUT_NS) {
+        printf("psd: peer flag timeout block %d (have %u want %u)\n", blockIdx.x, ld_acquire_sys(p), want);
+        __trap();
+      }
+      __nanosleep(200);
     }
   }
 }

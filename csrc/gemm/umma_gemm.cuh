@@ -358,7 +358,8 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
     const int gt = threadIdx.x - kGatherWarp0 * 32;      // 0..kGatherThreads-1
     const int j = gt & 7;                                 // this thread's 16-byte chunk column
     const int rg = gt >> 3;                               // first row; further rows every kGatherThreads/8
-    constexpr int kRowStep = kGatherThreads / 8;
+    constexpr int kRowStep = kGatherThreads / 8;      // 32: row r and r + 32 share (r & 7), i.e. the same swizzle
+    const GatherRegs gr = load_gather_regs(cg);
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -373,15 +374,17 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
         constexpr int kRows = BLOCK_M / kRowStep;
         RowPos pos[kRows];
 #pragma unroll
-        for (int i = 0; i < kRows; ++i) pos[i] = decode_row(cg, static_cast<long>(m_blk) * BLOCK_M + rg + i * kRowStep);
+        for (int i = 0; i < kRows; ++i) pos[i] = decode_row(gr, static_cast<long>(m_blk) * BLOCK_M + rg + i * kRowStep);
         for (int g = g0; g < g1; ++g) {
-          const ChunkTap t = decode_chunk(cg, g * BLOCK_K + j * 8);
+          const ChunkOff t = decode_chunk_off(gr, g * BLOCK_K + j * 8);
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+          const uint32_t sa = smem_u32(smem + stage * S::kStageBytes) + rg * 128 + ((j ^ (rg & 7)) << 4);
+          if (gr.mode == 0) {
 #pragma unroll
-          for (int i = 0; i < kRows; ++i) {
-            const int r = rg + i * kRowStep;
-            gather_chunk(cg, sa + r * 128 + ((j ^ (r & 7)) << 4), pos[i], t);
+            for (int i = 0; i < kRows; ++i) gather_chunk_tap(gr, sa + i * (kRowStep * 128), pos[i], t);
+          } else {
+#pragma unroll
+            for (int i = 0; i < kRows; ++i) gather_chunk_row(gr, sa + i * (kRowStep * 128), pos[i], t);
           }
           cp_async_mbar_arrive_noinc(&full_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -391,21 +394,21 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
         // fixed per tile (decode the taps once), the rows advance with the reduction index g
         constexpr int kChunks = BN / 64;
         constexpr int kRows = 64 / kRowStep;
-        ChunkTap taps[kChunks];
+        ChunkOff taps[kChunks];
 #pragma unroll
-        for (int c = 0; c < kChunks; ++c) taps[c] = decode_chunk(cg, n_blk * BN + c * 64 + j * 8);
+        for (int c = 0; c < kChunks; ++c) taps[c] = decode_chunk_off(gr, n_blk * BN + c * 64 + j * 8);
         for (int g = g0; g < g1; ++g) {
           RowPos pos[kRows];
 #pragma unroll
-          for (int i = 0; i < kRows; ++i) pos[i] = decode_row(cg, static_cast<long>(g) * BLOCK_K + rg + i * kRowStep);
+          for (int i = 0; i < kRows; ++i) pos[i] = decode_row(gr, static_cast<long>(g) * BLOCK_K + rg + i * kRowStep);
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          const uint32_t sb = smem_u32(smem + stage * S::kStageBytes) + S::kABytes;
+          const uint32_t sb = smem_u32(smem + stage * S::kStageBytes) + S::kABytes + rg * 128 + ((j ^ (rg & 7)) << 4);
 #pragma unroll
           for (int c = 0; c < kChunks; ++c) {
 #pragma unroll
             for (int i = 0; i < kRows; ++i) {
-              const int r = rg + i * kRowStep;
-              gather_chunk(cg, sb + c * 8192 + r * 128 + ((j ^ (r & 7)) << 4), pos[i], taps[c]);
+              if (gr.mode == 0) gather_chunk_tap(gr, sb + c * 8192 + i * (kRowStep * 128), pos[i], taps[c]);
+              else gather_chunk_row(gr, sb + c * 8192 + i * (kRowStep * 128), pos[i], taps[c]);
             }
           }
           cp_async_mbar_arrive_noinc(&full_bar[stage]);

@@ -178,7 +178,7 @@ class FusedBackend(Backend):
         for b in sync.buckets:
             b.flag_off = self._alloc_flag_block()
             b.segs = []
-            for p, hist in zip(b.params, b.history):
+            for pi, (p, hist) in enumerate(zip(b.params, b.history)):
                 s = _Seg()
                 s.param, s.numel = p, _round_up(p.numel(), 4)
                 s.g_off = ar.carve(s.numel * 4)
@@ -188,17 +188,15 @@ class FusedBackend(Backend):
                 # re-home the fp32 master into the arena, keeping shape/strides
                 wflat = ar.view(s.w_off, (s.numel,), torch.float32)
                 src = p.data
-                stor = src.as_strided((src.numel(),), (1,)) if src.is_non_overlapping_and_dense() else src.reshape(-1)
                 if not src.is_non_overlapping_and_dense():
                     raise RuntimeError("parameters must be dense")
                 wflat[: src.numel()].copy_(_storage_order_flat(src))
                 p.data = torch.as_strided(wflat, src.shape, src.stride())
-                del stor
                 # history must share the master's storage order
                 hflat = torch.zeros(s.numel, dtype=torch.float32, device=self.device)
                 hflat[: hist.numel()].copy_(_storage_order_flat(hist))
                 s.hist = hflat
-                b.history[b.params.index(p)] = torch.as_strided(hflat, src.shape, src.stride())
+                b.history[pi] = torch.as_strided(hflat, src.shape, src.stride())
                 self.seg_of[id(p)] = s
                 b.segs.append(s)
                 self._bind_shadow(p, s)
@@ -283,9 +281,8 @@ class FusedBackend(Backend):
             if st is not None and p is bucket.layer.weight and st.wb is not None and not getattr(st, "row_mode", False):
                 wb = st.wb
             g = p.grad
-            if g.stride() != p.data.stride():
-                g = g.contiguous(memory_format=torch.channels_last) if p.dim() == 4 and \
-                    p.data.is_contiguous(memory_format=torch.channels_last) else g.contiguous()
+            if not _same_order(g, p.data):
+                g = torch.empty_like(p.data).copy_(g)
             lr, mom, decay, rule, l1, delta, gscale = self._hyper_args(lm, dm)
             self.k.fused_update(p.data, g, h, wb, lr, mom, decay, rule, l1, delta, gscale, self.lr_t)
             self.launches += 1
@@ -305,7 +302,7 @@ class FusedBackend(Backend):
         self.stream.wait_stream(cur)
         self.epoch_of_bucket = self.epoch + 1
         with torch.cuda.stream(self.stream):
-            for p, seg, lm, dm in zip(bucket.params, bucket.segs, bucket.lr_mult, bucket.decay_mult):
+            for pi, (p, seg, lm, dm) in enumerate(zip(bucket.params, bucket.segs, bucket.lr_mult, bucket.decay_mult)):
                 if p.grad is None:
                     continue
                 n = seg.numel
@@ -313,7 +310,7 @@ class FusedBackend(Backend):
                 lr, mom, decay, rule, l1, delta, gscale = self._hyper_args(lm, dm)
                 use_mc = self.use_multimem and ar.multicast_ptr != 0
                 self.k.allreduce_sgd(ar.peer_ptrs(seg.g_off), ar.peer_ptrs(seg.w_off), ar.peer_ptrs(seg.wb_off),
-                                     ar.peer_ptrs(bucket.flag_off + 64 * bucket.params.index(p)),
+                                     ar.peer_ptrs(bucket.flag_off + 64 * pi),
                                      ar.mc_ptr(seg.g_off) if use_mc else 0,
                                      ar.mc_ptr(seg.w_off) if (use_mc and not one_shot) else 0,
                                      seg.hist, n, self.rank, self.epoch + 1, one_shot, self.done_counter,
@@ -349,6 +346,10 @@ class FusedBackend(Backend):
                 mine[: hi - lo] = seg.hist[lo:hi]
                 dist.all_gather_into_tensor(padded, mine)
                 seg.hist.copy_(padded[:n])
+
+
+def _same_order(a: torch.Tensor, b: torch.Tensor) -> bool:
+    return a.shape == b.shape and all(sa == sb for n, sa, sb in zip(a.shape, a.stride(), b.stride()) if n > 1)
 
 
 def _storage_order_flat(t: torch.Tensor) -> torch.Tensor:

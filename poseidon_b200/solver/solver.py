@@ -260,15 +260,19 @@ class Solver:
         if self.engine != "sm100" or self.rank_ctx.distributed or self.device.type != "cuda":
             raise RuntimeError("CUDA-graph steps need the sm100 engine on one GPU")
         from ..ops import sm100
-        for _ in range(warmup):
-            self._train_iteration()
         net = self.net
         k = net.num_leading_data_layers()
-        torch.cuda.synchronize(self.device)
-        self._g_inputs = {n: t.clone() for n, t in net.forward_data().items()}
-        self._g_first = k
+        # PyTorch's whole-network capture recipe: warm up on the side stream the capture will use, so that the
+        # autograd accumulators and the caching allocator are bound to it (not to the legacy default stream)
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._train_iteration()
+            self._g_inputs = {n: t.clone() for n, t in net.forward_data().items()}
+        side.synchronize()
+        torch.cuda.synchronize(self.device)
+        self._g_first = k
         self.sync.begin_iteration(learning_rate(self.param, self.iter))
         graph = torch.cuda.CUDAGraph()
         from ..ops import counting
@@ -280,6 +284,7 @@ class Solver:
                 loss.backward()
                 self.sync.finish_iteration()
         torch.cuda.current_stream().wait_stream(side)
+        graph.replay()       # capture only records: run the captured step once on the batch that was staged for it
         self.graph_launches = counting.total() - n0          # kernels of ours inside one replay
         self._graph, self._g_loss, self._g_outs = graph, loss.detach(), {n: o.detach() for n, o in outs.items()}
         self.iter += 1           # the capture pass executed one real step
