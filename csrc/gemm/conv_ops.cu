@@ -19,6 +19,8 @@ namespace psd {
 void encode_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner,
                          int box_outer);
 
+static int g_conv_cluster = 1;     // CTAs per cluster sharing the TMA operand by multicast (1 = off; measured slower at 2 on B200, kept as an option)
+
 template <int BN, bool A_MN, bool B_MN, int EPI, int GATHER>
 static void launch_conv(const TmapSet& tm, const GemmParams& p, const ConvGeom& cg, int grid, cudaStream_t stream) {
   auto kern = umma_gemm_kernel<BN, A_MN, B_MN, EPI, GATHER>;
@@ -28,8 +30,36 @@ static void launch_conv(const TmapSet& tm, const GemmParams& p, const ConvGeom& 
     C10_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  kern<<<grid, kNumThreads + kGatherThreads, smem, stream>>>(tm, p, cg);
+  if (p.cluster <= 1) {
+    kern<<<grid, kNumThreads + kGatherThreads, smem, stream>>>(tm, p, cg);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNumThreads + kGatherThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    C10_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm, p, cg));
+  }
   C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+// cluster size to use for a tile space of `tiles_along` blocks along the cluster dimension, and the grid
+static int pick_cluster(long tiles_along, long tiles_total, int sms, int* grid) {
+  int c = g_conv_cluster;
+  while (c > 1 && tiles_along < c) c >>= 1;
+  const int usable = c >= 4 ? (sms / 4) * 4 - 16 : sms;      // size-4 clusters strand ~16 SMs (GPC shapes)
+  const long ctiles = (tiles_total + c - 1) / c;              // cluster tiles (upper bound incl. edge padding)
+  long g = std::min<long>(ctiles * c, (usable / c) * c);
+  g = std::max<long>(c, (g / c) * c);
+  *grid = static_cast<int>(g);
+  return c;
 }
 
 struct ConvDesc {
@@ -92,11 +122,15 @@ at::Tensor conv_fprop(const at::Tensor& x, const at::Tensor& wb, const c10::opti
     ConvGeom cg = make_geom(x, xv, gidx * Cg, Cg, OH, OW, d, false);
     TORCH_CHECK(wb.size(1) == cg.K, "conv_fprop: weight K ", wb.size(1), " != expected ", cg.K);
     const int bn = pick_conv_bn(Cout_g);
+    const long m_blocks = (cg.M + BLOCK_M - 1) / BLOCK_M, n_blocks = (Cout_g + bn - 1) / bn;
+    int grid = 0;
+    const int cl = pick_cluster(m_blocks, m_blocks * n_blocks, sms, &grid);
     TmapSet tm;
     const __nv_bfloat16* wptr = reinterpret_cast<const __nv_bfloat16*>(wb.data_ptr()) + static_cast<long>(gidx) * Cout_g * cg.K;
-    encode_tmap_bf16_2d(&tm.b[0], wptr, cg.K, Cout_g, cg.K, BLOCK_K, bn);
+    encode_tmap_bf16_2d(&tm.b[0], wptr, cg.K, Cout_g, cg.K, BLOCK_K, bn / cl);     // each CTA multicasts 1/cl of the rows
     tm.a[0] = tm.b[0];
     GemmParams p{};
+    p.cluster = cl;
     p.M = static_cast<int>(cg.M);
     p.N = Cout_g;
     p.kb_per_src = (cg.K + BLOCK_K - 1) / BLOCK_K;
@@ -108,8 +142,6 @@ at::Tensor conv_fprop(const at::Tensor& x, const at::Tensor& wb, const c10::opti
     p.relu = relu;
     p.relu_slope = static_cast<float>(slope);
     p.alpha = 1.f;
-    const long tiles = ((cg.M + BLOCK_M - 1) / BLOCK_M) * ((Cout_g + bn - 1) / bn);
-    const int grid = static_cast<int>(std::min<long>(tiles, sms));
     switch (bn) {
       case 64: launch_conv<64, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
       case 128: launch_conv<128, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
@@ -144,11 +176,15 @@ at::Tensor conv_dgrad(const at::Tensor& dy, const at::Tensor& wt, at::IntArrayRe
     ConvGeom cg = make_geom(dy, dv, gidx * Cout_g, Cout_g, H, W, d, true);
     TORCH_CHECK(wt.size(1) == cg.K, "conv_dgrad: packed weight K mismatch");
     const int bn = pick_conv_bn(Cg);
+    const long m_blocks = (cg.M + BLOCK_M - 1) / BLOCK_M, n_blocks = (Cg + bn - 1) / bn;
+    int grid = 0;
+    const int cl = pick_cluster(m_blocks, m_blocks * n_blocks, sms, &grid);
     TmapSet tm;
     const __nv_bfloat16* wptr = reinterpret_cast<const __nv_bfloat16*>(wt.data_ptr()) + static_cast<long>(gidx) * Cg * cg.K;
-    encode_tmap_bf16_2d(&tm.b[0], wptr, cg.K, Cg, cg.K, BLOCK_K, bn);
+    encode_tmap_bf16_2d(&tm.b[0], wptr, cg.K, Cg, cg.K, BLOCK_K, bn / cl);
     tm.a[0] = tm.b[0];
     GemmParams p{};
+    p.cluster = cl;
     p.M = static_cast<int>(cg.M);
     p.N = Cg;
     p.kb_per_src = (cg.K + BLOCK_K - 1) / BLOCK_K;
@@ -160,8 +196,6 @@ at::Tensor conv_dgrad(const at::Tensor& dy, const at::Tensor& wt, at::IntArrayRe
     p.relu_slope = static_cast<float>(slope);
     p.alpha = 1.f;
     (void)mask_pitch;
-    const long tiles = ((cg.M + BLOCK_M - 1) / BLOCK_M) * ((Cg + bn - 1) / bn);
-    const int grid = static_cast<int>(std::min<long>(tiles, sms));
     switch (bn) {
       case 64: launch_conv<64, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
       case 128: launch_conv<128, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
@@ -192,22 +226,25 @@ void conv_wgrad(const at::Tensor& x, const at::Tensor& dy, at::Tensor dw, at::In
     TmapSet tm;
     // A = dYᵀ: MN-major, inner = Cout_g channels of this group, outer = M pixels, pitch = dy pixel pitch
     const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(dy.data_ptr()) + gidx * Cout_g;
-    encode_tmap_bf16_2d(&tm.a[0], dyp, Cout_g, cg.M, dv.pitch, 64, BLOCK_K);
-    tm.b[0] = tm.a[0];
     GemmParams p{};
     p.M = Cout_g;
     p.N = cg.K;
     p.kb_per_src = static_cast<int>((cg.M + BLOCK_K - 1) / BLOCK_K);
     p.num_src = 1;
-    const long tiles = ((Cout_g + BLOCK_M - 1) / BLOCK_M) * ((cg.K + bn - 1) / bn);
+    const long n_blocks = (cg.K + bn - 1) / bn;
+    const long tiles = ((Cout_g + BLOCK_M - 1) / BLOCK_M) * n_blocks;
     long split = std::max<long>(1, (2L * sms + tiles - 1) / tiles);
     split = std::min<long>(split, std::max<long>(1, p.kb_per_src / 8));
     p.split_k = static_cast<int>(split);
+    int grid = 0;
+    const int cl = pick_cluster(n_blocks, tiles * split, sms, &grid);
+    p.cluster = cl;
+    encode_tmap_bf16_2d(&tm.a[0], dyp, Cout_g, cg.M, dv.pitch, 64, BLOCK_K / cl);      // each CTA multicasts 1/cl of the k-rows
+    tm.b[0] = tm.a[0];
     p.c_f32 = dw.data_ptr<float>() + static_cast<long>(gidx) * Cout_g * cg.K;
     p.ldc = cg.K;
     p.atomic = 1;
     p.alpha = static_cast<float>(alpha);
-    const int grid = static_cast<int>(std::min<long>(tiles * split, sms));
     switch (bn) {
       case 64: launch_conv<64, true, true, EPI_F32, GATHER_B>(tm, p, cg, grid, stream); break;
       case 128: launch_conv<128, true, true, EPI_F32, GATHER_B>(tm, p, cg, grid, stream); break;
@@ -247,7 +284,15 @@ at::Tensor conv_pack_dgrad(const at::Tensor& w, int64_t Cout, int64_t RS, int64_
 
 }  // namespace psd
 
+namespace psd {
+void set_conv_cluster(int64_t c) {
+  TORCH_CHECK(c == 1 || c == 2 || c == 4, "cluster size must be 1, 2 or 4");
+  g_conv_cluster = static_cast<int>(c);
+}
+}  // namespace psd
+
 TORCH_LIBRARY_FRAGMENT(poseidon, m) {
+  m.def("set_conv_cluster(int c) -> ()", &psd::set_conv_cluster);
   m.def("conv_fprop(Tensor x, Tensor wb, Tensor? bias, int[] kernel, int[] stride, int[] pad, int groups, int mode, "
         "int OH, int OW, bool relu, float slope, Tensor? out) -> Tensor", &psd::conv_fprop);
   m.def("conv_dgrad(Tensor dy, Tensor wt, int[] kernel, int[] pad, int groups, int H, int W, Tensor? mask, float slope) "

@@ -46,6 +46,7 @@ struct GemmParams {
   int num_src;
   int split_k;           // >1: partial sums accumulated with atomics (EPI_F32 only)
   int src_rot;           // first source to visit (own rank for SFB: local data needs no flag wait)
+  int cluster;           // CTAs per cluster sharing the TMA operand by multicast (1 = no clusters); conv kernels only
   // --- epilogue operands
   __nv_bfloat16* c_bf16; // EPI_BF16 output [M, ldc]
   float* c_f32;          // EPI_F32 output [M, ldc]
@@ -230,6 +231,32 @@ struct TmaProducer {
   }
 };
 
+// Tile enumeration.  Without clusters: tile -> (m fastest, then n, then split).  With a cluster of C CTAs the
+// cluster walks "cluster tiles"; its CTAs take C consecutive blocks along the dimension the multicast (TMA)
+// operand does NOT depend on: m for fprop/dgrad (weights shared), n for wgrad (dY slice shared).  Blocks past
+// the edge are harmless: loads zero-fill / are out of range and the epilogue skips them.
+struct TileCoord {
+  int m_blk, n_blk, split;
+};
+template <int GATHER>
+__device__ __forceinline__ TileCoord tile_coord(int t, int m_blocks, int n_blocks, int C, int crank) {
+  TileCoord tc;
+  if (GATHER == GATHER_B) {
+    const int n_groups = (n_blocks + C - 1) / C;
+    tc.m_blk = t % m_blocks;
+    const int rest = t / m_blocks;
+    tc.n_blk = (rest % n_groups) * C + crank;
+    tc.split = rest / n_groups;
+  } else {
+    const int m_groups = (m_blocks + C - 1) / C;
+    tc.m_blk = (t % m_groups) * C + crank;
+    const int rest = t / m_groups;
+    tc.n_blk = rest % n_blocks;
+    tc.split = rest / n_blocks;
+  }
+  return tc;
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI, int GATHER = GATHER_NONE>
 __global__ void __launch_bounds__(kNumThreads + (GATHER != GATHER_NONE ? kGatherThreads : 0), 1)
 umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const ConvGeom cg) {
@@ -253,7 +280,12 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
   const int m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int n_blocks = (p.N + BN - 1) / BN;
   const int total_kb = p.kb_per_src * p.num_src;
-  const int num_tiles = m_blocks * n_blocks * p.split_k;
+  const int C = (GATHER != GATHER_NONE && p.cluster > 1) ? p.cluster : 1;
+  const int crank = C > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const uint16_t cmask = static_cast<uint16_t>((1u << C) - 1);
+  // cluster-level tile space and stride
+  const int num_tiles = (GATHER == GATHER_B ? m_blocks * ((n_blocks + C - 1) / C) : ((m_blocks + C - 1) / C) * n_blocks) * p.split_k;
+  const int tile0 = blockIdx.x / C, tile_step = gridDim.x / C;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.num_src; ++s) {
@@ -264,7 +296,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1 + (GATHER != GATHER_NONE ? kGatherThreads : 0));
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], C);        // released by the MMA thread of every CTA sharing the multicast operand
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -278,6 +310,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
   }
   tc_fence_before();
   __syncthreads();
+  if (C > 1) cluster_sync_all();        // peers' barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -286,11 +319,9 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % m_blocks;
-        const int rest = tile / m_blocks;
-        const int n_blk = rest % n_blocks;
-        const int split = rest / n_blocks;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const TileCoord tc = tile_coord<GATHER>(tile, m_blocks, n_blocks, C, crank);
+        const int m_blk = tc.m_blk, n_blk = tc.n_blk, split = tc.split;
         const int g0 = static_cast<int>(static_cast<long>(total_kb) * split / p.split_k);
         const int g1 = static_cast<int>(static_cast<long>(total_kb) * (split + 1) / p.split_k);
         int last_src = -1;
@@ -308,11 +339,27 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
             mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
             TmaProducer<BN, A_MN, B_MN>::load_stage(tm, src, kb, m_blk, n_blk, sa, sa + S::kABytes, &full_bar[stage]);
           } else if constexpr (GATHER == GATHER_A) {
-            mbar_arrive_expect_tx(&full_bar[stage], S::kBBytes);
-            TmaProducer<BN, A_MN, B_MN>::load_b(tm, src, kb, n_blk, sa + S::kABytes, &full_bar[stage]);
+            mbar_arrive_expect_tx(&full_bar[stage], S::kBBytes);     // the whole B tile lands here (C slices)
+            if (C == 1) {
+              TmaProducer<BN, A_MN, B_MN>::load_b(tm, src, kb, n_blk, sa + S::kABytes, &full_bar[stage]);
+            } else {
+              // this CTA fetches rows [crank*BN/C, (crank+1)*BN/C) of the K-major weight tile for the whole cluster
+              const int rows = BN / C;
+              tma_load_2d_mcast(sa + S::kABytes + crank * rows * 128, &tm.b[src], &full_bar[stage], kb * BLOCK_K,
+                                n_blk * BN + crank * rows, cmask);
+            }
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], S::kABytes);
-            TmaProducer<BN, A_MN, B_MN>::load_a(tm, src, kb, m_blk, sa, &full_bar[stage]);
+            if (C == 1) {
+              TmaProducer<BN, A_MN, B_MN>::load_a(tm, src, kb, m_blk, sa, &full_bar[stage]);
+            } else {
+              // dY^T tile (MN-major: 2 chunks of [64 k-rows][64 cout]); CTA `crank` fetches k-rows [crank*64/C, ...)
+              const int krows = BLOCK_K / C;
+#pragma unroll
+              for (int c = 0; c < BLOCK_M / 64; ++c)
+                tma_load_2d_mcast(sa + c * 8192 + crank * krows * 128, &tm.a[src], &full_bar[stage],
+                                  m_blk * BLOCK_M + 64 * c, kb * BLOCK_K + crank * krows, cmask);
+            }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -325,9 +372,8 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int rest = tile / m_blocks;
-        const int split = rest / n_blocks;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
+        const int split = tile_coord<GATHER>(tile, m_blocks, n_blocks, C, crank).split;
         const int g0 = static_cast<int>(static_cast<long>(total_kb) * split / p.split_k);
         const int g1 = static_cast<int>(static_cast<long>(total_kb) * (split + 1) / p.split_k);
         const int as = it & 1;
@@ -347,7 +393,9 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
                                      : make_smem_desc(b_addr + k * (UMMA_K * 2), 16, 1024);
             umma_bf16(d_tmem, da, db, idesc, (g > g0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+          // frees the smem slot when these MMAs retire — in every CTA that shares the multicast operand
+          if (C == 1) umma_commit(&empty_bar[stage]);
+          else umma_commit_mcast(&empty_bar[stage], cmask);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[as]);               // accumulator complete -> epilogue
@@ -362,11 +410,9 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
     const GatherRegs gr = load_gather_regs(cg);
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % m_blocks;
-      const int rest = tile / m_blocks;
-      const int n_blk = rest % n_blocks;
-      const int split = rest / n_blocks;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      const TileCoord tc = tile_coord<GATHER>(tile, m_blocks, n_blocks, C, crank);
+      const int m_blk = tc.m_blk, n_blk = tc.n_blk, split = tc.split;
       const int g0 = static_cast<int>(static_cast<long>(total_kb) * split / p.split_k);
       const int g1 = static_cast<int>(static_cast<long>(total_kb) * (split + 1) / p.split_k);
       if constexpr (GATHER == GATHER_A) {
@@ -423,9 +469,9 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
     const int q = e & 3;                          // TMEM lane quadrant == warp_id % 4
     const int half = e >> 2;                      // which of the two warps of this quadrant
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile % m_blocks;
-      const int n_blk = (tile / m_blocks) % n_blocks;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
+      const TileCoord tc = tile_coord<GATHER>(tile, m_blocks, n_blocks, C, crank);
+      const int m_blk = tc.m_blk, n_blk = tc.n_blk;
       const int as = it & 1;
       mbar_wait(&tmem_full[as], (it >> 1) & 1);
       tc_fence_after();
@@ -445,6 +491,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
 
   tc_fence_before();
   __syncthreads();
+  if (C > 1) cluster_sync_all();        // no CTA leaves while peers may still arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * BN);

@@ -188,7 +188,7 @@ class FusedBackend(Backend):
                 # re-home the fp32 master into the arena, keeping shape/strides
                 wflat = ar.view(s.w_off, (s.numel,), torch.float32)
                 src = p.data
-                if not src.is_non_overlapping_and_dense():
+                if not _is_dense(src):
                     raise RuntimeError("parameters must be dense")
                 wflat[: src.numel()].copy_(_storage_order_flat(src))
                 p.data = torch.as_strided(wflat, src.shape, src.stride())
@@ -346,6 +346,17 @@ class FusedBackend(Backend):
                 mine[: hi - lo] = seg.hist[lo:hi]
                 dist.all_gather_into_tensor(padded, mine)
                 seg.hist.copy_(padded[:n])
+
+
+def _is_dense(t: torch.Tensor) -> bool:
+    """Non-overlapping and dense: some permutation of the dims is contiguous."""
+    dims = sorted((st, n) for n, st in zip(t.shape, t.stride()) if n > 1)
+    expect = 1
+    for st, n in dims:
+        if st != expect:
+            return False
+        expect *= n
+    return True
 
 
 def _same_order(a: torch.Tensor, b: torch.Tensor) -> bool:

@@ -310,6 +310,10 @@ class GradSync:
 
     def _on_grad(self, p):
         b = self.bucket_of[id(p)]
+        # autograd also fires this hook when a Function returned None for the parameter (weights that were
+        # stepped inside their layer's backward by the fused SFB / wgrad kernel): those do not count
+        if p.grad is None or id(p) in b.self_updating:
+            return
         b.pending -= 1
         if b.pending == 0:
             self.launch_order.append(b.id)

