@@ -101,7 +101,15 @@ static ConvGeom make_geom(const at::Tensor& x, const NhwcView& xv, int c_off, in
   return g;
 }
 
-static int pick_conv_bn(int64_t n_cols) { return n_cols > 128 ? 256 : (n_cols > 64 ? 128 : 64); }
+// Widest N tile that does not over-pad the channel count and still yields a full wave of CTAs; small problems
+// (GoogLeNet's 14x14 / 7x7 stages at batch 32) take the narrowest tile so that more SMs get work.
+static int pick_conv_bn(int64_t n_cols, int64_t m_blocks, int sms) {
+  const int widest = n_cols > 128 ? 256 : (n_cols > 64 ? 128 : 64);
+  for (int bn = widest; bn >= 64; bn >>= 1) {
+    if (m_blocks * ((n_cols + bn - 1) / bn) >= sms) return bn;
+  }
+  return 64;
+}
 
 // y[N, Cout, OH, OW] (NHWC bf16) = act(conv(x, w) + bias).  wb: [Cout, Kw] bf16 (Kw = R*S*Cg or R*Lp).
 at::Tensor conv_fprop(const at::Tensor& x, const at::Tensor& wb, const c10::optional<at::Tensor>& bias, at::IntArrayRef kernel,
@@ -121,8 +129,9 @@ at::Tensor conv_fprop(const at::Tensor& x, const at::Tensor& wb, const c10::opti
   for (int gidx = 0; gidx < groups; ++gidx) {
     ConvGeom cg = make_geom(x, xv, gidx * Cg, Cg, OH, OW, d, false);
     TORCH_CHECK(wb.size(1) == cg.K, "conv_fprop: weight K ", wb.size(1), " != expected ", cg.K);
-    const int bn = pick_conv_bn(Cout_g);
-    const long m_blocks = (cg.M + BLOCK_M - 1) / BLOCK_M, n_blocks = (Cout_g + bn - 1) / bn;
+    const long m_blocks = (cg.M + BLOCK_M - 1) / BLOCK_M;
+    const int bn = pick_conv_bn(Cout_g, m_blocks, sms);
+    const long n_blocks = (Cout_g + bn - 1) / bn;
     int grid = 0;
     const int cl = pick_cluster(m_blocks, m_blocks * n_blocks, sms, &grid);
     TmapSet tm;
@@ -175,8 +184,9 @@ at::Tensor conv_dgrad(const at::Tensor& dy, const at::Tensor& wt, at::IntArrayRe
   for (int gidx = 0; gidx < groups; ++gidx) {
     ConvGeom cg = make_geom(dy, dv, gidx * Cout_g, Cout_g, H, W, d, true);
     TORCH_CHECK(wt.size(1) == cg.K, "conv_dgrad: packed weight K mismatch");
-    const int bn = pick_conv_bn(Cg);
-    const long m_blocks = (cg.M + BLOCK_M - 1) / BLOCK_M, n_blocks = (Cg + bn - 1) / bn;
+    const long m_blocks = (cg.M + BLOCK_M - 1) / BLOCK_M;
+    const int bn = pick_conv_bn(Cg, m_blocks, sms);
+    const long n_blocks = (Cg + bn - 1) / bn;
     int grid = 0;
     const int cl = pick_cluster(m_blocks, m_blocks * n_blocks, sms, &grid);
     TmapSet tm;

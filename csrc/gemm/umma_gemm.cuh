@@ -324,14 +324,15 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
         const int m_blk = tc.m_blk, n_blk = tc.n_blk, split = tc.split;
         const int g0 = static_cast<int>(static_cast<long>(total_kb) * split / p.split_k);
         const int g1 = static_cast<int>(static_cast<long>(total_kb) * (split + 1) / p.split_k);
-        int last_src = -1;
+        // (source, k-block) advance incrementally: no divisions in the single-thread producer loop
+        int src_lin = g0 / p.kb_per_src;
+        int kb = g0 - src_lin * p.kb_per_src;
+        int src = (src_lin + p.src_rot) % p.num_src;
+        bool new_src = true;
         for (int g = g0; g < g1; ++g) {
-          int src = g / p.kb_per_src;
-          const int kb = g - src * p.kb_per_src;
-          src = (src + p.src_rot) % p.num_src;
-          if (p.flags != nullptr && src != last_src) {
-            wait_flag_ge(p.flags + src, p.epoch);
-            last_src = src;
+          if (new_src) {
+            if (p.flags != nullptr) wait_flag_ge(p.flags + src, p.epoch);
+            new_src = false;
           }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kStageBytes;
@@ -362,6 +363,11 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
             }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++kb == p.kb_per_src) {
+            kb = 0;
+            if (++src == p.num_src) src = 0;
+            new_src = true;
+          }
         }
       }
     }
@@ -469,10 +475,28 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
     const int q = e & 3;                          // TMEM lane quadrant == warp_id % 4
     const int half = e >> 2;                      // which of the two warps of this quadrant
     int it = 0;
+    // EPI_SGD streams W and H (8 B read + 10 B written per element) — pure HBM traffic with nothing to reuse.
+    // Each epilogue thread asks the L2 for one row segment of the NEXT tile's W or H while the current tile is
+    // processed, so the dependent loads of the update hit L2 instead of paying DRAM latency.
+    auto prefetch_sgd_tile = [&](int t) {
+      if (EPI != EPI_SGD || t >= num_tiles || (p.N & 3) != 0 || (p.ldc & 3) != 0) return;
+      const TileCoord pc = tile_coord<GATHER>(t, m_blocks, n_blocks, C, crank);
+      const int te = (warp - kEpiWarp0) * 32 + lane;      // 0..255: row = te >> 1, W or H = te & 1
+      const int row = pc.m_blk * BLOCK_M + (te >> 1);
+      const int col = pc.n_blk * BN;
+      const int cols = min(BN, p.N - col);
+      if (row < p.M && cols > 0) {
+        const float* base = (te & 1) ? p.h : p.w;
+        if ((reinterpret_cast<uintptr_t>(base) & 15) == 0)
+          prefetch_l2_bulk(base + static_cast<long>(row) * p.ldc + col, static_cast<uint32_t>(cols) * 4u);
+      }
+    };
+    prefetch_sgd_tile(tile0);
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
       const TileCoord tc = tile_coord<GATHER>(tile, m_blocks, n_blocks, C, crank);
       const int m_blk = tc.m_blk, n_blk = tc.n_blk;
       const int as = it & 1;
+      prefetch_sgd_tile(tile + tile_step);
       mbar_wait(&tmem_full[as], (it >> 1) & 1);
       tc_fence_after();
       const int row0 = m_blk * BLOCK_M + q * 32;
