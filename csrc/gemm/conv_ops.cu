@@ -11,6 +11,10 @@
 #include <torch/library.h>
 #include <torch/types.h>
 
+#include <array>
+#include <map>
+#include <mutex>
+
 #include "../ops/nhwc_common.cuh"
 #include "umma_gemm.cuh"
 
@@ -62,6 +66,30 @@ static int pick_cluster(long tiles_along, long tiles_total, int sms, int* grid) 
   return c;
 }
 
+// Row tables (conv_gather.cuh) depend only on the geometry, not on the data pointer: built once per distinct
+// (device, geometry) and kept for the life of the process (8 bytes per output pixel).  The first call for a geometry
+// happens in the warm-up iterations, i.e. outside any CUDA-graph capture.
+static void attach_rowtab(ConvGeom& g, int device) {
+  using Key = std::array<long, 18>;
+  static std::map<Key, at::Tensor> cache;
+  static std::mutex mu;
+  const Key key{device, g.N, g.H, g.W, g.pitch, g.Cg, g.OH, g.OW, g.R, g.S, g.sh, g.sw, g.off_h, g.off_w, g.dr, g.mode, g.L, g.M};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    const long mtab = (g.M + BLOCK_M - 1) / BLOCK_M * BLOCK_M;
+    at::Tensor tab = at::empty({mtab, 2}, at::TensorOptions().dtype(at::kInt).device(at::kCUDA, device));
+    g.rowtab = nullptr;
+    g.Mtab = static_cast<int>(mtab);
+    conv_rowtab_kernel<<<static_cast<unsigned>((mtab + 255) / 256), 256, 0, at::cuda::getCurrentCUDAStream()>>>(
+        g, reinterpret_cast<int2*>(tab.data_ptr<int>()), static_cast<int>(mtab));
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    it = cache.emplace(key, tab).first;
+  }
+  g.rowtab = reinterpret_cast<const int2*>(it->second.data_ptr<int>());
+  g.Mtab = static_cast<int>(it->second.size(0));
+}
+
 struct ConvDesc {
   int R, S, sh, sw, ph, pw, groups;
   int mode;      // 0 TAP, 1 ROW
@@ -91,6 +119,8 @@ static ConvGeom make_geom(const at::Tensor& x, const NhwcView& xv, int c_off, in
   g.div_cg = make_fastdiv(Cg);
   g.div_s = make_fastdiv(d.S);
   g.div_lp = make_fastdiv(g.Lp);
+  TORCH_CHECK(d.R <= 15 && d.S <= 15, "conv: kernel extents up to 15 are supported");
+  TORCH_CHECK(static_cast<long>(xv.N) * xv.H * xv.W * xv.pitch < (1L << 31), "conv: gathered tensor must have < 2^31 elements");
   if (d.mode == 1) {
     TORCH_CHECK(xv.pitch == Cg, "ROW-mode conv needs a dense input (pitch == channels)");
     TORCH_CHECK(d.ph == 0 && d.pw == 0, "ROW-mode conv expects a pre-padded input");
@@ -98,6 +128,7 @@ static ConvGeom make_geom(const at::Tensor& x, const NhwcView& xv, int c_off, in
   } else {
     TORCH_CHECK(Cg % 8 == 0 && xv.pitch % 8 == 0 && c_off % 8 == 0, "TAP-mode conv: channels must be multiples of 8");
   }
+  attach_rowtab(g, x.device().index());
   return g;
 }
 

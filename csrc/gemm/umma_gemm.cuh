@@ -177,20 +177,22 @@ __device__ __forceinline__ void epilogue_tile32(const GemmParams& p, const uint3
   } else {  // EPI_SGD: W, H stepped in place (coalesced 128 B rows), bf16 shadow refreshed
     const float lr_eff = p.lr_dev != nullptr ? p.lr * __ldg(p.lr_dev) : p.lr;
     if (lane < ncols) {
+      constexpr int kBatch = 32;                      // 64 independent 128-byte row loads in flight per warp
+      const long off0 = static_cast<long>(row0) * p.ldc + col0 + lane;
 #pragma unroll 1
-      for (int r0 = 0; r0 < nrows; r0 += 16) {
-        float wv[16], hv[16];
+      for (int r0 = 0; r0 < nrows; r0 += kBatch) {
+        float wv[kBatch], hv[kBatch];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {                // 32 independent 128-byte row loads in flight per warp
-          const long off = static_cast<long>(row0 + r0 + j) * p.ldc + col0 + lane;
+        for (int j = 0; j < kBatch; ++j) {
+          const long off = off0 + static_cast<long>(r0 + j) * p.ldc;
           const bool ok = r0 + j < nrows;
           wv[j] = ok ? p.w[off] : 0.f;
           hv[j] = ok ? p.h[off] : 0.f;
         }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < kBatch; ++j) {
           if (r0 + j < nrows) {
-            const long off = static_cast<long>(row0 + r0 + j) * p.ldc + col0 + lane;
+            const long off = off0 + static_cast<long>(r0 + j) * p.ldc;
             sgd_apply(stage[(r0 + j) * 33 + lane], wv[j], hv[j], p, lr_eff);
             p.w[off] = wv[j];
             p.h[off] = hv[j];
@@ -422,11 +424,11 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
       const int g0 = static_cast<int>(static_cast<long>(total_kb) * split / p.split_k);
       const int g1 = static_cast<int>(static_cast<long>(total_kb) * (split + 1) / p.split_k);
       if constexpr (GATHER == GATHER_A) {
-        // rows of the A tile are fixed along K: decode them once per tile
+        // rows of the A tile are fixed along K: fetch their row-table entries once per tile
         constexpr int kRows = BLOCK_M / kRowStep;
         RowPos pos[kRows];
 #pragma unroll
-        for (int i = 0; i < kRows; ++i) pos[i] = decode_row(gr, static_cast<long>(m_blk) * BLOCK_M + rg + i * kRowStep);
+        for (int i = 0; i < kRows; ++i) pos[i] = load_row(gr, static_cast<long>(m_blk) * BLOCK_M + rg + i * kRowStep);
         for (int g = g0; g < g1; ++g) {
           const ChunkOff t = decode_chunk_off(gr, g * BLOCK_K + j * 8);
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -443,16 +445,22 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
         }
       } else {
         // B tile (MN-major): BN/64 chunk-columns of [64 reduction rows (m)][64 k-columns]; the k-columns are
-        // fixed per tile (decode the taps once), the rows advance with the reduction index g
+        // fixed per tile (decode the taps once), the rows advance with the reduction index g — their row-table
+        // entries for k-block g+1 are fetched before waiting for the slot of k-block g
         constexpr int kChunks = BN / 64;
         constexpr int kRows = 64 / kRowStep;
         ChunkOff taps[kChunks];
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) taps[c] = decode_chunk_off(gr, n_blk * BN + c * 64 + j * 8);
-        for (int g = g0; g < g1; ++g) {
-          RowPos pos[kRows];
+        RowPos pos[kRows], nxt[kRows];
 #pragma unroll
-          for (int i = 0; i < kRows; ++i) pos[i] = decode_row(gr, static_cast<long>(g) * BLOCK_K + rg + i * kRowStep);
+        for (int i = 0; i < kRows; ++i) nxt[i] = load_row(gr, static_cast<long>(g0) * BLOCK_K + rg + i * kRowStep);
+        for (int g = g0; g < g1; ++g) {
+#pragma unroll
+          for (int i = 0; i < kRows; ++i) {
+            pos[i] = nxt[i];
+            nxt[i] = load_row(gr, static_cast<long>(g + 1) * BLOCK_K + rg + i * kRowStep);
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const uint32_t sb = smem_u32(smem + stage * S::kStageBytes) + S::kABytes + rg * 128 + ((j ^ (rg & 7)) << 4);
 #pragma unroll
@@ -476,8 +484,10 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
     const int half = e >> 2;                      // which of the two warps of this quadrant
     int it = 0;
     // EPI_SGD streams W and H (8 B read + 10 B written per element) — pure HBM traffic with nothing to reuse.
-    // Each epilogue thread asks the L2 for one row segment of the NEXT tile's W or H while the current tile is
-    // processed, so the dependent loads of the update hit L2 instead of paying DRAM latency.
+    // Optional: each epilogue thread asks the L2 for one row segment of the NEXT tile's W or H while the current
+    // tile is processed.  Measured on B200 (AlexNet fc6+fc7 update): 336 us without vs 383 us with the prefetch —
+    // the extra DRAM stream collides with the write-back of the previous tile — so it is compiled out.
+    constexpr bool kSgdPrefetch = false;
     auto prefetch_sgd_tile = [&](int t) {
       if (EPI != EPI_SGD || t >= num_tiles || (p.N & 3) != 0 || (p.ldc & 3) != 0) return;
       const TileCoord pc = tile_coord<GATHER>(t, m_blocks, n_blocks, C, crank);
@@ -491,12 +501,12 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
           prefetch_l2_bulk(base + static_cast<long>(row) * p.ldc + col, static_cast<uint32_t>(cols) * 4u);
       }
     };
-    prefetch_sgd_tile(tile0);
+    if (kSgdPrefetch) prefetch_sgd_tile(tile0);
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
       const TileCoord tc = tile_coord<GATHER>(tile, m_blocks, n_blocks, C, crank);
       const int m_blk = tc.m_blk, n_blk = tc.n_blk;
       const int as = it & 1;
-      prefetch_sgd_tile(tile + tile_step);
+      if (kSgdPrefetch) prefetch_sgd_tile(tile + tile_step);
       mbar_wait(&tmem_full[as], (it >> 1) & 1);
       tc_fence_after();
       const int row0 = m_blk * BLOCK_M + q * 32;

@@ -120,97 +120,92 @@ lrn_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict_
 // Register/L1 variant for the usual small windows (local_size <= 9): each thread owns 8 channels of one pixel and
 // reads the neighbouring 16-byte vectors directly (they are L1 hits: the same lines are being read by the
 // adjacent threads), so there is no shared-memory staging, no bank conflicts and DRAM sees every byte once.
+// Register-resident variant (local_size <= 9): one thread = 8 channels of one pixel, neighbours' vectors loaded
+// directly (the channel window of a pixel is contiguous in NHWC).  ncu showed the first version issue-bound (90 %
+// issue-active, ~405 / ~470 instructions per thread fwd / bwd): 64-bit index divisions, libm log2f/exp2f and 5-tap
+// re-summation.  This version uses a magic-number divide, MUFU lg2/ex2 and sliding-window sums.
+template <int N>
+__device__ __forceinline__ void load_window(const __nv_bfloat16* p, int v, int c8, float (&w)[24]) {
+  float t[8];
+  bf16x8 z;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) z.v[i] = __floats2bfloat162_rn(0.f, 0.f);
+  unpack8(v > 0 ? ld8(p - 8) : z, t);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) w[j] = t[j];
+  unpack8(ld8(p), t);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) w[8 + j] = t[j];
+  unpack8(v + 1 < c8 ? ld8(p + 8) : z, t);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) w[16 + j] = t[j];
+}
+
 template <bool BWD, int PRE>
 __global__ void __launch_bounds__(256)
 lrn_reg_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ out,
-               long npix, int C, long xpitch, long dpitch, long opitch, int size, float alpha_over_n, float beta,
+               uint32_t total, FastDiv div_c8, int xpitch, int dpitch, int opitch, float alpha_over_n, float beta,
                int mask_relu) {
-  const int c8 = C / 8;
   constexpr int pre = PRE;             // compile-time window: all register-array indices below are static
-  const long total = npix * c8;
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const long p = i / c8;
-    const int v = static_cast<int>(i - p * c8);
+  const int c8 = static_cast<int>(div_c8.d);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t p = fdiv(i, div_c8);
+    const int v = static_cast<int>(i - p * div_c8.d);
     float xw[24];                                 // channels [8v-8, 8v+16)
-    {
-      const __nv_bfloat16* xp = x + p * xpitch + v * 8;
-      float t[8];
-      if (v > 0) { unpack8(ld8(xp - 8), t); } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) t[j] = 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) xw[j] = t[j];
-      unpack8(ld8(xp), t);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) xw[8 + j] = t[j];
-      if (v + 1 < c8) { unpack8(ld8(xp + 8), t); } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) t[j] = 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) xw[16 + j] = t[j];
-    }
+    load_window<0>(x + static_cast<long>(p) * xpitch + v * 8, v, c8, xw);
     float o[8];
     if constexpr (!BWD) {
+      // sliding window over the squares of channels [8v-pre, 8v+7+pre]
+      float sq[8 + 2 * pre];
+#pragma unroll
+      for (int q = 0; q < 8 + 2 * pre; ++q) sq[q] = xw[8 - pre + q] * xw[8 - pre + q];
+      float acc = 0.f;
+#pragma unroll
+      for (int q = 0; q < 2 * pre; ++q) acc += sq[q];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float acc = 0.f;
-#pragma unroll
-        for (int k = -pre; k <= pre; ++k) { const float a = xw[8 + j + k]; acc += a * a; }
-        o[j] = xw[8 + j] * exp2f(-beta * log2f(1.f + alpha_over_n * acc));
+        acc += sq[j + 2 * pre];
+        o[j] = xw[8 + j] * fast_ex2(-beta * fast_lg2(fmaf(alpha_over_n, acc, 1.f)));
+        acc -= sq[j];
       }
     } else {
       float dw[24];
-      {
-        const __nv_bfloat16* dp = dy + p * dpitch + v * 8;
-        float t[8];
-        if (v > 0) { unpack8(ld8(dp - 8), t); } else {
+      load_window<1>(dy + static_cast<long>(p) * dpitch + v * 8, v, c8, dw);
+      // squares of channels [8v-2pre, 8v+7+2pre] (zero outside the loaded 24: needs pre <= 4)
+      constexpr int NS = 8 + 4 * pre;
+      float sq[NS];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) t[j] = 0.f;
-        }
+      for (int q = 0; q < NS; ++q) sq[q] = xw[8 - 2 * pre + q] * xw[8 - 2 * pre + q];
+      // r_c = dy_c * x_c * scale_c^(-beta-1) for c in [8v-pre, 8v+7+pre]; keep scale_c^-beta of the centre 8
+      constexpr int NR = 8 + 2 * pre;
+      float rr[NR], sb[8];
+      float acc = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dw[j] = t[j];
-        unpack8(ld8(dp), t);
+      for (int q = 0; q < 2 * pre; ++q) acc += sq[q];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dw[8 + j] = t[j];
-        if (v + 1 < c8) { unpack8(ld8(dp + 8), t); } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) t[j] = 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dw[16 + j] = t[j];
-      }
-      // r_c = dy_c * x_c * scale_c^(-beta-1) for c in [8v-pre, 8v+7+pre]; keep log2(scale) of the centre 8
-      float rr[16], l2s[8];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const int jj = q - 4;                       // channel offset relative to 8v, covers [-4, 11]
-        float acc = 0.f;
-#pragma unroll
-        for (int k = -pre; k <= pre; ++k) {
-          const int idx = 8 + jj + k;
-          const float a = (idx >= 0 && idx < 24) ? xw[idx < 0 ? 0 : (idx > 23 ? 23 : idx)] : 0.f;
-          acc += a * a;
-        }
-        const float ls = log2f(1.f + alpha_over_n * acc);
-        rr[q] = dw[8 + jj] * xw[8 + jj] * exp2f((-beta - 1.f) * ls);
-        if (jj >= 0 && jj < 8) l2s[jj] = ls;
+      for (int q = 0; q < NR; ++q) {
+        acc += sq[q + 2 * pre];
+        const float s = fmaf(alpha_over_n, acc, 1.f);
+        const float t = fast_ex2(-beta * fast_lg2(s));            // scale^-beta
+        rr[q] = dw[8 - pre + q] * xw[8 - pre + q] * __fdividef(t, s);
+        if (q >= pre && q < pre + 8) sb[q - pre] = t;
+        acc -= sq[q];
       }
       const float ratio = 2.f * alpha_over_n * beta;
+      float racc = 0.f;
+#pragma unroll
+      for (int q = 0; q < 2 * pre; ++q) racc += rr[q];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float racc = 0.f;
-#pragma unroll
-        for (int k = -pre; k <= pre; ++k) racc += rr[4 + j + k];
+        racc += rr[j + 2 * pre];
         const float xc = xw[8 + j];
-        float g = dw[8 + j] * exp2f(-beta * l2s[j]) - ratio * xc * racc;
+        float g = fmaf(dw[8 + j], sb[j], -ratio * xc * racc);
         if (mask_relu && !(xc > 0.f)) g = 0.f;
         o[j] = g;
+        racc -= rr[j];
       }
     }
-    st8(out + p * opitch + v * 8, pack8(o));
+    st8(out + static_cast<long>(p) * opitch + v * 8, pack8(o));
   }
 }
 
@@ -239,13 +234,15 @@ static void lrn_launch(bool bwd, const at::Tensor& x, const at::Tensor* dy, at::
   auto op = reinterpret_cast<__nv_bfloat16*>(out.data_ptr());
   if (size <= 9) {
     const long total = npix * (v.C / 8);
+    TORCH_CHECK(total < (1L << 31) && v.pitch < (1L << 31), "lrn: tensor too large for 32-bit indexing");
     const int g2 = grid_for(total, 256, 148 * 32);
     const float aon = static_cast<float>(alpha / size), bt = static_cast<float>(beta);
+    const FastDiv dc8 = make_fastdiv(static_cast<uint32_t>(v.C / 8));
+    const uint32_t tot = static_cast<uint32_t>(total);
+    const int xpi = static_cast<int>(v.pitch), dpi = static_cast<int>(dpitch), opi = static_cast<int>(o.pitch);
 #define PSD_LRN(PRE)                                                                                                   \
-  if (bwd) lrn_reg_kernel<true, PRE><<<g2, 256, 0, stream>>>(xp, dyp, op, npix, v.C, v.pitch, dpitch, o.pitch,          \
-                                                              static_cast<int>(size), aon, bt, fuse_relu);             \
-  else lrn_reg_kernel<false, PRE><<<g2, 256, 0, stream>>>(xp, nullptr, op, npix, v.C, v.pitch, 0, o.pitch,              \
-                                                           static_cast<int>(size), aon, bt, fuse_relu)
+  if (bwd) lrn_reg_kernel<true, PRE><<<g2, 256, 0, stream>>>(xp, dyp, op, tot, dc8, xpi, dpi, opi, aon, bt, fuse_relu); \
+  else lrn_reg_kernel<false, PRE><<<g2, 256, 0, stream>>>(xp, nullptr, op, tot, dc8, xpi, 0, opi, aon, bt, fuse_relu)
     switch ((size - 1) / 2) {
       case 0: PSD_LRN(0); break;
       case 1: PSD_LRN(1); break;

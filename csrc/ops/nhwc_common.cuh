@@ -7,6 +7,8 @@
 #include <torch/library.h>
 #include <torch/types.h>
 
+#include "../gemm/fastdiv.cuh"
+
 namespace psd {
 
 struct alignas(16) bf16x8 {
@@ -26,6 +28,17 @@ __device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
   return p;
+}
+// MUFU approximations (the layer kernels feed bf16 outputs; inputs here are >= 1, no denormal handling needed)
+__device__ __forceinline__ float fast_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 __device__ __forceinline__ bf16x8 ld8(const __nv_bfloat16* p) { return *reinterpret_cast<const bf16x8*>(p); }
 __device__ __forceinline__ void st8(__nv_bfloat16* p, const bf16x8& v) { *reinterpret_cast<bf16x8*>(p) = v; }

@@ -13,87 +13,95 @@ namespace psd {
 
 struct PoolGeom {
   int N, C, H, W, OH, OW, kh, kw, sh, sw, ph, pw;
-  long xpitch, ypitch;   // pixel pitches of the input-side and output-side tensors
+  int xpitch, ypitch;    // pixel pitches of the input-side and output-side tensors
+  FastDiv d_c8, d_ow, d_oh, d_w, d_h, d_sh, d_sw;
 };
+
+// ncu showed the first versions of these kernels issue-bound (70-78 % issue-active; ~760 instructions per thread for the
+// 3x3 forward, ~500 for the backward): 64-bit index divisions and per-channel fp32 compare/select chains.  Now: 32-bit
+// indices with magic-number divides, MAX forward entirely in packed bf16x2 (max + compare-mask + one LOP3 per channel
+// pair and tap; bf16 compares are exact, so the result equals the fp32 computation), MAX backward with SIMD byte compares.
+
+__device__ __forceinline__ uint32_t bf2_as_u32(const __nv_bfloat162& v) { return *reinterpret_cast<const uint32_t*>(&v); }
 
 // KT > 0: compile-time square window (fully unrolled, all window loads issued before use); KT == 0: generic.
 template <bool MAXP, int KT>
 __global__ void __launch_bounds__(256)
 pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx,
-                PoolGeom g) {
-  const int c8 = g.C / 8;
-  const long total = static_cast<long>(g.N) * g.OH * g.OW * c8;
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int v = static_cast<int>(i % c8);
-    long t = i / c8;
-    const int ow = static_cast<int>(t % g.OW); t /= g.OW;
-    const int oh = static_cast<int>(t % g.OH);
-    const int n = static_cast<int>(t / g.OH);
-    int hs = oh * g.sh - g.ph, ws = ow * g.sw - g.pw;
-    const int he_pad = min(hs + g.kh, g.H + g.ph), we_pad = min(ws + g.kw, g.W + g.pw);
-    const int he = min(he_pad, g.H), we = min(we_pad, g.W);
-    const int h0 = max(hs, 0), w0 = max(ws, 0);
-    float acc[8];
-    int best[8];
+                PoolGeom g, uint32_t total) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t t = fdiv(i, g.d_c8);
+    const int v = static_cast<int>(i - t * g.d_c8.d);
+    const uint32_t opix = t;
+    uint32_t q = fdiv(t, g.d_ow);
+    const int ow = static_cast<int>(t - q * g.d_ow.d);
+    const uint32_t n = fdiv(q, g.d_oh);
+    const int oh = static_cast<int>(q - n * g.d_oh.d);
+    const int hs = oh * g.sh - g.ph, ws = ow * g.sw - g.pw;
+    const __nv_bfloat16* xb = x + static_cast<long>(n) * (g.H * g.W) * g.xpitch + v * 8;
+    if constexpr (MAXP) {
+      const __nv_bfloat162 ninf = __halves2bfloat162(__ushort_as_bfloat16(0xff80), __ushort_as_bfloat16(0xff80));
+      __nv_bfloat162 cur[4] = {ninf, ninf, ninf, ninf};
+      uint32_t best[4] = {0u, 0u, 0u, 0u};            // two 16-bit tap indices per register
+      auto take = [&](const bf16x8& w, uint32_t tap) {
+        const uint32_t tt = tap | (tap << 16);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { acc[j] = MAXP ? -3.402823466e38f : 0.f; best[j] = 0; }
-    const __nv_bfloat16* xb = x + (static_cast<long>(n) * g.H * g.W) * g.xpitch + v * 8;
-    if constexpr (KT > 0) {
-      bf16x8 win[KT * KT];
-      bool ok[KT * KT];
-#pragma unroll
-      for (int dh = 0; dh < KT; ++dh) {
-#pragma unroll
-        for (int dw = 0; dw < KT; ++dw) {
-          const int h = hs + dh, w = ws + dw;
-          ok[dh * KT + dw] = h >= 0 && h < g.H && w >= 0 && w < g.W;
-          if (ok[dh * KT + dw]) win[dh * KT + dw] = ld8(xb + (static_cast<long>(h) * g.W + w) * g.xpitch);
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t m = __hgt2_mask(w.v[k], cur[k]);      // 0xffff per half where the new value is larger
+          cur[k] = __hmax2(cur[k], w.v[k]);
+          best[k] = (best[k] & ~m) | (tt & m);
         }
-      }
+      };
+      if constexpr (KT > 0) {
+        bf16x8 win[KT * KT];
+        bool ok[KT * KT];
 #pragma unroll
-      for (int t = 0; t < KT * KT; ++t) {
-        if (!ok[t]) continue;
-        float f[8];
-        unpack8(win[t], f);
+        for (int dh = 0; dh < KT; ++dh) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (MAXP) {
-            if (f[j] > acc[j]) { acc[j] = f[j]; best[j] = t; }
-          } else {
-            acc[j] += f[j];
+          for (int dw = 0; dw < KT; ++dw) {
+            const int h = hs + dh, w = ws + dw;
+            ok[dh * KT + dw] = static_cast<unsigned>(h) < static_cast<unsigned>(g.H) &&
+                               static_cast<unsigned>(w) < static_cast<unsigned>(g.W);
+            if (ok[dh * KT + dw]) win[dh * KT + dw] = ld8(xb + static_cast<long>(h * g.W + w) * g.xpitch);
           }
         }
+#pragma unroll
+        for (int tp = 0; tp < KT * KT; ++tp)
+          if (ok[tp]) take(win[tp], tp);
+      } else {
+        const int he = min(hs + g.kh, g.H), we = min(ws + g.kw, g.W);
+        for (int h = max(hs, 0); h < he; ++h)
+          for (int w = max(ws, 0); w < we; ++w)
+            take(ld8(xb + static_cast<long>(h * g.W + w) * g.xpitch), static_cast<uint32_t>((h - hs) * g.kw + (w - ws)));
+      }
+      bf16x8 o;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o.v[k] = cur[k];
+      st8(y + static_cast<long>(opix) * g.ypitch + v * 8, o);
+      if (idx != nullptr) {
+        uint2 pk;                                        // byte j = tap of channel j
+        pk.x = __byte_perm(best[0], best[1], 0x6420);
+        pk.y = __byte_perm(best[2], best[3], 0x6420);
+        *reinterpret_cast<uint2*>(idx + static_cast<long>(opix) * g.C + v * 8) = pk;
       }
     } else {
-      for (int h = h0; h < he; ++h) {
-        for (int w = w0; w < we; ++w) {
-          float f[8];
-          unpack8(ld8(xb + (static_cast<long>(h) * g.W + w) * g.xpitch), f);
-          const int tap = (h - hs) * g.kw + (w - ws);
+      const int he_pad = min(hs + g.kh, g.H + g.ph), we_pad = min(ws + g.kw, g.W + g.pw);
+      const int he = min(he_pad, g.H), we = min(we_pad, g.W);
+      float acc[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (MAXP) {
-              if (f[j] > acc[j]) { acc[j] = f[j]; best[j] = tap; }
-            } else {
-              acc[j] += f[j];
-            }
-          }
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int h = max(hs, 0); h < he; ++h) {
+        for (int w = max(ws, 0); w < we; ++w) {
+          float f[8];
+          unpack8(ld8(xb + static_cast<long>(h * g.W + w) * g.xpitch), f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += f[j];
         }
       }
-    }
-    if (!MAXP) {
       const float inv = 1.f / static_cast<float>((he_pad - hs) * (we_pad - ws));
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] *= inv;
-    }
-    const long opix = (static_cast<long>(n) * g.OH + oh) * g.OW + ow;
-    st8(y + opix * g.ypitch + v * 8, pack8(acc));
-    if (MAXP && idx != nullptr) {
-      uint2 pk;
-      pk.x = best[0] | (best[1] << 8) | (best[2] << 16) | (best[3] << 24);
-      pk.y = best[4] | (best[5] << 8) | (best[6] << 16) | (best[7] << 24);
-      *reinterpret_cast<uint2*>(idx + opix * g.C + v * 8) = pk;
+      st8(y + static_cast<long>(opix) * g.ypitch + v * 8, pack8(acc));
     }
   }
 }
@@ -103,37 +111,42 @@ pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
 template <bool MAXP, int NC>
 __global__ void __launch_bounds__(256)
 pool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx, __nv_bfloat16* __restrict__ dx,
-                PoolGeom g) {
-  const int c8 = g.C / 8;
-  const long total = static_cast<long>(g.N) * g.H * g.W * c8;
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int v = static_cast<int>(i % c8);
-    long t = i / c8;
-    const int w = static_cast<int>(t % g.W); t /= g.W;
-    const int h = static_cast<int>(t % g.H);
-    const int n = static_cast<int>(t / g.H);
+                PoolGeom g, uint32_t total) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t t = fdiv(i, g.d_c8);
+    const int v = static_cast<int>(i - t * g.d_c8.d);
+    const uint32_t ipix = t;
+    uint32_t q = fdiv(t, g.d_w);
+    const int w = static_cast<int>(t - q * g.d_w.d);
+    const uint32_t n = fdiv(q, g.d_h);
+    const int h = static_cast<int>(q - n * g.d_h.d);
     // output windows that cover (h, w)
     const int hp = h + g.ph, wp = w + g.pw;
-    const int oh0 = hp < g.kh ? 0 : (hp - g.kh) / g.sh + 1;
-    const int oh1 = min(hp / g.sh + 1, g.OH);
-    const int ow0 = wp < g.kw ? 0 : (wp - g.kw) / g.sw + 1;
-    const int ow1 = min(wp / g.sw + 1, g.OW);
+    const int oh0 = hp < g.kh ? 0 : static_cast<int>(fdiv(static_cast<uint32_t>(hp - g.kh), g.d_sh)) + 1;
+    const int oh1 = min(static_cast<int>(fdiv(static_cast<uint32_t>(hp), g.d_sh)) + 1, g.OH);
+    const int ow0 = wp < g.kw ? 0 : static_cast<int>(fdiv(static_cast<uint32_t>(wp - g.kw), g.d_sw)) + 1;
+    const int ow1 = min(static_cast<int>(fdiv(static_cast<uint32_t>(wp), g.d_sw)) + 1, g.OW);
+    const uint32_t obase = n * static_cast<uint32_t>(g.OH * g.OW);
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     auto accumulate = [&](int oh, int ow, const bf16x8& dv, const uint2& pk) {
-      float d[8];
-      unpack8(dv, d);
       const int hs = oh * g.sh - g.ph, ws = ow * g.sw - g.pw;
       if (MAXP) {
-        const int tap = (h - hs) * g.kw + (w - ws);
+        // keep dy only where the recorded arg-max tap is this pixel: SIMD byte compare -> 16-bit lane masks
+        const uint32_t tap = static_cast<uint32_t>((h - hs) * g.kw + (w - ws)) * 0x01010101u;
+        const uint32_t m0 = __vcmpeq4(pk.x, tap), m1 = __vcmpeq4(pk.y, tap);
+        const uint32_t mk[4] = {__byte_perm(m0, 0, 0x1100), __byte_perm(m0, 0, 0x3322), __byte_perm(m1, 0, 0x1100),
+                                __byte_perm(m1, 0, 0x3322)};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int b = ((j < 4 ? pk.x : pk.y) >> (8 * (j & 3))) & 0xff;
-          if (b == tap) acc[j] += d[j];
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t d = bf2_as_u32(dv.v[k]) & mk[k];
+          acc[2 * k] += __uint_as_float(d << 16);
+          acc[2 * k + 1] += __uint_as_float(d & 0xffff0000u);
         }
       } else {
+        float d[8];
+        unpack8(dv, d);
         const int he_pad = min(hs + g.kh, g.H + g.ph), we_pad = min(ws + g.kw, g.W + g.pw);
         const float inv = 1.f / static_cast<float>((he_pad - hs) * (we_pad - ws));
 #pragma unroll
@@ -149,13 +162,13 @@ pool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict_
 #pragma unroll
         for (int b = 0; b < NC; ++b) {
           const int oh = oh0 + a, ow = ow0 + b;
-          const int t = a * NC + b;
-          ok[t] = oh < oh1 && ow < ow1;
-          pk[t] = make_uint2(0, 0);
-          if (ok[t]) {
-            const long opix = (static_cast<long>(n) * g.OH + oh) * g.OW + ow;
-            dv[t] = ld8(dy + opix * g.ypitch + v * 8);
-            if (MAXP) pk[t] = *reinterpret_cast<const uint2*>(idx + opix * g.C + v * 8);
+          const int tt = a * NC + b;
+          ok[tt] = oh < oh1 && ow < ow1;
+          pk[tt] = make_uint2(0, 0);
+          if (ok[tt]) {
+            const uint32_t opix = obase + static_cast<uint32_t>(oh * g.OW + ow);
+            dv[tt] = ld8(dy + static_cast<long>(opix) * g.ypitch + v * 8);
+            if (MAXP) pk[tt] = *reinterpret_cast<const uint2*>(idx + static_cast<long>(opix) * g.C + v * 8);
           }
         }
       }
@@ -168,16 +181,15 @@ pool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict_
     } else {
       for (int oh = oh0; oh < oh1; ++oh) {
         for (int ow = ow0; ow < ow1; ++ow) {
-          const long opix = (static_cast<long>(n) * g.OH + oh) * g.OW + ow;
-          const bf16x8 dv = ld8(dy + opix * g.ypitch + v * 8);
+          const uint32_t opix = obase + static_cast<uint32_t>(oh * g.OW + ow);
+          const bf16x8 dv = ld8(dy + static_cast<long>(opix) * g.ypitch + v * 8);
           uint2 pk = make_uint2(0, 0);
-          if (MAXP) pk = *reinterpret_cast<const uint2*>(idx + opix * g.C + v * 8);
+          if (MAXP) pk = *reinterpret_cast<const uint2*>(idx + static_cast<long>(opix) * g.C + v * 8);
           accumulate(oh, ow, dv, pk);
         }
       }
     }
-    const long ipix = (static_cast<long>(n) * g.H + h) * g.W + w;
-    st8(dx + ipix * g.xpitch + v * 8, pack8(acc));
+    st8(dx + static_cast<long>(ipix) * g.xpitch + v * 8, pack8(acc));
   }
 }
 
@@ -186,8 +198,17 @@ static PoolGeom make_geom(const NhwcView& x, int64_t oh, int64_t ow, at::IntArra
   PoolGeom g;
   g.N = x.N; g.C = x.C; g.H = x.H; g.W = x.W; g.OH = oh; g.OW = ow;
   g.kh = k[0]; g.kw = k[1]; g.sh = s[0]; g.sw = s[1]; g.ph = p[0]; g.pw = p[1];
-  g.xpitch = x.pitch;
+  TORCH_CHECK(x.pitch < (1L << 31) && static_cast<long>(x.N) * x.H * x.W * (x.C / 8) < (1L << 31) &&
+              static_cast<long>(x.N) * oh * ow * (x.C / 8) < (1L << 31), "pool: tensor too large for 32-bit indexing");
+  g.xpitch = static_cast<int>(x.pitch);
   g.ypitch = x.C;
+  g.d_c8 = make_fastdiv(x.C / 8);
+  g.d_ow = make_fastdiv(static_cast<uint32_t>(ow));
+  g.d_oh = make_fastdiv(static_cast<uint32_t>(oh));
+  g.d_w = make_fastdiv(x.W);
+  g.d_h = make_fastdiv(x.H);
+  g.d_sh = make_fastdiv(g.sh);
+  g.d_sw = make_fastdiv(g.sw);
   return g;
 }
 
@@ -208,7 +229,7 @@ std::tuple<at::Tensor, at::Tensor> pool_fwd(const at::Tensor& x, bool is_max, at
   uint8_t* ip = idx.defined() ? idx.data_ptr<uint8_t>() : nullptr;
   const int grid = grid_for(total, 256, 148 * 32);
   const int kt = (g.kh == g.kw && (g.kh == 2 || g.kh == 3)) ? g.kh : 0;
-#define PSD_PF(MX, KT) pool_fwd_kernel<MX, KT><<<grid, 256, 0, stream>>>(xp, yp, MX ? ip : nullptr, g)
+#define PSD_PF(MX, KT) pool_fwd_kernel<MX, KT><<<grid, 256, 0, stream>>>(xp, yp, MX ? ip : nullptr, g, static_cast<uint32_t>(total))
   if (is_max) { if (kt == 3) PSD_PF(true, 3); else if (kt == 2) PSD_PF(true, 2); else PSD_PF(true, 0); }
   else        { if (kt == 3) PSD_PF(false, 3); else if (kt == 2) PSD_PF(false, 2); else PSD_PF(false, 0); }
 #undef PSD_PF
@@ -224,7 +245,7 @@ at::Tensor pool_bwd(const at::Tensor& dy, const at::Tensor& idx, bool is_max, at
   at::Tensor dx = empty_nhwc(dv.N, dv.C, in_hw[0], in_hw[1], dy.options());
   NhwcView xv = nhwc_view(dx);
   PoolGeom g = make_geom(xv, dv.H, dv.W, k, s, p);
-  g.ypitch = dv.pitch;
+  g.ypitch = static_cast<int>(dv.pitch);
   const long total = static_cast<long>(g.N) * g.H * g.W * (g.C / 8);
   auto stream = at::cuda::getCurrentCUDAStream();
   auto dyp = reinterpret_cast<const __nv_bfloat16*>(dy.data_ptr());
@@ -237,7 +258,7 @@ at::Tensor pool_bwd(const at::Tensor& dy, const at::Tensor& idx, bool is_max, at
     TORCH_CHECK(idx.numel() == dy.numel(), "pool_bwd: index tensor missing");
     ip = idx.data_ptr<uint8_t>();
   }
-#define PSD_PB(MX, NCV) pool_bwd_kernel<MX, NCV><<<grid, 256, 0, stream>>>(dyp, ip, dxp, g)
+#define PSD_PB(MX, NCV) pool_bwd_kernel<MX, NCV><<<grid, 256, 0, stream>>>(dyp, ip, dxp, g, static_cast<uint32_t>(total))
   if (is_max) { if (nc == 1) PSD_PB(true, 1); else if (nc == 2) PSD_PB(true, 2); else if (nc == 3) PSD_PB(true, 3); else PSD_PB(true, 0); }
   else        { if (nc == 1) PSD_PB(false, 1); else if (nc == 2) PSD_PB(false, 2); else if (nc == 3) PSD_PB(false, 3); else PSD_PB(false, 0); }
 #undef PSD_PB

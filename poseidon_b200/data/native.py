@@ -1,0 +1,134 @@
+"""Native (C++) host runtime bindings: record-file batch loader + wire compression.
+
+``csrc_host/record_loader.cpp`` is plain C++17 + pybind11 (no CUDA), compiled in-tree to
+``poseidon_b200/_ext/poseidon_b200_host.so`` by :func:`build` (also called from ``__graft_entry__.build``).
+:class:`NativeDBSource` is the drop-in replacement of :class:`poseidon_b200.data.source.DBSource`: same cursor
+semantics (offset / stride sharding, wrap-around; reference: src/caffe/layers/data_layer.cpp:143-259) but the
+records are parsed and copied into page-locked batch buffers by a C++ thread pool running ahead of the trainer.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import subprocess
+import sys
+import sysconfig
+import threading
+
+import torch
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+SRC = os.path.join(_ROOT, "csrc_host", "record_loader.cpp")
+EXT_DIR = os.path.join(_ROOT, "poseidon_b200", "_ext")
+SO = os.path.join(EXT_DIR, "poseidon_b200_host.so")
+_mod = None
+_lock = threading.Lock()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """g++ -O3 -shared the host module (a few seconds); no-op when up to date."""
+    os.makedirs(EXT_DIR, exist_ok=True)
+    if not force and os.path.exists(SO) and os.path.getmtime(SO) >= os.path.getmtime(SRC):
+        return SO
+    import pybind11
+    cmd = ["g++", "-O3", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden", "-pthread",
+           "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"], SRC, "-o", SO + ".tmp"]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    os.replace(SO + ".tmp", SO)
+    return SO
+
+
+def module(build_if_missing: bool = True):
+    global _mod
+    with _lock:
+        if _mod is not None:
+            return _mod
+        if not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(SRC):
+            if not build_if_missing:
+                raise RuntimeError(f"{SO} not built")
+            build()
+        spec = importlib.util.spec_from_file_location("poseidon_b200_host", SO)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        sys.modules["poseidon_b200_host"] = mod
+        _mod = mod
+        return mod
+
+
+def available() -> bool:
+    try:
+        module()
+        return True
+    except Exception:
+        return False
+
+
+class NativeDBSource:
+    """Batches from a PDB record file, produced by the C++ loader into a ring of (pinned) host buffers.
+
+    ``next_batch()`` returns tensors that alias a ring slot; the slot is recycled ``depth`` calls later, which is
+    after the :class:`~poseidon_b200.data.source.Prefetcher` has issued (and event-synchronised) its H2D copy.
+    """
+
+    def __init__(self, path: str, batch: int, offset: int = 0, stride: int = 1, rand_skip: int = 0, seed=None,
+                 threads: int = 0, depth: int = 4, pin: bool | None = None):
+        m = module()
+        pdb = path if os.path.isfile(path) else os.path.join(path, "data.pdb")
+        threads = threads or max(2, min(16, (os.cpu_count() or 4) // 2))
+        self.loader = m.BatchLoader(pdb, batch, offset, max(1, stride), threads)
+        n = self.loader.num_records()
+        if rand_skip:
+            import numpy as np
+            rng = np.random.RandomState(seed)
+            self.loader.seek((offset + int(rng.randint(0, rand_skip)) * max(1, stride)) % n)
+        self.batch = batch
+        self.shape = tuple(self.loader.shape())
+        self.is_bytes = bool(self.loader.is_bytes())
+        pin = torch.cuda.is_available() if pin is None else pin
+        dt = torch.uint8 if self.is_bytes else torch.float32
+        self.slots = []
+        for _ in range(max(2, depth)):
+            x = torch.empty((batch,) + self.shape, dtype=dt)
+            y = torch.empty((batch,), dtype=torch.float32)
+            if pin:
+                x, y = x.pin_memory(), y.pin_memory()
+            self.slots.append((x, y))
+        self.loader.start([(x.data_ptr(), y.data_ptr()) for x, y in self.slots])
+        self._held = []               # slots handed out, oldest first
+        self._hold = max(1, len(self.slots) - 2)
+
+    def __len__(self):
+        return self.loader.num_records()
+
+    def next_batch(self):
+        while len(self._held) >= self._hold:
+            self.loader.release(self._held.pop(0))
+        s = self.loader.acquire()
+        self._held.append(s)
+        return self.slots[s]
+
+    def close(self):
+        self.loader.stop()
+
+    def __del__(self):
+        try:
+            self.loader.stop()
+        except Exception:
+            pass
+
+
+def f32_to_bf16(src: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Round-to-nearest-even fp32 -> bf16 on the host (wire compression for the CPU/gloo SSP path)."""
+    assert src.dtype == torch.float32 and src.is_contiguous() and src.device.type == "cpu"
+    out = torch.empty(src.shape, dtype=torch.bfloat16) if out is None else out
+    module().f32_to_bf16(src.data_ptr(), out.data_ptr(), src.numel())
+    return out
+
+
+def bf16_to_f32(src: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    assert src.dtype == torch.bfloat16 and src.is_contiguous() and src.device.type == "cpu"
+    out = torch.empty(src.shape, dtype=torch.float32) if out is None else out
+    module().bf16_to_f32(src.data_ptr(), out.data_ptr(), src.numel())
+    return out

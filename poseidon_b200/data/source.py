@@ -131,6 +131,11 @@ class Prefetcher:
                 gx = x.to(self.device, non_blocking=True)
                 gy = y.to(self.device, non_blocking=True)
                 ev.record(self.stream)
+            # the source recycles its page-locked buffers a couple of batches later: make sure the previous
+            # batch's copy has drained before asking for more (it almost always has — costs nothing)
+            prev, self._prev_pinned_ev = getattr(self, "_prev_pinned_ev", None), ev
+            if prev is not None:
+                prev.synchronize()
             return gx, gy, ev
         n_slots = self.depth + 2
         if len(self.ring) < n_slots:

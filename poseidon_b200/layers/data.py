@@ -15,7 +15,7 @@ import torch
 
 from .. import ops
 from .. import proto as P
-from ..data.db import open_db, shard_indices
+from ..data.db import RecordReader, open_db, shard_indices
 from ..data.source import ArraySource, DBSource, Prefetcher, SyntheticSource
 from ..data.transformer import DataTransformer
 from .base import Layer, fill, register
@@ -110,6 +110,8 @@ class BasePrefetchingDataLayer(Layer):
     def close(self):
         if self.prefetch is not None:
             self.prefetch.close()
+        if hasattr(self.source, "close"):
+            self.source.close()
 
 
 @register("DATA")
@@ -136,6 +138,13 @@ class DataLayer(BasePrefetchingDataLayer):
                 log.warning("DATA layer '%s': %s -> synthetic %s uint8 data", self.layer_name, e, shape)
             return SyntheticSource(batch, shape, ncls, seed=1234 + self.ctx.rank)
         off, stride = shard_indices(len(reader), shared, nclients, client, nthreads, thread)
+        if isinstance(reader, RecordReader) and os.environ.get("POSEIDON_NATIVE_LOADER", "1") != "0":
+            # C++ record loader: thread-pool Datum decode straight into pinned batch buffers
+            from ..data import native
+            if native.available():
+                pdb = reader.path
+                reader.close()
+                return native.NativeDBSource(pdb, batch, off, stride, int(dp.rand_skip), self.ctx.seed)
         return DBSource(reader, batch, off, stride, int(dp.rand_skip), self.ctx.seed)
 
 

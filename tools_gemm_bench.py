@@ -29,6 +29,21 @@ def bench(fn):
 flops = 2.0 * M * N * Kd
 for a_mn in (False, True):
     for b_mn in (False, True):
+        if a_mn and not b_mn:
+            continue          # MN-major A x K-major B is not instantiated (no layer needs it)
+        if a_mn and b_mn:
+            # the wgrad combination: fp32 epilogue only
+            a = torch.randn(Kd, M, device="cuda").to(torch.bfloat16)
+            b = torch.randn(Kd, N, device="cuda").to(torch.bfloat16)
+            o32 = torch.empty(M, N, device="cuda", dtype=torch.float32)
+            for bn in (256, 128):
+                ms = bench(lambda: K.gemm_f32(a, True, b, True, o32, 1.0, False, 1, bn))
+                print(f"f32 out   A_MN=1 B_MN=1 BN={bn:3d}: {ms*1e3:9.1f} us  {flops/ms/1e9:7.1f} TFLOP/s", flush=True)
+            a = torch.randn(M, Kd, device="cuda").to(torch.bfloat16)
+            b = torch.randn(N, Kd, device="cuda").to(torch.bfloat16)
+            ms = bench(lambda: K.gemm_f32(a, False, b, False, o32, 1.0, False, 1, 256))
+            print(f"f32 out   A_MN=0 B_MN=0 BN=256: {ms*1e3:9.1f} us  {flops/ms/1e9:7.1f} TFLOP/s", flush=True)
+            continue
         a = torch.randn((Kd, M) if a_mn else (M, Kd), device="cuda").to(torch.bfloat16)
         b = torch.randn((Kd, N) if b_mn else (N, Kd), device="cuda").to(torch.bfloat16)
         out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
