@@ -22,6 +22,10 @@ namespace psd {
 
 void encode_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner,
                          int box_outer);
+void encode_tmap_im2col_bf16(CUtensorMap* map, const void* base, int64_t C, int64_t W, int64_t H, int64_t N, int64_t pitch,
+                             int lower_w, int lower_h, int upper_w, int upper_h, int pixels, int stride_w, int stride_h);
+
+static int g_conv_im2col = 1;      // TMA im2col-mode operand fetch where the geometry allows it (C_g % 64 == 0)
 
 static int g_conv_cluster = 1;     // CTAs per cluster sharing the TMA operand by multicast (1 = off; measured slower at 2 on B200, kept as an option)
 
@@ -34,12 +38,13 @@ static void launch_conv(const TmapSet& tm, const GemmParams& p, const ConvGeom& 
     C10_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
+  constexpr int threads = kNumThreads + (has_gather_warps(GATHER) ? kGatherThreads : 0);
   if (p.cluster <= 1) {
-    kern<<<grid, kNumThreads + kGatherThreads, smem, stream>>>(tm, p, cg);
+    kern<<<grid, threads, smem, stream>>>(tm, p, cg);
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kNumThreads + kGatherThreads);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -132,6 +137,20 @@ static ConvGeom make_geom(const at::Tensor& x, const NhwcView& xv, int c_off, in
   return g;
 }
 
+// TMA im2col eligibility: TAP mode, 64-channel K slices never straddle a tap, corner offsets fit the descriptor.
+// On success fills `map` for boxes of `pixels` base pixels x 64 channels over the gathered tensor.
+static bool try_im2col_map(CUtensorMap* map, const ConvGeom& g, int pixels) {
+  if (!g_conv_im2col || g.mode != 0 || g.Cg % 64 != 0) return false;
+  const int org_w = g.off_w - (g.dr < 0 ? g.S - 1 : 0), org_h = g.off_h - (g.dr < 0 ? g.R - 1 : 0);
+  // the bounding box must enumerate exactly OW x OH base pixels: extent + upper - lower - 1 = (O - 1) * stride
+  const int up_w = (g.OW - 1) * g.sw + 1 + org_w - g.W, up_h = (g.OH - 1) * g.sh + 1 + org_h - g.H;
+  auto ok = [](int v) { return v >= -128 && v <= 127; };
+  if (!ok(org_w) || !ok(org_h) || !ok(up_w) || !ok(up_h) || g.sw > 8 || g.sh > 8) return false;
+  if ((reinterpret_cast<uintptr_t>(g.x) & 15) != 0 || (g.pitch * 2) % 16 != 0) return false;
+  encode_tmap_im2col_bf16(map, g.x, g.Cg, g.W, g.H, g.N, g.pitch, org_w, org_h, up_w, up_h, pixels, g.sw, g.sh);
+  return true;
+}
+
 // Widest N tile that does not over-pad the channel count and still yields a full wave of CTAs; small problems
 // (GoogLeNet's 14x14 / 7x7 stages at batch 32) take the narrowest tile so that more SMs get work.
 static int pick_conv_bn(int64_t n_cols, int64_t m_blocks, int sms) {
@@ -182,6 +201,14 @@ at::Tensor conv_fprop(const at::Tensor& x, const at::Tensor& wb, const c10::opti
     p.relu = relu;
     p.relu_slope = static_cast<float>(slope);
     p.alpha = 1.f;
+    if (cl == 1 && try_im2col_map(&tm.a[0], cg, BLOCK_M)) {
+      switch (bn) {
+        case 64: launch_conv<64, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
+        case 128: launch_conv<128, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
+        default: launch_conv<256, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
+      }
+      continue;
+    }
     switch (bn) {
       case 64: launch_conv<64, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
       case 128: launch_conv<128, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
@@ -237,6 +264,14 @@ at::Tensor conv_dgrad(const at::Tensor& dy, const at::Tensor& wt, at::IntArrayRe
     p.relu_slope = static_cast<float>(slope);
     p.alpha = 1.f;
     (void)mask_pitch;
+    if (cl == 1 && try_im2col_map(&tm.a[0], cg, BLOCK_M)) {
+      switch (bn) {
+        case 64: launch_conv<64, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
+        case 128: launch_conv<128, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
+        default: launch_conv<256, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
+      }
+      continue;
+    }
     switch (bn) {
       case 64: launch_conv<64, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
       case 128: launch_conv<128, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
@@ -286,6 +321,14 @@ void conv_wgrad(const at::Tensor& x, const at::Tensor& dy, at::Tensor dw, at::In
     p.ldc = cg.K;
     p.atomic = 1;
     p.alpha = static_cast<float>(alpha);
+    if (cl == 1 && try_im2col_map(&tm.b[0], cg, BLOCK_K)) {
+      switch (bn) {
+        case 64: launch_conv<64, true, true, EPI_F32, IM2COL_B>(tm, p, cg, grid, stream); break;
+        case 128: launch_conv<128, true, true, EPI_F32, IM2COL_B>(tm, p, cg, grid, stream); break;
+        default: launch_conv<256, true, true, EPI_F32, IM2COL_B>(tm, p, cg, grid, stream); break;
+      }
+      continue;
+    }
     switch (bn) {
       case 64: launch_conv<64, true, true, EPI_F32, GATHER_B>(tm, p, cg, grid, stream); break;
       case 128: launch_conv<128, true, true, EPI_F32, GATHER_B>(tm, p, cg, grid, stream); break;
@@ -326,6 +369,7 @@ at::Tensor conv_pack_dgrad(const at::Tensor& w, int64_t Cout, int64_t RS, int64_
 }  // namespace psd
 
 namespace psd {
+void set_conv_im2col(int64_t on) { g_conv_im2col = on != 0; }
 void set_conv_cluster(int64_t c) {
   TORCH_CHECK(c == 1 || c == 2 || c == 4, "cluster size must be 1, 2 or 4");
   g_conv_cluster = static_cast<int>(c);
@@ -334,6 +378,7 @@ void set_conv_cluster(int64_t c) {
 
 TORCH_LIBRARY_FRAGMENT(poseidon, m) {
   m.def("set_conv_cluster(int c) -> ()", &psd::set_conv_cluster);
+  m.def("set_conv_im2col(int on) -> ()", &psd::set_conv_im2col);
   m.def("conv_fprop(Tensor x, Tensor wb, Tensor? bias, int[] kernel, int[] stride, int[] pad, int groups, int mode, "
         "int OH, int OW, bool relu, float slope, Tensor? out) -> Tensor", &psd::conv_fprop);
   m.def("conv_dgrad(Tensor dy, Tensor wt, int[] kernel, int[] pad, int groups, int H, int W, Tensor? mask, float slope) "

@@ -41,6 +41,38 @@ void encode_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t inner, int6
               " outer=", outer, " ld=", ld);
 }
 
+// 4-D im2col-mode bf16 tensor map over an NHWC tensor (channels innermost, pixel pitch `pitch` elements).
+//   lower / upper : bounding-box corner offsets {w, h} (cuTensorMapEncodeIm2col semantics: base pixels run from
+//                   `lower` to `extent + upper - 1` in steps of the traversal stride)
+//   box           : `pixels` base pixels x 64 channels, 128B swizzle
+void encode_tmap_im2col_bf16(CUtensorMap* map, const void* base, int64_t C, int64_t W, int64_t H, int64_t N, int64_t pitch,
+                             int lower_w, int lower_h, int upper_w, int upper_h, int pixels, int stride_w, int stride_h) {
+  using Im2colFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static Im2colFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &ptr, cudaEnableDefault, &qres);
+    TORCH_CHECK(e == cudaSuccess && qres == cudaDriverEntryPointSuccess && ptr != nullptr,
+                "cuTensorMapEncodeIm2col not available from the driver");
+    fn = reinterpret_cast<Im2colFn>(ptr);
+  }
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (pitch * 2) % 16 == 0, "im2col TMA: 16-byte alignment");
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(pitch) * 2, static_cast<cuuint64_t>(pitch) * W * 2,
+                           static_cast<cuuint64_t>(pitch) * W * H * 2};
+  int lower[2] = {lower_w, lower_h}, upper[2] = {upper_w, upper_h};
+  cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride_w), static_cast<cuuint32_t>(stride_h), 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower, upper, 64,
+                  static_cast<cuuint32_t>(pixels), estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TORCH_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col failed: ", static_cast<int>(r), " C=", C, " W=", W, " H=", H,
+              " N=", N, " lower=", lower_w, ",", lower_h, " upper=", upper_w, ",", upper_h);
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
 static void launch(const TmapSet& tm, const GemmParams& p, int grid, cudaStream_t stream) {
   auto kern = umma_gemm_kernel<BN, A_MN, B_MN, EPI>;

@@ -98,6 +98,21 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// im2col-mode TMA (4-D NHWC tensor): loads `pixelsPerColumn` consecutive base pixels — walking w, then h, then n
+// inside the descriptor's bounding box, with its traversal strides — x `channelsPerPixel` channels starting at
+// channel c, each displaced by the filter-tap offsets (off_w, off_h); out-of-image elements are zero-filled.
+// (c, w, h, n) is the coordinate of the first base pixel; the smem image is the same 128B-swizzled
+// [pixel][channel] tile a tiled 2-D load would produce.
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c, int w,
+                                                   int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w),
+      "h"(off_h)
+      : "memory");
+}
+
 // Multicast variant: the box lands at the same smem offset of every CTA in `cta_mask` and completes the
 // transaction on the mbarrier at the same offset in each of them.
 __device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int x, int y,

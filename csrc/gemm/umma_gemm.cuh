@@ -31,7 +31,10 @@ constexpr int kEpiWarp0 = 4;
 constexpr int kGatherWarp0 = kEpiWarp0 + kEpiWarps;  // conv kernels: 8 more warps gather the implicit-im2col operand
 constexpr int kGatherThreads = 256;          // 8 warps: the producers are instruction-latency bound, not bandwidth bound
 constexpr int kGatherLag = 2;             // cp.async groups kept in flight per gather thread
-enum GatherMode : int { GATHER_NONE = 0, GATHER_A = 1, GATHER_B = 2 };
+// GATHER_A / GATHER_B: operand built by the cp.async gather warps (any channel count, ROW mode).
+// IM2COL_A / IM2COL_B: operand fetched by the TMA engine in im2col mode (C_g % 64 == 0): no gather warps at all.
+enum GatherMode : int { GATHER_NONE = 0, GATHER_A = 1, GATHER_B = 2, IM2COL_A = 3, IM2COL_B = 4 };
+__host__ __device__ constexpr bool has_gather_warps(int g) { return g == GATHER_A || g == GATHER_B; }
 
 enum EpiMode : int { EPI_BF16 = 0, EPI_F32 = 1, EPI_SGD = 2 };
 
@@ -174,36 +177,51 @@ __device__ __forceinline__ void epilogue_tile32(const GemmParams& p, const uint3
         else *dst = v;
       }
     }
-  } else {  // EPI_SGD: W, H stepped in place (coalesced 128 B rows), bf16 shadow refreshed
-    const float lr_eff = p.lr_dev != nullptr ? p.lr * __ldg(p.lr_dev) : p.lr;
-    if (lane < ncols) {
-      constexpr int kBatch = 32;                      // 64 independent 128-byte row loads in flight per warp
-      const long off0 = static_cast<long>(row0) * p.ldc + col0 + lane;
-#pragma unroll 1
-      for (int r0 = 0; r0 < nrows; r0 += kBatch) {
-        float wv[kBatch], hv[kBatch];
+  }
+  // EPI_SGD does not come through here: see sgd_rows_from_slab (CTA-cooperative, row-contiguous).
+  __syncwarp();
+}
+
+// EPI_SGD, CTA-cooperative form.  The optimizer step is pure HBM streaming (18 B per weight), and DRAM only streams
+// at full rate when whole rows of the tile (BN * 4 B = 1 KB) are touched back to back: the per-warp 32x32 sub-tile walk
+// above issues isolated 128-byte pieces 36 KB apart and measured 2.3 TB/s against 4.9 TB/s for the same update as a
+// linear stream.  Here the two warps that can read a TMEM lane quadrant dump its 32 x BN accumulators into one shared
+// slab, then ALL epilogue warps update 4 full rows each: every warp issues BN/32 consecutive 128-byte accesses per row
+// and array (one contiguous 1 KB burst), with 8 * BN/32 independent loads in flight.
+template <int BN>
+__device__ __forceinline__ void sgd_rows_from_slab(const GemmParams& p, const float* slab, int e, int lane, int row0,
+                                                   int col0, float lr_eff) {
+  constexpr int LD = BN + 1;
+  constexpr int NC = BN / 32;
+  constexpr int RW = 32 / kEpiWarps;                 // rows of the slab per warp
+  float wv[RW][NC], hv[RW][NC];
 #pragma unroll
-        for (int j = 0; j < kBatch; ++j) {
-          const long off = off0 + static_cast<long>(r0 + j) * p.ldc;
-          const bool ok = r0 + j < nrows;
-          wv[j] = ok ? p.w[off] : 0.f;
-          hv[j] = ok ? p.h[off] : 0.f;
-        }
+  for (int k = 0; k < RW; ++k) {
+    const int row = row0 + e * RW + k;
+    const long off0 = static_cast<long>(row) * p.ldc + col0 + lane;
 #pragma unroll
-        for (int j = 0; j < kBatch; ++j) {
-          if (r0 + j < nrows) {
-            const long off = off0 + static_cast<long>(r0 + j) * p.ldc;
-            sgd_apply(stage[(r0 + j) * 33 + lane], wv[j], hv[j], p, lr_eff);
-            p.w[off] = wv[j];
-            p.h[off] = hv[j];
-            if (p.wb != nullptr) p.wb[off] = __float2bfloat16(wv[j]);
-          }
-        }
+    for (int i = 0; i < NC; ++i) {
+      const bool ok = row < p.M && col0 + lane + 32 * i < p.N;
+      wv[k][i] = ok ? p.w[off0 + 32 * i] : 0.f;
+      hv[k][i] = ok ? p.h[off0 + 32 * i] : 0.f;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < RW; ++k) {
+    const int row = row0 + e * RW + k;
+    const long off0 = static_cast<long>(row) * p.ldc + col0 + lane;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      if (row < p.M && col0 + lane + 32 * i < p.N) {
+        sgd_apply(slab[(e * RW + k) * LD + lane + 32 * i], wv[k][i], hv[k][i], p, lr_eff);
+        p.w[off0 + 32 * i] = wv[k][i];
+        p.h[off0 + 32 * i] = hv[k][i];
+        if (p.wb != nullptr) p.wb[off0 + 32 * i] = __float2bfloat16(wv[k][i]);
       }
     }
   }
-  __syncwarp();
 }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 
 // Producer policy: both operands via TMA.
 template <int BN, bool A_MN, bool B_MN>
@@ -240,10 +258,17 @@ struct TmaProducer {
 struct TileCoord {
   int m_blk, n_blk, split;
 };
-template <int GATHER>
+// NFAST (optimizer-step epilogue): n fastest, so that the CTAs running at the same time update whole rows of W —
+// one contiguous region of memory — instead of a 1 KB column slab with a row-sized stride between pieces.
+template <int GATHER, bool NFAST = false>
 __device__ __forceinline__ TileCoord tile_coord(int t, int m_blocks, int n_blocks, int C, int crank) {
   TileCoord tc;
-  if (GATHER == GATHER_B) {
+  if (NFAST) {
+    tc.n_blk = t % n_blocks;
+    const int rest = t / n_blocks;
+    tc.m_blk = rest % m_blocks;
+    tc.split = rest / m_blocks;
+  } else if (GATHER == GATHER_B) {
     const int n_groups = (n_blocks + C - 1) / C;
     tc.m_blk = t % m_blocks;
     const int rest = t / m_blocks;
@@ -260,10 +285,12 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int m_blocks, int n_block
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI, int GATHER = GATHER_NONE>
-__global__ void __launch_bounds__(kNumThreads + (GATHER != GATHER_NONE ? kGatherThreads : 0), 1)
+__global__ void __launch_bounds__(kNumThreads + (has_gather_warps(GATHER) ? kGatherThreads : 0), 1)
 umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const ConvGeom cg) {
   static_assert(GATHER != GATHER_A || !A_MN, "gathered A is produced K-major");
   static_assert(GATHER != GATHER_B || B_MN, "gathered B is produced MN-major");
+  static_assert(GATHER != IM2COL_A || !A_MN, "im2col A is K-major");
+  static_assert(GATHER != IM2COL_B || B_MN, "im2col B is MN-major");
   using S = GemmSmem<BN>;
   constexpr int kStages = S::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -282,7 +309,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
   const int m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int n_blocks = (p.N + BN - 1) / BN;
   const int total_kb = p.kb_per_src * p.num_src;
-  const int C = (GATHER != GATHER_NONE && p.cluster > 1) ? p.cluster : 1;
+  const int C = (has_gather_warps(GATHER) && p.cluster > 1) ? p.cluster : 1;
   const int crank = C > 1 ? static_cast<int>(cluster_ctarank()) : 0;
   const uint16_t cmask = static_cast<uint16_t>((1u << C) - 1);
   // cluster-level tile space and stride
@@ -297,7 +324,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1 + (GATHER != GATHER_NONE ? kGatherThreads : 0));
+      mbar_init(&full_bar[s], 1 + (has_gather_warps(GATHER) ? kGatherThreads : 0));
       mbar_init(&empty_bar[s], C);        // released by the MMA thread of every CTA sharing the multicast operand
     }
     for (int s = 0; s < 2; ++s) {
@@ -322,10 +349,38 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const TileCoord tc = tile_coord<GATHER>(tile, m_blocks, n_blocks, C, crank);
+        const TileCoord tc = tile_coord<GATHER, EPI == EPI_SGD>(tile, m_blocks, n_blocks, C, crank);
         const int m_blk = tc.m_blk, n_blk = tc.n_blk, split = tc.split;
         const int g0 = static_cast<int>(static_cast<long>(total_kb) * split / p.split_k);
         const int g1 = static_cast<int>(static_cast<long>(total_kb) * (split + 1) / p.split_k);
+        // im2col modes: coordinates of the tile's first base pixel (A) / tap decode of the tile's k-columns (B)
+        [[maybe_unused]] int im_w = 0, im_h = 0, im_n = 0;
+        [[maybe_unused]] const int im_org_w = cg.off_w - (cg.dr < 0 ? cg.S - 1 : 0);
+        [[maybe_unused]] const int im_org_h = cg.off_h - (cg.dr < 0 ? cg.R - 1 : 0);
+        [[maybe_unused]] int im_c0[BN / 64];
+        [[maybe_unused]] uint16_t im_offw[BN / 64], im_offh[BN / 64];
+        if constexpr (GATHER == IM2COL_A) {
+          const uint32_t m0 = static_cast<uint32_t>(m_blk) * BLOCK_M;
+          const uint32_t n_img = fdiv(m0, cg.div_ohow);
+          const uint32_t rem = m0 - n_img * static_cast<uint32_t>(cg.OH * cg.OW);
+          const uint32_t oh = fdiv(rem, cg.div_ow);
+          const uint32_t ow = rem - oh * static_cast<uint32_t>(cg.OW);
+          im_w = static_cast<int>(ow) * cg.sw + im_org_w;
+          im_h = static_cast<int>(oh) * cg.sh + im_org_h;
+          im_n = static_cast<int>(n_img);
+        }
+        if constexpr (GATHER == IM2COL_B) {
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c) {
+            int kc = n_blk * BN + c * 64;
+            if (kc >= cg.K) kc = 0;                      // columns past K are dropped by the epilogue: load anything valid
+            const int tap = static_cast<int>(fdiv(static_cast<uint32_t>(kc), cg.div_cg));
+            im_c0[c] = kc - tap * cg.Cg;
+            const int r = static_cast<int>(fdiv(static_cast<uint32_t>(tap), cg.div_s));
+            im_offh[c] = static_cast<uint16_t>(r);
+            im_offw[c] = static_cast<uint16_t>(tap - r * cg.S);
+          }
+        }
         // (source, k-block) advance incrementally: no divisions in the single-thread producer loop
         int src_lin = g0 / p.kb_per_src;
         int kb = g0 - src_lin * p.kb_per_src;
@@ -341,6 +396,34 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
           if constexpr (GATHER == GATHER_NONE) {
             mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
             TmaProducer<BN, A_MN, B_MN>::load_stage(tm, src, kb, m_blk, n_blk, sa, sa + S::kABytes, &full_bar[stage]);
+          } else if constexpr (GATHER == IM2COL_A) {
+            // A tile = 128 output pixels x 64 channels of tap (r, s): one im2col-mode TMA instruction
+            const int k0 = g * BLOCK_K;
+            const int tap = static_cast<int>(fdiv(static_cast<uint32_t>(k0), cg.div_cg));
+            const int c0 = k0 - tap * cg.Cg;
+            const int r = static_cast<int>(fdiv(static_cast<uint32_t>(tap), cg.div_s));
+            const int sx = tap - r * cg.S;
+            const bool in_k = k0 < cg.K;
+            const int offw = cg.dr > 0 ? sx : cg.S - 1 - sx, offh = cg.dr > 0 ? r : cg.R - 1 - r;
+            mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+            // k-blocks past K (K % 64 != 0 never happens here: C_g % 64 == 0) — keep the guard cheap
+            tma_load_im2col_4d(smem_u32(sa), &tm.a[0], smem_u32(&full_bar[stage]), in_k ? c0 : 0, im_w, im_h, im_n,
+                               static_cast<uint16_t>(in_k ? offw : 0), static_cast<uint16_t>(in_k ? offh : 0));
+            TmaProducer<BN, A_MN, B_MN>::load_b(tm, src, kb, n_blk, sa + S::kABytes, &full_bar[stage]);
+          } else if constexpr (GATHER == IM2COL_B) {
+            // B tile = BN/64 chunks of [64 reduction pixels][64 channels of one tap]; the pixels advance with g
+            const uint32_t m0 = static_cast<uint32_t>(g) * BLOCK_K;
+            const uint32_t n_img = fdiv(m0, cg.div_ohow);
+            const uint32_t rem = m0 - n_img * static_cast<uint32_t>(cg.OH * cg.OW);
+            const uint32_t oh = fdiv(rem, cg.div_ow);
+            const uint32_t ow = rem - oh * static_cast<uint32_t>(cg.OW);
+            const int bw = static_cast<int>(ow) * cg.sw + im_org_w, bh = static_cast<int>(oh) * cg.sh + im_org_h;
+            mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_im2col_4d(smem_u32(sa + S::kABytes + c * 8192), &tm.b[0], smem_u32(&full_bar[stage]), im_c0[c], bw, bh,
+                                 static_cast<int>(n_img), im_offw[c], im_offh[c]);
+            TmaProducer<BN, A_MN, B_MN>::load_a(tm, src, kb, m_blk, sa, &full_bar[stage]);
           } else if constexpr (GATHER == GATHER_A) {
             mbar_arrive_expect_tx(&full_bar[stage], S::kBBytes);     // the whole B tile lands here (C slices)
             if (C == 1) {
@@ -381,7 +464,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
       uint32_t phase = 0;
       int it = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
-        const int split = tile_coord<GATHER>(tile, m_blocks, n_blocks, C, crank).split;
+        const int split = tile_coord<GATHER, EPI == EPI_SGD>(tile, m_blocks, n_blocks, C, crank).split;
         const int g0 = static_cast<int>(static_cast<long>(total_kb) * split / p.split_k);
         const int g1 = static_cast<int>(static_cast<long>(total_kb) * (split + 1) / p.split_k);
         const int as = it & 1;
@@ -409,7 +492,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
         umma_commit(&tmem_full[as]);               // accumulator complete -> epilogue
       }
     }
-  } else if (GATHER != GATHER_NONE && warp >= kGatherWarp0) {
+  } else if (has_gather_warps(GATHER) && warp >= kGatherWarp0) {
     // ===================== gather producers: implicit im2col -> swizzled smem via cp.async =====================
     const int gt = threadIdx.x - kGatherWarp0 * 32;      // 0..kGatherThreads-1
     const int j = gt & 7;                                 // this thread's 16-byte chunk column
@@ -419,7 +502,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-      const TileCoord tc = tile_coord<GATHER>(tile, m_blocks, n_blocks, C, crank);
+      const TileCoord tc = tile_coord<GATHER, EPI == EPI_SGD>(tile, m_blocks, n_blocks, C, crank);
       const int m_blk = tc.m_blk, n_blk = tc.n_blk, split = tc.split;
       const int g0 = static_cast<int>(static_cast<long>(total_kb) * split / p.split_k);
       const int g1 = static_cast<int>(static_cast<long>(total_kb) * (split + 1) / p.split_k);
@@ -490,7 +573,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
     constexpr bool kSgdPrefetch = false;
     auto prefetch_sgd_tile = [&](int t) {
       if (EPI != EPI_SGD || t >= num_tiles || (p.N & 3) != 0 || (p.ldc & 3) != 0) return;
-      const TileCoord pc = tile_coord<GATHER>(t, m_blocks, n_blocks, C, crank);
+      const TileCoord pc = tile_coord<GATHER, EPI == EPI_SGD>(t, m_blocks, n_blocks, C, crank);
       const int te = (warp - kEpiWarp0) * 32 + lane;      // 0..255: row = te >> 1, W or H = te & 1
       const int row = pc.m_blk * BLOCK_M + (te >> 1);
       const int col = pc.n_blk * BN;
@@ -503,19 +586,40 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
     };
     if (kSgdPrefetch) prefetch_sgd_tile(tile0);
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
-      const TileCoord tc = tile_coord<GATHER>(tile, m_blocks, n_blocks, C, crank);
+      const TileCoord tc = tile_coord<GATHER, EPI == EPI_SGD>(tile, m_blocks, n_blocks, C, crank);
       const int m_blk = tc.m_blk, n_blk = tc.n_blk;
       const int as = it & 1;
       if (kSgdPrefetch) prefetch_sgd_tile(tile + tile_step);
       mbar_wait(&tmem_full[as], (it >> 1) & 1);
       tc_fence_after();
       const int row0 = m_blk * BLOCK_M + q * 32;
+      if constexpr (EPI == EPI_SGD) {
+        static_assert(32 * (BN + 1) * 4 <= S::kEpiStageBytes, "SGD slab must fit the epilogue staging buffer");
+        const float lr_eff = p.lr_dev != nullptr ? p.lr * __ldg(p.lr_dev) : p.lr;
 #pragma unroll 1
-      for (int c = half; c < BN / 32; c += kEpiWarps / 4) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, r);
-        tmem_ld_wait();
-        epilogue_tile32<EPI>(p, r, epi_stage + e * (32 * 33), lane, row0, n_blk * BN + c * 32);
+        for (int qq = 0; qq < 4; ++qq) {
+          if (q == qq) {                                  // the two warps that own this TMEM lane quadrant
+#pragma unroll 1
+            for (int c = half; c < BN / 32; c += kEpiWarps / 4) {
+              uint32_t r[32];
+              tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) epi_stage[lane * (BN + 1) + c * 32 + j] = __uint_as_float(r[j]) * p.alpha;
+            }
+          }
+          epi_bar_sync();
+          sgd_rows_from_slab<BN>(p, epi_stage, e, lane, m_blk * BLOCK_M + qq * 32, n_blk * BN, lr_eff);
+          epi_bar_sync();                                 // slab free for the next quadrant
+        }
+      } else {
+#pragma unroll 1
+        for (int c = half; c < BN / 32; c += kEpiWarps / 4) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, r);
+          tmem_ld_wait();
+          epilogue_tile32<EPI>(p, r, epi_stage + e * (32 * 33), lane, row0, n_blk * BN + c * 32);
+        }
       }
       tc_fence_before();
       __syncwarp();

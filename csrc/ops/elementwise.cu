@@ -12,55 +12,65 @@ namespace psd {
 // out[n, oh+opad, ow+opad, 0..Cp) = (x[n, c, h_off+oh, w_off+(flip ? OW-1-ow : ow)] - mean) * scale, channels >= C zero.
 // Each thread produces PX consecutive output pixels of one row: PX*C independent loads in flight, and the PX
 // packed pixels leave as one or two 16-byte stores.
+// Threads walk the PHYSICAL output (border and alignment columns included) so the kernel itself writes the zeros —
+// no separate memset pass over the 100 MB activation — with 32-bit indices and magic-number divides (the first
+// version spent ~300 of its ~485 instructions per thread on three 64-bit divisions; ncu: 73 % issue-active).
 template <typename TIn, int CP, int PX>
 __global__ void __launch_bounds__(256)
 transform_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const int* __restrict__ h_off,
                  const int* __restrict__ w_off, const uint8_t* __restrict__ flip, const float* __restrict__ mean,
-                 int mean_mode, float scale, int N, int C, int H, int W, int OH, int OW, int opad, int wextra) {
-  const int OWG = (OW + PX - 1) / PX;
-  const long total = static_cast<long>(N) * OH * OWG;
-  const int OHp = OH + 2 * opad, OWp = OW + 2 * opad + wextra;
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int owg = static_cast<int>(i % OWG);
-    const int oh = static_cast<int>((i / OWG) % OH);
-    const int n = static_cast<int>(i / (static_cast<long>(OWG) * OH));
+                 int mean_mode, float scale, int C, int H, int W, int OH, int OW, int opad, int OWp, FastDiv d_owg,
+                 FastDiv d_ohp, uint32_t total) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t t = fdiv(i, d_owg);
+    const int owg = static_cast<int>(i - t * d_owg.d);
+    const uint32_t n = fdiv(t, d_ohp);
+    const int ohp = static_cast<int>(t - n * d_ohp.d);
+    const int oh = ohp - opad;
+    const bool row_ok = static_cast<unsigned>(oh) < static_cast<unsigned>(OH);
     const int h = h_off[n] + oh;
     const int wo = w_off[n];
     const bool fl = flip[n] != 0;
-    float v[PX][CP];
+    const TIn* xn = x + static_cast<long>(n) * C * H * W + static_cast<long>(h) * W;
+    uint32_t packed[PX][CP / 2];
 #pragma unroll
     for (int q = 0; q < PX; ++q) {
-      const int ow = owg * PX + q;
+      const int ow = owg * PX + q - opad;
+      const bool ok = row_ok && static_cast<unsigned>(ow) < static_cast<unsigned>(OW);
       const int w = wo + (fl ? (OW - 1 - ow) : ow);
+      float v[CP];
 #pragma unroll
       for (int c = 0; c < CP; ++c) {
         float f = 0.f;
-        if (c < C && ow < OW) {
-          const long src = ((static_cast<long>(n) * C + c) * H + h) * W + w;
-          f = static_cast<float>(x[src]);
+        if (ok && c < C) {
+          f = static_cast<float>(xn[c * (H * W) + w]);
           if (mean_mode == 1) f -= mean[c];
-          else if (mean_mode == 2) f -= mean[(static_cast<long>(c) * H + h) * W + w];
+          else if (mean_mode == 2) f -= mean[(c * H + h) * W + w];
           f *= scale;
         }
-        v[q][c] = f;
+        v[c] = f;
+      }
+#pragma unroll
+      for (int c = 0; c < CP / 2; ++c) {
+        const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * c], v[2 * c + 1]);
+        packed[q][c] = *reinterpret_cast<const uint32_t*>(&b2);
       }
     }
-    __nv_bfloat16* o = out + ((static_cast<long>(n) * OHp + oh + opad) * OWp + owg * PX + opad) * CP;
+    __nv_bfloat16* o = out + (static_cast<long>(t) * OWp + owg * PX) * CP;      // t = n * OHp + ohp
+    const int left = OWp - owg * PX;
+    if (CP == 4 && left >= PX && PX == 4) {
+      // 4 pixels x 4 channels = 32 bytes, 16-byte aligned (OWp is even and the group starts at a multiple of 4)
+      *reinterpret_cast<uint4*>(o) = make_uint4(packed[0][0], packed[0][1], packed[1][0], packed[1][1]);
+      *reinterpret_cast<uint4*>(o + 8) = make_uint4(packed[2][0], packed[2][1], packed[3][0], packed[3][1]);
+    } else {
 #pragma unroll
-    for (int q = 0; q < PX; ++q) {
-      if (owg * PX + q >= OW) break;
-      if constexpr (CP == 4) {
-        __nv_bfloat162 a = __floats2bfloat162_rn(v[q][0], v[q][1]), b = __floats2bfloat162_rn(v[q][2], v[q][3]);
-        uint2 u;
-        u.x = *reinterpret_cast<uint32_t*>(&a);
-        u.y = *reinterpret_cast<uint32_t*>(&b);
-        *reinterpret_cast<uint2*>(o + q * CP) = u;
-      } else {
-        float f8[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) f8[c] = v[q][c];
-        st8(o + q * CP, pack8(f8));
+      for (int q = 0; q < PX; ++q) {
+        if (q >= left) break;
+        if constexpr (CP == 4) {
+          *reinterpret_cast<uint2*>(o + q * CP) = make_uint2(packed[q][0], packed[q][1]);
+        } else {
+          *reinterpret_cast<uint4*>(o + q * CP) = make_uint4(packed[q][0], packed[q][1], packed[q][2], packed[q][3]);
+        }
       }
     }
   }
@@ -75,8 +85,8 @@ at::Tensor transform_nhwc(const at::Tensor& x, const at::Tensor& h_off, const at
   c10::cuda::CUDAGuard guard(x.device());
   const int N = x.size(0), C = x.size(1), H = x.size(2), W = x.size(3);
   TORCH_CHECK(C <= cp && (cp == 4 || cp == 8), "transform: channel padding must be 4 or 8");
-  at::Tensor out = empty_nhwc(N, cp, OH + 2 * opad, OW + 2 * opad + wextra, x.options().dtype(at::kBFloat16));
-  if (opad > 0 || wextra > 0) out.zero_();      // (at::zeros ignores the channels-last request)
+  const int OHp = OH + 2 * opad, OWp = OW + 2 * opad + wextra;
+  at::Tensor out = empty_nhwc(N, cp, OHp, OWp, x.options().dtype(at::kBFloat16));
   int mean_mode = 0;
   const float* mp = nullptr;
   if (mean.has_value()) {
@@ -87,12 +97,16 @@ at::Tensor transform_nhwc(const at::Tensor& x, const at::Tensor& h_off, const at
   }
   auto stream = at::cuda::getCurrentCUDAStream();
   constexpr int kPx = 4;
-  const long total = static_cast<long>(N) * OH * ((OW + kPx - 1) / kPx);
+  const int owg = (OWp + kPx - 1) / kPx;
+  const long total = static_cast<long>(N) * OHp * owg;
+  TORCH_CHECK(total < (1L << 31) && static_cast<long>(C) * H * W < (1L << 31), "transform: batch too large for 32-bit indexing");
+  TORCH_CHECK(cp == 8 || OWp % 2 == 0, "transform: padded width must be even for 4-channel outputs");
+  const FastDiv d_owg = make_fastdiv(owg), d_ohp = make_fastdiv(OHp);
   auto op = reinterpret_cast<__nv_bfloat16*>(out.data_ptr());
 #define PSD_XF(T, CPV)                                                                                          \
   transform_kernel<T, CPV, kPx><<<grid_for(total, 256, 148 * 32), 256, 0, stream>>>(                                         \
       x.data_ptr<T>(), op, h_off.data_ptr<int>(), w_off.data_ptr<int>(), flip.data_ptr<uint8_t>(), mp, mean_mode, \
-      static_cast<float>(scale), N, C, H, W, OH, OW, opad, wextra)
+      static_cast<float>(scale), C, H, W, OH, OW, opad, OWp, d_owg, d_ohp, static_cast<uint32_t>(total))
   if (x.scalar_type() == at::kByte) {
     if (cp == 4) PSD_XF(uint8_t, 4); else PSD_XF(uint8_t, 8);
   } else {

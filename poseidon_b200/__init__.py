@@ -11,3 +11,4 @@ from .net.net import Net  # noqa: F401
 from .parallel.context import RankContext, init_rank_context  # noqa: F401
 from .solver.solver import (AdaGradSolver, NesterovSolver, SGDSolver, Solver,  # noqa: F401
                             get_solver)
+from .engine import CaffeEngine  # noqa: F401,E402

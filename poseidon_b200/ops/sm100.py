@@ -316,7 +316,9 @@ class _IPFn(torch.autograd.Function):
         x2, y = ctx.saved_tensors
         dy = dy if dy.dtype == torch.bfloat16 else dy.to(torch.bfloat16)
         n_pad = (st.N + 7) // 8 * 8
-        if dy.stride(1) != 1 or dy.stride(0) % 8 or (y is not None):
+        if y is not None and n_pad == st.N and dy.is_contiguous() and y.is_contiguous():
+            dy = k.relu_bwd(y, dy, 0.0)                     # fused ReLU backward: one pass, dense [M, N] result
+        elif dy.stride(1) != 1 or dy.stride(0) % 8 or (y is not None):
             buf = torch.empty(dy.shape[0], n_pad, device=dy.device, dtype=torch.bfloat16)
             if n_pad != st.N:
                 buf[:, st.N:].zero_()
@@ -337,7 +339,11 @@ class _IPFn(torch.autograd.Function):
             else:
                 dx = dx2.view(xs)
         if layer.bias_term and ctx.needs_input_grad[2]:
-            db = dy.float().sum(0)
+            if st.N % 8 == 0 and dy.stride(1) == 1 and dy.stride(0) % 8 == 0:
+                db = torch.empty(st.N, device=dy.device, dtype=torch.float32)
+                k.colsum(dy, dy.shape[0], st.N, dy.stride(0), db, 1.0, False)
+            else:
+                db = dy.float().sum(0)
         sfb = getattr(layer, "sfb", None)
         if ctx.needs_input_grad[1]:
             if sfb is not None:

@@ -264,19 +264,23 @@ class FusedBackend(Backend):
         return (lm, hy.momentum, decay, hy.solver_type, hy.l1, hy.delta, gscale)
 
     def launch(self, bucket: Bucket):
+        st = getattr(bucket.layer, "_sm100", None)
         if self.world == 1:
-            self._launch_local(bucket)
+            fresh = self._launch_local(bucket)
         else:
             self._launch_peer(bucket)
-        st = getattr(bucket.layer, "_sm100", None)
+            fresh = False                           # arena shadows are refreshed by the kernels (arena_shadow flag)
         if st is not None:
-            st.mark_updated()
+            # the update kernels already rewrote the bf16 operand next to the fp32 master: do not re-derive it
+            st.mark_updated(keep_wb=fresh)
 
-    def _launch_local(self, bucket):
+    def _launch_local(self, bucket) -> bool:
+        """Steps the bucket's parameters; returns True when the layer's bf16 weight operand is still in sync."""
+        st = getattr(bucket.layer, "_sm100", None)
+        fresh = st is not None and not st.dirty_wb
         for p, h, lm, dm in zip(bucket.params, bucket.history, bucket.lr_mult, bucket.decay_mult):
             if p.grad is None:
                 continue                            # weight already stepped inside the fused SFB/wgrad kernel
-            st = getattr(bucket.layer, "_sm100", None)
             wb = None
             if st is not None and p is bucket.layer.weight and st.wb is not None and not getattr(st, "row_mode", False):
                 wb = st.wb
@@ -286,8 +290,9 @@ class FusedBackend(Backend):
             lr, mom, decay, rule, l1, delta, gscale = self._hyper_args(lm, dm)
             self.k.fused_update(p.data, g, h, wb, lr, mom, decay, rule, l1, delta, gscale, self.lr_t)
             self.launches += 1
-            if wb is not None:
-                st.dirty_wb = False
+            if p is getattr(bucket.layer, "weight", None):
+                fresh = wb is not None
+        return fresh
 
     def _launch_peer(self, bucket):
         ar = self.arena

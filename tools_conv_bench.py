@@ -13,6 +13,9 @@ CASES = {
     "conv4": (256, 384, 13, 13, 384, 3, 1, 1, 2),
     "conv5": (256, 384, 13, 13, 256, 3, 1, 1, 2),
 }
+import os
+if os.environ.get('PSD_CONV_IM2COL') == '0':
+    sm100.K().set_conv_im2col(0)
 which = sys.argv[1].split(",") if len(sys.argv) > 1 else list(CASES)
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 for name in which:
