@@ -154,11 +154,19 @@ static bool try_im2col_map(CUtensorMap* map, const ConvGeom& g, int pixels) {
 // Widest N tile that does not over-pad the channel count and still yields a full wave of CTAs; small problems
 // (GoogLeNet's 14x14 / 7x7 stages at batch 32) take the narrowest tile so that more SMs get work.
 static int pick_conv_bn(int64_t n_cols, int64_t m_blocks, int sms) {
-  const int widest = n_cols > 128 ? 256 : (n_cols > 64 ? 128 : 64);
-  for (int bn = widest; bn >= 64; bn >>= 1) {
-    if (m_blocks * ((n_cols + bn - 1) / bn) >= sms) return bn;
+  // candidates widest first; 192 only where it removes >= 15 % padding (a narrower tile pays the A operand again)
+  int best = 64;
+  long best_pad = -1;
+  for (int bn : {256, 192, 128, 64}) {
+    const long padded = (n_cols + bn - 1) / bn * bn;
+    if (best_pad < 0 || padded * 100 < best_pad * (bn == 192 ? 85 : 100)) {
+      if (best_pad < 0 || padded < best_pad) { best = bn; best_pad = padded; }
+    }
   }
-  return 64;
+  // small problems (GoogLeNet's 14x14 / 7x7 stages at batch 32): narrow the tile until a full wave of CTAs has work
+  int bn = best;
+  while (bn > 64 && m_blocks * ((n_cols + bn - 1) / bn) < sms) bn = (bn == 256 ? 128 : (bn == 192 ? 128 : 64));
+  return bn;
 }
 
 // y[N, Cout, OH, OW] (NHWC bf16) = act(conv(x, w) + bias).  wb: [Cout, Kw] bf16 (Kw = R*S*Cg or R*Lp).
@@ -205,6 +213,7 @@ at::Tensor conv_fprop(const at::Tensor& x, const at::Tensor& wb, const c10::opti
       switch (bn) {
         case 64: launch_conv<64, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
         case 128: launch_conv<128, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
+        case 192: launch_conv<192, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
         default: launch_conv<256, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
       }
       continue;
@@ -212,6 +221,7 @@ at::Tensor conv_fprop(const at::Tensor& x, const at::Tensor& wb, const c10::opti
     switch (bn) {
       case 64: launch_conv<64, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
       case 128: launch_conv<128, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
+      case 192: launch_conv<192, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
       default: launch_conv<256, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
     }
   }
@@ -268,6 +278,7 @@ at::Tensor conv_dgrad(const at::Tensor& dy, const at::Tensor& wt, at::IntArrayRe
       switch (bn) {
         case 64: launch_conv<64, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
         case 128: launch_conv<128, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
+        case 192: launch_conv<192, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
         default: launch_conv<256, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
       }
       continue;
@@ -275,6 +286,7 @@ at::Tensor conv_dgrad(const at::Tensor& dy, const at::Tensor& wt, at::IntArrayRe
     switch (bn) {
       case 64: launch_conv<64, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
       case 128: launch_conv<128, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
+      case 192: launch_conv<192, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
       default: launch_conv<256, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
     }
   }
@@ -298,7 +310,8 @@ void conv_wgrad(const at::Tensor& x, const at::Tensor& dy, at::Tensor dw, at::In
   for (int gidx = 0; gidx < groups; ++gidx) {
     ConvGeom cg = make_geom(x, xv, gidx * Cg, Cg, dv.H, dv.W, d, false);
     TORCH_CHECK(dw.size(0) == Cout && dw.size(1) == cg.K, "conv_wgrad: dw shape mismatch");
-    const int bn = cg.K > 128 ? 256 : (cg.K > 64 ? 128 : 64);
+    int bn = cg.K > 128 ? 256 : (cg.K > 64 ? 128 : 64);
+    if (bn == 256 && ((cg.K + 191) / 192 * 192) * 100 < ((cg.K + 255) / 256 * 256) * 85) bn = 192;   // e.g. K = 576
     TmapSet tm;
     // A = dYᵀ: MN-major, inner = Cout_g channels of this group, outer = M pixels, pitch = dy pixel pitch
     const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(dy.data_ptr()) + gidx * Cout_g;
@@ -325,6 +338,7 @@ void conv_wgrad(const at::Tensor& x, const at::Tensor& dy, at::Tensor dw, at::In
       switch (bn) {
         case 64: launch_conv<64, true, true, EPI_F32, IM2COL_B>(tm, p, cg, grid, stream); break;
         case 128: launch_conv<128, true, true, EPI_F32, IM2COL_B>(tm, p, cg, grid, stream); break;
+        case 192: launch_conv<192, true, true, EPI_F32, IM2COL_B>(tm, p, cg, grid, stream); break;
         default: launch_conv<256, true, true, EPI_F32, IM2COL_B>(tm, p, cg, grid, stream); break;
       }
       continue;
@@ -332,6 +346,7 @@ void conv_wgrad(const at::Tensor& x, const at::Tensor& dy, at::Tensor dw, at::In
     switch (bn) {
       case 64: launch_conv<64, true, true, EPI_F32, GATHER_B>(tm, p, cg, grid, stream); break;
       case 128: launch_conv<128, true, true, EPI_F32, GATHER_B>(tm, p, cg, grid, stream); break;
+      case 192: launch_conv<192, true, true, EPI_F32, GATHER_B>(tm, p, cg, grid, stream); break;
       default: launch_conv<256, true, true, EPI_F32, GATHER_B>(tm, p, cg, grid, stream); break;
     }
   }

@@ -79,7 +79,8 @@ struct GemmSmem {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;     // 16 KB
   static constexpr int kBBytes = BN * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kStages = (BN >= 192) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);   // power of two >= 2 accumulators
   static constexpr int kBarBytes = 256;
   static constexpr int kEpiStageBytes = kEpiWarps * 32 * 33 * 4;    // per epilogue warp: 32x32 fp32 transpose tile (+1 pad)
   static constexpr int kTotal = kStages * kStageBytes + kBarBytes + kEpiStageBytes + 1024;  // +1024 alignment slack
@@ -334,7 +335,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_alloc(tmem_slot, S::kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -345,7 +346,11 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop with uniform control flow and ONE elected lane issues the TMA / barrier
+    // instructions: the operands then live in uniform registers (UTMALDG straight from UR), whereas a loop under
+    // `if (lane == 0)` is divergent code in which every issue needs an R2UR waterfall.  ncu: the single-lane version
+    // cost ~600 cycles per k-block, the floor of every BN <= 128 kernel.
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -388,11 +393,15 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
         bool new_src = true;
         for (int g = g0; g < g1; ++g) {
           if (new_src) {
-            if (p.flags != nullptr) wait_flag_ge(p.flags + src, p.epoch);
+            if (p.flags != nullptr) {
+              if (lane == 0) wait_flag_ge(p.flags + src, p.epoch);
+              __syncwarp();
+            }
             new_src = false;
           }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kStageBytes;
+          if (elect_one()) {
           if constexpr (GATHER == GATHER_NONE) {
             mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
             TmaProducer<BN, A_MN, B_MN>::load_stage(tm, src, kb, m_blk, n_blk, sa, sa + S::kABytes, &full_bar[stage]);
@@ -447,6 +456,8 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
                                   m_blk * BLOCK_M + 64 * c, kb * BLOCK_K + crank * krows, cmask);
             }
           }
+          }  // elect_one
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
           if (++kb == p.kb_per_src) {
             kb = 0;
@@ -457,8 +468,8 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    {
       constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
@@ -476,20 +487,24 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * S::kStageBytes);
           const uint32_t b_addr = a_addr + S::kABytes;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = A_MN ? make_smem_desc(a_addr + k * (UMMA_K * 128), 8192, 1024)
-                                     : make_smem_desc(a_addr + k * (UMMA_K * 2), 16, 1024);
-            const uint64_t db = B_MN ? make_smem_desc(b_addr + k * (UMMA_K * 128), 8192, 1024)
-                                     : make_smem_desc(b_addr + k * (UMMA_K * 2), 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (g > g0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t da = A_MN ? make_smem_desc(a_addr + k * (UMMA_K * 128), 8192, 1024)
+                                       : make_smem_desc(a_addr + k * (UMMA_K * 2), 16, 1024);
+              const uint64_t db = B_MN ? make_smem_desc(b_addr + k * (UMMA_K * 128), 8192, 1024)
+                                       : make_smem_desc(b_addr + k * (UMMA_K * 2), 16, 1024);
+              umma_bf16(d_tmem, da, db, idesc, (g > g0 || k > 0) ? 1u : 0u);
+            }
+            // frees the smem slot when these MMAs retire — in every CTA that shares the multicast operand
+            if (C == 1) umma_commit(&empty_bar[stage]);
+            else umma_commit_mcast(&empty_bar[stage], cmask);
+            if (g == g1 - 1) umma_commit(&tmem_full[as]);      // accumulator complete -> epilogue
           }
-          // frees the smem slot when these MMAs retire — in every CTA that shares the multicast operand
-          if (C == 1) umma_commit(&empty_bar[stage]);
-          else umma_commit_mcast(&empty_bar[stage], cmask);
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[as]);               // accumulator complete -> epilogue
+        if (g0 >= g1 && elect_one()) umma_commit(&tmem_full[as]);      // (never: every split owns >= 1 k-block)
       }
     }
   } else if (has_gather_warps(GATHER) && warp >= kGatherWarp0) {
@@ -632,7 +647,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
   if (C > 1) cluster_sync_all();        // no CTA leaves while peers may still arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc(tmem_base, S::kTmemCols);
   }
 }
 

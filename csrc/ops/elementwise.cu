@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256)
 transform_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const int* __restrict__ h_off,
                  const int* __restrict__ w_off, const uint8_t* __restrict__ flip, const float* __restrict__ mean,
                  int mean_mode, float scale, int C, int H, int W, int OH, int OW, int opad, int OWp, FastDiv d_owg,
-                 FastDiv d_ohp, uint32_t total) {
+                 FastDiv d_ohp, uint32_t total, int s2d) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const uint32_t t = fdiv(i, d_owg);
     const int owg = static_cast<int>(i - t * d_owg.d);
@@ -57,6 +57,12 @@ transform_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, con
       }
     }
     __nv_bfloat16* o = out + (static_cast<long>(t) * OWp + owg * PX) * CP;      // t = n * OHp + ohp
+    if (s2d) {
+      // space-to-depth by 4 (stride-4 first layers): pixel (y, x), channel c -> block (y/4, x/4), channel
+      // (y%4)*16 + (x%4)*4 + c.  This thread's 4 pixels are one block row: 16 contiguous elements.
+      const int OHq = static_cast<int>(d_ohp.d) >> 2, OWq = OWp >> 2;
+      o = out + ((static_cast<long>(n) * OHq + (ohp >> 2)) * OWq + owg) * 64 + (ohp & 3) * 16;
+    }
     const int left = OWp - owg * PX;
     if (CP == 4 && left >= PX && PX == 4) {
       // 4 pixels x 4 channels = 32 bytes, 16-byte aligned (OWp is even and the group starts at a multiple of 4)
@@ -79,14 +85,16 @@ transform_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, con
 // x: [N,C,H,W] uint8|float32 contiguous -> [N, Cp, OH+2opad, OW+2opad] bf16 channels-last (border zero).
 at::Tensor transform_nhwc(const at::Tensor& x, const at::Tensor& h_off, const at::Tensor& w_off, const at::Tensor& flip,
                           const c10::optional<at::Tensor>& mean, double scale, int64_t OH, int64_t OW, int64_t cp,
-                          int64_t opad, int64_t wextra) {
+                          int64_t opad, int64_t wextra, int64_t hextra, bool s2d) {
   TORCH_CHECK(x.is_cuda() && x.dim() == 4 && x.is_contiguous());
   TORCH_CHECK(h_off.scalar_type() == at::kInt && w_off.scalar_type() == at::kInt && flip.scalar_type() == at::kByte);
   c10::cuda::CUDAGuard guard(x.device());
   const int N = x.size(0), C = x.size(1), H = x.size(2), W = x.size(3);
   TORCH_CHECK(C <= cp && (cp == 4 || cp == 8), "transform: channel padding must be 4 or 8");
-  const int OHp = OH + 2 * opad, OWp = OW + 2 * opad + wextra;
-  at::Tensor out = empty_nhwc(N, cp, OHp, OWp, x.options().dtype(at::kBFloat16));
+  const int OHp = OH + 2 * opad + hextra, OWp = OW + 2 * opad + wextra;
+  TORCH_CHECK(!s2d || (cp == 4 && OHp % 4 == 0 && OWp % 4 == 0), "transform: space-to-depth needs 4 channels and /4 extents");
+  at::Tensor out = s2d ? empty_nhwc(N, 64, OHp / 4, OWp / 4, x.options().dtype(at::kBFloat16))
+                       : empty_nhwc(N, cp, OHp, OWp, x.options().dtype(at::kBFloat16));
   int mean_mode = 0;
   const float* mp = nullptr;
   if (mean.has_value()) {
@@ -106,7 +114,7 @@ at::Tensor transform_nhwc(const at::Tensor& x, const at::Tensor& h_off, const at
 #define PSD_XF(T, CPV)                                                                                          \
   transform_kernel<T, CPV, kPx><<<grid_for(total, 256, 148 * 32), 256, 0, stream>>>(                                         \
       x.data_ptr<T>(), op, h_off.data_ptr<int>(), w_off.data_ptr<int>(), flip.data_ptr<uint8_t>(), mp, mean_mode, \
-      static_cast<float>(scale), C, H, W, OH, OW, opad, OWp, d_owg, d_ohp, static_cast<uint32_t>(total))
+      static_cast<float>(scale), C, H, W, OH, OW, opad, OWp, d_owg, d_ohp, static_cast<uint32_t>(total), s2d ? 1 : 0)
   if (x.scalar_type() == at::kByte) {
     if (cp == 4) PSD_XF(uint8_t, 4); else PSD_XF(uint8_t, 8);
   } else {
@@ -261,7 +269,7 @@ void colsum(const at::Tensor& dy, int64_t rows, int64_t C, int64_t ld, at::Tenso
 
 TORCH_LIBRARY_FRAGMENT(poseidon, m) {
   m.def("transform_nhwc(Tensor x, Tensor h_off, Tensor w_off, Tensor flip, Tensor? mean, float scale, int OH, int OW, "
-        "int cp, int opad, int wextra) -> Tensor", &psd::transform_nhwc);
+        "int cp, int opad, int wextra, int hextra, bool s2d) -> Tensor", &psd::transform_nhwc);
   m.def("relu_fwd(Tensor x, float slope) -> Tensor", &psd::relu_fwd);
   m.def("relu_bwd(Tensor y, Tensor dy, float slope) -> Tensor", &psd::relu_bwd);
   m.def("dropout_apply(Tensor x, float ratio, int seed, Tensor? seed_dev) -> Tensor", &psd::dropout_apply);

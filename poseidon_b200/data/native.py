@@ -73,7 +73,7 @@ class NativeDBSource:
     """
 
     def __init__(self, path: str, batch: int, offset: int = 0, stride: int = 1, rand_skip: int = 0, seed=None,
-                 threads: int = 0, depth: int = 4, pin: bool | None = None):
+                 threads: int = 0, depth: int = 6, pin: bool | None = None):
         m = module()
         pdb = path if os.path.isfile(path) else os.path.join(path, "data.pdb")
         threads = threads or max(2, min(16, (os.cpu_count() or 4) // 2))
@@ -87,6 +87,7 @@ class NativeDBSource:
         self.shape = tuple(self.loader.shape())
         self.is_bytes = bool(self.loader.is_bytes())
         pin = torch.cuda.is_available() if pin is None else pin
+        self.pinned = bool(pin)
         dt = torch.uint8 if self.is_bytes else torch.float32
         self.slots = []
         for _ in range(max(2, depth)):
@@ -107,7 +108,12 @@ class NativeDBSource:
             self.loader.release(self._held.pop(0))
         s = self.loader.acquire()
         self._held.append(s)
-        return self.slots[s]
+        x, y = self.slots[s]
+        if not self.pinned:
+            # CPU consumers keep references to what they are handed (prefetch queue, label blobs): give them
+            # private copies; only the pinned slots of the CUDA path are handed out in place (copied H2D at once)
+            return x.clone(), y.clone()
+        return x, y
 
     def close(self):
         self.loader.stop()

@@ -15,6 +15,8 @@ LRN, pooling, softmax-loss, dropout, transform): unsupported shapes raise, excep
 """
 from __future__ import annotations
 
+import os
+
 import math
 from typing import Optional
 
@@ -79,6 +81,7 @@ class ConvState:
         self.Cout = layer.num_output
         cg = cin_logical // self.groups
         self.row_mode = cg % 8 != 0
+        self.s2d = False
         if self.row_mode:
             if self.groups != 1 or cin_logical > 4:
                 raise ValueError(f"sm100 conv '{layer.layer_name}': input channels {cin_logical} (group "
@@ -89,6 +92,7 @@ class ConvState:
             self.Kw = self.R * self.Lp
             if (layer.stride[1] * self.Cp) % 8:
                 raise ValueError("sm100 first-layer conv needs an even horizontal stride")
+            self._try_s2d(layer)
         else:
             self.Cp = cin_logical
             self.Kw = self.R * self.S * cg
@@ -106,6 +110,28 @@ class ConvState:
         if not self.row_mode and not w.data.is_contiguous(memory_format=CL):
             w.data = w.data.contiguous(memory_format=CL)
 
+    def _try_s2d(self, layer):
+        """Stride-4 first layers (AlexNet / CaffeNet conv1): space-to-depth by 4 turns the 11x11/s4 convolution over
+        4 (padded) channels into a 3x3/s1 convolution over 4*4*4 = 64 channels — a plain TAP-mode implicit GEMM whose
+        operand the TMA engine fetches in im2col mode, instead of the cp.async ROW gather (conv1 fprop 300 us -> see
+        profiles/).  The data layer's transform kernel writes the s2d layout directly."""
+        if os.environ.get("POSEIDON_S2D", "1") == "0" or tuple(layer.stride) != (4, 4) or layer.pad[0] != layer.pad[1]:
+            return
+        in_hw = getattr(layer, "in_hw", None)
+        if in_hw is None:
+            return
+        h, w = in_hw
+        p = layer.pad[0]
+        hq, wq = -(-(h + 2 * p) // 4), -(-(w + 2 * p) // 4)
+        rq, sq = -(-self.R // 4), -(-self.S // 4)
+        oh, ow = (h + 2 * p - self.R) // 4 + 1, (w + 2 * p - self.S) // 4 + 1
+        if hq - rq + 1 != oh or wq - sq + 1 != ow:
+            return
+        self.s2d = True
+        self.s2d_hw = (hq, wq)
+        self.Rq, self.Sq = rq, sq
+        self.Kw = rq * sq * 64
+
     # physical [Cout, Kw] fp32 view of the master weight (TAP mode only)
     def w2d(self) -> torch.Tensor:
         w = self.layer.weight.data
@@ -122,7 +148,13 @@ class ConvState:
             return self.wb
         w = self.layer.weight
         with torch.no_grad():
-            if self.row_mode:
+            if self.s2d:
+                # W'[co][R'][S'][dy][dx][c] = W[co][c][4R'+dy][4S'+dx]  (zero outside the 11x11 support / c >= C)
+                t = torch.nn.functional.pad(w.data, (0, 4 * self.Sq - self.S, 0, 4 * self.Rq - self.R,
+                                                     0, self.Cp - self.cin_logical))       # Cout,4,4R',4S'
+                t = t.view(self.Cout, self.Cp, self.Rq, 4, self.Sq, 4).permute(0, 2, 4, 3, 5, 1)
+                src = t.reshape(self.Cout, self.Kw)
+            elif self.row_mode:
                 t = w.data.permute(0, 2, 3, 1)                                    # Cout,R,S,C
                 t = torch.nn.functional.pad(t, (0, self.Cp - self.cin_logical))  # -> Cp
                 t = t.reshape(self.Cout, self.R, self.L)
@@ -145,6 +177,10 @@ class ConvState:
 
     def grad_from_dw(self, dw: torch.Tensor) -> torch.Tensor:
         """[Cout, Kw] fp32 -> gradient tensor with the master weight's logical shape."""
+        if self.s2d:
+            g = dw.view(self.Cout, self.Rq, self.Sq, 4, 4, self.Cp).permute(0, 5, 1, 3, 2, 4)   # co,c,R',dy,S',dx
+            g = g.reshape(self.Cout, self.Cp, 4 * self.Rq, 4 * self.Sq)
+            return g[:, : self.cin_logical, : self.R, : self.S].contiguous()
         if self.row_mode:
             g = dw.view(self.Cout, self.R, self.Lp)[:, :, : self.L].reshape(self.Cout, self.R, self.S, self.Cp)
             return g[..., : self.cin_logical].permute(0, 3, 1, 2).contiguous()
@@ -164,6 +200,17 @@ def prepare_first_layer_input(x: torch.Tensor, st: ConvState, pad, in_hw) -> tor
     Cp, spatially pre-padded by the conv's own padding, physical width rounded up to even (16-byte rows).
     The data layers emit this layout straight from the transform kernel; anything else is converted here."""
     h, w = in_hw
+    if st.s2d:
+        hq, wq = st.s2d_hw
+        if (x.dtype == torch.bfloat16 and x.dim() == 4 and tuple(x.shape[1:]) == (64, hq, wq)
+                and x.is_contiguous(memory_format=CL)):
+            return x
+        n, c = x.shape[:2]
+        if x.shape[2] != h or x.shape[3] != w:
+            raise ValueError(f"first-layer conv: unexpected input shape {tuple(x.shape)} for logical {h}x{w}")
+        t = torch.nn.functional.pad(x.float(), (pad[1], 4 * wq - w - pad[1], pad[0], 4 * hq - h - pad[0], 0, st.Cp - c))
+        t = t.view(n, st.Cp, hq, 4, wq, 4).permute(0, 2, 4, 3, 5, 1).reshape(n, hq, wq, 64)      # n,Y,X,(dy,dx,c)
+        return t.to(torch.bfloat16).permute(0, 3, 1, 2)                                      # logical NCHW, CL memory
     wp = w + 2 * pad[1]
     extra = wp % 2
     if (x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[1] == st.Cp and x.shape[2] == h + 2 * pad[0]
@@ -193,8 +240,12 @@ class _ConvFn(torch.autograd.Function):
         oh = (h + 2 * pad[0] - st.R) // stride[0] + 1
         ow = (w + 2 * pad[1] - st.S) // stride[1] + 1
         relu = relu_slope is not None
-        y = k.conv_fprop(xin, st.shadow(), bias, [st.R, st.S], list(stride), list(conv_pad), st.groups,
-                         1 if st.row_mode else 0, oh, ow, relu, float(relu_slope or 0.0), None)
+        if st.s2d:
+            y = k.conv_fprop(xin, st.shadow(), bias, [st.Rq, st.Sq], [1, 1], [0, 0], 1, 0, oh, ow, relu,
+                             float(relu_slope or 0.0), None)
+        else:
+            y = k.conv_fprop(xin, st.shadow(), bias, [st.R, st.S], list(stride), list(conv_pad), st.groups,
+                             1 if st.row_mode else 0, oh, ow, relu, float(relu_slope or 0.0), None)
         ctx.layer, ctx.relu_slope, ctx.conv_pad = layer, relu_slope, conv_pad
         ctx.in_shape = tuple(x.shape)
         ctx.save_for_backward(xin, y if relu else None)
@@ -215,8 +266,11 @@ class _ConvFn(torch.autograd.Function):
             sink = getattr(layer, "_grad_sink", None)
             dw2 = sink.weight_buffer(layer, st) if sink is not None else \
                 torch.zeros(st.Cout, st.Kw, device=dy.device, dtype=torch.float32)
-            k.conv_wgrad(xin, dy, dw2, [st.R, st.S], list(stride), list(ctx.conv_pad), st.groups,
-                         1 if st.row_mode else 0, 1.0)
+            if st.s2d:
+                k.conv_wgrad(xin, dy, dw2, [st.Rq, st.Sq], [1, 1], [0, 0], 1, 0, 1.0)
+            else:
+                k.conv_wgrad(xin, dy, dw2, [st.R, st.S], list(stride), list(ctx.conv_pad), st.groups,
+                             1 if st.row_mode else 0, 1.0)
             dw = st.grad_from_dw(dw2)
         if layer.bias_term and ctx.needs_input_grad[2]:
             db = torch.empty(st.Cout, device=dy.device, dtype=torch.float32)
@@ -554,6 +608,15 @@ def transform(transformer, x, out_dtype, first_conv=None):
     if opad[0] != opad[1]:
         return TE.transform(transformer, x, out_dtype).contiguous(memory_format=CL)
     xin = x if x.dtype in (torch.uint8, torch.float32) else x.float()
+    st = first_conv._sm100
+    if st.s2d:
+        hq, wq = st.s2d_hw
+        if cp != 4 or (oh, ow) != tuple(first_conv.in_hw):
+            return TE.transform(transformer, x, out_dtype).contiguous(memory_format=CL)
+        return K().transform_nhwc(xin.contiguous(), h_off.to(dev, torch.int32), w_off.to(dev, torch.int32),
+                                  flip.to(dev, torch.uint8), mean, float(transformer.scale), oh, ow, cp, opad[0],
+                                  4 * wq - ow - 2 * opad[1], 4 * hq - oh - 2 * opad[0], True)
     wextra = (ow + 2 * opad[1]) % 2      # even physical width => every image row starts 16-byte aligned
     return K().transform_nhwc(xin.contiguous(), h_off.to(dev, torch.int32), w_off.to(dev, torch.int32),
-                              flip.to(dev, torch.uint8), mean, float(transformer.scale), oh, ow, cp, opad[0], wextra)
+                              flip.to(dev, torch.uint8), mean, float(transformer.scale), oh, ow, cp, opad[0], wextra,
+                              0, False)

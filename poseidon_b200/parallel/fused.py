@@ -424,9 +424,20 @@ class FusedSFB:
         x2 = x2.contiguous()
         M = dy.shape[0]
         if be.world == 1:
-            k.sfb_outer_sgd([dy.data_ptr()], [x2.data_ptr()], M, self.N, self.K, w, h, st.wb, gscale, lr, mom, decay,
-                            rule, l1, delta, None, 0, 0, 0, 0, be.lr_t)
-            be.launches += 1
+            if getattr(be, "fuse_local_sgd", False):
+                k.sfb_outer_sgd([dy.data_ptr()], [x2.data_ptr()], M, self.N, self.K, w, h, st.wb, gscale, lr, mom, decay,
+                                rule, l1, delta, None, 0, 0, 0, 0, be.lr_t)
+                be.launches += 1
+            else:
+                # Single GPU: the optimizer epilogue has only the 8 epilogue warps' loads in flight (64 KB/SM) and
+                # measured 2.4 TB/s, while the wgrad GEMM -> fp32 buffer followed by the streaming update kernel
+                # runs at 5.3 TB/s: 213 us vs 279 us for fc6 (tools_sgd_bench.py).  Use the faster pair.
+                g = getattr(self, "_gbuf", None)
+                if g is None:
+                    g = self._gbuf = torch.empty(self.N, self.K, device=w.device, dtype=torch.float32)
+                k.gemm_f32(dy, True, x2, True, g, 1.0, False, 1, 0)
+                k.fused_update(w, g, h, st.wb, lr, mom, decay, rule, l1, delta, gscale, be.lr_t)
+                be.launches += 2
             st.mark_updated(keep_wb=True)
             be.sfb_stats.dense_equiv_bytes += self.N * self.K * 4
             return None

@@ -111,10 +111,18 @@ def test_transform_kernel_matches_reference(ext):
     h_off, w_off, flip = draws
     mean = tr.mean_values.float().cuda()
     out = ext.transform_nhwc(x, h_off.int().cuda(), w_off.int().cuda(), flip.to(torch.uint8).cuda(), mean, 0.5, 27, 27, 4,
-                             0, 1)
+                             0, 1, 0, False)
     assert tuple(out.shape) == (8, 4, 27, 28)
     _close(out[:, :3, :, :27], ref, rel=1e-2, what="transform")
     assert out[:, 3].abs().max().item() == 0 and out[:, :, :, 27].abs().max().item() == 0
+    # border + space-to-depth output: pad 2 each side, extents rounded up to /4 -> 32x32 -> [8, 64, 8, 8]
+    s2d = ext.transform_nhwc(x, h_off.int().cuda(), w_off.int().cuda(), flip.to(torch.uint8).cuda(), mean, 0.5, 27, 27, 4,
+                             2, 1, 1, True)
+    assert tuple(s2d.shape) == (8, 64, 8, 8)
+    full = torch.zeros(8, 4, 32, 32, device="cuda")
+    full[:, :3, 2:29, 2:29] = ref
+    want = full.view(8, 4, 8, 4, 8, 4).permute(0, 2, 4, 3, 5, 1).reshape(8, 8, 8, 64).permute(0, 3, 1, 2)
+    _close(s2d, want, rel=1e-2, what="transform s2d")
 
 
 # ---------------------------------------------------------------------------------------------------- conv
@@ -170,7 +178,8 @@ def test_conv_fwd_bwd(ext, case, relu):
     _close(layer.bias.grad, bref.grad, rel=2e-2, what="conv bias grad")
 
 
-@pytest.mark.parametrize("case", [(4, 3, 227, 227, 96, 11, 4, 0), (2, 3, 224, 224, 64, 7, 2, 3), (2, 1, 30, 30, 24, 5, 2, 0)])
+@pytest.mark.parametrize("case", [(4, 3, 227, 227, 96, 11, 4, 0), (2, 3, 224, 224, 64, 7, 2, 3), (2, 1, 30, 30, 24, 5, 2, 0),
+                                  (2, 3, 64, 64, 32, 11, 4, 2), (2, 3, 67, 67, 32, 8, 4, 0)])
 def test_first_layer_conv_row_mode(ext, case):
     from poseidon_b200.ops import sm100
     n, cin, h, w, cout, k, stride, pad = case
