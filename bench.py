@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--sfb-mode", default="auto")
     ap.add_argument("--staleness", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--graph", type=int, default=-1, help="CUDA-graph the step (default: on for 1-GPU sm100)")
+    ap.add_argument("--graph", type=int, default=-1, help="CUDA-graph the step (default: on for the sm100 engine)")
     ap.add_argument("--vendor-dtype", default="bf16", choices=["bf16", "fp32"])
     return ap.parse_args()
 
@@ -173,7 +173,9 @@ def main():
     # ---------------- device-resident-input measurement (kernel + comm + update time)
     solver = build_solver(args, rc, device_resident=True)
     batch = solver.net.blob_shapes[solver.net.top_names[0][0]][0]
-    use_graph = (args.graph == 1) or (args.graph < 0 and args.engine == "sm100" and world == 1)
+    # CUDA-graph the step: sm100 engine on one GPU, or on several with the fused NVLink backend (device-side epochs)
+    use_graph = (args.graph == 1) or (args.graph < 0 and args.engine == "sm100" and
+                                       (world == 1 or (solver.comm_name == "fused" and args.staleness == 0)))
     if use_graph:
         solver.enable_cuda_graph(warmup=2)
     for _ in range(args.warmup):

@@ -165,8 +165,12 @@ __device__ __forceinline__ void peer_barrier(const PeerPtrs& pp, int rank, int w
 template <bool ONE_SHOT>
 __global__ void __launch_bounds__(512)
 allreduce_sgd_kernel(PeerPtrs pp, float* __restrict__ h, long n, int rank, int world, uint32_t epoch, UpdateHyper hp,
-                     unsigned int* __restrict__ done_counter, const float* __restrict__ lr_dev) {
+                     unsigned int* __restrict__ done_counter, const float* __restrict__ lr_dev,
+                     const uint32_t* __restrict__ epoch_dev) {
   if (lr_dev != nullptr) hp.lr *= __ldg(lr_dev);
+  // the step counter lives in device memory (bumped on this stream once per iteration) so that a captured CUDA graph
+  // of the whole training step sees a fresh epoch on every replay; `epoch` is then the offset inside the step
+  if (epoch_dev != nullptr) epoch += *reinterpret_cast<const volatile uint32_t*>(epoch_dev);
   // ---- phase 0: all ranks' gradients for this epoch are in place
   peer_barrier(pp, rank, world, 0, epoch);
 
@@ -233,8 +237,9 @@ void allreduce_sgd(std::vector<int64_t> g_ptrs, std::vector<int64_t> w_ptrs, std
                    std::vector<int64_t> flag_ptrs, int64_t g_mc, int64_t w_mc, at::Tensor h, int64_t n, int64_t rank,
                    int64_t epoch, bool one_shot, at::Tensor done_counter, double lr, double momentum, double decay,
                    int64_t rule, bool l1, double delta, double gscale, int64_t max_ctas,
-                   const c10::optional<at::Tensor>& lr_dev) {
+                   const c10::optional<at::Tensor>& lr_dev, const c10::optional<at::Tensor>& epoch_dev) {
   const int world = static_cast<int>(g_ptrs.size());
+  const uint32_t* edp = epoch_dev.has_value() ? reinterpret_cast<const uint32_t*>(epoch_dev->data_ptr()) : nullptr;
   const float* lrp = lr_dev.has_value() ? lr_dev->data_ptr<float>() : nullptr;
   TORCH_CHECK(world >= 1 && world <= kMaxRanks && w_ptrs.size() == g_ptrs.size() && flag_ptrs.size() == g_ptrs.size());
   TORCH_CHECK(h.is_cuda() && h.scalar_type() == at::kFloat && h.numel() >= n && n % 4 == 0);
@@ -256,10 +261,10 @@ void allreduce_sgd(std::vector<int64_t> g_ptrs, std::vector<int64_t> w_ptrs, std
   auto* dc = reinterpret_cast<unsigned int*>(done_counter.data_ptr());
   if (one_shot)
     allreduce_sgd_kernel<true><<<grid, 512, 0, stream>>>(pp, h.data_ptr<float>(), n, static_cast<int>(rank), world,
-                                                         static_cast<uint32_t>(epoch), hp, dc, lrp);
+                                                         static_cast<uint32_t>(epoch), hp, dc, lrp, edp);
   else
     allreduce_sgd_kernel<false><<<grid, 512, 0, stream>>>(pp, h.data_ptr<float>(), n, static_cast<int>(rank), world,
-                                                          static_cast<uint32_t>(epoch), hp, dc, lrp);
+                                                          static_cast<uint32_t>(epoch), hp, dc, lrp, edp);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
@@ -268,7 +273,14 @@ void allreduce_sgd(std::vector<int64_t> g_ptrs, std::vector<int64_t> w_ptrs, std
 // epoch flag on every peer.  The payload crosses NVLink exactly once per peer; consumers read it locally.
 __global__ void __launch_bounds__(512)
 peer_push_kernel(const uint4* __restrict__ src, PeerPtrs dst, uint4* __restrict__ dst_mc, long n16, int rank, int world,
-                 int slot, uint32_t epoch, int signal, unsigned int* __restrict__ done_counter) {
+                 int slot, uint32_t epoch, int signal, unsigned int* __restrict__ done_counter, int wait_slot,
+                 const uint32_t* __restrict__ epoch_dev) {
+  if (epoch_dev != nullptr) epoch += *reinterpret_cast<const volatile uint32_t*>(epoch_dev);
+  if (wait_slot >= 0) {
+    // single-buffered slots: every peer must have consumed the previous step's payload (it says so on MY flag block)
+    if (threadIdx.x < world) wait_flag_ge(dst.flags[rank] + wait_slot * kMaxRanks + threadIdx.x, epoch - 1);
+    __syncthreads();
+  }
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n16; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const uint4 v = src[i];
     if (dst_mc != nullptr) {
@@ -295,8 +307,10 @@ peer_push_kernel(const uint4* __restrict__ src, PeerPtrs dst, uint4* __restrict_
 
 // src: dense tensor (nbytes % 16 == 0).  dst_ptrs[p]: destination address inside rank p's arena.
 void peer_push(const at::Tensor& src, std::vector<int64_t> dst_ptrs, int64_t dst_mc, std::vector<int64_t> flag_ptrs,
-               int64_t rank, int64_t slot, int64_t epoch, bool signal, at::Tensor done_counter) {
+               int64_t rank, int64_t slot, int64_t epoch, bool signal, at::Tensor done_counter, int64_t wait_slot,
+               const c10::optional<at::Tensor>& epoch_dev) {
   const int world = static_cast<int>(dst_ptrs.size());
+  const uint32_t* edp = epoch_dev.has_value() ? reinterpret_cast<const uint32_t*>(epoch_dev->data_ptr()) : nullptr;
   TORCH_CHECK(world >= 1 && world <= kMaxRanks && src.is_cuda() && src.is_contiguous());
   const long nbytes = src.numel() * src.element_size();
   TORCH_CHECK(nbytes % 16 == 0 && reinterpret_cast<uintptr_t>(src.data_ptr()) % 16 == 0, "peer_push: 16-byte granularity");
@@ -304,14 +318,33 @@ void peer_push(const at::Tensor& src, std::vector<int64_t> dst_ptrs, int64_t dst
   PeerPtrs pp{};
   for (int p = 0; p < world; ++p) {
     pp.w[p] = reinterpret_cast<float*>(dst_ptrs[p]);
-    pp.flags[p] = signal ? reinterpret_cast<uint32_t*>(flag_ptrs[p]) : nullptr;
+    pp.flags[p] = (signal || wait_slot >= 0) ? reinterpret_cast<uint32_t*>(flag_ptrs[p]) : nullptr;
   }
   const long n16 = nbytes / 16;
   const int grid = static_cast<int>(std::max<long>(1, std::min<long>((n16 + 511) / 512, 32)));
   peer_push_kernel<<<grid, 512, 0, at::cuda::getCurrentCUDAStream()>>>(
       reinterpret_cast<const uint4*>(src.data_ptr()), pp, reinterpret_cast<uint4*>(dst_mc), n16, static_cast<int>(rank), world,
       static_cast<int>(slot), static_cast<uint32_t>(epoch), signal ? 1 : 0,
-      reinterpret_cast<unsigned int*>(done_counter.data_ptr()));
+      reinterpret_cast<unsigned int*>(done_counter.data_ptr()), static_cast<int>(wait_slot), edp);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+// Raise this rank's `slot` flag to `epoch` on every peer (stream-ordered after the kernels that consumed the data).
+__global__ void peer_signal_kernel(PeerPtrs dst, int rank, int world, int slot, uint32_t epoch,
+                                   const uint32_t* __restrict__ epoch_dev) {
+  if (epoch_dev != nullptr) epoch += *reinterpret_cast<const volatile uint32_t*>(epoch_dev);
+  __threadfence_system();
+  if (threadIdx.x < world) st_release_sys(dst.flags[threadIdx.x] + slot * kMaxRanks + rank, epoch);
+}
+void peer_signal(std::vector<int64_t> flag_ptrs, int64_t rank, int64_t slot, int64_t epoch,
+                 const c10::optional<at::Tensor>& epoch_dev) {
+  const int world = static_cast<int>(flag_ptrs.size());
+  TORCH_CHECK(world >= 1 && world <= kMaxRanks);
+  PeerPtrs pp{};
+  for (int p = 0; p < world; ++p) pp.flags[p] = reinterpret_cast<uint32_t*>(flag_ptrs[p]);
+  const uint32_t* edp = epoch_dev.has_value() ? reinterpret_cast<const uint32_t*>(epoch_dev->data_ptr()) : nullptr;
+  peer_signal_kernel<<<1, 32, 0, at::cuda::getCurrentCUDAStream()>>>(pp, static_cast<int>(rank), world, static_cast<int>(slot),
+                                                                     static_cast<uint32_t>(epoch), edp);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
@@ -322,7 +355,8 @@ TORCH_LIBRARY_FRAGMENT(poseidon, m) {
         "bool l1, float delta, float gscale, Tensor? lr_dev) -> ()", &psd::fused_update);
   m.def("allreduce_sgd(int[] g_ptrs, int[] w_ptrs, int[] wb_ptrs, int[] flag_ptrs, int g_mc, int w_mc, Tensor(a!) h, int n, "
         "int rank, int epoch, bool one_shot, Tensor(b!) done_counter, float lr, float momentum, float decay, int rule, "
-        "bool l1, float delta, float gscale, int max_ctas, Tensor? lr_dev) -> ()", &psd::allreduce_sgd);
+        "bool l1, float delta, float gscale, int max_ctas, Tensor? lr_dev, Tensor? epoch_dev) -> ()", &psd::allreduce_sgd);
   m.def("peer_push(Tensor src, int[] dst_ptrs, int dst_mc, int[] flag_ptrs, int rank, int slot, int epoch, bool signal, "
-        "Tensor(a!) done_counter) -> ()", &psd::peer_push);
+        "Tensor(a!) done_counter, int wait_slot, Tensor? epoch_dev) -> ()", &psd::peer_push);
+  m.def("peer_signal(int[] flag_ptrs, int rank, int slot, int epoch, Tensor? epoch_dev) -> ()", &psd::peer_signal);
 }

@@ -257,7 +257,7 @@ void sfb_outer_sgd(std::vector<int64_t> u_ptrs, std::vector<int64_t> v_ptrs, int
                    at::Tensor w, at::Tensor h, c10::optional<at::Tensor> wb, double alpha, double lr,
                    double momentum, double decay, int64_t rule, bool l1, double delta,
                    const c10::optional<at::Tensor>& flags, int64_t epoch, int64_t src_rot, int64_t bn,
-                   int64_t max_ctas, const c10::optional<at::Tensor>& lr_dev) {
+                   int64_t max_ctas, const c10::optional<at::Tensor>& lr_dev, const c10::optional<at::Tensor>& epoch_dev) {
   TORCH_CHECK(w.is_cuda() && w.scalar_type() == at::kFloat && h.scalar_type() == at::kFloat);
   TORCH_CHECK(w.numel() == N * K && h.numel() == N * K && w.is_contiguous() && h.is_contiguous());
   c10::cuda::CUDAGuard guard(w.device());
@@ -280,20 +280,46 @@ void sfb_outer_sgd(std::vector<int64_t> u_ptrs, std::vector<int64_t> v_ptrs, int
     TORCH_CHECK(flags->scalar_type() == at::kInt && flags->numel() >= static_cast<int64_t>(u_ptrs.size()));
     p.flags = reinterpret_cast<const uint32_t*>(flags->data_ptr());
     p.epoch = static_cast<uint32_t>(epoch);
+    p.epoch_dev = epoch_dev.has_value() ? reinterpret_cast<const uint32_t*>(epoch_dev->data_ptr()) : nullptr;
   }
   // A = Uᵀ : MN-major with "M" = N_out ; B = Vᵀ... : MN-major with "N" = K_in ; reduction = Mb rows.
   gemm_launch(u_ptrs, true, N, v_ptrs, true, K, N, K, Mb, EPI_SGD, p, static_cast<int>(bn),
               static_cast<int>(max_ctas), at::cuda::getCurrentCUDAStream());
 }
 
+// Same reduction over the P sufficient-factor slots, but into a dense fp32 buffer (no optimizer step): the
+// two-pass form  out = alpha * Σ_src U_srcᵀ V_src ; fused_update(out)  which streams W/H at full HBM rate.
+void sfb_outer_f32(std::vector<int64_t> u_ptrs, std::vector<int64_t> v_ptrs, int64_t Mb, int64_t N, int64_t K,
+                   at::Tensor out, double alpha, const c10::optional<at::Tensor>& flags, int64_t epoch, int64_t src_rot,
+                   int64_t bn, int64_t max_ctas, const c10::optional<at::Tensor>& epoch_dev) {
+  TORCH_CHECK(out.is_cuda() && out.scalar_type() == at::kFloat && out.numel() == N * K && out.is_contiguous());
+  c10::cuda::CUDAGuard guard(out.device());
+  GemmParams p{};
+  p.c_f32 = out.data_ptr<float>();
+  p.ldc = K;
+  p.alpha = static_cast<float>(alpha);
+  p.split_k = 1;
+  p.src_rot = static_cast<int>(src_rot);
+  if (flags.has_value()) {
+    TORCH_CHECK(flags->scalar_type() == at::kInt && flags->numel() >= static_cast<int64_t>(u_ptrs.size()));
+    p.flags = reinterpret_cast<const uint32_t*>(flags->data_ptr());
+    p.epoch = static_cast<uint32_t>(epoch);
+    p.epoch_dev = epoch_dev.has_value() ? reinterpret_cast<const uint32_t*>(epoch_dev->data_ptr()) : nullptr;
+  }
+  gemm_launch(u_ptrs, true, N, v_ptrs, true, K, N, K, Mb, EPI_F32, p, static_cast<int>(bn), static_cast<int>(max_ctas),
+              at::cuda::getCurrentCUDAStream());
+}
+
 }  // namespace psd
 
 TORCH_LIBRARY_FRAGMENT(poseidon, m) {
+  m.def("sfb_outer_f32(int[] u_ptrs, int[] v_ptrs, int Mb, int N, int K, Tensor(a!) out, float alpha, Tensor? flags, "
+        "int epoch, int src_rot, int bn, int max_ctas, Tensor? epoch_dev) -> ()", &psd::sfb_outer_f32);
   m.def("gemm_bf16(Tensor a, bool a_mn, Tensor b, bool b_mn, Tensor? bias, bool relu, float slope, Tensor? mask, "
         "Tensor? out, int bn) -> Tensor", &psd::gemm_bf16);
   m.def("gemm_f32(Tensor a, bool a_mn, Tensor b, bool b_mn, Tensor(a!) out, float alpha, bool accumulate, "
         "int split_k, int bn) -> ()", &psd::gemm_f32);
   m.def("sfb_outer_sgd(int[] u_ptrs, int[] v_ptrs, int Mb, int N, int K, Tensor(a!) w, Tensor(b!) h, "
         "Tensor(c!)? wb, float alpha, float lr, float momentum, float decay, int rule, bool l1, float delta, "
-        "Tensor? flags, int epoch, int src_rot, int bn, int max_ctas, Tensor? lr_dev) -> ()", &psd::sfb_outer_sgd);
+        "Tensor? flags, int epoch, int src_rot, int bn, int max_ctas, Tensor? lr_dev, Tensor? epoch_dev) -> ()", &psd::sfb_outer_sgd);
 }

@@ -72,6 +72,7 @@ struct GemmParams {
   // --- peer gating (SFB): flag[src] must reach `epoch` before src's tiles are read
   const uint32_t* flags;
   uint32_t epoch;
+  const uint32_t* epoch_dev;   // optional device-resident step counter added to `epoch` (CUDA-graph replays)
 };
 
 template <int BN>
@@ -394,7 +395,10 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
         for (int g = g0; g < g1; ++g) {
           if (new_src) {
             if (p.flags != nullptr) {
-              if (lane == 0) wait_flag_ge(p.flags + src, p.epoch);
+              if (lane == 0) {
+                const uint32_t ep = p.epoch + (p.epoch_dev != nullptr ? *reinterpret_cast<const volatile uint32_t*>(p.epoch_dev) : 0u);
+                wait_flag_ge(p.flags + src, ep);
+              }
               __syncwarp();
             }
             new_src = false;

@@ -117,6 +117,7 @@ class FusedBackend(Backend):
             self._build_arena(net, sync)
         self.done_counter = torch.zeros(4, dtype=torch.int32, device=self.device)
         self.lr_t = torch.zeros(1, dtype=torch.float32, device=self.device)     # global lr, read by the kernels
+        self.epoch_t = torch.zeros(1, dtype=torch.int32, device=self.device)    # step counter, read by the comm kernels
 
     def _ensure_layer_states(self, net):
         for li, layer in enumerate(net.layers):
@@ -318,8 +319,8 @@ class FusedBackend(Backend):
                                      ar.peer_ptrs(bucket.flag_off + 64 * pi),
                                      ar.mc_ptr(seg.g_off) if use_mc else 0,
                                      ar.mc_ptr(seg.w_off) if (use_mc and not one_shot) else 0,
-                                     seg.hist, n, self.rank, self.epoch + 1, one_shot, self.done_counter,
-                                     lr, mom, decay, rule, l1, delta, gscale, 64, self.lr_t)
+                                     seg.hist, n, self.rank, 1, one_shot, self.done_counter,
+                                     lr, mom, decay, rule, l1, delta, gscale, 64, self.lr_t, self.epoch_t)
                 ar.view(seg.g_off, (n,), torch.float32).zero_()
                 self.launches += 2
                 self.dense_bytes += n * 4
@@ -328,7 +329,17 @@ class FusedBackend(Backend):
             bucket.event.record(self.stream)
 
     def finish_iteration(self):
+        """Close the step: the device-resident epoch counter (read by every comm kernel of this step as
+        ``epoch_t + 1``) is bumped on the comm stream, i.e. after all of them in stream order.  Keeping it on the
+        device is what lets a captured CUDA graph of the whole step be replayed."""
         self.epoch += 1
+        if self.world > 1:
+            cur = torch.cuda.current_stream()
+            self.stream.wait_stream(cur)
+            with torch.cuda.stream(self.stream):
+                self.epoch_t.add_(1)
+            if torch.cuda.is_current_stream_capturing():
+                cur.wait_stream(self.stream)           # a capture must end with every forked stream joined
 
     def bytes_on_wire(self):
         return {"dense_allreduce_bytes": self.dense_bytes, "sfb_bytes": self.sfb_stats.sfb_bytes,
@@ -443,8 +454,7 @@ class FusedSFB:
             return None
         ar = be.arena
         P = be.world
-        par = be.epoch & 1
-        epoch = be.epoch + 1
+        par = 0                      # single-buffered slots: peers acknowledge consumption on flag slot 4
         cur = torch.cuda.current_stream()
         be.stream.wait_stream(cur)
         with torch.cuda.stream(be.stream):
@@ -453,16 +463,29 @@ class FusedSFB:
             mc = be.use_multimem and ar.multicast_ptr != 0
             u_dst = self.u_off[par] + be.rank * self.u_slot
             v_dst = self.v_off[par] + be.rank * self.v_slot
-            k.peer_push(dy, ar.peer_ptrs(u_dst), ar.mc_ptr(u_dst) if mc else 0, ar.peer_ptrs(self.flag_off), be.rank,
-                        2 + par, epoch, False, be.done_counter[1:2])
-            k.peer_push(x2, ar.peer_ptrs(v_dst), ar.mc_ptr(v_dst) if mc else 0, ar.peer_ptrs(self.flag_off), be.rank,
-                        2 + par, epoch, True, be.done_counter[1:2])
+            flags = ar.peer_ptrs(self.flag_off)
+            k.peer_push(dy, ar.peer_ptrs(u_dst), ar.mc_ptr(u_dst) if mc else 0, flags, be.rank,
+                        2 + par, 1, False, be.done_counter[1:2], 4, be.epoch_t)
+            k.peer_push(x2, ar.peer_ptrs(v_dst), ar.mc_ptr(v_dst) if mc else 0, flags, be.rank,
+                        2 + par, 1, True, be.done_counter[1:2], -1, be.epoch_t)
             base = ar.base_ptrs[be.rank]
             u_ptrs = [base + self.u_off[par] + p * self.u_slot for p in range(P)]
             v_ptrs = [base + self.v_off[par] + p * self.v_slot for p in range(P)]
-            k.sfb_outer_sgd(u_ptrs, v_ptrs, M, self.N, self.K, w, h, st.wb, gscale, lr, mom, decay, rule, l1, delta,
-                            self.local_flags[par], epoch, 0, 0, 0, be.lr_t)
-            be.launches += 3
+            if getattr(be, "fuse_sfb_sgd", True):
+                k.sfb_outer_sgd(u_ptrs, v_ptrs, M, self.N, self.K, w, h, st.wb, gscale, lr, mom, decay, rule, l1, delta,
+                                self.local_flags[par], 1, 0, 0, 0, be.lr_t, be.epoch_t)
+                be.launches += 4
+            else:
+                # two-pass variant: P-source outer product into a local fp32 buffer + streaming update (measured
+                # slower than the fused epilogue when it shares the GPU with the backward pass: 129 k vs 132 k img/s)
+                g = getattr(self, "_gbuf", None)
+                if g is None:
+                    g = self._gbuf = torch.empty(self.N, self.K, device=w.device, dtype=torch.float32)
+                g.record_stream(be.stream)
+                k.sfb_outer_f32(u_ptrs, v_ptrs, M, self.N, self.K, g, 1.0, self.local_flags[par], 1, 0, 0, 0, be.epoch_t)
+                k.fused_update(w, g, h, st.wb, lr, mom, decay, rule, l1, delta, gscale, be.lr_t)
+                be.launches += 5
+            k.peer_signal(flags, be.rank, 4, 1, be.epoch_t)      # "I have consumed every slot of this step"
             if self.event is None:
                 self.event = torch.cuda.Event()
             self.event.record(be.stream)

@@ -256,9 +256,12 @@ class Solver:
         """Capture forward+backward+update of everything after the data layers into a CUDA graph and replay it
         every iteration (launch-bound nets such as GoogLeNet at batch 32).  The data layers stay eager and feed
         static input tensors; the learning rate and the dropout iteration counter live in device memory so replays
-        see fresh values.  Single-GPU sm100 engine only (the multi-GPU epoch flags are kernel arguments)."""
-        if self.engine != "sm100" or self.rank_ctx.distributed or self.device.type != "cuda":
-            raise RuntimeError("CUDA-graph steps need the sm100 engine on one GPU")
+        see fresh values, and so does the fused NVLink backend's epoch counter (multi-GPU replays stay in lock step
+        through the in-kernel flag protocol)."""
+        fused_comm = type(self.sync.backend).__name__ == "FusedBackend"
+        if self.engine != "sm100" or self.device.type != "cuda" or (self.rank_ctx.distributed and not fused_comm):
+            raise RuntimeError("CUDA-graph steps need the sm100 engine (multi-GPU: with the fused NVLink backend, whose "
+                               "epoch counter lives on the device)")
         from ..ops import sm100
         net = self.net
         k = net.num_leading_data_layers()
@@ -272,6 +275,15 @@ class Solver:
             self._g_inputs = {n: t.clone() for n, t in net.forward_data().items()}
         side.synchronize()
         torch.cuda.synchronize(self.device)
+        if self.rank_ctx.distributed:
+            # the captured step must be self-contained: it forks the comm stream at its first bucket and joins it at
+            # the end, so it may not wait on events recorded by the eager warm-up steps
+            self.rank_ctx.barrier()
+            for b in self.sync.buckets:
+                b.event = None
+                b.sfb_event = None
+            for h in getattr(self.sync.backend, "sfb_layers", {}).values():
+                h.event = None
         self._g_first = k
         self.sync.begin_iteration(learning_rate(self.param, self.iter))
         graph = torch.cuda.CUDAGraph()
@@ -284,6 +296,12 @@ class Solver:
                 loss.backward()
                 self.sync.finish_iteration()
         torch.cuda.current_stream().wait_stream(side)
+        if self.rank_ctx.distributed:
+            for b in self.sync.buckets:      # events recorded during capture are graph-internal: never wait on them eagerly
+                b.event = None
+                b.sfb_event = None
+            for h in getattr(self.sync.backend, "sfb_layers", {}).values():
+                h.event = None
         graph.replay()       # capture only records: run the captured step once on the batch that was staged for it
         self.graph_launches = counting.total() - n0          # kernels of ours inside one replay
         self._graph, self._g_loss, self._g_outs = graph, loss.detach(), {n: o.detach() for n, o in outs.items()}

@@ -58,7 +58,7 @@ def test_sfb_outer_sgd_single_source(ext, rule):
     w_ref, h_ref = w.clone(), h.clone()
     lr, mom, wd, delta = 0.01, 0.0 if rule == 2 else 0.9, 5e-4, 1e-8
     ext.sfb_outer_sgd([u.data_ptr()], [v.data_ptr()], Mb, N, K, w, h, wb, 1.0 / Mb, lr, mom, wd, rule, False,
-                      delta, None, 0, 0, 0, 0, None)
+                      delta, None, 0, 0, 0, 0, None, None)
     g = (u.float().t() @ v.float()) / Mb + wd * w_ref
     if rule == 0:
         h_ref = lr * g + mom * h_ref
@@ -84,6 +84,6 @@ def test_sfb_outer_multi_source_local(ext):
     h = torch.zeros(N, K, device="cuda")
     flags = torch.full((P,), 7, dtype=torch.int32, device="cuda")
     ext.sfb_outer_sgd([u.data_ptr() for u in us], [v.data_ptr() for v in vs], Mb, N, K, w, h, None, 1.0, 1.0, 0.0,
-                      0.0, 0, False, 1e-8, flags, 7, 2, 0, 0, None)
+                      0.0, 0, False, 1e-8, flags, 4, 2, 0, 0, None, torch.full((1,), 3, device="cuda", dtype=torch.int32))
     ref = sum(u.float().t() @ v.float() for u, v in zip(us, vs))
     _close(-w, ref, rel=1e-2)

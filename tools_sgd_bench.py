@@ -17,7 +17,7 @@ for (M, N, Kd) in ((256, 4096, 9216), (256, 4096, 4096)):
     lr_t = torch.ones(1, device="cuda")
     def run():
         K.sfb_outer_sgd([dy.data_ptr()], [x.data_ptr()], M, N, Kd, w, h, wb, 1.0, 0.01, 0.9, 5e-4, 0, False, 1e-8,
-                        None, 0, 0, 0, 0, lr_t)
+                        None, 0, 0, 0, 0, lr_t, None)
     for _ in range(2):
         run()
     torch.cuda.synchronize()
