@@ -82,6 +82,7 @@ class ConvState:
         cg = cin_logical // self.groups
         self.row_mode = cg % 8 != 0
         self.s2d = False
+        self.pad8 = False
         if self.row_mode:
             if self.groups != 1 or cin_logical > 4:
                 raise ValueError(f"sm100 conv '{layer.layer_name}': input channels {cin_logical} (group "
@@ -91,8 +92,13 @@ class ConvState:
             self.Lp = (self.L + 7) // 8 * 8
             self.Kw = self.R * self.Lp
             if (layer.stride[1] * self.Cp) % 8:
-                raise ValueError("sm100 first-layer conv needs an even horizontal stride")
-            self._try_s2d(layer)
+                # odd horizontal stride (VGG conv1_1: 3x3/s1): kernel rows would start on 8-byte boundaries, so pad the
+                # image to 8 channels instead and run it as an ordinary TAP-mode conv (K = R*S*8)
+                self.pad8 = True
+                self.Cp = 8
+                self.Kw = self.R * self.S * 8
+            else:
+                self._try_s2d(layer)
         else:
             self.Cp = cin_logical
             self.Kw = self.R * self.S * cg
@@ -148,7 +154,10 @@ class ConvState:
             return self.wb
         w = self.layer.weight
         with torch.no_grad():
-            if self.s2d:
+            if self.pad8:
+                t = torch.nn.functional.pad(w.data.permute(0, 2, 3, 1), (0, self.Cp - self.cin_logical))   # Cout,R,S,8
+                src = t.reshape(self.Cout, self.Kw)
+            elif self.s2d:
                 # W'[co][R'][S'][dy][dx][c] = W[co][c][4R'+dy][4S'+dx]  (zero outside the 11x11 support / c >= C)
                 t = torch.nn.functional.pad(w.data, (0, 4 * self.Sq - self.S, 0, 4 * self.Rq - self.R,
                                                      0, self.Cp - self.cin_logical))       # Cout,4,4R',4S'
@@ -177,6 +186,8 @@ class ConvState:
 
     def grad_from_dw(self, dw: torch.Tensor) -> torch.Tensor:
         """[Cout, Kw] fp32 -> gradient tensor with the master weight's logical shape."""
+        if self.pad8:
+            return dw.view(self.Cout, self.R, self.S, self.Cp)[..., : self.cin_logical].permute(0, 3, 1, 2).contiguous()
         if self.s2d:
             g = dw.view(self.Cout, self.Rq, self.Sq, 4, 4, self.Cp).permute(0, 5, 1, 3, 2, 4)   # co,c,R',dy,S',dx
             g = g.reshape(self.Cout, self.Cp, 4 * self.Rq, 4 * self.Sq)
@@ -200,6 +211,12 @@ def prepare_first_layer_input(x: torch.Tensor, st: ConvState, pad, in_hw) -> tor
     Cp, spatially pre-padded by the conv's own padding, physical width rounded up to even (16-byte rows).
     The data layers emit this layout straight from the transform kernel; anything else is converted here."""
     h, w = in_hw
+    if st.pad8:
+        if (x.dtype == torch.bfloat16 and x.dim() == 4 and tuple(x.shape[1:]) == (8, h, w)
+                and x.is_contiguous(memory_format=CL)):
+            return x
+        t = torch.nn.functional.pad(x.float(), (0, 0, 0, 0, 0, 8 - x.shape[1]))
+        return t.to(torch.bfloat16).contiguous(memory_format=CL)
     if st.s2d:
         hq, wq = st.s2d_hw
         if (x.dtype == torch.bfloat16 and x.dim() == 4 and tuple(x.shape[1:]) == (64, hq, wq)
@@ -229,7 +246,11 @@ class _ConvFn(torch.autograd.Function):
         st: ConvState = layer._sm100
         k = K()
         stride, pad = layer.stride, layer.pad
-        if st.row_mode:
+        if st.pad8:
+            h, w = layer.in_hw
+            xin = prepare_first_layer_input(x, st, pad, (h, w))
+            conv_pad = pad
+        elif st.row_mode:
             h, w = layer.in_hw
             xin = prepare_first_layer_input(x, st, pad, (h, w))
             conv_pad = (0, 0)
@@ -245,7 +266,7 @@ class _ConvFn(torch.autograd.Function):
                              float(relu_slope or 0.0), None)
         else:
             y = k.conv_fprop(xin, st.shadow(), bias, [st.R, st.S], list(stride), list(conv_pad), st.groups,
-                             1 if st.row_mode else 0, oh, ow, relu, float(relu_slope or 0.0), None)
+                             1 if (st.row_mode and not st.pad8) else 0, oh, ow, relu, float(relu_slope or 0.0), None)
         ctx.layer, ctx.relu_slope, ctx.conv_pad = layer, relu_slope, conv_pad
         ctx.in_shape = tuple(x.shape)
         ctx.save_for_backward(xin, y if relu else None)
@@ -270,7 +291,7 @@ class _ConvFn(torch.autograd.Function):
                 k.conv_wgrad(xin, dy, dw2, [st.Rq, st.Sq], [1, 1], [0, 0], 1, 0, 1.0)
             else:
                 k.conv_wgrad(xin, dy, dw2, [st.R, st.S], list(stride), list(ctx.conv_pad), st.groups,
-                             1 if st.row_mode else 0, 1.0)
+                             1 if (st.row_mode and not st.pad8) else 0, 1.0)
             dw = st.grad_from_dw(dw2)
         if layer.bias_term and ctx.needs_input_grad[2]:
             db = torch.empty(st.Cout, device=dy.device, dtype=torch.float32)
@@ -609,6 +630,11 @@ def transform(transformer, x, out_dtype, first_conv=None):
         return TE.transform(transformer, x, out_dtype).contiguous(memory_format=CL)
     xin = x if x.dtype in (torch.uint8, torch.float32) else x.float()
     st = first_conv._sm100
+    if st.pad8:
+        if (oh, ow) != tuple(first_conv.in_hw):
+            return TE.transform(transformer, x, out_dtype).contiguous(memory_format=CL)
+        return K().transform_nhwc(xin.contiguous(), h_off.to(dev, torch.int32), w_off.to(dev, torch.int32),
+                                  flip.to(dev, torch.uint8), mean, float(transformer.scale), oh, ow, 8, 0, 0, 0, False)
     if st.s2d:
         hq, wq = st.s2d_hw
         if cp != 4 or (oh, ow) != tuple(first_conv.in_hw):

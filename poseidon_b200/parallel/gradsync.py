@@ -24,6 +24,8 @@ from collections import deque
 from typing import Callable, Dict, List, Optional
 
 import torch
+
+from ..utils.trace import nvtx_range
 import torch.distributed as dist
 
 from ..ops import reference as R
@@ -317,7 +319,8 @@ class GradSync:
         b.pending -= 1
         if b.pending == 0:
             self.launch_order.append(b.id)
-            self.backend.launch(b)
+            with nvtx_range(f"sync/{getattr(b.layer, 'layer_name', b.id)}"):
+                self.backend.launch(b)
             for q in b.params:
                 q.grad = None
 

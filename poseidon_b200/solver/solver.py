@@ -23,6 +23,7 @@ from ..net.net import Net
 from ..parallel.context import RankContext
 from ..parallel.gradsync import (ADAGRAD, NESTEROV, SGD, GradSync, Hyper, LocalBackend,
                                  SSPBackend, TorchDistBackend)
+from ..utils import fault, trace
 from ..utils.stats import STATS
 from .lr_policy import learning_rate
 
@@ -106,6 +107,7 @@ class Solver:
             raise ValueError(f"Unknown regularization type: {param.regularization_type}")
         self._sync_initial_weights()
         self.sync = self._make_sync(comm, grad_reduce, sfb_mode)
+        trace.annotate_net(self.net)                 # NVTX ranges per layer when POSEIDON_NVTX=1
         self.last_loss = None
 
     # ---- net construction ------------------------------------------------------------------
@@ -325,6 +327,7 @@ class Solver:
         STATS.count("iterations")
 
     def _train_iteration(self):
+        fault.maybe_inject(self.rank_ctx.rank, self.iter)
         if getattr(self, "_graph", None) is not None:
             return self._graph_iteration()
         sp = self.param

@@ -91,3 +91,12 @@ def test_ssp_bounded_staleness_converges_to_same_table(tmp_path):
     _assert_close(res[0], res[1], 1e-5)
     assert int(res[0]["max_lag"]) <= 2 and int(res[1]["max_lag"]) <= 2
     assert np.isfinite(res[0]["loss"])
+
+
+def test_injected_straggler_does_not_change_bsp_result(tmp_path, single, monkeypatch):
+    """POSEIDON_FAULT delay on one rank (fault-injection hook): BSP training waits for the straggler and
+    produces exactly the same weights."""
+    monkeypatch.setenv("POSEIDON_FAULT", "delay:rank=1,step=1,ms=300")
+    res = launch(2, str(tmp_path / "w"), ["--batch", "8", "--comm", "gloo"])
+    _assert_close(res[0], res[1], 1e-7)
+    _assert_close(res[0], single)

@@ -76,3 +76,28 @@ def test_hostfile_parser(tmp_path):
     f = tmp_path / "hosts"
     f.write_text("# comment\n1 10.0.0.2 9999\n0 127.0.0.1 9999\n")
     assert parse_hostfile(str(f)) == [(0, "127.0.0.1", 9999), (1, "10.0.0.2", 9999)]
+
+
+def test_fault_injection_directives(monkeypatch):
+    import time
+    from poseidon_b200.utils import fault
+    assert fault.parse("delay:rank=1,step=3,ms=20; kill:rank=2,step=5") == [
+        ("delay", {"rank": 1, "step": 3, "ms": 20}), ("kill", {"rank": 2, "step": 5})]
+    monkeypatch.setenv("POSEIDON_FAULT", "delay:rank=0,step=2,ms=30;raise:rank=0,step=4")
+    fault.reset()
+    t0 = time.time(); fault.maybe_inject(0, 1); assert time.time() - t0 < 0.02
+    t0 = time.time(); fault.maybe_inject(0, 2); assert time.time() - t0 >= 0.03
+    fault.maybe_inject(1, 4)                       # other rank: nothing
+    try:
+        fault.maybe_inject(0, 4)
+        raise AssertionError("expected the injected fault")
+    except RuntimeError as e:
+        assert "injected fault" in str(e)
+    monkeypatch.delenv("POSEIDON_FAULT")
+    fault.reset()
+
+
+def test_nvtx_ranges_are_noops_without_cuda():
+    from poseidon_b200.utils import trace
+    with trace.nvtx_range("x"):
+        pass

@@ -179,7 +179,7 @@ def test_conv_fwd_bwd(ext, case, relu):
 
 
 @pytest.mark.parametrize("case", [(4, 3, 227, 227, 96, 11, 4, 0), (2, 3, 224, 224, 64, 7, 2, 3), (2, 1, 30, 30, 24, 5, 2, 0),
-                                  (2, 3, 64, 64, 32, 11, 4, 2), (2, 3, 67, 67, 32, 8, 4, 0)])
+                                  (2, 3, 64, 64, 32, 11, 4, 2), (2, 3, 67, 67, 32, 8, 4, 0), (2, 3, 32, 30, 64, 3, 1, 1)])
 def test_first_layer_conv_row_mode(ext, case):
     from poseidon_b200.ops import sm100
     n, cin, h, w, cout, k, stride, pad = case
