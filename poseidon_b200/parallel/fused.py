@@ -87,6 +87,7 @@ class _Seg:
 
 
 class FusedBackend(Backend):
+    manages_operands = True        # its kernels rewrite the bf16 operands next to the fp32 masters
     name = "fused"
 
     def __init__(self, svb: bool = False, sfb_mode: str = "auto", grad_reduce: str = "sum",

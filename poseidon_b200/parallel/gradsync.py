@@ -228,7 +228,8 @@ class SSPBackend(Backend):
             delta = compute_update(hy, p.data, p.grad, h, lm, dm)
             with torch.no_grad():
                 p.data.sub_(delta)                       # read-my-writes
-            total = delta.clone()
+            # the wire buffer must be dense (NCCL rejects channels-last strided conv weights): logical-order copy
+            total = delta.contiguous().clone() if not delta.is_contiguous() else delta.clone()
             work = dist.all_reduce(total, async_op=True) if self.sync.rank_ctx.distributed else None
             self.wire_bytes += total.numel() * total.element_size()
             self.cur.append((p, total, delta, work))
@@ -239,6 +240,7 @@ class SSPBackend(Backend):
                 work.wait()
             with torch.no_grad():
                 p.data.sub_(total - own)
+            self.sync.invalidate_operands(p)         # bf16 shadows of the sm100 engine follow the fp32 master
 
     def finish_iteration(self):
         if self.delay_hook is not None:
@@ -321,8 +323,19 @@ class GradSync:
             self.launch_order.append(b.id)
             with nvtx_range(f"sync/{getattr(b.layer, 'layer_name', b.id)}"):
                 self.backend.launch(b)
+            if not getattr(self.backend, "manages_operands", False):
+                st = getattr(b.layer, "_sm100", None)
+                if st is not None:
+                    st.mark_updated()                # library backends step the fp32 master only
             for q in b.params:
                 q.grad = None
+
+    def invalidate_operands(self, p):
+        """A parameter's fp32 master was modified outside the fused kernels: its layer's bf16 operands are stale."""
+        b = self.bucket_of.get(id(p))
+        st = getattr(b.layer, "_sm100", None) if b is not None else None
+        if st is not None:
+            st.mark_updated()
 
     def finish_iteration(self):
         """Launch buckets whose grads never materialised this step (unused layers) — none in
