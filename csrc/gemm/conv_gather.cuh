@@ -48,6 +48,8 @@ struct ConvGeom {
   int N, H, W;              // its spatial extent
   long pitch;               // pixel pitch in elements
   int Cg;                   // channels per group (TAP) / padded channels (ROW)
+  int Cgk;                  // K-slots per tap (>= Cg: rounded up to 64 when the im2col-TMA path pads the channels; the
+                            // tensor map's channel extent stays Cg, so slots [Cg, Cgk) are zero-filled by the TMA)
   int OH, OW;               // extent of the row index m = (n, oh, ow)
   int R, S, sh, sw;
   int off_h, off_w;         // ih = oh*sh + off_h + r*dr  (fprop: off=-pad, dr=+1 ; dgrad: off=+pad, dr=-1)

@@ -101,12 +101,13 @@ struct ConvDesc {
 };
 
 static ConvGeom make_geom(const at::Tensor& x, const NhwcView& xv, int c_off, int Cg, int OH, int OW, const ConvDesc& d,
-                          bool dgrad) {
+                          bool dgrad, int Cgk = 0) {
   ConvGeom g{};
   g.x = reinterpret_cast<const __nv_bfloat16*>(x.data_ptr()) + c_off;
   g.N = xv.N; g.H = xv.H; g.W = xv.W;
   g.pitch = xv.pitch;
   g.Cg = Cg;
+  g.Cgk = Cgk > 0 ? Cgk : Cg;
   g.OH = OH; g.OW = OW;
   g.R = d.R; g.S = d.S;
   g.sh = dgrad ? 1 : d.sh; g.sw = dgrad ? 1 : d.sw;
@@ -116,12 +117,12 @@ static ConvGeom make_geom(const at::Tensor& x, const NhwcView& xv, int c_off, in
   g.mode = d.mode;
   g.L = d.S * Cg;
   g.Lp = (g.L + 7) / 8 * 8;
-  g.K = d.mode == 1 ? d.R * g.Lp : d.R * d.S * Cg;
+  g.K = d.mode == 1 ? d.R * g.Lp : d.R * d.S * g.Cgk;
   g.M = static_cast<long>(xv.N) * OH * OW;
   TORCH_CHECK(g.M < (1L << 31), "conv: N*OH*OW must fit in 31 bits");
   g.div_ow = make_fastdiv(OW);
   g.div_ohow = make_fastdiv(static_cast<uint32_t>(OH) * OW);
-  g.div_cg = make_fastdiv(Cg);
+  g.div_cg = make_fastdiv(g.Cgk);
   g.div_s = make_fastdiv(d.S);
   g.div_lp = make_fastdiv(g.Lp);
   TORCH_CHECK(d.R <= 15 && d.S <= 15, "conv: kernel extents up to 15 are supported");
@@ -140,7 +141,7 @@ static ConvGeom make_geom(const at::Tensor& x, const NhwcView& xv, int c_off, in
 // TMA im2col eligibility: TAP mode, 64-channel K slices never straddle a tap, corner offsets fit the descriptor.
 // On success fills `map` for boxes of `pixels` base pixels x 64 channels over the gathered tensor.
 static bool try_im2col_map(CUtensorMap* map, const ConvGeom& g, int pixels) {
-  if (!g_conv_im2col || g.mode != 0 || g.Cg % 64 != 0) return false;
+  if (!g_conv_im2col || g.mode != 0 || g.Cgk % 64 != 0) return false;
   const int org_w = g.off_w - (g.dr < 0 ? g.S - 1 : 0), org_h = g.off_h - (g.dr < 0 ? g.R - 1 : 0);
   // the bounding box must enumerate exactly OW x OH base pixels: extent + upper - lower - 1 = (O - 1) * stride
   const int up_w = (g.OW - 1) * g.sw + 1 + org_w - g.W, up_h = (g.OH - 1) * g.sh + 1 + org_h - g.H;
@@ -185,7 +186,9 @@ at::Tensor conv_fprop(const at::Tensor& x, const at::Tensor& wb, const c10::opti
   auto stream = at::cuda::getCurrentCUDAStream();
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
   for (int gidx = 0; gidx < groups; ++gidx) {
-    ConvGeom cg = make_geom(x, xv, gidx * Cg, Cg, OH, OW, d, false);
+    // channel-padded operand (R*S*Cgk columns, Cgk = Cg rounded up to 64): the TMA im2col path zero-fills slots >= Cg
+    const int Cgk = (d.mode == 0 && wb.size(1) != static_cast<int64_t>(d.R) * d.S * Cg) ? static_cast<int>(wb.size(1) / (d.R * d.S)) : 0;
+    ConvGeom cg = make_geom(x, xv, gidx * Cg, Cg, OH, OW, d, false, Cgk);
     TORCH_CHECK(wb.size(1) == cg.K, "conv_fprop: weight K ", wb.size(1), " != expected ", cg.K);
     const long m_blocks = (cg.M + BLOCK_M - 1) / BLOCK_M;
     const int bn = pick_conv_bn(Cout_g, m_blocks, sms);
@@ -218,6 +221,7 @@ at::Tensor conv_fprop(const at::Tensor& x, const at::Tensor& wb, const c10::opti
       }
       continue;
     }
+    TORCH_CHECK(cg.Cgk == cg.Cg, "conv_fprop: channel-padded operand needs the TMA im2col path");
     switch (bn) {
       case 64: launch_conv<64, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
       case 128: launch_conv<128, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
@@ -250,7 +254,8 @@ at::Tensor conv_dgrad(const at::Tensor& dy, const at::Tensor& wt, at::IntArrayRe
     mask_pitch = mv.pitch;
   }
   for (int gidx = 0; gidx < groups; ++gidx) {
-    ConvGeom cg = make_geom(dy, dv, gidx * Cout_g, Cout_g, H, W, d, true);
+    const int Cok = wt.size(1) != static_cast<int64_t>(d.R) * d.S * Cout_g ? static_cast<int>(wt.size(1) / (d.R * d.S)) : 0;
+    ConvGeom cg = make_geom(dy, dv, gidx * Cout_g, Cout_g, H, W, d, true, Cok);
     TORCH_CHECK(wt.size(1) == cg.K, "conv_dgrad: packed weight K mismatch");
     const long m_blocks = (cg.M + BLOCK_M - 1) / BLOCK_M;
     const int bn = pick_conv_bn(Cg, m_blocks, sms);
@@ -283,6 +288,7 @@ at::Tensor conv_dgrad(const at::Tensor& dy, const at::Tensor& wt, at::IntArrayRe
       }
       continue;
     }
+    TORCH_CHECK(cg.Cgk == cg.Cg, "conv_dgrad: channel-padded operand needs the TMA im2col path");
     switch (bn) {
       case 64: launch_conv<64, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
       case 128: launch_conv<128, false, false, EPI_BF16, GATHER_A>(tm, p, cg, grid, stream); break;
@@ -296,7 +302,7 @@ at::Tensor conv_dgrad(const at::Tensor& dy, const at::Tensor& wt, at::IntArrayRe
 // dw[Cout, Kw] fp32 += alpha * dYᵀ · im2col(x)   (atomic split-K over the N*OH*OW reduction; dw pre-zeroed
 // unless accumulating into an existing gradient).
 void conv_wgrad(const at::Tensor& x, const at::Tensor& dy, at::Tensor dw, at::IntArrayRef kernel, at::IntArrayRef stride,
-                at::IntArrayRef pad, int64_t groups, int64_t mode, double alpha) {
+                at::IntArrayRef pad, int64_t groups, int64_t mode, double alpha, int64_t cgk) {
   TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && dy.scalar_type() == at::kBFloat16);
   TORCH_CHECK(dw.scalar_type() == at::kFloat && dw.dim() == 2 && dw.is_contiguous());
   c10::cuda::CUDAGuard guard(x.device());
@@ -308,8 +314,11 @@ void conv_wgrad(const at::Tensor& x, const at::Tensor& dy, at::Tensor dw, at::In
   auto stream = at::cuda::getCurrentCUDAStream();
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
   for (int gidx = 0; gidx < groups; ++gidx) {
-    ConvGeom cg = make_geom(x, xv, gidx * Cg, Cg, dv.H, dv.W, d, false);
-    TORCH_CHECK(dw.size(0) == Cout && dw.size(1) == cg.K, "conv_wgrad: dw shape mismatch");
+    // cgk > Cg: the reduction's k-columns are channel-padded per tap (im2col TMA); dw itself stays unpadded and the
+    // epilogue maps column tap*cgk + c -> tap*Cg + c, dropping the pad
+    ConvGeom cg = make_geom(x, xv, gidx * Cg, Cg, dv.H, dv.W, d, false, (mode == 0 && cgk > Cg) ? static_cast<int>(cgk) : 0);
+    const int64_t k_real = mode == 1 ? cg.K : static_cast<int64_t>(d.R) * d.S * Cg;
+    TORCH_CHECK(dw.size(0) == Cout && dw.size(1) == k_real, "conv_wgrad: dw shape mismatch");
     int bn = cg.K > 128 ? 256 : (cg.K > 64 ? 128 : 64);
     if (bn == 256 && ((cg.K + 191) / 192 * 192) * 100 < ((cg.K + 255) / 256 * 256) * 85) bn = 192;   // e.g. K = 576
     TmapSet tm;
@@ -330,8 +339,9 @@ void conv_wgrad(const at::Tensor& x, const at::Tensor& dy, at::Tensor dw, at::In
     p.cluster = cl;
     encode_tmap_bf16_2d(&tm.a[0], dyp, Cout_g, cg.M, dv.pitch, 64, BLOCK_K / cl);      // each CTA multicasts 1/cl of the k-rows
     tm.b[0] = tm.a[0];
-    p.c_f32 = dw.data_ptr<float>() + static_cast<long>(gidx) * Cout_g * cg.K;
-    p.ldc = cg.K;
+    p.c_f32 = dw.data_ptr<float>() + static_cast<long>(gidx) * Cout_g * k_real;
+    p.ldc = k_real;
+    if (cg.Cgk != cg.Cg) { p.col_cg = cg.Cg; p.col_cgk = cg.Cgk; }
     p.atomic = 1;
     p.alpha = static_cast<float>(alpha);
     if (cl == 1 && try_im2col_map(&tm.b[0], cg, BLOCK_K)) {
@@ -343,6 +353,7 @@ void conv_wgrad(const at::Tensor& x, const at::Tensor& dy, at::Tensor dw, at::In
       }
       continue;
     }
+    TORCH_CHECK(cg.Cgk == cg.Cg, "conv_wgrad: channel-padded reduction needs the TMA im2col path");
     switch (bn) {
       case 64: launch_conv<64, true, true, EPI_F32, GATHER_B>(tm, p, cg, grid, stream); break;
       case 128: launch_conv<128, true, true, EPI_F32, GATHER_B>(tm, p, cg, grid, stream); break;
@@ -352,33 +363,63 @@ void conv_wgrad(const at::Tensor& x, const at::Tensor& dy, at::Tensor dw, at::In
   }
 }
 
-// Pack the dgrad operand from the fp32 master weights: w [Cout][R][S][Cg] -> wt [groups][Cg][R][S][Cout_g] bf16.
+// Pack the dgrad operand from the fp32 master weights: w [Cout][R][S][Cg] -> wt [groups][Cg][R][S][Cop] bf16, where
+// Cop >= Cout_g is the per-tap slot count (Cout_g rounded up to 64 on the channel-padded im2col path; pad = 0).
 __global__ void pack_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wt, int Cout, int RS, int Cg,
-                                  int groups) {
+                                  int groups, int Cop) {
   const int Cout_g = Cout / groups;
-  const long total = static_cast<long>(Cout) * RS * Cg;
+  const long total = static_cast<long>(groups) * Cg * RS * Cop;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
-    // i indexes wt: (((g*Cg + ci)*RS + tap)*Cout_g + co)
-    const int co = static_cast<int>(i % Cout_g);
-    long t = i / Cout_g;
+    // i indexes wt: (((g*Cg + ci)*RS + tap)*Cop + co)
+    const int co = static_cast<int>(i % Cop);
+    long t = i / Cop;
     const int tap = static_cast<int>(t % RS); t /= RS;
     const int ci = static_cast<int>(t % Cg);
     const int g = static_cast<int>(t / Cg);
-    wt[i] = __float2bfloat16(w[((static_cast<long>(g) * Cout_g + co) * RS + tap) * Cg + ci]);
+    wt[i] = co < Cout_g ? __float2bfloat16(w[((static_cast<long>(g) * Cout_g + co) * RS + tap) * Cg + ci])
+                        : __float2bfloat16(0.f);
   }
 }
 
 at::Tensor conv_pack_dgrad(const at::Tensor& w, int64_t Cout, int64_t RS, int64_t Cg, int64_t groups,
-                           c10::optional<at::Tensor> out) {
+                           c10::optional<at::Tensor> out, int64_t cop) {
   TORCH_CHECK(w.is_cuda() && w.scalar_type() == at::kFloat && w.numel() == Cout * RS * Cg);
   c10::cuda::CUDAGuard guard(w.device());
-  at::Tensor wt = out.has_value() ? *out : at::empty({groups * Cg, RS * (Cout / groups)}, w.options().dtype(at::kBFloat16));
-  const long total = Cout * RS * Cg;
+  const int64_t Cop = cop > 0 ? cop : Cout / groups;
+  TORCH_CHECK(Cop >= Cout / groups);
+  at::Tensor wt = out.has_value() ? *out : at::empty({groups * Cg, RS * Cop}, w.options().dtype(at::kBFloat16));
+  TORCH_CHECK(wt.numel() == groups * Cg * RS * Cop, "conv_pack_dgrad: output shape mismatch");
+  const long total = groups * Cg * RS * Cop;
   pack_dgrad_kernel<<<grid_for(total, 256), 256, 0, at::cuda::getCurrentCUDAStream()>>>(
-      w.data_ptr<float>(), reinterpret_cast<__nv_bfloat16*>(wt.data_ptr()), Cout, RS, Cg, groups);
+      w.data_ptr<float>(), reinterpret_cast<__nv_bfloat16*>(wt.data_ptr()), Cout, RS, Cg, groups, static_cast<int>(Cop));
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   return wt;
+}
+
+// Channel-padded fprop / wgrad operand: wb [Cout][RS][Cg] bf16 -> [Cout][RS][Cgk] bf16 (slots >= Cg zero).
+__global__ void pack_pad_channels_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, long rows,
+                                         int Cg, int Cgk) {
+  const long total = rows * Cgk;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / Cgk;
+    const int c = static_cast<int>(i - r * Cgk);
+    dst[i] = c < Cg ? src[r * Cg + c] : __float2bfloat16(0.f);
+  }
+}
+at::Tensor conv_pack_padded(const at::Tensor& wb, int64_t Cout, int64_t RS, int64_t Cg, int64_t Cgk,
+                            c10::optional<at::Tensor> out) {
+  TORCH_CHECK(wb.is_cuda() && wb.scalar_type() == at::kBFloat16 && wb.is_contiguous() && wb.numel() == Cout * RS * Cg);
+  c10::cuda::CUDAGuard guard(wb.device());
+  at::Tensor dst = out.has_value() ? *out : at::empty({Cout, RS * Cgk}, wb.options());
+  TORCH_CHECK(dst.numel() == Cout * RS * Cgk && dst.is_contiguous());
+  const long rows = Cout * RS;
+  pack_pad_channels_kernel<<<grid_for(rows * Cgk, 256), 256, 0, at::cuda::getCurrentCUDAStream()>>>(
+      reinterpret_cast<const __nv_bfloat16*>(wb.data_ptr()), reinterpret_cast<__nv_bfloat16*>(dst.data_ptr()), rows,
+      static_cast<int>(Cg), static_cast<int>(Cgk));
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  return dst;
 }
 
 }  // namespace psd
@@ -399,6 +440,7 @@ TORCH_LIBRARY_FRAGMENT(poseidon, m) {
   m.def("conv_dgrad(Tensor dy, Tensor wt, int[] kernel, int[] pad, int groups, int H, int W, Tensor? mask, float slope) "
         "-> Tensor", &psd::conv_dgrad);
   m.def("conv_wgrad(Tensor x, Tensor dy, Tensor(a!) dw, int[] kernel, int[] stride, int[] pad, int groups, int mode, "
-        "float alpha) -> ()", &psd::conv_wgrad);
-  m.def("conv_pack_dgrad(Tensor w, int Cout, int RS, int Cg, int groups, Tensor? out) -> Tensor", &psd::conv_pack_dgrad);
+        "float alpha, int cgk) -> ()", &psd::conv_wgrad);
+  m.def("conv_pack_dgrad(Tensor w, int Cout, int RS, int Cg, int groups, Tensor? out, int cop) -> Tensor", &psd::conv_pack_dgrad);
+  m.def("conv_pack_padded(Tensor wb, int Cout, int RS, int Cg, int Cgk, Tensor? out) -> Tensor", &psd::conv_pack_padded);
 }

@@ -59,6 +59,7 @@ struct GemmParams {
   int relu;              // EPI_BF16: apply max(0, x) (negative_slope below)
   float relu_slope;
   int atomic;            // EPI_F32: atomicAdd instead of store
+  int col_cg, col_cgk;   // EPI_F32 (conv wgrad over channel-padded K): output column (tap*cgk + c) -> tap*cg + c, c >= cg dropped
   float alpha;           // scale applied to the accumulator
   // --- EPI_SGD: W[M,N] fp32 master, H history, Wb bf16 shadow, in place
   float* w;
@@ -170,10 +171,17 @@ __device__ __forceinline__ void epilogue_tile32(const GemmParams& p, const uint3
       }
     }
   } else if constexpr (EPI == EPI_F32) {
-    if (lane < ncols) {
+    int col = col0 + lane;
+    bool col_ok = lane < ncols;
+    if (p.col_cgk > 0) {
+      const int tap = col / p.col_cgk, c = col - tap * p.col_cgk;
+      col_ok = col_ok && c < p.col_cg;
+      col = tap * p.col_cg + c;
+    }
+    if (col_ok) {
 #pragma unroll 4
       for (int rr = 0; rr < nrows; ++rr) {
-        float* dst = p.c_f32 + static_cast<long>(row0 + rr) * p.ldc + col0 + lane;
+        float* dst = p.c_f32 + static_cast<long>(row0 + rr) * p.ldc + col;
         const float v = stage[rr * 33 + lane];
         if (p.atomic) atomicAdd(dst, v);
         else *dst = v;
@@ -381,7 +389,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
             int kc = n_blk * BN + c * 64;
             if (kc >= cg.K) kc = 0;                      // columns past K are dropped by the epilogue: load anything valid
             const int tap = static_cast<int>(fdiv(static_cast<uint32_t>(kc), cg.div_cg));
-            im_c0[c] = kc - tap * cg.Cg;
+            im_c0[c] = kc - tap * cg.Cgk;
             const int r = static_cast<int>(fdiv(static_cast<uint32_t>(tap), cg.div_s));
             im_offh[c] = static_cast<uint16_t>(r);
             im_offw[c] = static_cast<uint16_t>(tap - r * cg.S);
@@ -413,7 +421,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
             // A tile = 128 output pixels x 64 channels of tap (r, s): one im2col-mode TMA instruction
             const int k0 = g * BLOCK_K;
             const int tap = static_cast<int>(fdiv(static_cast<uint32_t>(k0), cg.div_cg));
-            const int c0 = k0 - tap * cg.Cg;
+            const int c0 = k0 - tap * cg.Cgk;
             const int r = static_cast<int>(fdiv(static_cast<uint32_t>(tap), cg.div_s));
             const int sx = tap - r * cg.S;
             const bool in_k = k0 < cg.K;

@@ -68,6 +68,14 @@ def as_kernel_input(x: torch.Tensor) -> torch.Tensor:
     return x.contiguous(memory_format=CL) if x.dim() == 4 else x.contiguous()
 
 
+def _pad64(c: int) -> int:
+    """Per-tap slot count on the im2col-TMA path: c rounded up to a multiple of 64 if that costs <= 34 % extra work."""
+    if c % 64 == 0 or c % 8 != 0 or c < 48:
+        return c
+    p = (c + 63) // 64 * 64
+    return p if (p - c) * 100 <= 34 * c else c
+
+
 # =====================================================================================================
 # Convolution
 # =====================================================================================================
@@ -104,6 +112,18 @@ class ConvState:
             self.Kw = self.R * self.S * cg
         self.cg = self.Cp // self.groups
         self.cin_logical = cin_logical
+        # Channel-padded K for the TMA im2col path: when C_g is not a multiple of 64 (AlexNet conv2: 48, GoogLeNet:
+        # 96 / 112 / 144 / 160 / 480 / 528 ...) the per-tap slot count is rounded up to 64 as long as that wastes at
+        # most a third of the MMA work; the TMA zero-fills the extra slots, the weight operand carries zeros there.
+        self.cgk = self.cg            # K slots per tap of the fprop / wgrad operand
+        self.cok = self.Cout // self.groups      # K slots per tap of the dgrad operand
+        # Opt-in (POSEIDON_PAD_K=1): numerically validated on B200, but AlexNet throughput was unchanged (conv2: a third
+        # more MMA work bought back by the cheaper producer: 78.9 k vs 80.0 k img/s) and GoogLeNet is not yet measured.
+        if not self.row_mode and os.environ.get("POSEIDON_PAD_K", "0") == "1":
+            self.cgk = _pad64(self.cg)
+            self.cok = _pad64(self.Cout // self.groups)
+        self.wbp: Optional[torch.Tensor] = None      # channel-padded copy of wb (derived, refreshed when wb changes)
+        self.dirty_wbp = True
         self.wb: Optional[torch.Tensor] = None
         self.wt: Optional[torch.Tensor] = None
         self.dirty_wb = True               # bf16 fprop/wgrad operand is stale w.r.t. the fp32 master
@@ -146,6 +166,7 @@ class ConvState:
     def mark_updated(self, keep_wb: bool = False):
         """The fp32 master changed (optimizer step / weight load)."""
         self.dirty_wt = True
+        self.dirty_wbp = True
         if not keep_wb and not self.arena_shadow:
             self.dirty_wb = True
 
@@ -177,10 +198,21 @@ class ConvState:
         self.dirty_wb = False
         return self.wb
 
+    def operand(self) -> torch.Tensor:
+        """The bf16 fprop operand the kernels consume: the shadow itself, or its channel-padded copy."""
+        wb = self.shadow()
+        if self.cgk == self.cg:
+            return wb
+        if self.wbp is None or self.dirty_wbp:
+            self.wbp = K().conv_pack_padded(wb.reshape(-1), self.Cout, self.R * self.S, self.cg, self.cgk, self.wbp)
+            self.dirty_wbp = False
+        return self.wbp
+
     def dgrad_pack(self) -> torch.Tensor:
         if self.wt is not None and not self.dirty_wt:
             return self.wt
-        self.wt = K().conv_pack_dgrad(self.w2d().reshape(-1), self.Cout, self.R * self.S, self.cg, self.groups, self.wt)
+        self.wt = K().conv_pack_dgrad(self.w2d().reshape(-1), self.Cout, self.R * self.S, self.cg, self.groups, self.wt,
+                                      self.cok)
         self.dirty_wt = False
         return self.wt
 
@@ -265,7 +297,7 @@ class _ConvFn(torch.autograd.Function):
             y = k.conv_fprop(xin, st.shadow(), bias, [st.Rq, st.Sq], [1, 1], [0, 0], 1, 0, oh, ow, relu,
                              float(relu_slope or 0.0), None)
         else:
-            y = k.conv_fprop(xin, st.shadow(), bias, [st.R, st.S], list(stride), list(conv_pad), st.groups,
+            y = k.conv_fprop(xin, st.operand(), bias, [st.R, st.S], list(stride), list(conv_pad), st.groups,
                              1 if (st.row_mode and not st.pad8) else 0, oh, ow, relu, float(relu_slope or 0.0), None)
         ctx.layer, ctx.relu_slope, ctx.conv_pad = layer, relu_slope, conv_pad
         ctx.in_shape = tuple(x.shape)
@@ -288,10 +320,10 @@ class _ConvFn(torch.autograd.Function):
             dw2 = sink.weight_buffer(layer, st) if sink is not None else \
                 torch.zeros(st.Cout, st.Kw, device=dy.device, dtype=torch.float32)
             if st.s2d:
-                k.conv_wgrad(xin, dy, dw2, [st.Rq, st.Sq], [1, 1], [0, 0], 1, 0, 1.0)
+                k.conv_wgrad(xin, dy, dw2, [st.Rq, st.Sq], [1, 1], [0, 0], 1, 0, 1.0, 0)
             else:
                 k.conv_wgrad(xin, dy, dw2, [st.R, st.S], list(stride), list(ctx.conv_pad), st.groups,
-                             1 if (st.row_mode and not st.pad8) else 0, 1.0)
+                             1 if (st.row_mode and not st.pad8) else 0, 1.0, st.cgk if not st.row_mode else 0)
             dw = st.grad_from_dw(dw2)
         if layer.bias_term and ctx.needs_input_grad[2]:
             db = torch.empty(st.Cout, device=dy.device, dtype=torch.float32)

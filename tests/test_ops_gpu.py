@@ -146,14 +146,21 @@ CONV_CASES = [
     (2, 16, 28, 28, 32, 5, 1, 2, 1),       # GoogLeNet 5x5
     (2, 64, 56, 56, 192, 3, 1, 1, 1),      # conv2/3x3
     (3, 24, 7, 9, 40, 3, 1, 1, 1),         # odd sizes
+    (2, 96, 28, 28, 128, 3, 1, 1, 1),      # GoogLeNet 3x3 after a 96-channel reduce: channel-padded im2col (96 -> 128)
+    (2, 480, 14, 14, 208, 1, 1, 0, 1),     # 1x1 on 480 channels (-> 512), Cout 208 (dgrad slots 208 -> 256)
+    (2, 160, 14, 14, 320, 3, 1, 1, 1),     # 160 -> 192
 ]
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
 @pytest.mark.parametrize("relu", [False, True])
-def test_conv_fwd_bwd(ext, case, relu):
+@pytest.mark.parametrize("pad_k", ["0", "1"])
+def test_conv_fwd_bwd(ext, case, relu, pad_k, monkeypatch):
     from poseidon_b200.ops import sm100
     n, cin, h, w, cout, k, stride, pad, group = case
+    if pad_k == "1" and sm100._pad64(cin // group) == cin // group and sm100._pad64(cout // group) == cout // group:
+        pytest.skip("no channel padding applies to this shape")
+    monkeypatch.setenv("POSEIDON_PAD_K", pad_k)       # channel-padded K on the TMA im2col path (read at ConvState creation)
     layer = _FakeLayer(cout, cin, k, stride, pad, group)
     layer.in_hw = (h, w)
     x = _nhwc((n, cin, h, w), 5)

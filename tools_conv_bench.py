@@ -15,6 +15,7 @@ CASES = {
 }
 import os
 if os.environ.get('PSD_CONV_IM2COL') == '0':
+    os.environ['POSEIDON_PAD_K'] = '0'
     sm100.K().set_conv_im2col(0)
 which = sys.argv[1].split(",") if len(sys.argv) > 1 else list(CASES)
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
