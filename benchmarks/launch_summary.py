@@ -1,5 +1,5 @@
 """Summarise an ncu launch list (gpu__time_duration per kernel) into one training step's kernel budget.
-    python tools_launch_summary.py gpurun_out/launches.csv [min_us]
+    python benchmarks/launch_summary.py gpurun_out/launches.csv [min_us]
 """
 import collections
 import csv

@@ -1,5 +1,5 @@
 """Fused outer-product + optimizer-step GEMM (EPI_SGD) micro-benchmark: fc6 / fc7 shapes of AlexNet.
-    python tools_sgd_bench.py [iters]
+    python benchmarks/sgd_bench.py [iters]
 Reports time and achieved HBM traffic (18 B per weight: W, H read + written, bf16 shadow written)."""
 import sys
 import torch

@@ -443,7 +443,7 @@ class FusedSFB:
             else:
                 # Single GPU: the optimizer epilogue has only the 8 epilogue warps' loads in flight (64 KB/SM) and
                 # measured 2.4 TB/s, while the wgrad GEMM -> fp32 buffer followed by the streaming update kernel
-                # runs at 5.3 TB/s: 213 us vs 279 us for fc6 (tools_sgd_bench.py).  Use the faster pair.
+                # runs at 5.3 TB/s: 213 us vs 279 us for fc6 (benchmarks/sgd_bench.py).  Use the faster pair.
                 g = getattr(self, "_gbuf", None)
                 if g is None:
                     g = self._gbuf = torch.empty(self.N, self.K, device=w.device, dtype=torch.float32)

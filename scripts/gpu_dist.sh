@@ -1,6 +1,6 @@
 #!/bin/bash
-# usage: scripts_gpu_dist.sh <ngpu>
-cd "$(dirname "$0")"
+# usage: scripts/gpu_dist.sh <ngpu>
+cd "$(dirname "$0")/.."
 N=${1:-2}
 mkdir -p gpurun_out
 L=gpurun_out/dist$N.log

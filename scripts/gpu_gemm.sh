@@ -1,6 +1,6 @@
 #!/bin/bash
 # run each GEMM test group in its own process (a device-side trap kills the CUDA context)
-cd "$(dirname "$0")"
+cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/gemm_tests.log 2>&1
 for t in test_gemm_tn_bf16 test_gemm_dgrad test_gemm_wgrad test_sfb_outer_sgd_single test_sfb_outer_multi; do

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")"
+cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 L=gpurun_out/ops_tests.log
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > $L 2>&1

@@ -1,6 +1,6 @@
 #!/bin/bash
-# usage: scripts_gpu_scale.sh <ngpu> [tests]   — fused-engine benches at N GPUs (+ the dist test-suite when asked)
-cd "$(dirname "$0")"
+# usage: scripts/gpu_scale.sh <ngpu> [tests]   — fused-engine benches at N GPUs (+ the dist test-suite when asked)
+cd "$(dirname "$0")/.."
 N=${1:-2}
 mkdir -p gpurun_out
 L=gpurun_out/scale$N.log
