@@ -9,7 +9,9 @@
 //   weight-gradient / sufficient-factor outer product  dW = Uᵀ·V  a plain TMA GEMM with no transposes
 // * the reduction may span several *sources* (one tensor map per source): for SFB the sources are the
 //   peers' symmetric (u, v) buffers read over NVLink, gated by per-peer epoch flags
-// * A may instead be produced by gather warps (implicit-GEMM convolution, see conv_gather.cuh)
+// * for implicit-GEMM convolution one operand is fetched by the TMA engine in im2col mode (IM2COL_A / IM2COL_B) or, where
+//   the channel count does not allow that, built by cp.async gather warps (GATHER_A / GATHER_B, see conv_gather.cuh)
+// * the TMA-producer and MMA-issuer loops run warp-uniform with one elected issuing lane (operands in uniform registers)
 // * fused epilogues: bias + ReLU (+ mask) -> bf16 ; fp32 store / atomic split-K ; in-place SGD update
 //
 // Replaces the reference's cublasSgemm call sites (src/caffe/util/math_functions.cu:15-45) used by
@@ -30,7 +32,6 @@ constexpr int kNumThreads = 128 + 32 * kEpiWarps;   // warp0 TMA, warp1 MMA, war
 constexpr int kEpiWarp0 = 4;
 constexpr int kGatherWarp0 = kEpiWarp0 + kEpiWarps;  // conv kernels: 8 more warps gather the implicit-im2col operand
 constexpr int kGatherThreads = 256;          // 8 warps: the producers are instruction-latency bound, not bandwidth bound
-constexpr int kGatherLag = 2;             // cp.async groups kept in flight per gather thread
 // GATHER_A / GATHER_B: operand built by the cp.async gather warps (any channel count, ROW mode).
 // IM2COL_A / IM2COL_B: operand fetched by the TMA engine in im2col mode (C_g % 64 == 0): no gather warps at all.
 enum GatherMode : int { GATHER_NONE = 0, GATHER_A = 1, GATHER_B = 2, IM2COL_A = 3, IM2COL_B = 4 };

@@ -398,8 +398,31 @@ def vgg16_solver(net_path="train_val.prototxt", **over):
     return sp
 
 
+def cifar10_quick_solver(net_path="cifar10_quick_train_test.prototxt", **over):
+    """reference: examples/cifar10/cifar10_quick_solver.prototxt."""
+    sp = P.SolverParameter(net=net_path, test_interval=500, base_lr=0.0007, momentum=0.9, weight_decay=0.004,
+                           lr_policy="fixed", display=100, max_iter=4000, snapshot=4000,
+                           snapshot_prefix="cifar10_quick", solver_mode="GPU")
+    sp.test_iter = [100]
+    for k, v in over.items():
+        setattr(sp, k, v)
+    return sp
+
+
+def cifar10_full_solver(net_path="cifar10_full_train_test.prototxt", **over):
+    """reference: examples/cifar10/cifar10_full_solver.prototxt."""
+    sp = P.SolverParameter(net=net_path, test_interval=1000, base_lr=0.001, momentum=0.9, weight_decay=0.004,
+                           lr_policy="fixed", display=200, max_iter=60000, snapshot=10000,
+                           snapshot_prefix="cifar10_full", solver_mode="GPU")
+    sp.test_iter = [100]
+    for k, v in over.items():
+        setattr(sp, k, v)
+    return sp
+
+
 MODELS = {
-    "lenet": (lenet, lenet_solver), "cifar10_quick": (cifar10_quick, None), "cifar10_full": (cifar10_full, None),
+    "lenet": (lenet, lenet_solver), "cifar10_quick": (cifar10_quick, cifar10_quick_solver),
+    "cifar10_full": (cifar10_full, cifar10_full_solver),
     "alexnet": (alexnet, alexnet_solver), "caffenet": (caffenet, caffenet_solver),
     "googlenet": (googlenet, googlenet_solver), "vgg16": (vgg16, vgg16_solver),
 }
@@ -427,10 +450,12 @@ def get_solver_param(name: str, net=None, **over):
     return sp
 
 
-def write_zoo(out_dir: str):
-    """Emit ``<model>/train_val.prototxt`` + ``solver.prototxt`` for every zoo model."""
+def write_zoo(out_dir: str, only=None):
+    """Emit ``<model>/train_val.prototxt`` + ``solver.prototxt`` for every (or the named) zoo model."""
     import os
     for name, (net_fn, solver_fn) in MODELS.items():
+        if only and name not in only:
+            continue
         d = os.path.join(out_dir, name)
         os.makedirs(d, exist_ok=True)
         with open(os.path.join(d, "train_val.prototxt"), "w") as f:
@@ -439,3 +464,23 @@ def write_zoo(out_dir: str):
             sp = solver_fn(net_path=os.path.join(d, "train_val.prototxt"))
             with open(os.path.join(d, "solver.prototxt"), "w") as f:
                 f.write(to_text(sp))
+
+
+def main(argv=None) -> int:
+    """``python -m poseidon_b200.models.zoo --out models [--only alexnet,googlenet]``"""
+    import argparse
+    ap = argparse.ArgumentParser(description="write the model zoo as Caffe prototxt files")
+    ap.add_argument("--out", default="models")
+    ap.add_argument("--only", default="", help="comma separated subset of: " + ", ".join(MODELS))
+    a = ap.parse_args(argv)
+    only = [x for x in a.only.split(",") if x]
+    for x in only:
+        if x not in MODELS:
+            ap.error(f"unknown model '{x}'")
+    write_zoo(a.out, only or None)
+    return 0
+
+
+if __name__ == "__main__":
+    import sys
+    sys.exit(main())

@@ -479,6 +479,7 @@ class Solver:
         """reference: src/caffe/solver.cpp:699-756 (CSV, values averaged over workers)."""
         if not self.rank_ctx.is_root:
             return
+        os.makedirs(os.path.dirname(os.path.abspath(filename)) or ".", exist_ok=True)
         with open(filename, "w") as f:
             if self.param.display and hasattr(self, "train_table"):
                 self.train_table.write(f, self.rank_ctx.world_size)

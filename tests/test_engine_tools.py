@@ -64,3 +64,29 @@ def test_caffe_engine_plan_and_start(tmp_path):
     assert solver.iter == 2
     assert os.path.exists(str(tmp_path / "run") + ".netoutputs")
     eng.close()
+
+
+def test_zoo_cli_writes_prototxts_that_train(tmp_path):
+    """`python -m poseidon_b200.models.zoo` (used by examples/*.sh) + caffe_main train on the written solver."""
+    from poseidon_b200.models import zoo
+    from poseidon_b200.tools import caffe_main
+    out = tmp_path / "models"
+    assert zoo.main(["--out", str(out), "--only", "lenet,cifar10_quick"]) == 0
+    assert sorted(os.listdir(out)) == ["cifar10_quick", "lenet"]
+    sp = P.read_solver(str(out / "cifar10_quick" / "solver.prototxt"))
+    assert abs(sp.base_lr - 0.0007) < 1e-9 and sp.max_iter == 4000 and list(sp.test_iter) == [100]
+    # shorten the LeNet solver and run the CLI on CPU for two iterations
+    lp = out / "lenet" / "solver.prototxt"
+    sp = P.read_solver(str(lp))
+    sp.max_iter, sp.display, sp.snapshot, sp.test_interval = 2, 1, 0, 0
+    sp.snapshot_after_train = False
+    sp.clear("test_iter")
+    sp.solver_mode = "CPU"
+    P.write_text(str(lp), sp)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        assert caffe_main.main(["train", f"--solver={lp}", f"--net_outputs={tmp_path / 'run'}"]) == 0
+    finally:
+        os.chdir(cwd)
+    assert os.path.exists(str(tmp_path / "run") + ".netoutputs")
