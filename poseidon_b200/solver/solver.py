@@ -32,6 +32,31 @@ log = logging.getLogger("poseidon_b200")
 _NUM_FIXED_COLS = 3   # iter, time, loss — reference: include/caffe/common.hpp:65-70
 
 
+class LossHandle:
+    """Deferred read of a scalar device tensor (see :meth:`Solver.read_loss_async`)."""
+
+    def __init__(self, t):
+        self._t = t
+        self._host = None
+        self._ev = None
+        if t is not None and t.is_cuda:
+            try:
+                self._host = torch.empty((), dtype=torch.float32, pin_memory=True)
+                self._host.copy_(t.detach().float().reshape(()), non_blocking=True)
+                self._ev = torch.cuda.Event()
+                self._ev.record()
+            except RuntimeError:
+                self._host = None           # fall back to a synchronous read
+
+    def value(self) -> float:
+        if self._t is None:
+            return float("nan")
+        if self._host is None:
+            return float(self._t)
+        self._ev.synchronize()
+        return float(self._host)
+
+
 class OutputTable:
     """The "net outputs" table: every worker adds its row entries, rows are summed across
     workers (one tiny all-reduce per display point) and divided by #workers when printed.
@@ -254,6 +279,13 @@ class Solver:
             self._train_iteration()
 
     # ---- CUDA-graph execution: the whole step (forward, backward, DWBP hooks, fused updates) is one graph ----
+    def read_loss_async(self):
+        """Start a device->host copy of the latest step's loss into page-locked memory and return a handle whose
+        ``.value()`` blocks only on that copy.  Reading the handle one step later keeps the copy off the critical
+        path (``float(solver.last_loss)`` instead stalls the host until the whole step has drained, which opens a
+        launch bubble before the next step)."""
+        return LossHandle(self.last_loss)
+
     def enable_cuda_graph(self, warmup: int = 3):
         """Capture forward+backward+update of everything after the data layers into a CUDA graph and replay it
         every iteration (launch-bound nets such as GoogLeNet at batch 32).  The data layers stay eager and feed
