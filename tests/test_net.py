@@ -30,7 +30,7 @@ def test_googlenet_structure():
     assert net.blob_shapes["inception_3a/output"] == (1, 256, 28, 28)
     assert net.blob_shapes["inception_5b/output"] == (1, 1024, 7, 7)
     assert net.blob_shapes["pool5/7x7_s1"] == (1, 1024, 1, 1)
-    assert net.output_names == ["loss1/loss1", "loss2/loss2", "loss3/loss3"]
+    assert net.output_names == ["loss1/loss1", "loss2/loss1", "loss3/loss3"]
     w = {t: lw for tn, lws in zip(net.top_names, net.loss_weights) for t, lw in zip(tn, lws)}
     assert w["loss1/loss1"] == pytest.approx(0.3) and w["loss3/loss3"] == 1.0
 
@@ -126,3 +126,36 @@ def test_errors():
     with pytest.raises(ValueError, match="takes 1 bottom"):
         Net(parse_text('input: "x" input_dim: 1 input_dim: 1 input_dim: 1 input_dim: 1 '
                        'layers { name: "r" type: RELU bottom: "x" bottom: "x" top: "r" }', P.NetParameter))
+
+
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir(REF), reason="reference tree not mounted")
+@pytest.mark.parametrize("model,ref_net,ref_solver", [
+    ("alexnet", "models/bvlc_alexnet/train_val.prototxt", "models/bvlc_alexnet/solver.prototxt"),
+    ("caffenet", "models/bvlc_reference_caffenet/train_val.prototxt", "models/bvlc_reference_caffenet/solver.prototxt"),
+    ("googlenet", "models/bvlc_googlenet/train_test.prototxt", "models/bvlc_googlenet/quick_solver.prototxt"),
+])
+def test_zoo_matches_reference_prototxt(model, ref_net, ref_solver):
+    """Golden parity: the zoo builders produce the same graph as the reference's shipped model files — layer for layer
+    (name, type, tops, blob shapes, parameter shapes, lr / decay multipliers, loss weights) — and the same solver."""
+    import os
+    ref_np = P.read_net(os.path.join(REF, ref_net))
+    for phase in (P.TRAIN, P.TEST):
+        ours = Net(zoo.get_model(model), phase=phase)
+        theirs = Net(ref_np, phase=phase)
+        assert ours.layer_names == theirs.layer_names
+        assert [l.type_name for l in ours.layers] == [l.type_name for l in theirs.layers]
+        assert ours.top_names == theirs.top_names and ours.bottom_names == theirs.bottom_names
+        assert {k: v[1:] for k, v in ours.blob_shapes.items()} == {k: v[1:] for k, v in theirs.blob_shapes.items()}
+        for a, b in zip(ours.layers, theirs.layers):
+            assert [tuple(p.shape) for p in a.blobs] == [tuple(p.shape) for p in b.blobs], a.layer_name
+        assert ours.loss_weights == theirs.loss_weights
+        assert ours.params_lr == theirs.params_lr and ours.params_weight_decay == theirs.params_weight_decay
+    a, b = zoo.MODELS[model][1](), P.read_solver(os.path.join(REF, ref_solver))
+    # (`display` is left out: the reference's CaffeNet solver ships a debugging leftover, "display: 1 #20")
+    for f in ("base_lr", "lr_policy", "gamma", "stepsize", "power", "momentum", "weight_decay", "max_iter",
+              "test_interval", "snapshot"):
+        assert getattr(a, f) == pytest.approx(getattr(b, f)) if isinstance(getattr(b, f), float) else getattr(a, f) == getattr(b, f), f
+    assert list(a.test_iter) == list(b.test_iter)
