@@ -146,16 +146,21 @@ def mvn(x, normalize_variance=True, across_channels=False, eps=1e-10):
 # ---- softmax / losses ----------------------------------------------------------------
 def softmax(x):
     """softmax over the channel axis per (n, h·w). reference: softmax_layer.cu:88-125."""
-    return F.softmax(x.float(), dim=1).to(x.dtype)
+    return F.softmax(_f(x), dim=1).to(x.dtype)
 
 
 _FLT_MIN = 1.17549435e-38
 
 
+def _f(x: torch.Tensor) -> torch.Tensor:
+    """Accumulation dtype: fp32 for bf16/fp16/fp32 activations, fp64 kept (the gradient checker runs in double)."""
+    return x if x.dtype == torch.float64 else x.float()
+
+
 def softmax_loss(x, label, return_prob=False):
     """loss = -Σ log(max(p[label], FLT_MIN)) / (num·spatial).
     reference: src/caffe/layers/softmax_loss_layer.cpp:38-87."""
-    xf = x.float()
+    xf = _f(x)
     if xf.dim() == 2:
         xf = xf[:, :, None, None]
     n, c, h, w = xf.shape
@@ -168,13 +173,13 @@ def softmax_loss(x, label, return_prob=False):
 
 def euclidean_loss(a, b):
     """‖a−b‖²/(2N). reference: src/caffe/layers/euclidean_loss_layer.cpp:30-46."""
-    d = (a - b).float()
+    d = _f(a - b)
     return (d * d).sum() / (2.0 * a.shape[0])
 
 
 def hinge_loss(x, label, norm="L1"):
     """reference: src/caffe/layers/hinge_loss_layer.cpp:33-67."""
-    xf = x.float().reshape(x.shape[0], -1)
+    xf = _f(x).reshape(x.shape[0], -1)
     sign = torch.ones_like(xf)
     sign.scatter_(1, label.reshape(-1, 1).long(), -1.0)
     m = (1.0 + sign * xf).clamp_min(0)
@@ -186,36 +191,37 @@ def hinge_loss(x, label, norm="L1"):
 def sigmoid_cross_entropy_loss(x, target):
     """-Σ[x(t−[x≥0]) − log(1+e^{x−2x[x≥0]})]/N.
     reference: src/caffe/layers/sigmoid_cross_entropy_loss_layer.cpp:47-52."""
-    xf, t = x.float(), target.float().reshape(x.shape)
-    pos = (xf >= 0).float()
+    xf = _f(x)
+    t = target.to(xf.dtype).reshape(x.shape)
+    pos = (xf >= 0).to(xf.dtype)
     l = xf * (t - pos) - torch.log1p(torch.exp(xf - 2 * xf * pos))
     return -l.sum() / x.shape[0]
 
 
 def multinomial_logistic_loss(prob, label):
     """-Σ log(max(p[label], 1e-20))/N. reference: multinomial_logistic_loss_layer.cpp:29-36."""
-    p = prob.float().reshape(prob.shape[0], -1).gather(1, label.reshape(-1, 1).long())
+    p = _f(prob).reshape(prob.shape[0], -1).gather(1, label.reshape(-1, 1).long())
     return -(p.clamp_min(1e-20).log()).sum() / prob.shape[0]
 
 
 def infogain_loss(prob, label, H):
     """-Σ_i Σ_j H[l_i,j] log(max(p_ij,1e-20))/N. reference: infogain_loss_layer.cpp:65-73."""
-    p = prob.float().reshape(prob.shape[0], -1).clamp_min(1e-20).log()
-    rows = H.to(p.device).float()[label.reshape(-1).long()]
+    p = _f(prob).reshape(prob.shape[0], -1).clamp_min(1e-20).log()
+    rows = H.to(p.device).to(p.dtype)[label.reshape(-1).long()]
     return -(rows * p).sum() / prob.shape[0]
 
 
 def contrastive_loss(a, b, sim, margin):
     """(Σ_sim d² + Σ_dis max(m−d²,0))/(2N). reference: contrastive_loss_layer.cpp:46-58."""
-    d2 = ((a - b).float().reshape(a.shape[0], -1) ** 2).sum(1)
-    s = sim.reshape(-1).float()
+    d2 = (_f(a - b).reshape(a.shape[0], -1) ** 2).sum(1)
+    s = sim.reshape(-1).to(d2.dtype)
     loss = s * d2 + (1 - s) * (margin - d2).clamp_min(0)
     return loss.sum() / (2.0 * a.shape[0])
 
 
 def accuracy(x, label, top_k=1):
     """fraction of rows whose label is within the top-k scores. reference: accuracy_layer.cpp:34-66."""
-    xf = x.float().reshape(x.shape[0], -1)
+    xf = _f(x).reshape(x.shape[0], -1)
     topk = xf.topk(top_k, dim=1).indices
     hit = (topk == label.reshape(-1, 1).long()).any(1)
     return hit.float().mean()
@@ -223,7 +229,7 @@ def accuracy(x, label, top_k=1):
 
 def argmax(x, top_k=1, out_max_val=False):
     """reference: src/caffe/layers/argmax_layer.cpp:10-60. Output (N, 1|2, top_k, 1)."""
-    xf = x.float().reshape(x.shape[0], -1)
+    xf = _f(x).reshape(x.shape[0], -1)
     vals, idx = xf.topk(top_k, dim=1)
     out = idx.float().unsqueeze(1)
     if out_max_val:
