@@ -185,7 +185,12 @@ def main():
     use_graph = (args.graph == 1) or (args.graph < 0 and args.engine == "sm100" and
                                        (world == 1 or (solver.comm_name == "fused" and args.staleness == 0)))
     if use_graph:
-        solver.enable_cuda_graph(warmup=2)
+        try:
+            solver.enable_cuda_graph(warmup=2)
+        except Exception as exc:              # deterministic across ranks; the eager path is always available
+            if rc.is_root:
+                print(f"[bench] CUDA-graph capture failed ({type(exc).__name__}: {exc}); running eager", file=sys.stderr)
+            use_graph = False
     for _ in range(args.warmup):
         solver.step(1)
     solver.sync.wait_all()
