@@ -23,6 +23,8 @@ import logging
 from collections import deque
 from typing import Callable, Dict, List, Optional
 
+import math
+
 import torch
 
 from ..utils.trace import nvtx_range
@@ -266,6 +268,101 @@ class SSPBackend(Backend):
 
     def bytes_on_wire(self):
         return {"ssp_delta_bytes": self.wire_bytes}
+
+
+class SSPAggrBackend(Backend):
+    """Bösen's SSPAggr consistency model: bandwidth-managed, magnitude-prioritised communication under a staleness bound.
+
+    Every clock a worker computes its own step Δ (own momentum history), applies it locally (read-my-writes) and adds it
+    to a per-parameter *residual* of not-yet-communicated updates.  Only the ``fraction`` of residual entries with the
+    largest relative magnitude |r| / (|w| + ε) — the reference's ``update_sort_policy = RelativeMagnitude`` under a
+    ``client_bandwidth_mbps`` budget — is exchanged (index / value pairs, all-gather) and folded into the peers' weights;
+    the rest waits.  Every ``staleness + 1`` clocks the whole residual is flushed, so no update is ever older than the
+    bound (the reference flushes its oplogs on the clock message for the same reason), and each residual entry is
+    sent exactly once.  ``fraction = 1`` degenerates to BSP with summed per-worker updates.
+
+    reference: ps/src/petuum_ps/thread/ssp_aggr_bg_worker.cpp:576-647 (budgeted oplog sends),
+    ps/src/petuum_ps/server/server_table.cpp:263-287 + ps/src/petuum_ps_common/storage/numeric_container_row.hpp:21-29
+    (importance = relative magnitude), ssp_aggr_server_thread.cpp:13-55."""
+    name = "ssp_aggr"
+
+    def __init__(self, staleness=0, fraction=0.1, eps=1e-8):
+        self.staleness = int(staleness)
+        self.fraction = float(fraction)
+        if not 0.0 < self.fraction <= 1.0:
+            raise ValueError("SSPAggr: fraction of the update sent per clock must be in (0, 1]")
+        self.eps = eps
+        self.clock = 0
+        self.wire_bytes = 0
+        self.dense_equiv_bytes = 0
+        self.residual = {}            # id(param) -> flat fp32 residual
+        self.touched = []
+
+    def launch(self, bucket):
+        hy = self.sync.hyper
+        for p, h, lm, dm in zip(bucket.params, bucket.history, bucket.lr_mult, bucket.decay_mult):
+            delta = compute_update(hy, p.data, p.grad, h, lm, dm)
+            with torch.no_grad():
+                p.data.sub_(delta)                                   # read-my-writes
+                r = self.residual.get(id(p))
+                if r is None:
+                    r = self.residual[id(p)] = torch.zeros(p.numel(), dtype=torch.float32, device=p.device)
+                r.add_(delta.reshape(-1).float() if delta.is_contiguous() else delta.contiguous().reshape(-1).float())
+            self.touched.append(p)
+
+    def _exchange(self, p, flush: bool):
+        r = self.residual[id(p)]
+        n = r.numel()
+        k = n if flush else max(1, int(math.ceil(self.fraction * n)))
+        rc = self.sync.rank_ctx
+        with torch.no_grad():
+            if k >= n:
+                idx = torch.arange(n, device=r.device)
+            else:
+                w = p.data.contiguous().reshape(-1).float() if not p.data.is_contiguous() else p.data.reshape(-1).float()
+                idx = torch.topk(r.abs() / (w.abs() + self.eps), k, sorted=False).indices
+            val = r[idx]
+            r[idx] = 0.0                                             # sent exactly once
+            self.wire_bytes += k * (4 + (0 if k >= n else 4))
+            self.dense_equiv_bytes += n * 4
+            if not rc.distributed:
+                return
+            ws = rc.world_size
+            vals = [torch.empty_like(val) for _ in range(ws)]
+            dist.all_gather(vals, val)
+            if k >= n:
+                total = torch.stack(vals).sum(0) - val               # everybody else's flushed residual (logical order)
+                p.data.sub_(total.view(p.shape))
+            else:
+                idxs = [torch.empty_like(idx) for _ in range(ws)]
+                dist.all_gather(idxs, idx)
+                upd = torch.zeros(n, dtype=torch.float32, device=r.device)
+                for q in range(ws):
+                    if q != rc.rank:
+                        upd.index_add_(0, idxs[q], vals[q])
+                p.data.sub_(upd.view(p.shape))
+        self.sync.invalidate_operands(p)
+
+    def finish_iteration(self):
+        self.clock += 1
+        flush = self.fraction >= 1.0 or (self.clock % (self.staleness + 1) == 0)
+        seen = set()
+        for p in self.touched:
+            if id(p) in seen:
+                continue
+            seen.add(id(p))
+            self._exchange(p, flush)
+        self.touched = []
+
+    def drain(self):
+        """Flush every residual (end of training / before a snapshot or a test pass)."""
+        for b in self.sync.buckets:
+            for p in b.params:
+                if id(p) in self.residual:
+                    self._exchange(p, True)
+
+    def bytes_on_wire(self):
+        return {"ssp_aggr_bytes": self.wire_bytes, "dense_equiv_bytes": self.dense_equiv_bytes}
 
 
 class GradSync:

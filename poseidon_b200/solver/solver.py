@@ -22,7 +22,7 @@ from ..layers import NetContext, set_filler_seed
 from ..net.net import Net
 from ..parallel.context import RankContext
 from ..parallel.gradsync import (ADAGRAD, NESTEROV, SGD, GradSync, Hyper, LocalBackend,
-                                 SSPBackend, TorchDistBackend)
+                                 SSPAggrBackend, SSPBackend, TorchDistBackend)
 from ..utils import fault, trace
 from ..utils.stats import STATS
 from .lr_policy import learning_rate
@@ -92,7 +92,7 @@ class Solver:
     def __init__(self, param, rank_ctx: Optional[RankContext] = None, engine: str = "torch",
                  comm: str = "auto", staleness: int = 0, svb: bool = False, grad_reduce: str = "sum",
                  dtype=None, model_dir: Optional[str] = None, data_shape_hint=None,
-                 snapshot_dir: Optional[str] = None, sfb_mode: str = "auto"):
+                 snapshot_dir: Optional[str] = None, sfb_mode: str = "auto", aggr_fraction: float = 0.1):
         if isinstance(param, str):
             model_dir = model_dir or os.path.dirname(os.path.abspath(param))
             param = P.read_solver(param)
@@ -109,6 +109,7 @@ class Solver:
         self.rank_ctx = rank_ctx
         self.engine = engine
         self.staleness = int(staleness)
+        self.aggr_fraction = float(aggr_fraction)
         self.svb = bool(svb)
         self.iter = 0
         self.display_counter = 0
@@ -261,6 +262,8 @@ class Solver:
             backend = TorchDistBackend(grad_reduce)
         elif comm == "ssp":
             backend = SSPBackend(self.staleness)
+        elif comm == "ssp_aggr":
+            backend = SSPAggrBackend(self.staleness, self.aggr_fraction)
         else:
             raise ValueError(f"unknown comm backend '{comm}' for engine '{self.engine}'")
         sync = GradSync(self.net, rc, self.hyper, backend)

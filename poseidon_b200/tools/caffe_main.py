@@ -58,7 +58,9 @@ def make_parser():
     ap.add_argument("--client_id", type=int, default=None)
     # framework-specific
     ap.add_argument("--engine", default="auto", choices=["auto", "sm100", "torch"])
-    ap.add_argument("--comm", default="auto", choices=["auto", "fused", "nccl", "gloo", "ssp", "local"])
+    ap.add_argument("--comm", default="auto", choices=["auto", "fused", "nccl", "gloo", "ssp", "ssp_aggr", "local"])
+    ap.add_argument("--aggr_fraction", type=float, default=0.1,
+                    help="SSPAggr: fraction of the pending update sent per clock (the rest waits, bounded by --table_staleness)")
     ap.add_argument("--sfb_mode", default="auto", choices=["auto", "all", "none"])
     ap.add_argument("--grad_reduce", default="sum", choices=["sum", "mean"])
     ap.add_argument("--synthetic_shape", default="", help="CxHxW of stand-in data when a DB is absent")
@@ -74,7 +76,15 @@ def parse_args(argv=None):
     # gflags accepts "-flag=value" and "--flag=value"
     argv = [("-" + a if a.startswith("-") and not a.startswith("--") and len(a) > 2 else a) for a in argv]
     args = make_parser().parse_args(argv)
-    ignored = [f for f in _PS_FLAGS if getattr(args, f) is not None and f not in ("stats_path", "num_rows_per_table")]
+    # --consistency_model keeps its meaning: SSP / SSPPush -> bounded staleness (BSP at staleness 0), SSPAggr -> budgeted,
+    # magnitude-prioritised updates
+    cm = (getattr(args, "consistency_model", None) or "").lower()
+    if args.comm == "auto" and cm == "sspaggr":
+        args.comm = "ssp_aggr"
+    elif args.comm == "auto" and cm == "ssp" and args.table_staleness > 0:
+        args.comm = "ssp"
+    ignored = [f for f in _PS_FLAGS if getattr(args, f) is not None and
+               f not in ("stats_path", "num_rows_per_table", "consistency_model")]
     args.ignored_ps_flags = ignored
     return args
 
@@ -128,7 +138,7 @@ def cmd_train(args) -> int:
     solver = get_solver(sp, rank_ctx=rc, engine=_engine(args, rc.device), comm=args.comm,
                         staleness=args.table_staleness, svb=_bool(args.svb), grad_reduce=args.grad_reduce,
                         model_dir=os.path.dirname(os.path.abspath(args.solver)), data_shape_hint=hint,
-                        sfb_mode=args.sfb_mode)
+                        sfb_mode=args.sfb_mode, aggr_fraction=args.aggr_fraction)
     if rc.is_root:
         log.info("Starting Optimization (world_size=%d, engine=%s, comm=%s, svb=%s, staleness=%d)",
                  rc.world_size, solver.engine, solver.comm_name, _bool(args.svb), args.table_staleness)

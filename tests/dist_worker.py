@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--device", default=None)
     ap.add_argument("--delay_rank", type=int, default=-1)
     ap.add_argument("--solver_type", default="SGD")
+    ap.add_argument("--aggr_fraction", type=float, default=0.1)
     args = ap.parse_args()
     rc = init_rank_context(args.device)
     M, W = args.batch, rc.world_size
@@ -39,7 +40,7 @@ def main():
     if rc.device.type == "cpu":
         sp.solver_mode = "CPU"
     s = get_solver(sp, rank_ctx=rc, engine=args.engine, comm=args.comm, svb=bool(args.svb), sfb_mode=args.sfb_mode,
-                   staleness=args.staleness, grad_reduce=args.grad_reduce,
+                   staleness=args.staleness, grad_reduce=args.grad_reduce, aggr_fraction=args.aggr_fraction,
                    dtype=torch.float32 if args.engine == "torch" else None)
     x, y = make_data(M * W * args.steps, hw=args.hw)
     # global batch t = samples [t*M*W, (t+1)*M*W); this rank takes the slice [r*M, (r+1)*M) of it

@@ -100,3 +100,26 @@ def test_injected_straggler_does_not_change_bsp_result(tmp_path, single, monkeyp
     res = launch(2, str(tmp_path / "w"), ["--batch", "8", "--comm", "gloo"])
     _assert_close(res[0], res[1], 1e-7)
     _assert_close(res[0], single)
+
+
+def test_ssp_aggr_full_fraction_is_bsp(tmp_path, single):
+    """SSPAggr sending the whole residual every clock = BSP with summed per-worker updates."""
+    res = launch(2, str(tmp_path / "w"), ["--batch", "8", "--comm", "ssp_aggr", "--aggr_fraction", "1.0"])
+    _assert_close(res[0], res[1], 1e-6)
+    _assert_close(res[0], single, 5e-5)
+
+
+def test_ssp_aggr_budgeted_updates_are_exactly_once_and_cheaper(tmp_path):
+    """10 % of the pending update per clock (largest relative magnitude first), flush bound = staleness 2: after the final
+    drain every update has been applied exactly once everywhere, and far fewer bytes crossed the wire."""
+    res = launch(2, str(tmp_path / "w"), ["--batch", "8", "--comm", "ssp_aggr", "--aggr_fraction", "0.1", "--staleness", "2",
+                                            "--steps", "7"])
+    _assert_close(res[0], res[1], 1e-5)
+    assert np.isfinite(res[0]["loss"])
+    sent, dense = int(res[0]["wire_ssp_aggr_bytes"]), int(res[0]["wire_dense_equiv_bytes"])
+    assert 0 < sent < 0.75 * dense
+    # the same schedule with nothing held back gives the BSP result; the budgeted run must stay close to it after the drain
+    ref = launch(2, str(tmp_path / "r"), ["--batch", "8", "--comm", "ssp_aggr", "--aggr_fraction", "1.0", "--steps", "7"])
+    diffs = [np.abs(res[0][k] - ref[0][k]).max() for k in _weights(ref[0])]
+    scale = max(np.abs(v).max() for v in _weights(ref[0]).values())
+    assert max(diffs) < 0.2 * scale
