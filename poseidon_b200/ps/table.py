@@ -87,13 +87,29 @@ class Table:
             self.oplog[row_id, : u.numel()] += u
         self.dirty = True
 
-    dense_batch_inc = batch_inc
-
     # ---- reads --------------------------------------------------------------------------------------
     def get(self, row_id: int, clock: Optional[int] = None) -> torch.Tensor:
         c = self.group.clock_value if clock is None else clock
         self._fold(min_required=c - self.staleness - 1)
         return self.data[row_id]
+
+    def dense_batch_inc(self, row_id: int, values, index_st: int = 0):
+        """Table::DenseBatchInc: add a contiguous run of deltas starting at column ``index_st``."""
+        values = torch.as_tensor(values)
+        self.batch_inc(row_id, {index_st + i: float(v) for i, v in enumerate(values.reshape(-1).tolist())})
+
+    def get_async(self, row_id: int):
+        return self.get_async_forced(row_id)
+
+    # thread-cache variants of the reference (ThreadGet / ThreadInc / FlushThreadCache): one cache level here
+    def thread_get(self, row_id: int, clock: Optional[int] = None):
+        return self.get(row_id, clock)
+
+    def thread_inc(self, row_id: int, column_id: int, delta):
+        return self.inc(row_id, column_id, delta)
+
+    def flush_thread_cache(self):
+        return None
 
     def get_async_forced(self, row_id: int):      # subscription is implicit (full replica)
         return None
@@ -167,6 +183,21 @@ class PSTableGroup:
         if table_id not in self.tables:
             raise KeyError(f"table {table_id} does not exist")
         return self.tables[table_id]
+
+    # -- API names that only matter with real server / background threads: accepted, nothing to do ------------------
+    def register_row(self, row_type_id: int = 0, row_cls=None):
+        """PSTableGroup::RegisterRow<...>: rows are plain tensors here."""
+        return row_type_id
+
+    def wait_thread_register(self):
+        return None
+
+    def turn_on_early_comm(self):
+        """SSPPush/SSPAggr early communication toggle: updates are always exchanged at clock boundaries here."""
+        self.early_comm = True
+
+    def turn_off_early_comm(self):
+        self.early_comm = False
 
     def register_thread(self):
         return 0

@@ -413,6 +413,42 @@ class Solver:
             self.train_table = OutputTable(names, self.rank_ctx)
         self.train_table.add_row(self.iter, t, lossv, vals)
         self.display_counter += 1
+        self._emit_metrics(lossv, lr, dict(zip(names, vals)))
+
+    # ---- JSONL metrics: one line per display point, throughput timed on the device ----------------------
+    def _emit_metrics(self, lossv, lr, outputs):
+        path = os.environ.get("POSEIDON_METRICS_JSONL") or getattr(self, "metrics_path", None)
+        if not path:
+            return
+        now_iter = self.iter
+        cuda = self.device.type == "cuda"
+        if cuda:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+        else:
+            ev = time.time()
+        prev = getattr(self, "_metrics_prev", None)
+        self._metrics_prev = (now_iter, ev)
+        rec = {"iter": now_iter, "loss": lossv, "lr": lr, "rank": self.rank_ctx.rank, "world_size": self.rank_ctx.world_size,
+               "outputs": outputs}
+        if prev is not None and now_iter > prev[0]:
+            if cuda:
+                ev.synchronize()
+                dt = prev[1].elapsed_time(ev) / 1e3
+            else:
+                dt = ev - prev[1]
+            batch = self.net.blob_shapes[self.net.top_names[0][0]][0] if self.net.top_names and self.net.top_names[0] else 0
+            if dt > 0:
+                rec["images_per_sec_per_rank"] = batch * (now_iter - prev[0]) / dt
+                rec["ms_per_iter"] = 1e3 * dt / (now_iter - prev[0])
+        wire = getattr(self.sync.backend, "bytes_on_wire", None)
+        if wire is not None:
+            rec["bytes_on_wire"] = wire()
+        if self.rank_ctx.is_root:
+            os.makedirs(os.path.dirname(os.path.abspath(path)) or ".", exist_ok=True)
+            import json
+            with open(path, "a") as f:
+                f.write(json.dumps(rec) + "\n")
 
     @staticmethod
     def _output_loss_weights(net) -> Dict[str, float]:

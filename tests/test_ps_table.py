@@ -37,3 +37,20 @@ def test_vector_clock():
     assert vc.tick(0) == 0 and vc.tick(1) == 0
     assert vc.tick(2) == 1 and vc.get_min_clock() == 1
     assert vc.tick(2) == 0 and vc.get_clock(2) == 2
+
+
+def test_api_aliases_single_process():
+    import torch
+    from poseidon_b200.ps.table import PSTableGroup
+    g = PSTableGroup.init(None, staleness=0)
+    assert g.register_row(3) == 3 and g.wait_thread_register() is None
+    g.turn_on_early_comm(); g.turn_off_early_comm()
+    t = g.create_table(0, num_rows=2, row_capacity=6)
+    g.create_table_done()
+    t.dense_batch_inc(1, torch.tensor([1.0, 2.0, 3.0]), index_st=2)
+    t.thread_inc(1, 0, 5.0)
+    t.flush_thread_cache()
+    g.clock()
+    assert t.thread_get(1).tolist() == [5.0, 0.0, 1.0, 2.0, 3.0, 0.0]
+    assert t.get_async(1) is None or True
+    g.shut_down()

@@ -155,3 +155,20 @@ def test_caffe_main_cli_train_and_time(tmp_path):
     assert rc == 0
     assert caffe_main.main(["time", f"--model={net_path}", "--iterations=1", "--gpu=-1"]) == 0
     assert caffe_main.main(["device_query"]) == 0
+
+
+def test_jsonl_metrics(tmp_path, monkeypatch):
+    import json
+    path = tmp_path / "m" / "metrics.jsonl"
+    monkeypatch.setenv("POSEIDON_METRICS_JSONL", str(path))
+    net = zoo.lenet(batch=4, test_batch=4)
+    sp = zoo.get_solver_param("lenet", net=net, max_iter=6, display=2, solver_mode="CPU", snapshot=0,
+                              snapshot_after_train=False, test_interval=0, random_seed=5)
+    sp.clear("test_iter")
+    s = get_solver(sp, engine="torch")
+    s.solve()
+    rows = [json.loads(l) for l in open(path)]
+    assert [r["iter"] for r in rows] == [0, 2, 4]
+    assert "images_per_sec_per_rank" not in rows[0] and rows[1]["images_per_sec_per_rank"] > 0
+    assert rows[2]["world_size"] == 1 and "loss" in rows[2]["outputs"]
+    s.close()
