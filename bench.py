@@ -33,7 +33,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--model", default="alexnet", choices=["alexnet", "caffenet", "googlenet", "vgg16"])
+    ap.add_argument("--model", default="alexnet", choices=["alexnet", "caffenet", "googlenet", "vgg16", "lenet"])
+    ap.add_argument("--allow-cpu", action="store_true",
+                    help="self-test of the harness on a box without a GPU (wall-clock timed, torch engine; NOT a benchmark)")
     ap.add_argument("--engine", default="sm100", choices=["sm100", "torch"])
     ap.add_argument("--comm", default="auto")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the reference prototxt's)")
@@ -130,9 +132,13 @@ def timed_steps(solver, rank_ctx, steps, read_loss: bool):
     import torch
     dev = rank_ctx.device
     rank_ctx.barrier()
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    cuda = dev.type == "cuda"
+    if cuda:
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    else:
+        t0 = time.perf_counter()      # --allow-cpu self-test only
     last = None
     pending = None
     for _ in range(steps):
@@ -147,11 +153,30 @@ def timed_steps(solver, rank_ctx, steps, read_loss: bool):
     if pending is not None:
         last = pending.value()
     solver.sync.wait_all()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    rank_ctx.barrier()
-    ms = e0.elapsed_time(e1)
+    if cuda:
+        e1.record()
+        torch.cuda.synchronize(dev)
+        rank_ctx.barrier()
+        ms = e0.elapsed_time(e1)
+    else:
+        rank_ctx.barrier()
+        ms = (time.perf_counter() - t0) * 1e3
     return rank_ctx.max_over_ranks(ms), last
+
+
+def measure_e2e(args, solver, rc, batch, world):
+    """The same K steps through the public API with, every step, the raw uint8 batch copied host->device from pinned
+    memory (prefetch thread + copy stream) and the step's loss copied device->host."""
+    for dl in solver.net.data_layers():
+        dl.device_resident = False
+    for _ in range(max(3, args.warmup)):
+        solver.step(1)
+        float(solver.last_loss)
+    ms2, _ = timed_steps(solver, rc, args.steps, read_loss=True)
+    h2d = sum(getattr(dl.prefetch, "h2d_bytes", 0) for dl in solver.net.data_layers() if getattr(dl, "prefetch", None))
+    return {"value": batch * world * args.steps / (ms2 / 1e3), "unit": "images/sec", "ms_per_step": ms2 / args.steps,
+            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+            "d2h": "loss of every step copied to pinned memory (async), read one step later"}
 
 
 def main():
@@ -168,10 +193,12 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), __file__] + sys.argv[1:]
         return subprocess.call(cmd)
-    rc = init_rank_context()
+    rc = init_rank_context("cpu" if (args.allow_cpu and not torch.cuda.is_available()) else None)
     if rc.device.type != "cuda":
-        print(json.dumps({"error": "bench.py needs a CUDA device"}))
-        return 1
+        if not args.allow_cpu:
+            print(json.dumps({"error": "bench.py needs a CUDA device"}))
+            return 1
+        args.engine, args.graph = "torch", 0
     torch.backends.cudnn.benchmark = True
     if args.engine == "torch":
         torch.backends.cuda.matmul.allow_tf32 = args.vendor_dtype != "fp32"
@@ -194,7 +221,7 @@ def main():
     for _ in range(args.warmup):
         solver.step(1)
     solver.sync.wait_all()
-    sampler = ClockSampler(rc.device.index)
+    sampler = ClockSampler(rc.device.index if rc.device.type == "cuda" else 0)
     if rc.is_root:
         sampler.start()
     counting.reset()
@@ -207,19 +234,10 @@ def main():
     # ---------------- end-to-end through the public API: pinned H2D of every batch + D2H of every loss
     e2e = None
     if not args.no_e2e:
-      try:
-        for dl in solver.net.data_layers():
-            dl.device_resident = False
-        for _ in range(max(3, args.warmup)):
-            solver.step(1)
-            float(solver.last_loss)
-        ms2, _ = timed_steps(solver, rc, args.steps, read_loss=True)
-        h2d = sum(getattr(dl.prefetch, "h2d_bytes", 0) for dl in solver.net.data_layers() if getattr(dl, "prefetch", None))
-        e2e = {"value": batch * world * args.steps / (ms2 / 1e3), "unit": "images/sec", "ms_per_step": ms2 / args.steps,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-               "d2h": "loss of every step copied to pinned memory (async), read one step later"}
-      except Exception as exc:      # never lose the device-timed result to a failure of the end-to-end leg
-        e2e = {"error": f"{type(exc).__name__}: {exc}"}
+        try:
+            e2e = measure_e2e(args, solver, rc, batch, world)
+        except Exception as exc:      # never lose the device-timed result to a failure of the end-to-end leg
+            e2e = {"error": f"{type(exc).__name__}: {exc}"}
     solver.close()
     if rc.is_root:
         shape = solver.net.blob_shapes[solver.net.top_names[0][0]]
@@ -227,7 +245,8 @@ def main():
             "metric": f"{args.model}_train_images_per_sec", "value": value, "unit": "images/sec", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": value / (BASELINE_IMG_S_PER_GPU * world) if args.model == "alexnet" else None,
-            "dtype": "bf16" if (args.engine == "sm100" or args.vendor_dtype == "bf16") else "fp32",
+            "dtype": "fp32" if rc.device.type != "cuda" else
+                     ("bf16" if (args.engine == "sm100" or args.vendor_dtype == "bf16") else "fp32"),
             "data": "synthetic (random uint8 images, random-init weights)",
             "config": {"model": args.model, "global_batch": batch * world, "per_gpu_batch": batch,
                        "input": list(shape[1:]), "seq_len": None,

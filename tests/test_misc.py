@@ -101,3 +101,26 @@ def test_nvtx_ranges_are_noops_without_cuda():
     from poseidon_b200.utils import trace
     with trace.nvtx_range("x"):
         pass
+
+
+def test_bench_harness_self_test_on_cpu():
+    """bench.py --allow-cpu: the whole harness (device-resident leg, end-to-end leg with deferred loss reads, JSON contract)
+    runs on a GPU-less box; numbers are meaningless, the control flow and the output keys are what is checked."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--allow-cpu", "--model", "lenet", "--steps", "3",
+                          "--warmup", "3"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "gpu_launches", "e2e"):
+        assert k in d, k
+    assert d["steps"] == 3 and d["warmup"] == 3 and d["n_gpus"] == 1 and d["value"] > 0
+    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] == 4
+    ref = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference"], capture_output=True,
+                         text=True, timeout=120, cwd=root)
+    r = json.loads(ref.stdout.strip().splitlines()[-1])
+    assert r["impl"] == "reference" and "unavailable" in r
