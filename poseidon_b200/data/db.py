@@ -2,8 +2,10 @@
 
 The reference reads LevelDB/LMDB (src/caffe/layers/data_layer.cpp:102-140); neither
 library exists in this image, so the framework ships its own flat-file record store
-("PDB") with the same cursor semantics (ordered keys, seek-to-first, next, wrap) and uses
-``lmdb`` transparently if it happens to be importable.
+("PDB") with the same cursor semantics (ordered keys, seek-to-first, next, wrap), reads
+existing LMDB environments with a built-in parser of the ``data.mdb`` format
+(``lmdb_reader.py``; the ``lmdb`` module is used instead when importable), and leaves
+LevelDB to a one-off conversion.
 
 PDB layout:  b"PDB1" | u64 n | n × (u32 klen, u32 vlen, key, value)   — little endian.
 """
@@ -123,14 +125,15 @@ def open_db(path: str, backend: str = "LEVELDB"):
     pdb = path if os.path.isfile(path) else os.path.join(path, "data.pdb")
     if os.path.isfile(pdb):
         return RecordReader(pdb)
-    if os.path.isdir(path) and backend == "LMDB":
+    if os.path.isdir(path) and os.path.isfile(os.path.join(path, "data.mdb")):
         try:
-            return LMDBReader(path)
+            return LMDBReader(path)                     # liblmdb bindings, when installed
         except ImportError:
-            pass
-    raise IOError(f"cannot open database '{path}' (backend {backend}); "
-                  "LevelDB/LMDB are not available in this build — use tools.convert_imageset "
-                  "to create a PDB, or run with synthetic data")
+            from .lmdb_reader import LMDBFile
+            return LMDBFile(path)                       # built-in read-only parser of the data.mdb format
+    raise IOError(f"cannot open database '{path}' (backend {backend}): no data.pdb / data.mdb found there "
+                  "(LMDB environments are read natively; LevelDB is not supported — convert with "
+                  "tools.convert_imageset, or run with synthetic data)")
 
 
 def shard_indices(n_records: int, shared_fs: bool, num_clients: int, client_id: int,
