@@ -52,22 +52,33 @@ class RecordFile {
     fd_ = ::open(path.c_str(), O_RDONLY);
     if (fd_ < 0) throw std::runtime_error("cannot open " + path);
     struct stat st;
-    if (fstat(fd_, &st) != 0 || st.st_size < 12) { ::close(fd_); throw std::runtime_error(path + ": not a PDB record file"); }
+    if (fstat(fd_, &st) != 0 || st.st_size < 12) { ::close(fd_); throw std::runtime_error(path + ": not a record database"); }
     size_ = static_cast<size_t>(st.st_size);
     base_ = static_cast<const uint8_t*>(mmap(nullptr, size_, PROT_READ, MAP_SHARED, fd_, 0));
     if (base_ == MAP_FAILED) { ::close(fd_); throw std::runtime_error("mmap failed for " + path); }
-    if (std::memcmp(base_, "PDB1", 4) != 0) { close(); throw std::runtime_error(path + ": not a PDB record file"); }
-    uint64_t n;
-    std::memcpy(&n, base_ + 4, 8);
-    size_t off = 12;
-    recs_.reserve(n);
-    while (off + 8 <= size_ && recs_.size() < n) {
-      uint32_t kl, vl;
-      std::memcpy(&kl, base_ + off, 4);
-      std::memcpy(&vl, base_ + off + 4, 4);
-      if (off + 8 + kl + static_cast<size_t>(vl) > size_) break;       // truncated tail: ignore
-      recs_.push_back(Record{base_ + off + 8, kl, base_ + off + 8 + kl, vl});
-      off += 8 + kl + static_cast<size_t>(vl);
+    if (std::memcmp(base_, "PDB1", 4) == 0) {
+      uint64_t n;
+      std::memcpy(&n, base_ + 4, 8);
+      size_t off = 12;
+      recs_.reserve(n);
+      while (off + 8 <= size_ && recs_.size() < n) {
+        uint32_t kl, vl;
+        std::memcpy(&kl, base_ + off, 4);
+        std::memcpy(&vl, base_ + off + 4, 4);
+        if (off + 8 + kl + static_cast<size_t>(vl) > size_) break;       // truncated tail: ignore
+        recs_.push_back(Record{base_ + off + 8, kl, base_ + off + 8 + kl, vl});
+        off += 8 + kl + static_cast<size_t>(vl);
+      }
+    } else if (is_lmdb()) {
+      try {
+        index_lmdb(path);
+      } catch (...) {
+        close();
+        throw;
+      }
+    } else {
+      close();
+      throw std::runtime_error(path + ": neither a PDB record file nor an LMDB data.mdb");
     }
     madvise(const_cast<uint8_t*>(base_), size_, MADV_SEQUENTIAL);
   }
@@ -79,6 +90,71 @@ class RecordFile {
   const Record& at(size_t i) const { return recs_[i]; }
 
  private:
+  // ---- LMDB 0.9 data.mdb (read-only; same definition as poseidon_b200/data/lmdb_reader.py) ---------------------------
+  //   page header 16 B: pgno u64 | pad u16 | flags u16 | lower u16 upper u16 ; node: lo u16 hi u16 flags u16 ksize u16 key data
+  template <class T>
+  T rd(size_t off) const {
+    if (off + sizeof(T) > size_) throw std::runtime_error("LMDB: read past end of file");
+    T v;
+    std::memcpy(&v, base_ + off, sizeof(T));
+    return v;
+  }
+  bool is_lmdb() const {
+    return size_ >= 1024 && (rd<uint16_t>(10) & 0x08) && rd<uint32_t>(16) == 0xBEEFC0DEu;
+  }
+  struct LmdbMeta { uint32_t psize; uint16_t flags; uint64_t entries, root, txnid; };
+  LmdbMeta lmdb_meta(size_t off) const {
+    if (!(rd<uint16_t>(off + 10) & 0x08) || rd<uint32_t>(off + 16) != 0xBEEFC0DEu) throw std::runtime_error("LMDB: bad meta page");
+    if (rd<uint32_t>(off + 20) != 1) throw std::runtime_error("LMDB: unsupported data version");
+    const size_t dbs = off + 16 + 24;
+    LmdbMeta m;
+    m.psize = rd<uint32_t>(dbs);
+    m.flags = rd<uint16_t>(dbs + 48 + 4);
+    m.entries = rd<uint64_t>(dbs + 48 + 32);
+    m.root = rd<uint64_t>(dbs + 48 + 40);
+    m.txnid = rd<uint64_t>(dbs + 96 + 8);
+    return m;
+  }
+  void lmdb_walk(uint64_t pgno, uint32_t psize, int depth) {
+    if (depth > 64) throw std::runtime_error("LMDB: tree too deep");
+    const size_t off = static_cast<size_t>(pgno) * psize;
+    const uint16_t flags = rd<uint16_t>(off + 10), lower = rd<uint16_t>(off + 12);
+    const int n = (lower - 16) >> 1;
+    for (int i = 0; i < n; ++i) {
+      const size_t node = off + rd<uint16_t>(off + 16 + 2 * static_cast<size_t>(i));
+      const uint32_t lo = rd<uint16_t>(node), hi = rd<uint16_t>(node + 2);
+      const uint16_t nflags = rd<uint16_t>(node + 4), ksize = rd<uint16_t>(node + 6);
+      if (flags & 0x01) {                                                     // branch
+        lmdb_walk(lo | (static_cast<uint64_t>(hi) << 16) | (static_cast<uint64_t>(nflags) << 32), psize, depth + 1);
+      } else if (flags & 0x02) {                                              // leaf
+        if ((flags & 0x20) || (nflags & 0x06)) throw std::runtime_error("LMDB: DUPSORT / sub-databases are not supported");
+        const uint32_t dsize = lo | (hi << 16);
+        const uint8_t* key = base_ + node + 8;
+        const uint8_t* val = key + ksize;
+        if (nflags & 0x01) {                                                  // F_BIGDATA: overflow run
+          const uint64_t opg = rd<uint64_t>(node + 8 + ksize);
+          const size_t ooff = static_cast<size_t>(opg) * psize;
+          if (!(rd<uint16_t>(ooff + 10) & 0x04)) throw std::runtime_error("LMDB: expected an overflow page");
+          val = base_ + ooff + 16;
+        }
+        if (static_cast<size_t>(val - base_) + dsize > size_) throw std::runtime_error("LMDB: value past end of file");
+        recs_.push_back(Record{key, ksize, val, dsize});
+      } else {
+        throw std::runtime_error("LMDB: unexpected page type");
+      }
+    }
+  }
+  void index_lmdb(const std::string& path) {
+    const LmdbMeta m0 = lmdb_meta(0);
+    if (m0.psize < 512 || m0.psize > 65536 || (m0.psize & (m0.psize - 1))) throw std::runtime_error(path + ": implausible LMDB page size");
+    const LmdbMeta m1 = lmdb_meta(m0.psize);
+    const LmdbMeta& m = m1.txnid > m0.txnid ? m1 : m0;
+    if (m.flags & 0x04) throw std::runtime_error(path + ": DUPSORT LMDB databases are not supported");
+    recs_.reserve(m.entries);
+    if (m.root != ~0ull) lmdb_walk(m.root, m0.psize, 0);
+    if (m.entries && recs_.size() != m.entries) throw std::runtime_error(path + ": LMDB record count does not match its meta page");
+  }
+
   void close() {
     if (base_ != nullptr && base_ != MAP_FAILED) munmap(const_cast<uint8_t*>(base_), size_);
     base_ = nullptr;

@@ -75,7 +75,12 @@ class NativeDBSource:
     def __init__(self, path: str, batch: int, offset: int = 0, stride: int = 1, rand_skip: int = 0, seed=None,
                  threads: int = 0, depth: int = 6, pin: bool | None = None):
         m = module()
-        pdb = path if os.path.isfile(path) else os.path.join(path, "data.pdb")
+        if os.path.isfile(path):
+            pdb = path
+        else:                                       # a directory: PDB record store or an LMDB environment
+            pdb = os.path.join(path, "data.pdb")
+            if not os.path.isfile(pdb) and os.path.isfile(os.path.join(path, "data.mdb")):
+                pdb = os.path.join(path, "data.mdb")
         threads = threads or max(2, min(16, (os.cpu_count() or 4) // 2))
         self.loader = m.BatchLoader(pdb, batch, offset, max(1, stride), threads)
         n = self.loader.num_records()

@@ -138,7 +138,8 @@ class DataLayer(BasePrefetchingDataLayer):
                 log.warning("DATA layer '%s': %s -> synthetic %s uint8 data", self.layer_name, e, shape)
             return SyntheticSource(batch, shape, ncls, seed=1234 + self.ctx.rank)
         off, stride = shard_indices(len(reader), shared, nclients, client, nthreads, thread)
-        if isinstance(reader, RecordReader) and os.environ.get("POSEIDON_NATIVE_LOADER", "1") != "0":
+        from ..data.lmdb_reader import LMDBFile
+        if isinstance(reader, (RecordReader, LMDBFile)) and os.environ.get("POSEIDON_NATIVE_LOADER", "1") != "0":
             # C++ record loader: thread-pool Datum decode straight into pinned batch buffers
             from ..data import native
             if native.available():

@@ -172,3 +172,25 @@ def test_rejects_garbage(tmp_path):
     (p / "data.mdb").write_bytes(b"\0" * 8192)
     with pytest.raises(LMDBFormatError):
         LMDBFile(str(p))
+
+
+def test_native_loader_reads_lmdb(tmp_path):
+    """The C++ batch loader indexes data.mdb with the same parser and fills batches identical to the Python path."""
+    import torch
+    from poseidon_b200.data import native
+    from poseidon_b200.data.source import DBSource
+    if not native.available():
+        pytest.skip("host extension could not be built")
+    rng = np.random.RandomState(3)
+    big = _records(11, (3, 40, 40), rng)                    # overflow pages
+    write_lmdb(str(tmp_path / "big"), big)
+    small = _records(50, (1, 4, 4), rng)
+    write_lmdb(str(tmp_path / "small"), small, max_leaf_nodes=4)
+    for name, batch in (("big", 4), ("small", 8)):
+        py = DBSource(LMDBFile(str(tmp_path / name)), batch, 1, 2)
+        nat = native.NativeDBSource(str(tmp_path / name), batch, 1, 2, threads=2, depth=3, pin=False)
+        for _ in range(5):
+            xa, ya = py.next_batch()
+            xb, yb = nat.next_batch()
+            assert torch.equal(xa, xb) and torch.equal(ya, yb)
+        nat.close()
