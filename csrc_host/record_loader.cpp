@@ -15,6 +15,8 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include "leveldb_reader.h"
+
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -48,7 +50,22 @@ struct Record {
 
 class RecordFile {
  public:
-  explicit RecordFile(const std::string& path) {
+  explicit RecordFile(const std::string& path_in) {
+    // a directory is a LevelDB (CURRENT + MANIFEST), an LMDB environment (data.mdb) or a PDB store (data.pdb)
+    std::string path = path_in;
+    struct stat dst;
+    if (::stat(path.c_str(), &dst) == 0 && S_ISDIR(dst.st_mode)) {
+      auto exists = [](const std::string& p) { struct stat s; return ::stat(p.c_str(), &s) == 0; };
+      if (exists(path + "/data.pdb")) path += "/data.pdb";
+      else if (exists(path + "/data.mdb")) path += "/data.mdb";
+      else if (exists(path + "/CURRENT")) {
+        ldb_.reset(new LevelDBIndex(path));
+        for (const LdbRecord& r : ldb_->records()) recs_.push_back(Record{r.key, r.klen, r.val, r.vlen});
+        return;
+      } else {
+        throw std::runtime_error(path + ": no data.pdb, data.mdb or LevelDB CURRENT file in this directory");
+      }
+    }
     fd_ = ::open(path.c_str(), O_RDONLY);
     if (fd_ < 0) throw std::runtime_error("cannot open " + path);
     struct stat st;
@@ -165,6 +182,7 @@ class RecordFile {
   size_t size_ = 0;
   const uint8_t* base_ = nullptr;
   std::vector<Record> recs_;
+  std::unique_ptr<LevelDBIndex> ldb_;      // LevelDB directories: owns the table mappings the records point into
 };
 
 // ----------------------------------------------------------------------------- Datum wire format
@@ -502,6 +520,25 @@ PYBIND11_MODULE(poseidon_b200_host, m) {
       .def("release", &BatchLoader::release)
       .def("stop", &BatchLoader::stop)
       .def("batches_produced", &BatchLoader::batches_produced);
+  // random access to the records of any supported database (PDB / LMDB / LevelDB), e.g. for the Python DBSource
+  py::class_<RecordFile>(m, "RecordDB")
+      .def(py::init<const std::string&>())
+      .def("size", &RecordFile::size)
+      .def("key", [](const RecordFile& f, size_t i) {
+        if (i >= f.size()) throw py::index_error();
+        const Record& r = f.at(i);
+        return py::bytes(reinterpret_cast<const char*>(r.key), r.klen);
+      })
+      .def("value", [](const RecordFile& f, size_t i) {
+        if (i >= f.size()) throw py::index_error();
+        const Record& r = f.at(i);
+        return py::bytes(reinterpret_cast<const char*>(r.val), r.vlen);
+      });
+  m.def("snappy_uncompress", [](py::bytes b) {
+    const std::string s = b;
+    const std::vector<uint8_t> out = snappy_uncompress(reinterpret_cast<const uint8_t*>(s.data()), s.size());
+    return py::bytes(reinterpret_cast<const char*>(out.data()), out.size());
+  });
   m.def("f32_to_bf16", &f32_to_bf16);
   m.def("bf16_to_f32", &bf16_to_f32);
 }

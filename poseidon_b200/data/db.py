@@ -4,8 +4,8 @@ The reference reads LevelDB/LMDB (src/caffe/layers/data_layer.cpp:102-140); neit
 library exists in this image, so the framework ships its own flat-file record store
 ("PDB") with the same cursor semantics (ordered keys, seek-to-first, next, wrap), reads
 existing LMDB environments with a built-in parser of the ``data.mdb`` format
-(``lmdb_reader.py``; the ``lmdb`` module is used instead when importable), and leaves
-LevelDB to a one-off conversion.
+(``lmdb_reader.py``; the ``lmdb`` module is used instead when importable) and existing
+LevelDB directories through the C++ host runtime (``csrc_host/leveldb_reader.cpp``).
 
 PDB layout:  b"PDB1" | u64 n | n × (u32 klen, u32 vlen, key, value)   — little endian.
 """
@@ -131,9 +131,12 @@ def open_db(path: str, backend: str = "LEVELDB"):
         except ImportError:
             from .lmdb_reader import LMDBFile
             return LMDBFile(path)                       # built-in read-only parser of the data.mdb format
-    raise IOError(f"cannot open database '{path}' (backend {backend}): no data.pdb / data.mdb found there "
-                  "(LMDB environments are read natively; LevelDB is not supported — convert with "
-                  "tools.convert_imageset, or run with synthetic data)")
+    if os.path.isdir(path) and os.path.isfile(os.path.join(path, "CURRENT")):
+        from . import native
+        if native.available():
+            return native.NativeRecordDB(path)          # LevelDB directory, read by the C++ host runtime
+    raise IOError(f"cannot open database '{path}' (backend {backend}): no PDB store, LMDB environment or LevelDB "
+                  "directory found there — create one with tools.convert_imageset, or run with synthetic data")
 
 
 def shard_indices(n_records: int, shared_fs: bool, num_clients: int, client_id: int,

@@ -18,7 +18,9 @@ import threading
 import torch
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-SRC = os.path.join(_ROOT, "csrc_host", "record_loader.cpp")
+SRC_DIR = os.path.join(_ROOT, "csrc_host")
+SRCS = [os.path.join(SRC_DIR, "record_loader.cpp"), os.path.join(SRC_DIR, "leveldb_reader.cpp")]
+SRC = SRCS[0]
 EXT_DIR = os.path.join(_ROOT, "poseidon_b200", "_ext")
 SO = os.path.join(EXT_DIR, "poseidon_b200_host.so")
 _mod = None
@@ -28,11 +30,12 @@ _lock = threading.Lock()
 def build(force: bool = False, verbose: bool = False) -> str:
     """g++ -O3 -shared the host module (a few seconds); no-op when up to date."""
     os.makedirs(EXT_DIR, exist_ok=True)
-    if not force and os.path.exists(SO) and os.path.getmtime(SO) >= os.path.getmtime(SRC):
+    newest = max(os.path.getmtime(f) for f in SRCS + [os.path.join(SRC_DIR, "leveldb_reader.h")])
+    if not force and os.path.exists(SO) and os.path.getmtime(SO) >= newest:
         return SO
     import pybind11
     cmd = ["g++", "-O3", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden", "-pthread",
-           "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"], SRC, "-o", SO + ".tmp"]
+           "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"], "-I", SRC_DIR] + SRCS + ["-o", SO + ".tmp"]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
@@ -45,7 +48,7 @@ def module(build_if_missing: bool = True):
     with _lock:
         if _mod is not None:
             return _mod
-        if not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(SRC):
+        if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(f) for f in SRCS):
             if not build_if_missing:
                 raise RuntimeError(f"{SO} not built")
             build()
@@ -81,6 +84,8 @@ class NativeDBSource:
             pdb = os.path.join(path, "data.pdb")
             if not os.path.isfile(pdb) and os.path.isfile(os.path.join(path, "data.mdb")):
                 pdb = os.path.join(path, "data.mdb")
+            elif not os.path.isfile(pdb) and os.path.isfile(os.path.join(path, "CURRENT")):
+                pdb = path                          # LevelDB directory
         threads = threads or max(2, min(16, (os.cpu_count() or 4) // 2))
         self.loader = m.BatchLoader(pdb, batch, offset, max(1, stride), threads)
         n = self.loader.num_records()
@@ -143,3 +148,32 @@ def bf16_to_f32(src: torch.Tensor, out: torch.Tensor | None = None) -> torch.Ten
     out = torch.empty(src.shape, dtype=torch.float32) if out is None else out
     module().bf16_to_f32(src.data_ptr(), out.data_ptr(), src.numel())
     return out
+
+
+class NativeRecordDB:
+    """Random-access reader over any database the C++ runtime understands (PDB file, LMDB ``data.mdb``, LevelDB
+    directory) with the interface of :class:`poseidon_b200.data.db.RecordReader`."""
+
+    def __init__(self, path: str):
+        self.path = path
+        self._db = module().RecordDB(path)
+
+    def __len__(self):
+        return self._db.size()
+
+    def key(self, i: int) -> bytes:
+        return self._db.key(i)
+
+    def value(self, i: int) -> bytes:
+        return self._db.value(i)
+
+    def datum(self, i: int):
+        from .. import proto as P
+        return P.Datum.FromString(self.value(i))
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self.key(i), self.value(i)
+
+    def close(self):
+        self._db = None

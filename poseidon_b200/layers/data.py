@@ -139,7 +139,9 @@ class DataLayer(BasePrefetchingDataLayer):
             return SyntheticSource(batch, shape, ncls, seed=1234 + self.ctx.rank)
         off, stride = shard_indices(len(reader), shared, nclients, client, nthreads, thread)
         from ..data.lmdb_reader import LMDBFile
-        if isinstance(reader, (RecordReader, LMDBFile)) and os.environ.get("POSEIDON_NATIVE_LOADER", "1") != "0":
+        from ..data.native import NativeRecordDB
+        if isinstance(reader, (RecordReader, LMDBFile, NativeRecordDB)) and \
+                os.environ.get("POSEIDON_NATIVE_LOADER", "1") != "0":
             # C++ record loader: thread-pool Datum decode straight into pinned batch buffers
             from ..data import native
             if native.available():
