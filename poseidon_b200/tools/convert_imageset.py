@@ -3,7 +3,7 @@
     python -m poseidon_b200.tools.convert_imageset [--gray] [--shuffle] [--resize_height H --resize_width W]
         ROOTFOLDER/ LISTFILE DB_NAME
 
-Output is the framework's PDB record store (LevelDB/LMDB are not available in this image; the Datum
+Output is the framework's PDB record store or (``--backend lmdb``) an LMDB environment; the Datum
 payload is byte-identical to what the reference writes, keys are "%08d_<path>" as there).
 reference: tools/convert_imageset.cpp:33-43 (flags), :60-160 (main loop), src/caffe/util/io.cpp:83-130.
 """
@@ -45,17 +45,31 @@ def main(argv=None):
     if args.shuffle:
         random.shuffle(lines)
     n = 0
-    with RecordWriter(args.db) as w:
+    backend = args.backend.lower()
+    if backend not in ("pdb", "lmdb"):
+        raise SystemExit("--backend must be pdb (native record store) or lmdb (export for stock Caffe / Poseidon)")
+
+    def records():
+        nonlocal n
         for i, (name, label) in enumerate(lines):
             try:
                 d = image_to_datum(args.root + name, label, args.resize_height, args.resize_width, not args.gray)
             except IOError as e:
                 print(e, file=sys.stderr)
                 continue
-            w.put("%08d_%s" % (i, name), d.SerializeToString())
             n += 1
             if n % 1000 == 0:
                 print(f"Processed {n} files.", file=sys.stderr)
+            yield ("%08d_%s" % (i, name)).encode(), d.SerializeToString()
+
+    if backend == "lmdb":
+        # an LMDB environment (data.mdb) that the reference's DataLayer reads with `backend: LMDB`
+        from ..data.lmdb_writer import write_lmdb
+        write_lmdb(args.db, records())
+    else:
+        with RecordWriter(args.db) as w:
+            for key, value in records():
+                w.put(key, value)
     print(f"Processed {n} files.", file=sys.stderr)
     return 0
 
