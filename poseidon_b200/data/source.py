@@ -15,7 +15,6 @@ from typing import Optional, Tuple
 import numpy as np
 import torch
 
-from .. import proto as P
 
 
 class SyntheticSource:

@@ -10,7 +10,6 @@ from __future__ import annotations
 import os
 from typing import Optional
 
-import numpy as np
 import torch
 
 from .. import proto as P

@@ -14,9 +14,8 @@ import numpy as np
 import torch
 
 from .. import ops
-from .. import proto as P
 from ..data.db import RecordReader, open_db, shard_indices
-from ..data.source import ArraySource, DBSource, Prefetcher, SyntheticSource
+from ..data.source import DBSource, Prefetcher, SyntheticSource
 from ..data.transformer import DataTransformer
 from .base import Layer, fill, register
 

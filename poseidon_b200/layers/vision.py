@@ -5,7 +5,6 @@ reference: include/caffe/vision_layers.hpp:36 (Convolution), :132 (Im2col), :171
 """
 from __future__ import annotations
 
-import torch
 
 from .. import ops
 from .base import Layer, hw_param, register

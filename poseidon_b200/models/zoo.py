@@ -11,7 +11,6 @@ batch size / data source / class count are parameters.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence
 
 from .. import proto as P
 from ..proto import to_text

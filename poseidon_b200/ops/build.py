@@ -54,7 +54,7 @@ def build_extension(verbose: bool = False, force: bool = False) -> str:
         cpp_extension.load(
             name=EXT_NAME, sources=sources(), extra_cflags=["-O3", "-std=c++17"],
             extra_cuda_cflags=NVCC_FLAGS, extra_include_paths=[CSRC, os.path.join(CSRC, "gemm")],
-            extra_ldflags=["-lcuda"] if False else [], build_directory=EXT_DIR, verbose=verbose,
+            build_directory=EXT_DIR, verbose=verbose,
             is_python_module=False, with_cuda=True)
     return so_path()
 

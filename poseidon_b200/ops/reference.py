@@ -9,7 +9,7 @@ Semantics follow SURVEY.md Appendix A; file:line citations are on each function.
 from __future__ import annotations
 
 import math
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence
 
 import torch
 import torch.nn.functional as F

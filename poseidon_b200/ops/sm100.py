@@ -16,8 +16,6 @@ LRN, pooling, softmax-loss, dropout, transform): unsupported shapes raise, excep
 from __future__ import annotations
 
 import os
-
-import math
 from typing import Optional
 
 import torch

@@ -21,7 +21,7 @@ import io
 import math
 import re
 import struct
-from typing import Any, Dict, List, Optional
+from typing import Dict, List, Optional
 
 import numpy as np
 

@@ -18,7 +18,7 @@ from __future__ import annotations
 
 import enum
 from collections import deque
-from typing import Dict, List, Optional
+from typing import Dict, Optional
 
 import torch
 import torch.distributed as dist

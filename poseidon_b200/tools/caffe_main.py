@@ -21,7 +21,6 @@ import logging
 import os
 import subprocess
 import sys
-import time
 
 log = logging.getLogger("poseidon_b200")
 

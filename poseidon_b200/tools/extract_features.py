@@ -14,7 +14,6 @@ import argparse
 import os
 import sys
 
-import numpy as np
 
 
 def main(argv=None):

@@ -142,7 +142,6 @@ def make_db(path, compress):
     truth[b"00000050"], truth[b"00000000"] = v50, v0
     del truth[b"00000049"]
     big = struct.pack("<QI", 600, 1) + b"\x01" + lp(b"00000051") + lp(_datum(51, rng, shape=(3, 120, 120)))   # spans log blocks
-    truth[b"00000051"] = big[12 + 1 + 1 + 8:][len(varint(3 * 120 * 120 + 20)) - 0:] if False else None
     write_log(os.path.join(path, "000009.log"), [batch, big])
     write_log(os.path.join(path, "000002.log"), [struct.pack("<QI", 1, 1) + b"\x01" + lp(b"old") + lp(b"flushed long ago")])
     # MANIFEST: comparator, log number 9, new files 4 / 5 / 7, then delete 4
