@@ -205,9 +205,11 @@ class Net(nn.Module):
         self.force_backward = bool(pd.force_backward)
         self.debug_info = False
         self.skip_layer = [False] * len(self.layers)
-        if self.ctx.engine == "sm100" and self.ctx.device.type == "cuda":
-            from .fusion import plan_sm100
-            plan_sm100(self)
+        if self.ctx.engine == "sm100":
+            from ..ops import sm100
+            if sm100.active(self.ctx.device):
+                from .fusion import plan_sm100
+                plan_sm100(self)
 
     def _consumed_later(self, blob: str) -> bool:
         last_prod = max(i for i, tn in enumerate(self.top_names) if blob in tn)

@@ -25,15 +25,41 @@ from . import torch_engine as TE
 from .build import load_extension
 
 _ops = None
+_emulate = os.environ.get("POSEIDON_EMULATE", "0") == "1"
+
+
+def emulating() -> bool:
+    """True when the engine runs on ops/emulate.py's CPU stand-ins for the kernels (tests of the Python side only)."""
+    return _emulate
+
+
+def set_emulation(on: bool) -> None:
+    """Switch between the compiled kernels and their CPU emulation (never implicit: POSEIDON_EMULATE=1 or this call)."""
+    global _emulate, _ops
+    if bool(on) != _emulate:
+        _emulate, _ops = bool(on), None
+
+
+def active(device) -> bool:
+    """Does the sm100 engine own tensors on this device?  (CUDA always; the CPU only under emulation.)"""
+    return torch.device(device).type == "cuda" or _emulate
+
+
+def _on(x: torch.Tensor) -> bool:
+    return x.is_cuda or _emulate
 
 
 def K():
     """torch.ops.poseidon, loading the in-tree extension on first use (fails loudly if absent)."""
     global _ops
     if _ops is None:
-        load_extension()
         from .counting import CountingOps
-        _ops = CountingOps(torch.ops.poseidon)
+        if _emulate:
+            from .emulate import EmulatedKernels
+            _ops = CountingOps(EmulatedKernels())
+        else:
+            load_extension()
+            _ops = CountingOps(torch.ops.poseidon)
     return _ops
 
 
@@ -339,7 +365,7 @@ class _ConvFn(torch.autograd.Function):
 
 
 def conv2d(x, w, b, stride, pad, groups, relu_slope=None, layer=None):
-    if layer is None or not x.is_cuda:
+    if layer is None or not _on(x):
         return TE.conv2d(x, w, b, stride, pad, groups, relu_slope, layer)
     conv_state(layer, w.shape[1] * groups)
     return _ConvFn.apply(x, w, b, layer, relu_slope)
@@ -462,7 +488,7 @@ class _IPFn(torch.autograd.Function):
 
 
 def inner_product(x, w, b, relu=False, layer=None):
-    if layer is None or not x.is_cuda:
+    if layer is None or not _on(x):
         return TE.inner_product(x, w, b, relu, layer)
     if getattr(layer, "_sm100", None) is None:
         layer._sm100 = IPState(layer, tuple(x.shape))
@@ -489,7 +515,7 @@ class _LRNFn(torch.autograd.Function):
 
 
 def lrn_across(x, size, alpha, beta, mask_input=False):
-    if not x.is_cuda or x.shape[1] % 8:
+    if not _on(x) or x.shape[1] % 8:
         return R.lrn_across(x, size, alpha, beta)
     return _LRNFn.apply(x, size, alpha, beta, mask_input)
 
@@ -521,13 +547,13 @@ class _PoolFn(torch.autograd.Function):
 
 
 def max_pool(x, kernel, stride, pad, return_mask=False, mask_input=False):
-    if return_mask or not x.is_cuda or x.shape[1] % 8:
+    if return_mask or not _on(x) or x.shape[1] % 8:
         return R.max_pool(x, kernel, stride, pad, return_mask)
     return _PoolFn.apply(x, True, tuple(kernel), tuple(stride), tuple(pad), mask_input)
 
 
 def ave_pool(x, kernel, stride, pad, mask_input=False):
-    if not x.is_cuda or x.shape[1] % 8:
+    if not _on(x) or x.shape[1] % 8:
         return R.ave_pool(x, kernel, stride, pad)
     return _PoolFn.apply(x, False, tuple(kernel), tuple(stride), tuple(pad), False)
 
@@ -551,7 +577,7 @@ class _ReLUFn(torch.autograd.Function):
 
 def relu(x, negative_slope=0.0):
     dense = x.is_contiguous() or (x.dim() == 4 and x.is_contiguous(memory_format=CL))
-    if not x.is_cuda or x.dtype != torch.bfloat16 or x.numel() % 8 or not dense:
+    if not _on(x) or x.dtype != torch.bfloat16 or x.numel() % 8 or not dense:
         return R.relu(x, negative_slope)
     return _ReLUFn.apply(x, float(negative_slope))
 
@@ -591,7 +617,7 @@ def dropout(x, ratio, train):
     if not train:
         return x
     dense = x.is_contiguous() or (x.dim() == 4 and x.is_contiguous(memory_format=CL))
-    if not x.is_cuda or x.dtype != torch.bfloat16 or x.numel() % 8 or not dense:
+    if not _on(x) or x.dtype != torch.bfloat16 or x.numel() % 8 or not dense:
         return R.dropout(x, ratio, train)
     _dropout_counter[0] += 1          # distinct per call site within an iteration (a constant under graph replay)
     seed = (torch.initial_seed() * 1000003 + _dropout_counter[0] * 7919) & 0x7FFFFFFFFFFFFFFF
@@ -620,7 +646,7 @@ class _SoftmaxLossFn(torch.autograd.Function):
 
 def softmax_loss(x, label, return_prob=False):
     spatial = x.dim() == 4 and x.shape[2] * x.shape[3] > 1
-    if not x.is_cuda or spatial:
+    if not _on(x) or spatial:
         return R.softmax_loss(x, label, return_prob)
     loss, prob = _SoftmaxLossFn.apply(x, label, return_prob)
     if return_prob:
@@ -637,7 +663,7 @@ def concat(xs, dim):
 
 def transform(transformer, x, out_dtype, first_conv=None):
     """uint8/float NCHW batch -> bf16 NHWC in one kernel (crop / mirror / mean / scale / channel pad)."""
-    if not x.is_cuda or out_dtype != torch.bfloat16:
+    if not _on(x) or out_dtype != torch.bfloat16:
         return TE.transform(transformer, x, out_dtype)
     n, c, h, w = x.shape
     oh, ow = transformer.out_hw(h, w)

@@ -251,7 +251,8 @@ class Solver:
                 comm = "nccl"
         self.comm_name = comm
         if self.engine == "sm100" and comm in ("fused", "local"):
-            if self.device.type != "cuda":
+            from ..ops import sm100
+            if not sm100.active(self.device) or (rc.distributed and self.device.type != "cuda"):
                 raise RuntimeError("the sm100 engine needs a CUDA device (B200)")
             from ..parallel.fused import FusedBackend
             self.comm_name = "fused"
@@ -370,9 +371,10 @@ class Solver:
         self.net.debug_info = display and bool(sp.debug_info)
         lr = learning_rate(sp, self.iter)
         self.sync.begin_iteration(lr)
-        if self.engine == "sm100" and self.device.type == "cuda":
+        if self.engine == "sm100":
             from ..ops import sm100
-            sm100.bump_iteration_seed(self.device)
+            if sm100.active(self.device):
+                sm100.bump_iteration_seed(self.device)
         with STATS.timer("forward_backward"):
             loss, outputs = self.net.forward()
             if loss is not None and loss.requires_grad:

@@ -1,0 +1,293 @@
+"""The sm100 engine's Python side, exercised on the CPU.
+
+``ops/emulate.py`` stands in for the CUDA kernels (same op surface, same operand layouts), so everything AROUND the
+kernels runs here: operand layouts per first-layer mode, bf16 shadows vs fp32 masters, the epilogue-fusion plan, the
+single-process FusedBackend path, (h, w, c) inner-product weights and their checkpoint conversion.  The kernels
+themselves are tested on a B200 (tests/test_ops_gpu.py, test_engine_gpu.py)."""
+import numpy as np
+import pytest
+import torch
+
+from smallnet import feed, make_data, small_net, small_solver_param
+
+
+@pytest.fixture
+def emu():
+    from poseidon_b200.ops import counting, sm100
+    sm100.set_emulation(True)
+    counting.reset()
+    yield sm100
+    sm100.set_emulation(False)
+
+
+def _run(engine, steps, solver_type="SGD", momentum=0.9, net_fn=None, batch=8, hw=35, classes=16):
+    from poseidon_b200 import get_solver
+    net = (net_fn or (lambda: small_net(batch=batch, hw=hw, classes=classes)))()
+    sp = small_solver_param(net, max_iter=steps, solver_type=solver_type, momentum=momentum)
+    s = get_solver(sp, engine=engine, dtype=torch.float32 if engine == "torch" else None)
+    x, y = make_data(batch * steps, hw=hw, classes=classes)
+    feed(s, x, y)
+    losses = []
+    for _ in range(steps):
+        s.step(1)
+        losses.append(float(s.last_loss))
+    weights = {f"{n}.{j}": l.export_blob(j) for n, l in zip(s.net.layer_names, s.net.layers)
+               for j in range(len(l.blobs))}
+    return losses, weights, s
+
+
+def _close(l_ref, l_sm, w_ref, w_sm, const_bias=()):
+    for a, b in zip(l_ref, l_sm):
+        assert abs(a - b) < 0.05 * max(1.0, abs(a)), (l_ref, l_sm)
+    for name in w_ref:
+        d = np.abs(w_ref[name] - w_sm[name]).max()
+        init = 0.1 if name in const_bias else 0.0
+        mm = np.abs(w_ref[name] - init).max() if name.endswith(".1") else np.abs(w_ref[name]).max()
+        assert d <= 0.08 * mm + 3e-4, f"{name}: max diff {d} vs magnitude {mm}"
+
+
+def test_emulation_is_explicit():
+    """Without the switch the engine refuses to run on a CPU (no silent fallback)."""
+    from poseidon_b200 import get_solver
+    from poseidon_b200.ops import sm100
+    assert not sm100.emulating()
+    sp = small_solver_param(small_net(batch=4), max_iter=1)
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        get_solver(sp, engine="sm100")
+
+
+@pytest.mark.parametrize("solver_type,momentum", [("SGD", 0.9), ("NESTEROV", 0.9), ("ADAGRAD", 0.0)])
+def test_engine_matches_fp32_engine(emu, solver_type, momentum):
+    steps = 3
+    l_ref, w_ref, _ = _run("torch", steps, solver_type, momentum)
+    l_sm, w_sm, s = _run("sm100", steps, solver_type, momentum)
+    assert type(s.sync.backend).__name__ == "FusedBackend"
+    # conv1 (3 input channels, 5x5/s2) runs in ROW mode; ReLUs after conv / IP are folded into epilogues
+    st = s.net.layer_by_name["conv1"]._sm100
+    assert st.row_mode and not st.s2d and not st.pad8
+    assert sum(s.net.skip_layer) >= 4
+    if solver_type != "ADAGRAD":     # first AdaGrad steps are ±lr·sign(g): dominated by bf16 sign flips
+        _close(l_ref, l_sm, w_ref, w_sm, const_bias=("conv1.1", "conv2.1", "fc4.1"))
+    else:
+        for a, b in zip(l_ref, l_sm):
+            assert abs(a - b) < 0.05 * max(1.0, abs(a))
+
+
+def _first_layer_net(k, stride, pad, hw, batch=4, classes=8):
+    from poseidon_b200.models.zoo import NetBuilder
+    b = NetBuilder("firstlayer")
+    b.layer("data", "MEMORY_DATA", (), ("data", "label"),
+            memory_data_param={"batch_size": batch, "channels": 3, "height": hw, "width": hw})
+    g = {"type": "gaussian", "std": 0.05}
+    b.conv("conv1", "data", 32, k, stride=stride, pad=pad, wf=g, bf={"type": "constant", "value": 0.1})
+    b.relu("relu1", "conv1")
+    b.pool("pool1", "conv1", "MAX", 3, 2)
+    b.conv("conv2", "pool1", 48, 3, pad=1, wf=g, bf={"type": "constant", "value": 0.0})
+    b.relu("relu2", "conv2")
+    b.conv("conv3", "conv2", 32, 3, pad=1, group=1, wf=g, bf={"type": "constant", "value": 0.0})
+    b.relu("relu3", "conv3")
+    b.pool("pool3", "conv3", "AVE", 2, 2)
+    b.fc("fc4", "pool3", classes, wf=g, bf={"type": "constant", "value": 0.0})
+    b.softmax_loss("loss", "fc4")
+    return b.net
+
+
+@pytest.mark.parametrize("mode,k,stride,pad,hw", [
+    ("s2d", 11, 4, 0, 67),      # AlexNet / CaffeNet conv1 -> 3x3/s1 over 64 channels
+    ("s2d", 11, 4, 2, 63),      # with padding (the transform / conversion writes it)
+    ("pad8", 3, 1, 1, 24),      # VGG conv1_1: image padded to 8 channels, ordinary TAP conv
+    ("row", 7, 2, 3, 37),       # GoogLeNet conv1: ROW-mode gather
+])
+def test_first_layer_modes(emu, mode, k, stride, pad, hw):
+    fn = lambda: _first_layer_net(k, stride, pad, hw)   # noqa: E731
+    l_ref, w_ref, _ = _run("torch", 2, net_fn=fn, batch=4, hw=hw, classes=8)
+    l_sm, w_sm, s = _run("sm100", 2, net_fn=fn, batch=4, hw=hw, classes=8)
+    st = s.net.layer_by_name["conv1"]._sm100
+    assert {"s2d": st.s2d, "pad8": st.pad8, "row": st.row_mode and not st.s2d and not st.pad8}[mode]
+    _close(l_ref, l_sm, w_ref, w_sm, const_bias=("conv1.1",))
+    # the master weight keeps the reference's logical shape whatever the operand layout is
+    assert tuple(s.net.layer_by_name["conv1"].weight.shape) == (32, 3, k, k)
+
+
+def test_channel_padded_k(emu, monkeypatch):
+    """POSEIDON_PAD_K=1: C_g = 48 is padded to 64 slots per tap in the fprop / wgrad operand and in the dgrad pack."""
+    monkeypatch.setenv("POSEIDON_PAD_K", "1")
+    fn = lambda: _first_layer_net(7, 2, 3, 37)   # noqa: E731
+    l_ref, w_ref, _ = _run("torch", 2, net_fn=fn, batch=4, hw=37, classes=8)
+    l_sm, w_sm, s = _run("sm100", 2, net_fn=fn, batch=4, hw=37, classes=8)
+    st3 = s.net.layer_by_name["conv3"]._sm100          # 48 input channels
+    assert (st3.cg, st3.cgk) == (48, 64)
+    assert st3.operand().shape == (32, 9 * 64) and st3.shadow().shape == (32, 9 * 48)
+    st2 = s.net.layer_by_name["conv2"]._sm100          # 48 output channels -> dgrad operand padded
+    assert st2.cok == 64 and st2.dgrad_pack().shape == (32, 9 * 64)
+    _close(l_ref, l_sm, w_ref, w_sm, const_bias=("conv1.1",))
+
+
+def test_transform_layouts_match_conversion(emu):
+    """What the transform op writes for a first layer == what prepare_first_layer_input derives from a plain batch."""
+    from poseidon_b200 import proto as P
+    from poseidon_b200.data.transformer import DataTransformer
+    from poseidon_b200.ops import torch_engine as TE
+
+    class Conv:                      # the attributes ConvState reads
+        def __init__(self, k, stride, pad, in_hw):
+            self.kernel, self.stride, self.pad, self.group, self.num_output = (k, k), (stride, stride), (pad, pad), 1, 16
+            self.layer_name, self.in_hw = "conv1", in_hw
+            self.weight = torch.nn.Parameter(torch.randn(16, 3, k, k))
+
+    x = torch.randint(0, 256, (3, 3, 40, 40), dtype=torch.uint8)
+    for k, stride, pad, crop in [(11, 4, 2, 35), (3, 1, 1, 32), (7, 2, 3, 33)]:
+        tp = P.TransformationParameter(crop_size=crop, mirror=True, scale=0.017, mean_value=[104.0, 117.0, 123.0])
+        conv = Conv(k, stride, pad, (crop, crop))
+        st = emu.conv_state(conv, 3)
+        outs = []
+        for fn in (emu.transform, None):
+            tr = DataTransformer(tp, P.TRAIN, torch.device("cpu"), seed=3)
+            if fn is not None:
+                outs.append(fn(tr, x, torch.bfloat16, first_conv=conv))
+            else:
+                plain = TE.transform(tr, x, torch.float32)
+                outs.append(emu.prepare_first_layer_input(plain, st, conv.pad, conv.in_hw))
+        a, b = outs
+        assert a.shape == b.shape and a.dtype == b.dtype == torch.bfloat16, (k, a.shape, b.shape)
+        assert torch.equal(a.float(), b.float()), k
+        # the transform's output is accepted as-is (no second conversion pass)
+        assert emu.prepare_first_layer_input(a, st, conv.pad, conv.in_hw) is a
+
+
+def test_shadows_are_not_rederived_every_step(emu):
+    """The optimizer op refreshes the bf16 operand next to the fp32 master; the layer state must not convert the
+    whole weight again on the next forward (a regression here costs ~7 % of an AlexNet step on the GPU)."""
+    from poseidon_b200.ops import counting
+    _, _, s = _run("sm100", 2)
+    for name in ("conv2", "conv3", "fc4", "fc5"):
+        st = s.net.layer_by_name[name]._sm100
+        assert st.wb is not None and not st.dirty_wb, name
+        master = s.net.layer_by_name[name].weight.data
+        flat = master.permute(0, 2, 3, 1).reshape(st.wb.shape) if master.dim() == 4 else master
+        assert torch.equal(st.wb.float(), flat.to(torch.bfloat16).float()), name
+    counting.reset()
+    s.step(1)
+    ops = counting.by_op()
+    n_params = sum(len(l.blobs) for l in s.net.layers)
+    # every blob stepped by exactly one optimizer launch; IP weights take wgrad GEMM + update
+    assert ops["fused_update"] == n_params, ops
+    assert ops["gemm_f32"] == 2, ops
+    assert ops["conv_wgrad"] == 3 and ops["conv_fprop"] == 3 and ops["conv_dgrad"] == 2, ops
+    assert "relu_fwd" not in ops, ops        # all four ReLUs live in epilogues
+    for name in ("conv2", "conv3", "fc4", "fc5"):
+        assert not s.net.layer_by_name[name]._sm100.dirty_wb
+
+
+def test_snapshot_roundtrip_between_engines(emu, tmp_path):
+    """Checkpoints are engine-neutral: (h, w, c) inner-product weights and channels-last conv weights are converted at
+    the file boundary."""
+    from poseidon_b200 import get_solver
+    net = small_net(batch=8)
+    sp = small_solver_param(net, max_iter=2)
+    sp.snapshot_prefix = str(tmp_path / "small")
+    s = get_solver(sp, engine="sm100")
+    x, y = make_data(32)
+    feed(s, x, y)
+    s.step(2)
+    s.snapshot()
+    assert s.net.layer_by_name["fc4"]._sm100.perm is not None
+    ref = {n: l.export_blob(0) for n, l in zip(s.net.layer_names, s.net.layers) if len(l.blobs)}
+    s2 = get_solver(sp, engine="torch", dtype=torch.float32)
+    s2.restore(str(tmp_path / "small_iter_2.solverstate"))
+    for n, l in zip(s2.net.layer_names, s2.net.layers):
+        if len(l.blobs):
+            assert np.allclose(l.export_blob(0), ref[n], atol=1e-6), n
+    assert s2.iter == 2
+    # and back: the sm100 engine resumes from the fp32 engine's file and both take the same next step
+    feed(s2, x, y)
+    s2.step(1)
+    s2.snapshot()
+    s3 = get_solver(sp, engine="sm100")
+    s3.restore(str(tmp_path / "small_iter_3.solverstate"))
+    for n, l in zip(s3.net.layer_names, s3.net.layers):
+        if len(l.blobs):
+            assert np.allclose(l.export_blob(0), s2.net.layer_by_name[n].export_blob(0), atol=1e-6), n
+    st = s3.net.layer_by_name["conv2"]._sm100
+    assert torch.equal(st.shadow().float(), st.w2d().to(torch.bfloat16).float())
+
+
+def _inception_net(batch=4, hw=20, classes=8):
+    from poseidon_b200.models.zoo import NetBuilder
+    b = NetBuilder("miniception")
+    b.layer("data", "MEMORY_DATA", (), ("data", "label"),
+            memory_data_param={"batch_size": batch, "channels": 3, "height": hw, "width": hw})
+    g = {"type": "gaussian", "std": 0.08}
+    z = {"type": "constant", "value": 0.0}
+    b.conv("conv1", "data", 32, 3, stride=2, pad=1, wf=g, bf=z)
+    b.relu("relu1", "conv1")
+    b.conv("b1", "conv1", 16, 1, wf=g, bf=z)
+    b.relu("b1r", "b1")
+    b.conv("b2r", "conv1", 16, 1, wf=g, bf=z)
+    b.relu("b2rr", "b2r")
+    b.conv("b2", "b2r", 24, 3, pad=1, wf=g, bf=z)
+    b.relu("b2relu", "b2")
+    b.pool("b3p", "conv1", "MAX", 3, 1, pad=1)
+    b.conv("b3", "b3p", 8, 1, wf=g, bf=z)
+    b.relu("b3r", "b3")
+    b.layer("cat", "CONCAT", ("b1", "b2", "b3"), ("cat",))
+    b.pool("gap", "cat", "AVE", 10, 1)
+    b.dropout("drop", "gap", 0.4)
+    b.fc("fc", "gap", classes, wf=g, bf=z)
+    b.softmax_loss("loss", "fc")
+    return b.net
+
+
+def test_inception_block_with_concat_and_dropout(emu):
+    """Branches, CONCAT, global AVE pooling and dropout: the loss falls and the gradient reaches every branch."""
+    from poseidon_b200 import get_solver
+    sp = small_solver_param(_inception_net(), base_lr=0.05, max_iter=12)
+    s = get_solver(sp, engine="sm100")
+    x, y = make_data(4, classes=8, hw=20)
+    before = {n: l.export_blob(0).copy() for n, l in zip(s.net.layer_names, s.net.layers) if len(l.blobs)}
+    losses = []
+    for _ in range(12):
+        feed(s, x, y)                  # the same 4 images every step: the net must memorise them
+        s.step(1)
+        losses.append(float(s.last_loss))
+    assert losses[-1] < 0.8 * losses[0] and all(b < a + 0.05 for a, b in zip(losses, losses[1:])), losses
+    for n, l in zip(s.net.layer_names, s.net.layers):
+        if len(l.blobs):
+            assert np.abs(l.export_blob(0) - before[n]).max() > 0, f"{n} never updated"
+    # dropout masks differ between iterations (device-resident iteration counter) but repeat within one
+    d = emu.dropout(torch.ones(2, 8, 2, 2, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last), 0.5, True)
+    emu.bump_iteration_seed(torch.device("cpu"))
+    e = emu.dropout(torch.ones(2, 8, 2, 2, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last), 0.5, True)
+    assert set(d.float().unique().tolist()) <= {0.0, 2.0} and not torch.equal(d, e)
+
+
+@pytest.mark.parametrize("name,steps", [("alexnet", 3), ("caffenet", 2), ("googlenet", 3)])
+def test_zoo_models_follow_fp32_engine(emu, name, steps):
+    """The reference's ImageNet models, full size (batch 2, synthetic data), dropout neutralised: the sm100 engine's
+    loss trajectory (space-to-depth conv1, fused ReLU / LRN masks, CONCAT slices, auxiliary losses) tracks fp32."""
+    from poseidon_b200 import get_solver
+    from poseidon_b200.models import zoo
+
+    def run(engine):
+        net = getattr(zoo, name)(batch=2, test_batch=2)
+        for l in net.layers:
+            if l.enum_name("type") == "DROPOUT":
+                l.dropout_param.dropout_ratio = 1e-7
+        sp = zoo.get_solver_param(name, net=net, display=0, snapshot=0, snapshot_after_train=False, test_interval=0,
+                                  max_iter=steps, random_seed=3)
+        sp.clear("test_iter")
+        sp.base_lr = 0.001
+        s = get_solver(sp, engine=engine, dtype=torch.float32 if engine == "torch" else None)
+        out = []
+        for _ in range(steps):
+            s.step(1)
+            out.append(float(s.last_loss))
+        s.close()
+        return out, s
+
+    l_sm, s = run("sm100")
+    l_ref, _ = run("torch")
+    if name != "googlenet":
+        assert s.net.layer_by_name["conv1"]._sm100.s2d
+    for a, b in zip(l_ref, l_sm):
+        assert abs(a - b) < 0.01 * abs(a), (l_ref, l_sm)
