@@ -198,7 +198,10 @@ def main():
         if not args.allow_cpu:
             print(json.dumps({"error": "bench.py needs a CUDA device"}))
             return 1
-        args.engine, args.graph = "torch", 0
+        from poseidon_b200.ops import sm100 as _sm100
+        if not (args.engine == "sm100" and _sm100.emulating()):     # POSEIDON_EMULATE=1: the sm100 control flow on CPU stand-ins
+            args.engine = "torch"
+        args.graph = 0
     torch.backends.cudnn.benchmark = True
     if args.engine == "torch":
         torch.backends.cuda.matmul.allow_tf32 = args.vendor_dtype != "fp32"

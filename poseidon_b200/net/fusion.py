@@ -62,7 +62,8 @@ def plan_sm100(net) -> None:
             layer.fused_relu_slope = slope
         net.skip_layer[j] = True
         # who applies the backward mask?
-        if layer.type_name == "CONVOLUTION" and slope == 0.0:
+        if layer.type_name == "CONVOLUTION" and slope == 0.0 and layer.num_output % 8 == 0:
+            # (consumers mask inside kernels that need channel counts in multiples of 8)
             readers = [k for k in nxt if k != j]
             ok = bool(readers)
             for k in readers:

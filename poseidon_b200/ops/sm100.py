@@ -115,8 +115,21 @@ class ConvState:
         self.row_mode = cg % 8 != 0
         self.s2d = False
         self.pad8 = False
-        if self.row_mode:
-            if self.groups != 1 or cin_logical > 4:
+        self.Coutp = self.Cout             # physical output channels (multiple of 8)
+        if (cg % 8 != 0 and cin_logical > 4) or (self.Cout // self.groups) % 8 != 0:
+            # Channel counts that are not multiples of 8 (LeNet: 1 -> 20 -> 50): input and output channels are
+            # zero-padded to the next multiple of 8 around the kernels (the operand carries zero rows / columns, the
+            # output is a channel slice of the padded tensor).  Small legacy nets only — costs extra passes.
+            if self.groups != 1:
+                raise ValueError(f"sm100 conv '{layer.layer_name}': grouped convolution needs channel counts per "
+                                 f"group that are multiples of 8 (got {cg} -> {self.Cout // self.groups})")
+            self.row_mode = True           # operand derived lazily from the master; no arena shadow / gradient sink
+            self.pad8 = True
+            self.Cp = (cin_logical + 7) // 8 * 8
+            self.Coutp = (self.Cout + 7) // 8 * 8
+            self.Kw = self.R * self.S * self.Cp
+        elif self.row_mode:
+            if self.groups != 1:
                 raise ValueError(f"sm100 conv '{layer.layer_name}': input channels {cin_logical} (group "
                                  f"{self.groups}) must be a multiple of 8 or <= 4 (first layer)")
             self.Cp = 4
@@ -200,8 +213,10 @@ class ConvState:
         w = self.layer.weight
         with torch.no_grad():
             if self.pad8:
-                t = torch.nn.functional.pad(w.data.permute(0, 2, 3, 1), (0, self.Cp - self.cin_logical))   # Cout,R,S,8
+                t = torch.nn.functional.pad(w.data.permute(0, 2, 3, 1), (0, self.Cp - self.cin_logical))   # Cout,R,S,Cp
                 src = t.reshape(self.Cout, self.Kw)
+                if self.Coutp != self.Cout:
+                    src = torch.nn.functional.pad(src, (0, 0, 0, self.Coutp - self.Cout))                  # zero rows
             elif self.s2d:
                 # W'[co][R'][S'][dy][dx][c] = W[co][c][4R'+dy][4S'+dx]  (zero outside the 11x11 support / c >= C)
                 t = torch.nn.functional.pad(w.data, (0, 4 * self.Sq - self.S, 0, 4 * self.Rq - self.R,
@@ -235,6 +250,13 @@ class ConvState:
     def dgrad_pack(self) -> torch.Tensor:
         if self.wt is not None and not self.dirty_wt:
             return self.wt
+        if self.pad8:
+            with torch.no_grad():
+                src = torch.nn.functional.pad(self.layer.weight.data.permute(0, 2, 3, 1), (0, self.Cp - self.cin_logical))
+            self.wt = K().conv_pack_dgrad(src.reshape(-1).contiguous(), self.Cout, self.R * self.S, self.Cp, 1, self.wt,
+                                          self.Coutp)
+            self.dirty_wt = False
+            return self.wt
         self.wt = K().conv_pack_dgrad(self.w2d().reshape(-1), self.Cout, self.R * self.S, self.cg, self.groups, self.wt,
                                       self.cok)
         self.dirty_wt = False
@@ -243,7 +265,8 @@ class ConvState:
     def grad_from_dw(self, dw: torch.Tensor) -> torch.Tensor:
         """[Cout, Kw] fp32 -> gradient tensor with the master weight's logical shape."""
         if self.pad8:
-            return dw.view(self.Cout, self.R, self.S, self.Cp)[..., : self.cin_logical].permute(0, 3, 1, 2).contiguous()
+            return dw[: self.Cout].view(self.Cout, self.R, self.S, self.Cp)[..., : self.cin_logical] \
+                .permute(0, 3, 1, 2).contiguous()
         if self.s2d:
             g = dw.view(self.Cout, self.Rq, self.Sq, 4, 4, self.Cp).permute(0, 5, 1, 3, 2, 4)   # co,c,R',dy,S',dx
             g = g.reshape(self.Cout, self.Cp, 4 * self.Rq, 4 * self.Sq)
@@ -268,10 +291,12 @@ def prepare_first_layer_input(x: torch.Tensor, st: ConvState, pad, in_hw) -> tor
     The data layers emit this layout straight from the transform kernel; anything else is converted here."""
     h, w = in_hw
     if st.pad8:
-        if (x.dtype == torch.bfloat16 and x.dim() == 4 and tuple(x.shape[1:]) == (8, h, w)
+        if (x.dtype == torch.bfloat16 and x.dim() == 4 and tuple(x.shape[1:]) == (st.Cp, h, w)
                 and x.is_contiguous(memory_format=CL)):
             return x
-        t = torch.nn.functional.pad(x.float(), (0, 0, 0, 0, 0, 8 - x.shape[1]))
+        if x.shape[1] == st.Cp:
+            return as_kernel_input(x)
+        t = torch.nn.functional.pad(x.float(), (0, 0, 0, 0, 0, st.Cp - x.shape[1]))
         return t.to(torch.bfloat16).contiguous(memory_format=CL)
     if st.s2d:
         hq, wq = st.s2d_hw
@@ -321,8 +346,12 @@ class _ConvFn(torch.autograd.Function):
             y = k.conv_fprop(xin, st.shadow(), bias, [st.Rq, st.Sq], [1, 1], [0, 0], 1, 0, oh, ow, relu,
                              float(relu_slope or 0.0), None)
         else:
+            if st.Coutp != st.Cout and bias is not None:
+                bias = torch.nn.functional.pad(bias.detach(), (0, st.Coutp - st.Cout))
             y = k.conv_fprop(xin, st.operand(), bias, [st.R, st.S], list(stride), list(conv_pad), st.groups,
                              1 if (st.row_mode and not st.pad8) else 0, oh, ow, relu, float(relu_slope or 0.0), None)
+            if st.Coutp != st.Cout:
+                y = y[:, : st.Cout]            # channel slice of the padded tensor (pixel pitch Coutp)
         ctx.layer, ctx.relu_slope, ctx.conv_pad = layer, relu_slope, conv_pad
         ctx.in_shape = tuple(x.shape)
         ctx.save_for_backward(xin, y if relu else None)
@@ -334,15 +363,24 @@ class _ConvFn(torch.autograd.Function):
         st: ConvState = layer._sm100
         k = K()
         xin, y = ctx.saved_tensors
-        dy = as_kernel_input(dy)
-        if y is not None and not st.consumer_masks:
-            dy = k.relu_bwd(y, dy.contiguous(memory_format=CL), float(ctx.relu_slope))
+        if st.Coutp != st.Cout:
+            # zero-padded output channels: mask (if any) on the logical slice, then widen dY to the padded layout
+            if y is not None and not st.consumer_masks:
+                dy = torch.where(y > 0, dy, dy * float(ctx.relu_slope))
+            dyp = torch.zeros(dy.shape[0], st.Coutp, dy.shape[2], dy.shape[3], device=dy.device,
+                              dtype=torch.bfloat16).contiguous(memory_format=CL)
+            dyp[:, : st.Cout].copy_(dy)
+            dy = dyp
+        else:
+            dy = as_kernel_input(dy)
+            if y is not None and not st.consumer_masks:
+                dy = k.relu_bwd(y, dy.contiguous(memory_format=CL), float(ctx.relu_slope))
         stride = layer.stride
         dw = db = dx = None
         if ctx.needs_input_grad[1]:
             sink = getattr(layer, "_grad_sink", None)
             dw2 = sink.weight_buffer(layer, st) if sink is not None else \
-                torch.zeros(st.Cout, st.Kw, device=dy.device, dtype=torch.float32)
+                torch.zeros(st.Coutp, st.Kw, device=dy.device, dtype=torch.float32)
             if st.s2d:
                 k.conv_wgrad(xin, dy, dw2, [st.Rq, st.Sq], [1, 1], [0, 0], 1, 0, 1.0, 0)
             else:
@@ -350,17 +388,20 @@ class _ConvFn(torch.autograd.Function):
                              1 if (st.row_mode and not st.pad8) else 0, 1.0, st.cgk if not st.row_mode else 0)
             dw = st.grad_from_dw(dw2)
         if layer.bias_term and ctx.needs_input_grad[2]:
-            db = torch.empty(st.Cout, device=dy.device, dtype=torch.float32)
+            db = torch.empty(st.Coutp, device=dy.device, dtype=torch.float32)
             pitch = dy.stride(3) if dy.shape[3] > 1 else (dy.stride(2) if dy.shape[2] > 1 else dy.stride(0))
-            k.colsum(dy, dy.shape[0] * dy.shape[2] * dy.shape[3], st.Cout, pitch, db, 1.0, False)
+            k.colsum(dy, dy.shape[0] * dy.shape[2] * dy.shape[3], st.Coutp, pitch, db, 1.0, False)
+            db = db[: st.Cout]
         if ctx.needs_input_grad[0]:
-            if st.row_mode or stride != (1, 1):
+            if (st.row_mode and not st.pad8) or stride != (1, 1):
                 raise NotImplementedError(f"sm100 conv '{layer.layer_name}': data gradient is implemented for "
                                           "stride-1 convolutions (first / strided layers never need it in the "
                                           "supported model families)")
             mask = xin if st.mask_input else None
             dx = k.conv_dgrad(dy, st.dgrad_pack(), [st.R, st.S], list(layer.pad), st.groups, xin.shape[2],
                               xin.shape[3], mask, 0.0)
+            if st.pad8 and st.Cp != st.cin_logical:
+                dx = dx[:, : st.cin_logical]
         return dx, dw, db, None, None
 
 
@@ -390,8 +431,10 @@ class IPState:
                 wd = layer.weight.data
                 layer.weight.data = wd.view(self.N, c, h, w).permute(0, 2, 3, 1).reshape(self.N, self.K).contiguous()
             layer._k_perm = self.perm
-        if self.K % 8:
-            raise ValueError(f"sm100 inner product '{layer.layer_name}': K={self.K} must be a multiple of 8")
+        # K not a multiple of 8 (LeNet ip2: 500): the reduction dimension is zero-padded around the kernels (TMA rows
+        # must be 16-byte multiples).  The operand is then derived from the master like a first-layer conv operand.
+        self.Kp = (self.K + 7) // 8 * 8
+        self.row_mode = self.Kp != self.K      # "derived operand": no arena shadow, no gradient sink, no SFB
 
     def mark_updated(self, keep_wb: bool = False):
         if not keep_wb and not self.arena_shadow:
@@ -402,10 +445,11 @@ class IPState:
             return self.wb
         w = self.layer.weight
         with torch.no_grad():
+            src = w.data if self.Kp == self.K else torch.nn.functional.pad(w.data, (0, self.Kp - self.K))
             if self.wb is None:
-                self.wb = w.data.to(torch.bfloat16)
+                self.wb = src.to(torch.bfloat16)
             else:
-                self.wb.copy_(w.data)
+                self.wb.copy_(src)
         self.dirty_wb = False
         return self.wb
 
@@ -428,6 +472,8 @@ class _IPFn(torch.autograd.Function):
         st: IPState = layer._sm100
         k = K()
         x2 = _flatten_nhwc(x)
+        if st.Kp != st.K:
+            x2 = torch.nn.functional.pad(x2, (0, st.Kp - st.K))
         n_pad = (st.N + 7) // 8 * 8
         if n_pad != st.N:
             out = torch.empty(x2.shape[0], n_pad, device=x.device, dtype=torch.bfloat16)[:, : st.N]
@@ -464,11 +510,13 @@ class _IPFn(torch.autograd.Function):
             # dX[M, K] = dY[M, N] · W[N, K]   (W row-major is the MN-major B operand).  Must be issued before the
             # fused SFB kernel below, which rewrites W / its bf16 shadow in place.
             dx2 = k.gemm_bf16(dy, False, st.shadow(), True, None, False, 0.0, None, None, 0)
+            if st.Kp != st.K:
+                dx2 = dx2[:, : st.K]
             xs = ctx.x_shape
             if len(xs) == 4 and xs[2] * xs[3] > 1:
-                dx = dx2.view(xs[0], xs[2], xs[3], xs[1]).permute(0, 3, 1, 2)
+                dx = dx2.reshape(xs[0], xs[2], xs[3], xs[1]).permute(0, 3, 1, 2)
             else:
-                dx = dx2.view(xs)
+                dx = dx2.reshape(xs)
         if layer.bias_term and ctx.needs_input_grad[2]:
             if st.N % 8 == 0 and dy.stride(1) == 1 and dy.stride(0) % 8 == 0:
                 db = torch.empty(st.N, device=dy.device, dtype=torch.float32)
@@ -478,12 +526,15 @@ class _IPFn(torch.autograd.Function):
         sfb = getattr(layer, "sfb", None)
         if ctx.needs_input_grad[1]:
             if sfb is not None:
-                dw = sfb.exchange_and_update(layer, dy, x2)     # fused path: returns None (W updated in place)
+                dw = sfb.exchange_and_update(layer, dy, x2 if st.Kp == st.K else x2[:, : st.K].contiguous())
+                # (fused path: returns None, W updated in place)
             else:
                 sink = getattr(layer, "_grad_sink", None)
                 dw = sink.weight_buffer(layer, st) if sink is not None else \
-                    torch.empty(st.N, st.K, device=dy.device, dtype=torch.float32)
+                    torch.empty(st.N, st.Kp, device=dy.device, dtype=torch.float32)
                 k.gemm_f32(dy, True, x2, True, dw, 1.0, False, 1, 0)
+                if st.Kp != st.K:
+                    dw = dw[:, : st.K]
         return dx, dw, db, None, None
 
 

@@ -230,8 +230,8 @@ class FusedBackend(Backend):
         st = getattr(layer, "_sm100", None)
         if st is None or p is not layer.weight:
             return
-        if isinstance(st, sm100.ConvState) and st.row_mode:
-            return                                  # packed first-layer operand is derived lazily
+        if getattr(st, "row_mode", False):
+            return                                  # derived operand (first-layer / channel-padded layouts): refreshed lazily
         shape = (st.Cout, st.Kw) if isinstance(st, sm100.ConvState) else (st.N, st.K)
         st.wb = self.arena.view(seg.wb_off, (seg.numel,), torch.bfloat16)[: p.numel()].view(*shape)
         st.arena_shadow = True

@@ -291,3 +291,67 @@ def test_zoo_models_follow_fp32_engine(emu, name, steps):
         assert s.net.layer_by_name["conv1"]._sm100.s2d
     for a, b in zip(l_ref, l_sm):
         assert abs(a - b) < 0.01 * abs(a), (l_ref, l_sm)
+
+
+def _odd_channel_net(batch=4, hw=12, classes=10):
+    """Channel counts that are not multiples of 8 everywhere (LeNet-like 20 / 50, K = 180, N = 30 / 10)."""
+    from poseidon_b200.models.zoo import NetBuilder
+    b = NetBuilder("oddnet")
+    b.layer("data", "MEMORY_DATA", (), ("data", "label"),
+            memory_data_param={"batch_size": batch, "channels": 3, "height": hw, "width": hw})
+    g = {"type": "gaussian", "std": 0.1}
+    c = {"type": "constant", "value": 0.1}
+    b.conv("conv1", "data", 20, 5, pad=2, wf=g, bf=c)
+    b.relu("relu1", "conv1")
+    b.pool("pool1", "conv1", "MAX", 2, 2)
+    b.conv("conv2", "pool1", 50, 3, pad=1, wf=g, bf=c)
+    b.relu("relu2", "conv2")
+    b.conv("conv3", "conv2", 20, 1, wf=g, bf=c)
+    b.relu("relu3", "conv3")
+    b.pool("pool3", "conv3", "AVE", 2, 2)
+    b.fc("ip1", "pool3", 30, wf=g, bf=c)
+    b.relu("relu4", "ip1")
+    b.fc("ip2", "ip1", classes, wf=g, bf=c)
+    b.softmax_loss("loss", "ip2")
+    return b.net
+
+
+def test_channel_counts_not_multiples_of_8(emu):
+    """The kernels want channel counts (and inner-product K) in multiples of 8; other nets are zero-padded around them."""
+    fn = _odd_channel_net
+    l_ref, w_ref, _ = _run("torch", 3, net_fn=fn, batch=4, hw=12, classes=10)
+    l_sm, w_sm, s = _run("sm100", 3, net_fn=fn, batch=4, hw=12, classes=10)
+    L = s.net.layer_by_name
+    st1, st2, st3 = (L[n]._sm100 for n in ("conv1", "conv2", "conv3"))
+    assert (st1.Cp, st1.Coutp, st2.Cp, st2.Coutp, st3.Cp, st3.Coutp) == (8, 24, 24, 56, 56, 24)
+    assert st2.shadow().shape == (56, 9 * 24) and st2.dgrad_pack().shape == (24, 9 * 56)
+    assert not st1.consumer_masks and not st2.consumer_masks          # masks stay with the producer for such layers
+    assert (L["ip1"]._sm100.K, L["ip1"]._sm100.Kp) == (180, 184) and L["ip1"]._sm100.shadow().shape == (30, 184)
+    assert (L["ip2"]._sm100.K, L["ip2"]._sm100.Kp) == (30, 32)
+    assert tuple(s.net.blobs["conv2"].shape) == (4, 50, 6, 6)           # logical shapes are the reference's
+    assert tuple(L["conv2"].weight.shape) == (50, 20, 3, 3) and tuple(L["ip1"].weight.shape) == (30, 180)
+    _close(l_ref, l_sm, w_ref, w_sm, const_bias=("conv1.1", "conv2.1", "conv3.1", "ip1.1", "ip2.1"))
+
+
+@pytest.mark.parametrize("name", ["lenet", "cifar10_quick"])
+def test_small_zoo_models_follow_fp32_engine(emu, name):
+    """examples/mnist and examples/cifar10 of the reference, on the sm100 engine (LeNet: 1 -> 20 -> 50 channels, K = 500)."""
+    from poseidon_b200 import get_solver
+    from poseidon_b200.models import zoo
+
+    def run(engine):
+        net = getattr(zoo, name)(batch=8)
+        sp = zoo.get_solver_param(name, net=net, display=0, snapshot=0, snapshot_after_train=False, test_interval=0,
+                                  max_iter=4, random_seed=3)
+        sp.clear("test_iter")
+        s = get_solver(sp, engine=engine, dtype=torch.float32 if engine == "torch" else None)
+        out = []
+        for _ in range(4):
+            s.step(1)
+            out.append(float(s.last_loss))
+        s.close()
+        return out
+
+    l_sm, l_ref = run("sm100"), run("torch")
+    for a, b in zip(l_ref, l_sm):
+        assert abs(a - b) < 0.02 * max(1.0, abs(a)), (l_ref, l_sm)
