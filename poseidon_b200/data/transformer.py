@@ -25,9 +25,8 @@ class DataTransformer:
         self.mean = None          # (C,H,W) tensor
         self.mean_values = None   # (C,) tensor
         if tp.has("mean_file"):
-            path = tp.mean_file
-            if model_dir and not os.path.isabs(path) and not os.path.exists(path):
-                path = os.path.join(model_dir, path)
+            from ..utils.paths import resolve
+            path = resolve(tp.mean_file, model_dir)
             if os.path.exists(path):
                 blob = P.read_binary(path, P.BlobProto)
                 self.mean = torch.from_numpy(P.blob_to_array(blob)[0].copy()).to(self.device)

@@ -23,11 +23,8 @@ log = logging.getLogger("poseidon_b200")
 
 
 def _resolve(ctx, path):
-    if path and not os.path.isabs(path) and not os.path.exists(path) and ctx.model_dir:
-        cand = os.path.join(ctx.model_dir, path)
-        if os.path.exists(cand):
-            return cand
-    return path
+    from ..utils.paths import resolve
+    return resolve(path, ctx.model_dir)
 
 
 def _guess_shape(ctx, source: str, crop: int):

@@ -100,7 +100,8 @@ class InfogainLossLayer(LossLayer):
             src = self.lp.infogain_loss_param.source
             if not src:
                 raise ValueError("infogain matrix needs a source file or a third bottom")
-            path = src if os.path.isabs(src) or not self.ctx.model_dir else os.path.join(self.ctx.model_dir, src)
+            from ..utils.paths import resolve
+            path = resolve(src, self.ctx.model_dir)
             blob = P.read_binary(path, P.BlobProto)
             self.H = torch.from_numpy(P.blob_to_array(blob).reshape(blob.height, blob.width).copy())
 

@@ -149,16 +149,9 @@ class Solver:
         return ctx
 
     def _resolve(self, path):
-        if path and not os.path.isabs(path) and not os.path.exists(path) and self.model_dir:
-            # prototxt paths in shipped solvers are relative to the repo root they were run from
-            for base in (self.model_dir, os.path.dirname(self.model_dir), os.getcwd()):
-                cand = os.path.join(base, path)
-                if os.path.exists(cand):
-                    return cand
-                cand = os.path.join(base, os.path.basename(path))
-                if os.path.exists(cand):
-                    return cand
-        return path
+        """Net files named by the solver: CAFFE_ROOT placeholder, model directory, its ancestors, working directory."""
+        from ..utils.paths import resolve
+        return resolve(path, self.model_dir, basename_fallback=True)
 
     def _init_train_net(self):
         sp = self.param
@@ -564,7 +557,8 @@ class Solver:
 
     # ---- snapshot / restore ---------------------------------------------------------------------------
     def _snapshot_prefix(self):
-        prefix = self.param.snapshot_prefix or "snapshot"
+        from ..utils.paths import expand_placeholder
+        prefix = expand_placeholder(self.param.snapshot_prefix or "snapshot", self.model_dir, must_exist=False)
         if self.snapshot_dir:
             prefix = os.path.join(self.snapshot_dir, os.path.basename(prefix))
         d = os.path.dirname(prefix)

@@ -124,3 +124,57 @@ def test_bench_harness_self_test_on_cpu():
                          text=True, timeout=120, cwd=root)
     r = json.loads(ref.stdout.strip().splitlines()[-1])
     assert r["impl"] == "reference" and "unavailable" in r
+
+
+def test_caffe_root_placeholder_and_relative_paths(tmp_path, monkeypatch):
+    """The reference's shipped prototxts spell paths as CAFFE_ROOT/...; they load without hand-editing."""
+    from poseidon_b200.utils import paths
+    monkeypatch.setattr(paths, "_root_hint", None)
+    monkeypatch.delenv("CAFFE_ROOT", raising=False)
+    root = tmp_path / "app"
+    (root / "examples" / "mnist").mkdir(parents=True)
+    net = root / "examples" / "mnist" / "lenet_train_test.prototxt"
+    net.write_text("name: 'x'")
+    model_dir = str(root / "examples" / "mnist")
+    # placeholder resolved against the ancestors of the referring file
+    assert paths.resolve("CAFFE_ROOT/examples/mnist/lenet_train_test.prototxt", model_dir) == str(net)
+    # later lookups reuse the discovered root, also for files that do not exist (yet)
+    assert paths.expand_placeholder("CAFFE_ROOT/examples/mnist/lenet", model_dir, must_exist=False) == \
+        str(root / "examples" / "mnist" / "lenet")
+    assert paths.resolve("CAFFE_ROOT/examples/mnist/mnist_train_lmdb", model_dir) == \
+        str(root / "examples" / "mnist" / "mnist_train_lmdb")
+    # repo-root-relative and model-dir-relative spellings
+    assert paths.resolve("examples/mnist/lenet_train_test.prototxt", model_dir) == str(net)
+    assert paths.resolve("lenet_train_test.prototxt", model_dir) == str(net)
+    # a solver copied next to its net: stale directory part, found by file name (solver lookups only)
+    assert paths.resolve("CAFFE_ROOT/old/place/lenet_train_test.prototxt", model_dir, basename_fallback=True) == str(net)
+    assert paths.resolve("missing/file.prototxt", model_dir) == "missing/file.prototxt"
+    # the environment variable wins
+    monkeypatch.setenv("CAFFE_ROOT", "/opt/app")
+    assert paths.resolve("CAFFE_ROOT/a/b", model_dir, must_exist=False) == "/opt/app/a/b"
+    # models/bvlc_* of the reference use POSEIDON_ROOT
+    assert paths.resolve("POSEIDON_ROOT/examples/mnist/lenet_train_test.prototxt", model_dir) == str(net)
+
+
+def test_reference_example_solvers_load_unmodified():
+    """examples/mnist + examples/cifar10 solver files of the reference (CAFFE_ROOT placeholders included) build nets."""
+    import os
+    import pytest
+    from poseidon_b200 import get_solver, proto as P
+    ref = "/root/reference/examples"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not mounted")
+    for rel in ("mnist/lenet_solver.prototxt", "cifar10/cifar10_quick_solver.prototxt"):
+        sp = P.read_solver(os.path.join(ref, rel))
+        sp.snapshot, sp.snapshot_after_train, sp.display, sp.test_interval, sp.max_iter = 0, False, 0, 0, 1
+        sp.clear("test_iter")
+        s = get_solver(sp, engine="torch", model_dir=os.path.dirname(os.path.join(ref, rel)))
+        s.step(1)
+        assert s.net.layer_names and float(s.last_loss) > 0
+        s.close()
+    # models/: POSEIDON_ROOT placeholders in net:, source:, mean_file:, snapshot_prefix: (built, not stepped: batch 256)
+    mref = "/root/reference/models/bvlc_alexnet/solver.prototxt"
+    s = get_solver(P.read_solver(mref), engine="torch", model_dir=os.path.dirname(mref))
+    assert s.net.layer_by_name["fc8"].weight.shape == (1000, 4096)
+    assert "POSEIDON_ROOT" not in s._snapshot_prefix.__func__(type("S", (), {"param": s.param, "model_dir": s.model_dir, "snapshot_dir": "/tmp"})())
+    s.close()
