@@ -21,6 +21,7 @@ import logging
 import os
 import subprocess
 import sys
+import time
 
 log = logging.getLogger("poseidon_b200")
 
@@ -221,12 +222,33 @@ def cmd_time(args) -> int:
     net.zero_grad_()
     n = len(net.layers)
     fwd = [0.0] * n
+    bwd = [0.0] * n
     total_f = total_b = 0.0
     hooks = []
     timers = [Timer(dev) for _ in range(n)]
+    cuda = dev.type == "cuda"
+    marks = []                    # (layer index | -1 for "backward finished", timestamp or CUDA event) in firing order
+
+    def mark(i):
+        if cuda:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((i, ev))
+        else:
+            marks.append((i, time.perf_counter()))
+
+    def after_forward(i, outs):
+        timers[i].stop()
+        # Backward of layer i starts when the gradient of its output is complete and ends when the next such
+        # gradient (an earlier layer's output) is: autograd runs the graph in reverse topological order.
+        for o in (outs if isinstance(outs, (tuple, list)) else (outs,)):
+            if torch.is_tensor(o) and o.requires_grad:
+                o.register_hook(lambda g, i=i: mark(i))
+                break
+
     for i, layer in enumerate(net.layers):
         hooks.append(layer.register_forward_pre_hook(lambda m, a, i=i: timers[i].start()))
-        hooks.append(layer.register_forward_hook(lambda m, a, o, i=i: timers[i].stop()))
+        hooks.append(layer.register_forward_hook(lambda m, a, o, i=i: after_forward(i, o)))
     for _ in range(args.iterations):
         tf = Timer(dev)
         tf.start()
@@ -236,14 +258,21 @@ def cmd_time(args) -> int:
             fwd[i] += timers[i].milliseconds()
         tb = Timer(dev)
         tb.start()
+        del marks[:]
         if loss is not None and loss.requires_grad:
             loss.backward()
+        mark(-1)
         total_b += tb.milliseconds()
+        for (i, t0), (_, t1) in zip(marks, marks[1:]):
+            if i >= 0:
+                bwd[i] += t0.elapsed_time(t1) if cuda else (t1 - t0) * 1e3
         net.zero_grad_()
     for h in hooks:
         h.remove()
     for i, name in enumerate(net.layer_names):
         log.info("%-28s forward: %.4f ms.", name, fwd[i] / args.iterations)
+    for i in range(n - 1, -1, -1):
+        log.info("%-28s backward: %.4f ms.", net.layer_names[i], bwd[i] / args.iterations)
     log.info("Average Forward pass: %.4f ms.", total_f / args.iterations)
     log.info("Average Backward pass: %.4f ms.", total_b / args.iterations)
     log.info("Average Forward-Backward: %.4f ms.", (total_f + total_b) / args.iterations)

@@ -153,7 +153,27 @@ def test_caffe_main_cli_train_and_time(tmp_path):
     rc = caffe_main.main(["test", f"--model={net_path}", f"--weights={tmp_path / 'lenet_iter_4.caffemodel'}",
                           "--iterations=2", "--gpu=-1"])
     assert rc == 0
-    assert caffe_main.main(["time", f"--model={net_path}", "--iterations=1", "--gpu=-1"]) == 0
+    import logging
+    records = []
+
+    class Grab(logging.Handler):
+        def emit(self, r):
+            records.append(r.getMessage())
+    h = Grab()
+    lg = logging.getLogger("poseidon_b200")
+    old_level = lg.level
+    lg.addHandler(h)
+    lg.setLevel(logging.INFO)
+    try:
+        assert caffe_main.main(["time", f"--model={net_path}", "--iterations=1", "--gpu=-1"]) == 0
+    finally:
+        lg.removeHandler(h)
+        lg.setLevel(old_level)
+    # per-layer forward AND backward lines, like the reference's `caffe time` (tools/caffe_main.cpp:255-328)
+    fw = [m for m in records if " forward: " in m]
+    bw = [m for m in records if " backward: " in m]
+    assert len(fw) == len(bw) > 5 and bw[0].startswith("loss") and fw[0].startswith("data")
+    assert float([m for m in bw if m.startswith("conv2")][0].split("backward:")[1].split()[0]) > 0
     assert caffe_main.main(["device_query"]) == 0
 
 
