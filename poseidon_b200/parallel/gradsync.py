@@ -195,7 +195,11 @@ class TorchDistBackend(Backend):
             bucket.event.record(self.stream)
 
     def bytes_on_wire(self):
-        return {"dense_allreduce_bytes": self.dense_bytes}
+        out = {"dense_allreduce_bytes": self.dense_bytes}
+        st = getattr(self.sync, "sfb_stats", None)          # library sufficient-factor path (parallel/sfb.py)
+        if st is not None:
+            out["sfb_bytes"], out["sfb_dense_equiv_bytes"] = st.sfb_bytes, st.dense_equiv_bytes
+        return out
 
 
 class SSPBackend(Backend):

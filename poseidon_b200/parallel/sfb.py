@@ -153,6 +153,30 @@ class SFBHandle:
     def apply(self, layer, x, w, b, relu):
         return _SFBLinear.apply(x, w, b, relu, self.world, layer.layer_name, self.stats)
 
+    def exchange_and_update(self, layer, dy: torch.Tensor, x2: torch.Tensor):
+        """Entry point of the sm100 engine's inner-product backward (ops/sm100.py::_IPFn) when the communication
+        backend is a library one (NCCL / gloo: multi-node jobs): all-gather the bf16 factors u = dY [M,N], v = X [M,K],
+        rebuild the global ΔW = Σ_p u_pᵀ v_p with our GEMM kernel and hand it to the optimizer as an already-global
+        gradient (same contract as ``_SFBLinear.backward``; the fused NVLink engine has its own handle, FusedSFB)."""
+        P = self.world
+        M, N = dy.shape
+        K = x2.shape[1]
+        fac = torch.cat([dy.reshape(-1), x2.reshape(-1)])
+        gathered = torch.empty(P * fac.numel(), dtype=fac.dtype, device=fac.device)
+        dist.all_gather_into_tensor(gathered, fac)
+        gathered = gathered.view(P, fac.numel())
+        U = gathered[:, : M * N].reshape(P * M, N)
+        V = gathered[:, M * N:].reshape(P * M, K)
+        if N % 8 == 0 and K % 8 == 0 and U.dtype == torch.bfloat16:
+            from ..ops import sm100
+            dw = torch.empty(N, K, device=dy.device, dtype=torch.float32)
+            sm100.K().gemm_f32(U, True, V, True, dw, 1.0, False, 1, 0)
+        else:
+            dw = U.float().t() @ V.float()
+        self.stats.sfb_bytes += fac.numel() * fac.element_size()
+        self.stats.dense_equiv_bytes += N * K * 4
+        return dw
+
 
 def enable_sfb(net, sync, rank_ctx, mode: str = "auto") -> SFBStats:
     """Mark IP weights for SFB. ``mode``: "all" (reference behaviour), "auto" (cost model),

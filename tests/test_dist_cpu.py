@@ -123,3 +123,46 @@ def test_ssp_aggr_budgeted_updates_are_exactly_once_and_cheaper(tmp_path):
     diffs = [np.abs(res[0][k] - ref[0][k]).max() for k in _weights(ref[0])]
     scale = max(np.abs(v).max() for v in _weights(ref[0]).values())
     assert max(diffs) < 0.2 * scale
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The sm100 engine (bf16 operands, fused epilogues, shadows) under the LIBRARY communication backends — the
+# configuration multi-node jobs run in.  The kernels are replaced by their CPU emulation (ops/emulate.py), the
+# communication is real (gloo, 2 processes).
+@pytest.fixture(scope="module")
+def single_sm100(tmp_path_factory):
+    os.environ["POSEIDON_EMULATE"] = "1"
+    try:
+        out = str(tmp_path_factory.mktemp("single_sm100") / "w")
+        return launch(1, out, ["--batch", "16", "--base_lr", "0.02", "--engine", "sm100", "--comm", "local"])[0]
+    finally:
+        os.environ.pop("POSEIDON_EMULATE", None)
+
+
+def _rel(a, b):
+    return max(np.abs(a[k] - b[k]).max() / (np.abs(a[k]).max() + 1e-6) for k in _weights(a))
+
+
+@pytest.mark.parametrize("extra,sfb", [(["--comm", "gloo"], False),
+                                       (["--comm", "gloo", "--svb", "1", "--sfb_mode", "all"], True)])
+def test_sm100_engine_with_library_backend(tmp_path, monkeypatch, single_sm100, extra, sfb):
+    monkeypatch.setenv("POSEIDON_EMULATE", "1")
+    res = launch(2, str(tmp_path / "w"), ["--batch", "8", "--engine", "sm100"] + extra)
+    assert _rel(res[0], res[1]) < 1e-6                    # replicas identical
+    assert _rel(res[0], single_sm100) < 1e-4              # == one process on the concatenated batch with lr x2
+    if sfb:
+        assert int(res[0]["wire_sfb_bytes"]) > 0 and int(res[0]["wire_sfb_dense_equiv_bytes"]) > int(res[0]["wire_sfb_bytes"])
+    else:
+        assert int(res[0]["wire_dense_allreduce_bytes"]) > 0
+
+
+@pytest.mark.parametrize("comm", ["ssp", "ssp_aggr"])
+def test_sm100_engine_bounded_staleness(tmp_path, monkeypatch, single_sm100, comm):
+    """SSP / SSPAggr exchange dense wire buffers whatever the parameter's memory format is (channels-last conv
+    weights on this engine) and the bf16 operands are re-derived after remote updates are applied."""
+    monkeypatch.setenv("POSEIDON_EMULATE", "1")
+    res = launch(2, str(tmp_path / "w"), ["--batch", "8", "--engine", "sm100", "--comm", comm, "--staleness", "1"])
+    assert _rel(res[0], res[1]) < 1e-5                    # drained at the end: replicas agree
+    assert _rel(res[0], single_sm100) < 0.25              # and stay near the synchronous trajectory
+    if "max_lag" in res[0]:
+        assert int(res[0]["max_lag"]) <= 1
