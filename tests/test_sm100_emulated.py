@@ -355,3 +355,32 @@ def test_small_zoo_models_follow_fp32_engine(emu, name):
     l_sm, l_ref = run("sm100"), run("torch")
     for a, b in zip(l_ref, l_sm):
         assert abs(a - b) < 0.02 * max(1.0, abs(a)), (l_ref, l_sm)
+
+
+def test_train_snapshot_then_extract_features_both_engines(emu, tmp_path):
+    """caffe_main train on the sm100 engine -> .caffemodel -> tools.extract_features on either engine: the feature
+    databases hold the same logical (C, H, W) datums (LeNet: channel-sliced 20 / 50-channel blobs, K-padded ip2)."""
+    from poseidon_b200 import proto as P
+    from poseidon_b200.data.db import open_db
+    from poseidon_b200.models import zoo
+    from poseidon_b200.tools import caffe_main, extract_features
+    net_path = tmp_path / "lenet.prototxt"
+    P.write_text(str(net_path), zoo.lenet(batch=8, test_batch=8))
+    sp = zoo.lenet_solver(net_path=str(net_path), max_iter=3, display=0, test_interval=0, solver_mode="CPU", snapshot=3,
+                          snapshot_prefix=str(tmp_path / "lenet"))
+    sp.clear("test_iter")
+    solver_path = tmp_path / "solver.prototxt"
+    P.write_text(str(solver_path), sp)
+    assert caffe_main.main(["train", f"--solver={solver_path}", "--engine=sm100"]) == 0
+    weights = str(tmp_path / "lenet_iter_3.caffemodel")
+    for eng in ("sm100", "torch"):
+        extract_features.main([weights, str(net_path), "conv2,ip1", f"{tmp_path}/{eng}_conv2,{tmp_path}/{eng}_ip1", "1",
+                               "--gpu", "-1", "--engine", eng])
+    for blob, shape in (("conv2", (50, 8, 8)), ("ip1", (500, 1, 1))):
+        a, b = open_db(f"{tmp_path}/sm100_{blob}_0_0"), open_db(f"{tmp_path}/torch_{blob}_0_0")
+        assert len(a) == len(b) == 8
+        for i in range(len(a)):
+            da, db = a.datum(i), b.datum(i)
+            assert (da.channels, da.height, da.width) == (db.channels, db.height, db.width) == shape
+            fa, fb = np.array(da.float_data), np.array(db.float_data)
+            assert np.abs(fa - fb).max() <= 0.02 * max(1.0, np.abs(fb).max()), blob
