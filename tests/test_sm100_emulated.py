@@ -384,3 +384,83 @@ def test_train_snapshot_then_extract_features_both_engines(emu, tmp_path):
             assert (da.channels, da.height, da.width) == (db.channels, db.height, db.width) == shape
             fa, fb = np.array(da.float_data), np.array(db.float_data)
             assert np.abs(fa - fb).max() <= 0.02 * max(1.0, np.abs(fb).max()), blob
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The layer catalogue beyond the ImageNet models (siamese / autoencoder style nets) on bf16 activations
+def _lt_base(b, batch=4, hw=12):
+    b.layer("data", "MEMORY_DATA", (), ("data", "label"), memory_data_param={"batch_size": batch, "channels": 3, "height": hw, "width": hw})
+    g = {"type": "gaussian", "std": 0.1}
+    b.conv("conv1", "data", 16, 3, pad=1, wf=g, bf={"type": "constant", "value": 0.1})
+    return g
+
+def _lt_neurons():
+    from poseidon_b200.models.zoo import NetBuilder
+    b = NetBuilder("neurons"); g = _lt_base(b)
+    x = "conv1"
+    for i, (t, kw) in enumerate([("SIGMOID", {}), ("TANH", {}), ("ABSVAL", {}), ("BNLL", {}), ("POWER", {"power_param": {"power": 2.0, "scale": 0.5, "shift": 0.1}})]):
+        b.layer(f"n{i}", t, (x,), (f"n{i}",), **kw); x = f"n{i}"
+    b.pool("pool", x, "MAX", 2, 2)
+    b.fc("fc", "pool", 16, wf=g, bf={"type": "constant", "value": 0.0})
+    b.softmax_loss("loss", "fc")
+    return b.net
+
+def _lt_eltwise():
+    from poseidon_b200.models.zoo import NetBuilder
+    b = NetBuilder("elt"); g = _lt_base(b)
+    b.layer("slice", "SLICE", ("conv1",), ("s1", "s2"), slice_param={"slice_dim": 1})
+    b.layer("sum", "ELTWISE", ("s1", "s2"), ("sum",), eltwise_param={"operation": "SUM"})
+    b.layer("mx", "ELTWISE", ("s1", "s2"), ("mx",), eltwise_param={"operation": "MAX"})
+    b.layer("pr", "ELTWISE", ("sum", "mx"), ("pr",), eltwise_param={"operation": "PROD"})
+    b.layer("cat", "CONCAT", ("pr", "s1"), ("cat",))
+    b.layer("mvn", "MVN", ("cat",), ("mvn",))
+    b.layer("flat", "FLATTEN", ("mvn",), ("flat",))
+    b.fc("fc", "flat", 16, wf=g, bf={"type": "constant", "value": 0.0})
+    b.softmax_loss("loss", "fc")
+    return b.net
+
+def _lt_losses(kind):
+    from poseidon_b200.models.zoo import NetBuilder
+    b = NetBuilder(kind); g = _lt_base(b)
+    b.pool("pool", "conv1", "AVE", 4, 4)
+    if kind == "EUCLIDEAN_LOSS":
+        b.fc("fc", "pool", 1, wf=g, bf={"type": "constant", "value": 0.0})
+        b.layer("loss", kind, ("fc", "label"), ("loss",))
+    elif kind == "SIGMOID_CROSS_ENTROPY_LOSS":
+        b.fc("fc", "pool", 1, wf=g, bf={"type": "constant", "value": 0.0})
+        b.layer("thr", "THRESHOLD", ("label",), ("lab01",), threshold_param={"threshold": 7.5})
+        b.layer("loss", kind, ("fc", "lab01"), ("loss",))
+    elif kind == "HINGE_LOSS":
+        b.fc("fc", "pool", 16, wf=g, bf={"type": "constant", "value": 0.0})
+        b.layer("loss", kind, ("fc", "label"), ("loss",))
+    elif kind == "MULTINOMIAL_LOGISTIC_LOSS":
+        b.fc("fc", "pool", 16, wf=g, bf={"type": "constant", "value": 0.0})
+        b.layer("prob", "SOFTMAX", ("fc",), ("prob",))
+        b.layer("loss", kind, ("prob", "label"), ("loss",))
+    elif kind == "CONTRASTIVE_LOSS":
+        b.fc("fa", "pool", 8, wf=g, bf={"type": "constant", "value": 0.0})
+        b.fc("fb", "pool", 8, wf={"type": "gaussian", "std": 0.2}, bf={"type": "constant", "value": 0.0})
+        b.layer("thr", "THRESHOLD", ("label",), ("sim",), threshold_param={"threshold": 7.5})
+        b.layer("loss", kind, ("fa", "fb", "sim"), ("loss",), contrastive_loss_param={"margin": 1.0})
+    return b.net
+
+
+@pytest.mark.parametrize("case", ["neurons", "eltwise", "EUCLIDEAN_LOSS", "SIGMOID_CROSS_ENTROPY_LOSS", "HINGE_LOSS",
+                                  "MULTINOMIAL_LOGISTIC_LOSS", "CONTRASTIVE_LOSS"])
+def test_layer_catalogue_on_sm100_engine(emu, case):
+    from poseidon_b200 import get_solver
+    from poseidon_b200.models.zoo import NetBuilder      # noqa: F401  (used by the builders above)
+    fn = {"neurons": _lt_neurons, "eltwise": _lt_eltwise}.get(case, lambda: _lt_losses(case))
+    out = {}
+    for eng in ("torch", "sm100"):
+        sp = small_solver_param(fn(), base_lr=0.01, max_iter=3)
+        s = get_solver(sp, engine=eng, dtype=torch.float32 if eng == "torch" else None)
+        x, y = make_data(12, hw=12)
+        feed(s, x, y)
+        out[eng] = []
+        for _ in range(3):
+            s.step(1)
+            out[eng].append(float(s.last_loss))
+        s.close()
+    for a, b in zip(out["torch"], out["sm100"]):
+        assert abs(a - b) <= 0.02 * max(1.0, abs(a)), out
