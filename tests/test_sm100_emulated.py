@@ -464,3 +464,49 @@ def test_layer_catalogue_on_sm100_engine(emu, case):
         s.close()
     for a, b in zip(out["torch"], out["sm100"]):
         assert abs(a - b) <= 0.02 * max(1.0, abs(a)), out
+
+
+@pytest.mark.parametrize("k,stride,pad,crop,mode", [(11, 4, 2, 35, "s2d"), (3, 1, 1, 32, "pad8"), (7, 2, 3, 33, "row"),
+                                                   (5, 2, 0, 33, "row")])
+def test_data_layer_hands_first_conv_its_layout(emu, tmp_path, k, stride, pad, crop, mode):
+    """LMDB -> (native) batch loader -> transform op (random crop, mirror, mean, scale) writing the first
+    convolution's operand layout directly -> conv.  Same crops as the fp32 engine (same seeded draws), same losses."""
+    from poseidon_b200 import get_solver, proto as P
+    from poseidon_b200.data.lmdb_writer import write_lmdb
+    from poseidon_b200.models.zoo import NetBuilder
+    rng = np.random.RandomState(0)
+    recs = []
+    for i in range(40):
+        dt = P.Datum(channels=3, height=44, width=44, label=int(rng.randint(0, 8)))
+        dt.data = rng.randint(0, 256, size=(3, 44, 44)).astype(np.uint8).tobytes()
+        recs.append((b"%08d" % i, dt.SerializeToString()))
+    write_lmdb(str(tmp_path / "db"), recs)
+
+    def net():
+        b = NetBuilder("d")
+        b.data(str(tmp_path / "db"), 8, crop=crop, mirror=True, mean_values=[104, 117, 123], scale=0.02)
+        g = {"type": "gaussian", "std": 0.05}
+        b.conv("conv1", "data", 16, k, stride=stride, pad=pad, wf=g, bf={"type": "constant", "value": 0.1})
+        b.relu("relu1", "conv1")
+        b.pool("pool1", "conv1", "MAX", 2, 2)
+        b.fc("fc", "pool1", 8, wf=g, bf={"type": "constant", "value": 0.0})
+        b.softmax_loss("loss", "fc")
+        return b.net
+
+    out = {}
+    for eng in ("torch", "sm100"):
+        s = get_solver(small_solver_param(net(), base_lr=0.01, max_iter=3), engine=eng,
+                       dtype=torch.float32 if eng == "torch" else None)
+        out[eng] = []
+        for _ in range(3):
+            s.step(1)
+            out[eng].append(float(s.last_loss))
+        if eng == "sm100":
+            st = s.net.layer_by_name["conv1"]._sm100
+            assert ("s2d" if st.s2d else "pad8" if st.pad8 else "row") == mode
+            assert s.net.layers[0].first_conv is s.net.layer_by_name["conv1"]
+            from poseidon_b200.ops import counting
+            assert counting.by_op().get("transform_nhwc", 0) >= 3
+        s.close()
+    for a, b in zip(out["torch"], out["sm100"]):
+        assert abs(a - b) <= 0.02 * max(1.0, abs(a)), out
