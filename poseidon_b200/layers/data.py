@@ -201,8 +201,10 @@ class WindowDataLayer(BasePrefetchingDataLayer):
 
 @register("HDF5_DATA")
 class HDF5DataLayer(Layer):
-    """Reads "data"/"label" datasets from the files listed in ``source`` (HDF5 via h5py when
-    importable; ``.npz`` containers always). reference: src/caffe/layers/hdf5_data_layer.cpp:38-108."""
+    """Reads the "data" / "label" datasets of every file listed in ``source`` into memory, file after file (HDF5 through
+    the built-in reader data/hdf5.py — contiguous or chunked / gzip / shuffle datasets of the classic file format —
+    and ``.npz`` archives).  reference: src/caffe/layers/hdf5_data_layer.cpp:38-108, src/caffe/util/io.cpp
+    (hdf5_load_nd_dataset: float / double data of at most 4 dimensions)."""
     exact_bottoms = 0
     exact_tops = 2
     is_data = True
@@ -211,12 +213,17 @@ class HDF5DataLayer(Layer):
         if path.endswith(".npz") or path.endswith(".npy"):
             z = np.load(path)
             return z["data"].astype(np.float32), z["label"].astype(np.float32)
-        try:
-            import h5py
-        except ImportError as e:
-            raise IOError("h5py is not available; use .npz files in the HDF5 source list") from e
-        with h5py.File(path, "r") as f:
-            return np.asarray(f["data"], dtype=np.float32), np.asarray(f["label"], dtype=np.float32)
+        from ..data import hdf5
+        with hdf5.File(path) as f:
+            for name in ("data", "label"):
+                if name not in f:
+                    raise IOError(f"{path}: dataset '{name}' not found (have: {', '.join(f.keys()) or 'none'})")
+            d, l = f["data"], f["label"]
+        if d.ndim > 4 or d.ndim < 1:
+            raise ValueError(f"{path}: 'data' must have 1..4 dimensions, has {d.ndim}")
+        if d.shape[0] != l.shape[0]:
+            raise ValueError(f"{path}: 'data' has {d.shape[0]} rows but 'label' has {l.shape[0]}")
+        return d.astype(np.float32), l.astype(np.float32)
 
     def setup(self, bottom_shapes):
         hp = self.lp.hdf5_data_param
@@ -256,8 +263,9 @@ class HDF5DataLayer(Layer):
 
 @register("HDF5_OUTPUT")
 class HDF5OutputLayer(Layer):
-    """Writes (data, label) bottoms to a file at every forward.
-    reference: src/caffe/layers/hdf5_output_layer.cpp."""
+    """Writes the (data, label) bottoms seen so far to ``file_name`` as the float datasets "data" / "label" of an HDF5
+    file (built-in writer; an ``.npz`` name selects a numpy archive instead).
+    reference: src/caffe/layers/hdf5_output_layer.cpp:17-68."""
     exact_bottoms = 2
     exact_tops = 0
 
@@ -270,13 +278,11 @@ class HDF5OutputLayer(Layer):
         self.saved.append((data.detach().float().cpu().numpy(), label.detach().float().cpu().numpy()))
         d = np.concatenate([s[0] for s in self.saved])
         l = np.concatenate([s[1] for s in self.saved])
-        try:
-            import h5py
-            with h5py.File(self.file_name, "w") as f:
-                f["data"], f["label"] = d, l
-        except ImportError:
-            np.savez(self.file_name if self.file_name.endswith(".npz") else self.file_name + ".npz",
-                     data=d, label=l)
+        if self.file_name.endswith(".npz"):
+            np.savez(self.file_name, data=d, label=l)
+        else:
+            from ..data import hdf5
+            hdf5.save(self.file_name, {"data": d.astype(np.float32), "label": l.astype(np.float32)})
         return ()
 
 
