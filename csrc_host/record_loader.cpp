@@ -502,6 +502,10 @@ static void bf16_to_f32(uintptr_t src, uintptr_t dst, size_t n) {
 
 }  // namespace psd_host
 
+namespace psd_host {
+void bind_ml(py::module_& m);      // libsvm_parser.cpp
+}
+
 PYBIND11_MODULE(poseidon_b200_host, m) {
   using namespace psd_host;
   m.doc() = "poseidon-b200 native host runtime (record reader, batch loader, wire compression)";
@@ -541,4 +545,5 @@ PYBIND11_MODULE(poseidon_b200_host, m) {
   });
   m.def("f32_to_bf16", &f32_to_bf16);
   m.def("bf16_to_f32", &bf16_to_f32);
+  bind_ml(m);
 }

@@ -19,7 +19,8 @@ import torch
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 SRC_DIR = os.path.join(_ROOT, "csrc_host")
-SRCS = [os.path.join(SRC_DIR, "record_loader.cpp"), os.path.join(SRC_DIR, "leveldb_reader.cpp")]
+SRCS = [os.path.join(SRC_DIR, "record_loader.cpp"), os.path.join(SRC_DIR, "leveldb_reader.cpp"),
+        os.path.join(SRC_DIR, "libsvm_parser.cpp")]
 SRC = SRCS[0]
 EXT_DIR = os.path.join(_ROOT, "poseidon_b200", "_ext")
 SO = os.path.join(EXT_DIR, "poseidon_b200_host.so")
