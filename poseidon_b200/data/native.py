@@ -23,7 +23,8 @@ SRCS = [os.path.join(SRC_DIR, "record_loader.cpp"), os.path.join(SRC_DIR, "level
         os.path.join(SRC_DIR, "libsvm_parser.cpp")]
 SRC = SRCS[0]
 EXT_DIR = os.path.join(_ROOT, "poseidon_b200", "_ext")
-SO = os.path.join(EXT_DIR, "poseidon_b200_host.so")
+# POSEIDON_HOST_SO: use a module built elsewhere (scripts/sanitize_host.sh points it at an ASan / TSan build)
+SO = os.environ.get("POSEIDON_HOST_SO") or os.path.join(EXT_DIR, "poseidon_b200_host.so")
 _mod = None
 _lock = threading.Lock()
 
