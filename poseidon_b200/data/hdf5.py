@@ -73,10 +73,21 @@ class Dataset:
 class File:
     """Read-only view of an HDF5 file: ``f["data"]`` -> numpy array, ``f.keys()``, nested groups as ``"g/name"``."""
 
+    _CORRUPT = (IndexError, ValueError, struct.error, zlib.error, OverflowError, MemoryError, RecursionError)
+
     def __init__(self, path: str):
         with open(path, "rb") as fh:
             buf = fh.read()
         self.path = path
+        try:
+            self._parse(buf)
+        except HDF5Error:
+            raise
+        except self._CORRUPT as e:
+            raise HDF5Error(f"{path}: corrupt or truncated HDF5 file ({type(e).__name__}: {e})") from e
+
+    def _parse(self, buf: bytes):
+        path = self.path
         r = self.r = _Reader(buf)
         sb = -1
         off = 0
@@ -296,10 +307,22 @@ class File:
         return self.read(ds)
 
     def read(self, ds: Dataset) -> np.ndarray:
+        try:
+            return self._read(ds)
+        except HDF5Error:
+            raise
+        except self._CORRUPT as e:
+            raise HDF5Error(f"{self.path}: dataset '{ds.name}' is corrupt or truncated ({type(e).__name__}: {e})") from e
+
+    def _read(self, ds: Dataset) -> np.ndarray:
         r = self.r
         if ds.dtype is None:
             raise HDF5Error(f"dataset '{ds.name}': unsupported datatype")
-        count = int(np.prod(ds.shape, dtype=np.int64)) if ds.shape else 1
+        count = 1
+        for d in ds.shape:
+            count *= int(d)
+        if count * ds.dtype.itemsize > (1 << 40):
+            raise HDF5Error(f"dataset '{ds.name}': implausible extent {ds.shape}")
         nbytes = count * ds.dtype.itemsize
         kind = ds.layout[0]
         if kind == "compact":

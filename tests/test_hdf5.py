@@ -118,3 +118,23 @@ def test_hdf5_data_and_output_layers_with_real_h5_files(tmp_path):
     bad = f'layers {{ name: "h" type: HDF5_DATA top: "data" top: "label" hdf5_data_param {{ source: "{tmp_path / "bad.txt"}" batch_size: 1 }} }}'
     with pytest.raises(IOError, match="dataset 'data' not found"):
         Net(parse_text(bad, P.NetParameter), phase=P.TRAIN)
+
+
+def test_corrupt_files_raise_one_exception_type(tmp_path):
+    """Mutated files end in HDF5Error (an IOError) or read fine — no stray IndexError / zlib.error / MemoryError."""
+    from test_host_fuzz import _mutations
+    rng = np.random.RandomState(0)
+    hdf5.save(str(tmp_path / "a.h5"), {"data": rng.randn(20, 3, 4, 4).astype(np.float32), "label": np.arange(20.0)},
+              chunks={"data": (6, 3, 4, 4)}, gzip=4, shuffle=True)
+    raw = (tmp_path / "a.h5").read_bytes()
+    outcomes = {"ok": 0, "error": 0}
+    for mut in _mutations(raw, rng, 400):
+        (tmp_path / "m.h5").write_bytes(mut)
+        try:
+            with hdf5.File(str(tmp_path / "m.h5")) as f:
+                for k in f.keys():
+                    f[k]
+            outcomes["ok"] += 1
+        except hdf5.HDF5Error:
+            outcomes["error"] += 1
+    assert outcomes["error"] > 100 and outcomes["ok"] > 10, outcomes
