@@ -27,6 +27,11 @@ import numpy as np
 
 from . import schema as _schema
 
+
+class DecodeError(ValueError):
+    """Malformed binary protobuf input."""
+
+
 _VARINT_TYPES = {"int32", "int64", "uint32", "uint64", "bool", "enum", "sint32", "sint64"}
 _WT_VARINT, _WT_64, _WT_LEN, _WT_32 = 0, 1, 2, 5
 
@@ -317,13 +322,23 @@ class Message:
     @classmethod
     def FromString(cls, data) -> "Message":
         m = cls()
-        m._decode(memoryview(data) if not isinstance(data, memoryview) else data)
+        m._decode_checked(memoryview(data) if not isinstance(data, memoryview) else data)
         return m
 
     def ParseFromString(self, data):
         object.__setattr__(self, "_v", {})
-        self._decode(memoryview(data))
+        self._decode_checked(memoryview(data))
         return self
+
+    def _decode_checked(self, buf) -> None:
+        """Top-level entry: malformed wire data (truncated fields, runaway varints, wrong wire types, bad UTF-8) always
+        surfaces as DecodeError, as protobuf's ParseFromString does."""
+        try:
+            self._decode(buf)
+        except DecodeError:
+            raise
+        except (IndexError, ValueError, struct.error, AttributeError, TypeError, OverflowError, RecursionError) as e:
+            raise DecodeError(f"{type(self).__name__}: malformed protobuf wire data ({type(e).__name__}: {e})") from e
 
     def _decode(self, buf) -> None:
         pos, end = 0, len(buf)

@@ -121,3 +121,21 @@ def test_legacy_data_transform_upgrade():
     tp = net.layers[0].transform_param
     assert tp.scale == 0.5 and tp.crop_size == 7 and tp.mirror is True
     assert not net.layers[0].data_param.has("scale")
+
+
+def test_malformed_wire_data_raises_decode_error():
+    """Mutated .caffemodel-style bytes: a clean parse or DecodeError (a ValueError) — nothing else, and no hang."""
+    import numpy as np
+    from poseidon_b200.models import zoo
+    from test_host_fuzz import _mutations
+    raw = zoo.lenet(batch=4, test_batch=4).SerializeToString()
+    assert P.NetParameter.FromString(raw).SerializeToString() == raw
+    rng = np.random.RandomState(0)
+    seen = {"ok": 0, "err": 0}
+    for mut in _mutations(raw, rng, 600):
+        try:
+            P.NetParameter.FromString(mut)
+            seen["ok"] += 1
+        except P.DecodeError:
+            seen["err"] += 1
+    assert seen["err"] > 100 and seen["ok"] > 50, seen
