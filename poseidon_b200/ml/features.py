@@ -105,7 +105,11 @@ class SparseBatch:
         return SparseFeature(self.indices[a:b], self.values[a:b], self.feature_dim)
 
     def to_sparse_csr(self) -> torch.Tensor:
-        return torch.sparse_csr_tensor(self.indptr, self.indices, self.values, size=(len(self), self.feature_dim))
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", UserWarning)       # "sparse CSR is beta" / "invariant checks implicit"
+            return torch.sparse_csr_tensor(self.indptr, self.indices, self.values,
+                                           size=(len(self), self.feature_dim), check_invariants=True)
 
     def to_dense(self) -> torch.Tensor:
         out = torch.zeros(len(self), self.feature_dim)
