@@ -1,9 +1,11 @@
 """CaffeEngine facade + dataset converters."""
 import gzip
+import json
 import os
 import struct
 
 import numpy as np
+import pytest
 import torch
 
 from poseidon_b200 import CaffeEngine, proto as P
@@ -90,3 +92,90 @@ def test_zoo_cli_writes_prototxts_that_train(tmp_path):
     finally:
         os.chdir(cwd)
     assert os.path.exists(str(tmp_path / "run") + ".netoutputs")
+
+
+def _free_ports(n):
+    import socket
+    socks = [socket.socket() for _ in range(n)]
+    for s in socks:
+        s.bind(("127.0.0.1", 0))
+    ports = [s.getsockname()[1] for s in socks]
+    for s in socks:
+        s.close()
+    return ports
+
+
+def _lenet_job(tmp_path, max_iter):
+    from poseidon_b200 import proto as P
+    from poseidon_b200.models import zoo
+    net_path = tmp_path / "lenet.prototxt"
+    P.write_text(str(net_path), zoo.lenet(batch=4, test_batch=4))
+    sp = zoo.lenet_solver(net_path=str(net_path), max_iter=max_iter, display=1, test_interval=0, solver_mode="CPU",
+                          snapshot=0, snapshot_prefix=str(tmp_path / "lenet"))
+    sp.clear("test_iter")
+    P.write_text(str(tmp_path / "solver.prototxt"), sp)
+    p0, p1 = _free_ports(2)
+    (tmp_path / "hosts").write_text(f"0 127.0.0.1 {p0}\n1 127.0.0.1 {p1}\n")
+    return str(tmp_path / "solver.prototxt"), str(tmp_path / "hosts")
+
+
+def test_launcher_runs_one_process_per_hostfile_line(tmp_path, capsys):
+    """tools.launch: two hostfile lines on 127.0.0.1 = a 2-process gloo job (the reference's way of simulating a cluster
+    on one box), logs per client, exit code of the job; --dry_run prints the ssh fan-out for remote hosts."""
+    from poseidon_b200.tools import launch
+    solver, hosts = _lenet_job(tmp_path, 3)
+    run = str(tmp_path / "run")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rc = launch.main(["train", "--hostfile", hosts, "--solver", solver, "--run_dir", run, "--workdir", root,
+                      "--env", "OMP_NUM_THREADS=2", "--", "--svb=true", "--comm=gloo"])
+    logs = [open(os.path.join(run, f"client_{i}.log")).read() for i in range(2)]
+    assert rc == 0, logs
+    assert "Optimization Done" in logs[0] and "world_size=2" in logs[0]
+    assert os.path.exists(tmp_path / "lenet_iter_3.caffemodel")
+    recs = json.load(open(os.path.join(run, "pids.json")))["clients"]
+    assert [r["client"] for r in recs] == [0, 1] and all(r["local"] for r in recs)
+    capsys.readouterr()
+    (tmp_path / "remote").write_text("0 10.0.0.1 9999\n1 10.0.0.2 9999\n")
+    assert launch.main(["train", "--hostfile", str(tmp_path / "remote"), "--solver", solver, "--dry_run",
+                        "--run_dir", run, "--", "--table_staleness=1"]) == 0
+    out = capsys.readouterr().out
+    assert out.count("ssh ") == 2 and "10.0.0.2" in out and "--client_id=1" in out and "--table_staleness=1" in out
+
+
+def test_launcher_fails_fast_and_kill_stops_recorded_processes(tmp_path):
+    import subprocess
+    import sys
+    import time
+    from poseidon_b200.tools import launch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    # a client that cannot start (missing solver) takes the whole job down with a non-zero exit code
+    _, hosts = _lenet_job(tmp_path, 3)
+    rc = launch.main(["train", "--hostfile", hosts, "--solver", str(tmp_path / "missing.prototxt"),
+                      "--run_dir", str(tmp_path / "bad"), "--workdir", root])
+    assert rc != 0
+    # a long job is stopped by `kill` through the recorded PIDs
+    solver, hosts = _lenet_job(tmp_path, 1000000)
+    run = str(tmp_path / "long")
+    sup = subprocess.Popen([sys.executable, "-m", "poseidon_b200.tools.launch", "train", "--hostfile", hosts, "--solver",
+                            solver, "--run_dir", run, "--workdir", root, "--", "--comm=gloo"], cwd=root,
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        deadline = time.time() + 120
+        while time.time() < deadline:
+            log0 = os.path.join(run, "client_0.log")
+            if os.path.exists(log0) and "Iteration" in open(log0).read():
+                break
+            time.sleep(0.5)
+        else:
+            raise AssertionError("job did not start")
+        assert launch.main(["kill", "--run_dir", run]) == 0
+        out, _ = sup.communicate(timeout=60)
+        assert sup.returncode != 0 and "stopping the others" in out or "exit code" in out
+    finally:
+        if sup.poll() is None:
+            sup.kill()
+    recs = json.load(open(os.path.join(run, "pids.json")))["clients"]
+    time.sleep(0.5)
+    for r in recs:
+        with pytest.raises(ProcessLookupError):
+            os.kill(r["pid"], 0)
