@@ -255,8 +255,10 @@ def main():
                        "input": list(shape[1:]), "seq_len": None,
                        "parallelism": f"dp{world}" + ("+dwbp" if world > 1 else "") +
                                       ("+sfb" if any(v == "sfb" for v in sfb_layers.values()) and world > 1 else ""),
-                       "engine": args.engine, "comm": solver.comm_name, "cuda_graph": bool(use_graph), "solver": "SGD momentum 0.9 wd 5e-4 (reference solver.prototxt)",
-                       "l2": "per-step working set (weights+history+grads+activations) >> 126 MB L2; inputs rotate over 4 batches",
+                       "engine": args.engine, "comm": solver.comm_name, "cuda_graph": bool(use_graph),
+                       "solver": "SGD momentum 0.9 wd 5e-4 (reference solver.prototxt)",
+                       "l2": "per-step working set (weights+history+grads+activations) >> 126 MB L2; "
+                             "inputs rotate over 4 batches",
                        "sfb_layers": sfb_layers, "wire_bytes_total": wire,
                        "baseline_ref": "133 img/s per K20 derived in BASELINE.md §1 (reference publishes no img/s)"},
             "clocks": clocks, "gpu_launches": launches, "impl": "ours",

@@ -1,5 +1,5 @@
 """Standalone conv micro-benchmark (AlexNet shapes) for ncu captures and CUDA-event timings."""
-import sys, time
+import sys
 import torch
 sys.path.insert(0, ".")
 sys.path.insert(0, "tests")

@@ -7,7 +7,6 @@ loss_weight 1 on the first top).
 """
 from __future__ import annotations
 
-import os
 
 import torch
 

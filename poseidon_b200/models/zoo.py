@@ -322,7 +322,8 @@ def googlenet(batch=32, test_batch=50, classes=1000, source="ilsvrc12_train_lmdb
         b.relu(p + "relu_fc", p + "fc")
         b.dropout(p + "drop_fc", p + "fc", 0.7)
         b.fc(p + "classifier", p + "fc", classes, wf=xf, bf=_c(0))
-        b.softmax_loss(p + "loss", p + "classifier", top=p + "loss1", weight=0.3)     # sic: the reference names both aux tops ".../loss1"
+        # sic: the reference names both auxiliary tops ".../loss1"
+        b.softmax_loss(p + "loss", p + "classifier", top=p + "loss1", weight=0.3)
         b.accuracy(p + "top-1", p + "classifier")
         b.accuracy(p + "top-5", p + "classifier", top_k=5)
 

@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import logging
 from collections import OrderedDict
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional
 
 import numpy as np
 import torch

@@ -122,7 +122,8 @@ def _stop(records, ssh: str, only=None, sig=signal.SIGTERM) -> int:
             if r["local"]:
                 os.killpg(r["pid"], sig)                      # start_new_session: pid == process-group id
             else:
-                remote = f"kill -{int(sig)} -- -$(cat {shlex.quote(r['pidfile'])}) 2>/dev/null || kill -{int(sig)} $(cat {shlex.quote(r['pidfile'])})"
+                pf = shlex.quote(r["pidfile"])
+                remote = f"kill -{int(sig)} -- -$(cat {pf}) 2>/dev/null || kill -{int(sig)} $(cat {pf})"
                 subprocess.call(shlex.split(ssh) + [r["ip"], remote])
                 os.kill(r["pid"], sig)                         # the local ssh client
             n += 1

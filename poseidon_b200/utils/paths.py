@@ -1,12 +1,13 @@
 """File-name resolution for prototxt fields (net:, source:, mean_file:, snapshot_prefix:, infogain source:).
 
-The reference's shipped solvers and nets spell paths as ``CAFFE_ROOT/examples/mnist/...`` (``POSEIDON_ROOT/models/...`` under models/) and ask the user to replace the
-placeholder by hand with the full application directory before launching (examples/mnist/run_local.py:19-20,
-examples/mnist/lenet_solver.prototxt:2, examples/cifar10/cifar10_quick_train_test.prototxt).  Here the placeholder is
-resolved at load time: ``$CAFFE_ROOT`` / ``$POSEIDON_ROOT`` if set, otherwise the nearest ancestor of the referring file under which the rest
-of the path exists.  Relative paths are tried against the referring file's directory, its ancestors and the working
-directory, which covers both conventions found in the wild (relative to the model directory / relative to the repo root
-the tools were started from).
+The reference's shipped solvers and nets spell paths as ``CAFFE_ROOT/examples/mnist/...`` (``POSEIDON_ROOT/models/...``
+under models/) and ask the user to replace the placeholder by hand with the full application directory before launching
+(examples/mnist/run_local.py:19-20, examples/mnist/lenet_solver.prototxt:2,
+examples/cifar10/cifar10_quick_train_test.prototxt).  Here the placeholder is resolved at load time: ``$CAFFE_ROOT`` /
+``$POSEIDON_ROOT`` if set, otherwise the nearest ancestor of the referring file under which the rest of the path exists.
+Relative paths are tried against the referring file's directory, its ancestors and the working directory, which covers
+both conventions found in the wild (relative to the model directory / relative to the repo root the tools were started
+from).
 """
 from __future__ import annotations
 

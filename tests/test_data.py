@@ -1,5 +1,4 @@
 """Record DB, worker sharding, DataTransformer, data layers and dataset tools."""
-import os
 
 import numpy as np
 import pytest

@@ -1,7 +1,6 @@
 """Caffe op semantics of the reference (torch) engine: the oracle the CUDA kernels are tested against."""
 import math
 
-import numpy as np
 import pytest
 import torch
 

@@ -1,6 +1,5 @@
 """Read-only LMDB parser vs a writer that follows the LMDB 0.9 on-disk definition (no liblmdb in the image)."""
 import os
-import struct
 
 import numpy as np
 import pytest

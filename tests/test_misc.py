@@ -1,5 +1,4 @@
 """Smaller API-parity pieces: split insertion, flag context, sufficient-vector containers, SFB cost model."""
-import numpy as np
 import torch
 
 from poseidon_b200 import Net

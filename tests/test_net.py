@@ -1,9 +1,8 @@
 """Net construction from Caffe definitions: zoo shapes, filtering, in-place, sharing, loss weights, IO."""
-import numpy as np
 import pytest
 import torch
 
-from poseidon_b200 import Net, NetContext
+from poseidon_b200 import Net
 from poseidon_b200 import proto as P
 from poseidon_b200.models import zoo
 from poseidon_b200.proto import parse_text

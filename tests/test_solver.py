@@ -1,8 +1,6 @@
 """Solver semantics on CPU: lr policies, update rules through the solver, test nets, snapshots, outputs."""
-import math
 import os
 
-import numpy as np
 import pytest
 import torch
 
