@@ -177,3 +177,13 @@ def test_reference_example_solvers_load_unmodified():
     assert s.net.layer_by_name["fc8"].weight.shape == (1000, 4096)
     assert "POSEIDON_ROOT" not in s._snapshot_prefix.__func__(type("S", (), {"param": s.param, "model_dir": s.model_dir, "snapshot_dir": "/tmp"})())
     s.close()
+
+
+def test_lint_is_clean():
+    """`make lint`: every Python file compiles, no unused imports, bounded line lengths (scripts/lint.py)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "lint.py")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout[-3000:]
