@@ -9,7 +9,8 @@ the hostfile), scripts/kill_caffe.py (``killall caffe_main`` on every host), mac
 * the hostfile has one line per *process* = per GPU (``<id> <ip> <port>``; repeat a host for each of its GPUs, as the
   reference does to simulate several nodes on one box); line 0 is the rendezvous;
 * a client that dies takes the job down (the reference's peers would wait forever in the PS clock, SURVEY §5.3);
-* ``kill`` signals the recorded PIDs (and their process groups) instead of every process with a matching name.
+* ``kill`` signals the recorded PIDs (and their process groups) instead of every process with a matching name;
+* ``--max_restarts N``: a failed job is relaunched from its newest ``.solverstate`` (the reference's manual recovery).
 
     python -m poseidon_b200.tools.launch train --hostfile machinefiles/localserver --solver models/lenet/solver.prototxt \\
         --run_dir output/lenet -- --svb=true --table_staleness=0
@@ -63,16 +64,49 @@ def _remote_shell(args, ip: str, cmd: List[str], pidfile: str, env: Dict[str, st
     return shlex.split(args.ssh) + [ip, f"sh -c {shlex.quote(inner)}"]
 
 
+def latest_solverstate(solver_path: str):
+    """Newest ``<snapshot_prefix>_iter_N.solverstate`` of the solver's run (None if there is none yet)."""
+    import glob
+    import re
+    from .. import proto as P
+    from ..utils.paths import expand_placeholder
+    sp = P.read_solver(solver_path)
+    prefix = expand_placeholder(sp.snapshot_prefix or "snapshot", os.path.dirname(os.path.abspath(solver_path)),
+                                must_exist=False)
+    best = (-1, None)
+    for f in glob.glob(glob.escape(prefix) + "_iter_*.solverstate"):
+        m = re.search(r"_iter_(\d+)\.solverstate$", f)
+        if m and int(m.group(1)) > best[0]:
+            best = (int(m.group(1)), f)
+    return best[1]
+
+
 def cmd_train(args, extra: List[str]) -> int:
+    """Run the job; with --max_restarts, a failed job is restarted from its newest snapshot (the reference's recovery
+    procedure — kill everything, relaunch with --snapshot — done by the supervisor instead of the operator)."""
+    attempt = 0
+    while True:
+        rc = _run_once(args, extra, attempt)
+        if rc == 0 or rc == 130 or args.dry_run or attempt >= args.max_restarts or args.command != "train":
+            return rc
+        attempt += 1
+        state = latest_solverstate(args.solver) if args.solver else None
+        if state:
+            args.snapshot, args.weights = state, ""
+        print(f"[launch] restart {attempt}/{args.max_restarts} from {state or 'scratch (no snapshot yet)'}", flush=True)
+
+
+def _run_once(args, extra: List[str], attempt: int) -> int:
     hosts = parse_hostfile(args.hostfile)
     if not hosts:
         raise SystemExit(f"{args.hostfile}: no hosts")
     os.makedirs(args.run_dir, exist_ok=True)
     env_extra = dict(kv.split("=", 1) for kv in args.env)
+    env_extra["POSEIDON_ATTEMPT"] = str(attempt)
     procs, records = [], []
     for cid, ip, port in hosts:
         cmd = client_command(args, cid, extra)
-        log_path = os.path.join(args.run_dir, f"client_{cid}.log")
+        log_path = os.path.join(args.run_dir, f"client_{cid}.log" if attempt == 0 else f"client_{cid}.restart{attempt}.log")
         local = _is_local(ip) and not args.force_ssh
         pidfile = os.path.join(args.run_dir, f"client_{cid}.pid")
         full = cmd if local else _remote_shell(args, ip, cmd, pidfile, env_extra)
@@ -163,6 +197,8 @@ def main(argv=None) -> int:
     ap.add_argument("--force_ssh", action="store_true", help="use ssh for local addresses too")
     ap.add_argument("--env", action="append", default=[], metavar="K=V", help="environment for every client (repeatable)")
     ap.add_argument("--dry_run", action="store_true", help="print the per-host command lines and exit")
+    ap.add_argument("--max_restarts", type=int, default=0,
+                    help="restart a failed training job up to N times from its newest .solverstate")
     ap.add_argument("--force", action="store_true", help="kill: SIGKILL instead of SIGTERM")
     args = ap.parse_args(argv)
     if args.command == "kill":

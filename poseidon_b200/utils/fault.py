@@ -8,6 +8,9 @@
                                       collective timeout instead of hanging forever)
     raise:rank=0,step=2               raise RuntimeError on rank 0 (exercises the snapshot-and-restart path)
 
+A directive with ``attempt=k`` fires only in the k-th start of a supervised job (``tools.launch --max_restarts`` exports
+``POSEIDON_ATTEMPT``), so a restarted job does not die again at the same step.
+
 ``maybe_inject(rank, step)`` is called by ``Solver`` at the top of every training iteration; with the variable unset
 it is a dictionary lookup.
 """
@@ -49,6 +52,8 @@ def reset():
 def maybe_inject(rank: int, step: int) -> None:
     for kind, kv in directives():
         if kv.get("rank", 0) != rank or kv.get("step", -1) != step:
+            continue
+        if "attempt" in kv and kv["attempt"] != int(os.environ.get("POSEIDON_ATTEMPT", "0")):
             continue
         if kind == "delay":
             time.sleep(kv.get("ms", 100) / 1e3)

@@ -179,3 +179,26 @@ def test_launcher_fails_fast_and_kill_stops_recorded_processes(tmp_path):
     for r in recs:
         with pytest.raises(ProcessLookupError):
             os.kill(r["pid"], 0)
+
+
+def test_launcher_restarts_from_latest_snapshot(tmp_path):
+    """Rank 1 is killed before iteration 5 of the first attempt; the supervisor stops rank 0, finds lenet_iter_4
+    .solverstate and relaunches both; the job then runs to max_iter."""
+    from poseidon_b200 import proto as P
+    from poseidon_b200.tools import launch
+    solver, hosts = _lenet_job(tmp_path, 8)
+    sp = P.read_solver(solver)
+    sp.snapshot = 2
+    P.write_text(solver, sp)
+    run = str(tmp_path / "run")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rc = launch.main(["train", "--hostfile", hosts, "--solver", solver, "--run_dir", run, "--workdir", root,
+                      "--max_restarts", "2", "--env", "POSEIDON_FAULT=kill:rank=1,step=5,attempt=0",
+                      "--env", "OMP_NUM_THREADS=2", "--", "--comm=gloo"])
+    first = open(os.path.join(run, "client_0.log")).read()
+    second = open(os.path.join(run, "client_0.restart1.log")).read()
+    assert rc == 0, (first[-1500:], second[-1500:])
+    assert "Optimization Done" not in first and "Optimization Done" in second
+    assert "lenet_iter_4.solverstate" in second                     # resumed from the newest snapshot
+    assert os.path.exists(tmp_path / "lenet_iter_8.caffemodel")
+    assert launch.latest_solverstate(solver).endswith("lenet_iter_8.solverstate")
