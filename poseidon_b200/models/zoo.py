@@ -420,6 +420,18 @@ def cifar10_full_solver(net_path="cifar10_full_train_test.prototxt", **over):
     return sp
 
 
+# Follow-up solver stages the reference ships next to the main solver: the same run continued from the last snapshot
+# with a lower learning rate (examples/cifar10/cifar10_{quick,full}_solver_lr{1,2}.prototxt), and GoogLeNet's long
+# schedule (models/bvlc_googlenet/solver.prototxt).  name -> {file stem: overrides of the main solver}
+SOLVER_STAGES = {
+    "cifar10_quick": {"solver_lr1": dict(base_lr=0.0001, max_iter=5000, snapshot=5000)},
+    "cifar10_full": {"solver_lr1": dict(base_lr=0.0001, max_iter=65000, snapshot=5000),
+                     "solver_lr2": dict(base_lr=0.00001, max_iter=70000, snapshot=5000)},
+    "googlenet": {"solver_long": dict(test_initialization=False, stepsize=320000, gamma=0.96, max_iter=10000000,
+                                      snapshot_prefix="bvlc_googlenet")},
+}
+
+
 MODELS = {
     "lenet": (lenet, lenet_solver), "cifar10_quick": (cifar10_quick, cifar10_quick_solver),
     "cifar10_full": (cifar10_full, cifar10_full_solver),
@@ -450,8 +462,73 @@ def get_solver_param(name: str, net=None, **over):
     return sp
 
 
+_DATA_TYPES = ("DATA", "IMAGE_DATA", "WINDOW_DATA", "HDF5_DATA", "MEMORY_DATA", "DUMMY_DATA")
+_LOSS_TYPES = ("SOFTMAX_LOSS", "EUCLIDEAN_LOSS", "HINGE_LOSS", "SIGMOID_CROSS_ENTROPY_LOSS", "MULTINOMIAL_LOGISTIC_LOSS",
+               "INFOGAIN_LOSS", "CONTRASTIVE_LOSS")
+
+
+def deploy(net, batch: int = 10, input_shape=None):
+    """train_val -> deploy net, the transformation behind the reference's ``deploy.prototxt`` files
+    (models/bvlc_alexnet/deploy.prototxt, examples/cifar10/cifar10_quick.prototxt): data layers become
+    ``input: "data"`` + ``input_dim`` x 4, TEST/TRAIN-only layers and ACCURACY go away, the main SOFTMAX_LOSS becomes a
+    SOFTMAX layer "prob", everything that does not feed "prob" (auxiliary heads, other losses, dropout keeps) is pruned.
+    Layer names are kept, so a ``.caffemodel`` trained with the train_val net loads by name."""
+    from ..net.net import filter_net
+    layers = list(filter_net(net, P.NetState(phase=P.TEST)).layers)          # what a TEST-phase net would instantiate
+    data_tops, shape, kept = [], input_shape, []
+    for l in layers:
+        t = l.enum_name("type")
+        if t in _DATA_TYPES:
+            if not data_tops:
+                data_tops = list(l.top)
+                if shape is None:
+                    crop = int(l.transform_param.crop_size) if l.has("transform_param") else 0
+                    src = (l.data_param.source if l.has("data_param") else "").lower()
+                    if t == "MEMORY_DATA":
+                        mp = l.memory_data_param
+                        shape = (int(mp.channels), int(mp.height), int(mp.width))
+                    elif "mnist" in src:
+                        shape = (1, 28, 28)
+                    elif "cifar" in src:
+                        shape = (3, 32, 32)
+                    else:
+                        shape = (3, crop or 224, crop or 224)
+            continue
+        if t == "ACCURACY":
+            continue
+        kept.append(l)
+    if not data_tops:
+        raise ValueError("deploy(): the net has no data layer")
+    # the main loss = the last loss layer with weight 1 (auxiliary heads carry 0.3 in GoogLeNet)
+    main = None
+    for l in kept:
+        if l.enum_name("type") in _LOSS_TYPES and (not len(l.loss_weight) or float(l.loss_weight[0]) == 1.0):
+            main = l
+    out = P.NetParameter(name=net.name)
+    out.input.append(data_tops[0])
+    for d in (batch,) + tuple(shape):
+        out.input_dim.append(int(d))
+    body = [l for l in kept if l.enum_name("type") not in _LOSS_TYPES]
+    if main is not None and main.enum_name("type") == "SOFTMAX_LOSS":
+        prob = P.LayerParameter(name="prob", type="SOFTMAX")
+        prob.bottom.append(main.bottom[0])
+        prob.top.append("prob")
+        body.append(prob)
+        want = {"prob"}
+    else:
+        want = {main.bottom[0]} if main is not None else {body[-1].top[0]}
+    needed = []
+    for l in reversed(body):                                  # prune everything that does not reach the output
+        if set(l.top) & want:
+            needed.append(l)
+            want |= set(l.bottom)
+    for l in reversed(needed):
+        out.layers.append(l.copy())
+    return out
+
+
 def write_zoo(out_dir: str, only=None):
-    """Emit ``<model>/train_val.prototxt`` + ``solver.prototxt`` for every (or the named) zoo model."""
+    """Emit ``<model>/train_val.prototxt`` + ``solver.prototxt`` + ``deploy.prototxt`` for every (or the named) model."""
     import os
     for name, (net_fn, solver_fn) in MODELS.items():
         if only and name not in only:
@@ -460,10 +537,18 @@ def write_zoo(out_dir: str, only=None):
         os.makedirs(d, exist_ok=True)
         with open(os.path.join(d, "train_val.prototxt"), "w") as f:
             f.write(to_text(net_fn()))
+        with open(os.path.join(d, "deploy.prototxt"), "w") as f:
+            f.write(to_text(deploy(net_fn())))
         if solver_fn is not None:
             sp = solver_fn(net_path=os.path.join(d, "train_val.prototxt"))
             with open(os.path.join(d, "solver.prototxt"), "w") as f:
                 f.write(to_text(sp))
+            for stem, over in SOLVER_STAGES.get(name, {}).items():
+                st = solver_fn(net_path=os.path.join(d, "train_val.prototxt"), **over)
+                if "stepsize" in over and "power" not in over:
+                    st.clear("power")                       # the reference's long GoogLeNet solver: stepsize / gamma, no power
+                with open(os.path.join(d, stem + ".prototxt"), "w") as f:
+                    f.write(to_text(st))
 
 
 def main(argv=None) -> int:

@@ -158,3 +158,55 @@ def test_zoo_matches_reference_prototxt(model, ref_net, ref_solver):
               "test_interval", "snapshot"):
         assert getattr(a, f) == pytest.approx(getattr(b, f)) if isinstance(getattr(b, f), float) else getattr(a, f) == getattr(b, f), f
     assert list(a.test_iter) == list(b.test_iter)
+
+
+def test_deploy_nets_match_reference_and_share_weights_by_name(tmp_path):
+    """zoo.deploy(): the generated AlexNet / CaffeNet deploy nets have the reference deploy.prototxt's layers (names,
+    types, bottoms / tops, parameters); a deploy net loads a .caffemodel of its train_val net by name and reproduces
+    the TEST-phase class probabilities."""
+    import os
+    import torch
+    from poseidon_b200.models import zoo
+    for ours, ref in (("alexnet", "bvlc_alexnet"), ("caffenet", "bvlc_reference_caffenet")):
+        path = f"/root/reference/models/{ref}/deploy.prototxt"
+        if not os.path.exists(path):
+            continue
+        want = P.read_net(path)
+        got = zoo.deploy(zoo.MODELS[ours][0]())
+        assert list(got.input) == list(want.input) and list(got.input_dim) == list(want.input_dim)
+        assert [(l.name, l.enum_name("type"), list(l.bottom), list(l.top)) for l in got.layers] == \
+               [(l.name, l.enum_name("type"), list(l.bottom), list(l.top)) for l in want.layers]
+        for a, b in zip(got.layers, want.layers):
+            for f in ("convolution_param", "pooling_param", "lrn_param", "inner_product_param", "dropout_param"):
+                if b.has(f):
+                    ga, gb = getattr(a, f), getattr(b, f)
+                    for k in ("num_output", "kernel_size", "stride", "pad", "group", "pool", "local_size", "alpha", "beta",
+                              "dropout_ratio"):
+                        if hasattr(gb, k) and gb.has(k):
+                            va, vb = getattr(ga, k), getattr(gb, k)
+                            same = abs(va - vb) <= 1e-6 * abs(vb) if isinstance(vb, float) else va == vb
+                            assert same, (a.name, f, k, va, vb)
+    # weights by name + identical probabilities (LeNet, small)
+    train = zoo.lenet(batch=4, test_batch=4)
+    tnet = Net(train, phase=P.TEST)
+    P.write_binary(str(tmp_path / "w.caffemodel"), tnet.to_proto())
+    dnet = Net(zoo.deploy(train, batch=4), phase=P.TEST)
+    dnet.copy_trained_layers_from(str(tmp_path / "w.caffemodel"))
+    x = torch.rand(4, 1, 28, 28)
+    _, out = dnet.forward({"data": x})
+    # run the train_val net's layers by hand on the same input: conv1..ip2 then softmax
+    blobs = {"data": x * 1.0}
+    for name, layer, bn, tn in zip(tnet.layer_names, tnet.layers, tnet.bottom_names, tnet.top_names):
+        if layer.type_name in ("DATA", "ACCURACY", "SOFTMAX_LOSS"):
+            continue
+        outs = layer(*[blobs[b] for b in bn])
+        for t, o in zip(tn, outs):
+            blobs[t] = o
+    want_prob = torch.softmax(blobs["ip2"].reshape(4, -1), 1)
+    assert torch.allclose(out["prob"].reshape(4, -1), want_prob, atol=1e-6)
+    assert "accuracy" not in dnet.layer_names and "loss" not in dnet.layer_names
+    # GoogLeNet: auxiliary classifiers are pruned, the main path ends in prob
+    g = zoo.deploy(zoo.googlenet(batch=2, test_batch=2))
+    names = [l.name for l in g.layers]
+    assert not any(n.startswith("loss1/") or n.startswith("loss2/") for n in names) and names[-1] == "prob"
+    assert g.layers[-1].bottom[0] == "loss3/classifier"
