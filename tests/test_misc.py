@@ -171,6 +171,18 @@ def test_reference_example_solvers_load_unmodified():
         s.step(1)
         assert s.net.layer_names and float(s.last_loss) > 0
         s.close()
+    # deploy / full-convolutional / feature-extraction nets of the examples directory
+    import torch
+    from poseidon_b200 import Net
+    for rel, top, shape in (("imagenet/bvlc_caffenet_full_conv.prototxt", "prob", (1, 1000, 8, 8)),
+                            ("cifar10/cifar10_quick.prototxt", "prob", (1, 10, 1, 1)),
+                            ("cifar10/cifar10_full.prototxt", "prob", (1, 10, 1, 1)),
+                            ("feature_extraction/imagenet_val.prototxt", "loss", ())):
+        net = Net(P.read_net(os.path.join(ref, rel)), phase=P.TEST)
+        with torch.no_grad():
+            _, out = net.forward({n: torch.rand(*net.blob_shapes[n]) for n in net.input_names})
+        assert tuple(out[top].shape) == shape, rel
+        net.close()
     # models/: POSEIDON_ROOT placeholders in net:, source:, mean_file:, snapshot_prefix: (built, not stepped: batch 256)
     mref = "/root/reference/models/bvlc_alexnet/solver.prototxt"
     s = get_solver(P.read_solver(mref), engine="torch", model_dir=os.path.dirname(mref))
