@@ -10,7 +10,8 @@ whole engine (``Solver(engine="sm100")``, fusion plan, FusedBackend's single-pro
 Every method documents the layout contract of the kernel it stands in for (file:line of the CUDA implementation); the
 arithmetic is fp32 with one bf16 rounding at the output, which is also what the kernels do (fp32 accumulation in TMEM,
 bf16 store), so results agree with the GPU to bf16 rounding.  This is a *test double*: it is never selected implicitly,
-it is slow, and the multi-GPU peer-memory ops (which take raw device pointers) are not provided.
+it is slow.  The multi-GPU peer-memory ops run too: ranks are processes, the symmetric arena is host shared memory
+(:class:`EmulatedArena`), the flag protocol is the kernels'.
 """
 from __future__ import annotations
 
@@ -298,8 +299,209 @@ class EmulatedKernels:
         if wb is not None:
             wb.view(-1).copy_(_storage_order_flat(w))
 
-    # ------------------------------------------------------------------------------------------ multi-GPU (not emulated)
-    def _peer(self, *a, **k):
-        raise NotImplementedError("peer-memory ops take raw device pointers and are not emulated on the CPU")
+    # ------------------------------------------------------------------------------------------ multi-rank peer memory
+    # The kernels address other ranks' memory by raw pointer (NVLink peer mappings of one symmetric arena per rank).
+    # On the CPU the arena is a POSIX shared-memory segment per rank, mapped by every rank (EmulatedArena below); the
+    # "pointers" are the addresses of those mappings in this process and resolve through the arena registry.  Ranks are
+    # processes, the flag protocol is the kernels' (st.release / spin on ld.acquire become plain stores and polling).
+    _K_MAX_RANKS = 8
 
-    allreduce_sgd = peer_push = peer_signal = sfb_outer_sgd = sfb_outer_f32 = _peer
+    @staticmethod
+    def _mem(ptr: int, nbytes: int, dtype) -> torch.Tensor:
+        for base, size, buf in EmulatedArena.mappings:
+            if base <= ptr and ptr + nbytes <= base + size:
+                return buf[ptr - base: ptr - base + nbytes].view(dtype)
+        raise RuntimeError(f"emulated peer op: address {ptr:#x} (+{nbytes}) is not inside a mapped arena")
+
+    @staticmethod
+    def _epoch(epoch: int, epoch_dev) -> int:
+        return (int(epoch) + (int(epoch_dev[0]) if epoch_dev is not None else 0)) & 0xFFFFFFFF
+
+    @staticmethod
+    def _wait_ge(word: torch.Tensor, value: int, what: str, timeout_s: float = 60.0) -> None:
+        import time
+        t0 = time.time()
+        while (int(word) & 0xFFFFFFFF) < value:
+            if time.time() - t0 > timeout_s:
+                raise RuntimeError(f"emulated peer op: timed out waiting for {what} >= {value} (have {int(word)})")
+            time.sleep(0.0002)
+
+    def _flags(self, ptr: int) -> torch.Tensor:
+        return self._mem(ptr, 8 * self._K_MAX_RANKS * 4, torch.int32)            # [slot][rank] u32, 8 slots
+
+    def _peer_barrier(self, flag_ptrs, rank, phase, ep):
+        """csrc/comm/fused_update.cu:150-158."""
+        world = len(flag_ptrs)
+        for t in range(world):
+            self._flags(flag_ptrs[t])[phase * self._K_MAX_RANKS + rank] = ep
+        mine = self._flags(flag_ptrs[rank])
+        for t in range(world):
+            self._wait_ge(mine[phase * self._K_MAX_RANKS + t], ep, f"barrier phase {phase} flag of rank {t}")
+
+    @staticmethod
+    def _step(w, g, h, lr, momentum, decay, rule, l1, delta, gscale):
+        g = g * gscale
+        if decay != 0:
+            g = g + decay * (torch.sign(w) if l1 else w)
+        if rule == 0:
+            h.mul_(momentum).add_(g, alpha=lr)
+            w.sub_(h)
+        elif rule == 1:
+            h_old = h.clone()
+            h.mul_(momentum).add_(g, alpha=lr)
+            w.sub_((1.0 + momentum) * h - momentum * h_old)
+        else:
+            h.add_(g * g)
+            w.sub_(lr * g / (h.sqrt() + delta))
+
+    def allreduce_sgd(self, g_ptrs, w_ptrs, wb_ptrs, flag_ptrs, g_mc, w_mc, h, n, rank, epoch, one_shot, done_counter,
+                      lr, momentum, decay, rule, l1, delta, gscale, max_ctas, lr_dev, epoch_dev):
+        """All-reduce + optimizer step + weight broadcast in one launch (csrc/comm/fused_update.cu:160-262).
+        one-shot: every rank reduces the whole bucket and steps its own copy; two-shot: rank r reduces and steps shard
+        r (its slice of the history) and writes the new weights / bf16 shadows into every rank's arena."""
+        world = len(g_ptrs)
+        ep = self._epoch(epoch, epoch_dev)
+        if lr_dev is not None:
+            lr = lr * float(lr_dev[0])
+        self._peer_barrier(flag_ptrs, rank, 0, ep)
+        n4 = n // 4
+        lo, hi = 0, n4
+        if not one_shot:
+            per = (n4 + world - 1) // world
+            lo = min(n4, per * rank)
+            hi = min(n4, lo + per)
+        sl = slice(4 * lo, 4 * hi)
+        g = self._mem(g_ptrs[rank], n * 4, torch.float32)[sl].clone()
+        for q in range(1, world):
+            g += self._mem(g_ptrs[(rank + q) % world], n * 4, torch.float32)[sl]
+        w = self._mem(w_ptrs[rank], n * 4, torch.float32)[sl].clone()
+        hv = h[:n][sl]
+        self._step(w, g, hv, lr, momentum, decay, rule, l1, delta, gscale)
+        targets = [rank] if one_shot else [(rank + q) % world for q in range(world)]
+        for p in targets:
+            self._mem(w_ptrs[p], n * 4, torch.float32)[sl] = w
+            if wb_ptrs:
+                self._mem(wb_ptrs[p], n * 2, BF16)[sl] = w.to(BF16)
+        self._peer_barrier(flag_ptrs, rank, 1, ep)
+
+    def peer_push(self, src, dst_ptrs, dst_mc, flag_ptrs, rank, slot, epoch, signal, done_counter, wait_slot, epoch_dev):
+        """Payload into every rank's arena, then (optionally) this rank's epoch flag on every peer
+        (csrc/comm/fused_update.cu:264-330)."""
+        world = len(dst_ptrs)
+        ep = self._epoch(epoch, epoch_dev)
+        if wait_slot >= 0:
+            mine = self._flags(flag_ptrs[rank])
+            for t in range(world):
+                self._wait_ge(mine[wait_slot * self._K_MAX_RANKS + t], (ep - 1) & 0xFFFFFFFF, f"consumed flag of rank {t}")
+        raw = src.contiguous().view(-1).view(torch.uint8)
+        for q in range(world):
+            self._mem(dst_ptrs[(rank + q) % world], raw.numel(), torch.uint8).copy_(raw)
+        if signal:
+            for t in range(world):
+                self._flags(flag_ptrs[t])[slot * self._K_MAX_RANKS + rank] = ep
+
+    def peer_signal(self, flag_ptrs, rank, slot, epoch, epoch_dev):
+        ep = self._epoch(epoch, epoch_dev)
+        for t in range(len(flag_ptrs)):
+            self._flags(flag_ptrs[t])[slot * self._K_MAX_RANKS + rank] = ep
+
+    def _sfb_outer(self, u_ptrs, v_ptrs, Mb, N, K, flags, epoch, src_rot, epoch_dev):
+        ep = self._epoch(epoch, epoch_dev)
+        P = len(u_ptrs)
+        g = torch.zeros(N, K)
+        for s_ in range(P):
+            src = (s_ + src_rot) % P
+            if flags is not None:
+                self._wait_ge(flags[src], ep, f"factor flag of rank {src}")
+            u = self._mem(u_ptrs[src], Mb * N * 2, BF16).view(Mb, N).float()
+            v = self._mem(v_ptrs[src], Mb * K * 2, BF16).view(Mb, K).float()
+            g += u.t() @ v
+        return g
+
+    def sfb_outer_sgd(self, u_ptrs, v_ptrs, Mb, N, K, w, h, wb, alpha, lr, momentum, decay, rule, l1, delta, flags, epoch,
+                      src_rot, bn, max_ctas, lr_dev, epoch_dev=None):
+        """W -= step(alpha * sum_p U_p^T V_p) with the factors read from this rank's staging slots, gated per source by
+        its epoch flag (csrc/gemm/gemm_ops.cu:256-290, umma_gemm.cuh producer loop)."""
+        g = self._sfb_outer(u_ptrs, v_ptrs, Mb, N, K, flags, epoch, src_rot, epoch_dev)
+        if lr_dev is not None:
+            lr = lr * float(lr_dev[0])
+        self._step(w, g.view_as(w), h, lr, momentum, decay, rule, l1, delta, alpha)
+        if wb is not None:
+            wb.view(-1).copy_(_storage_order_flat(w))
+
+    def sfb_outer_f32(self, u_ptrs, v_ptrs, Mb, N, K, out, alpha, flags, epoch, src_rot, bn, max_ctas, epoch_dev=None):
+        out.copy_(self._sfb_outer(u_ptrs, v_ptrs, Mb, N, K, flags, epoch, src_rot, epoch_dev) * alpha)
+
+
+class EmulatedArena:
+    """``parallel/fused.py::SymmetricArena`` on host shared memory: one POSIX segment per rank, mapped by every rank.
+    ``base_ptrs[p]`` is the address of rank p's segment in THIS process — what the peer-mapped device pointers are on
+    the GPU.  No multicast object (``multicast_ptr == 0`` selects the P2P code paths)."""
+    mappings = []          # (base address, size, uint8 tensor) of every segment mapped in this process
+
+    def __init__(self, nbytes: int, rank_ctx):
+        import os
+        from multiprocessing import shared_memory
+        self.rank, self.world, self.device = rank_ctx.rank, rank_ctx.world_size, rank_ctx.device
+        nbytes = (nbytes + (2 << 20) - 1) // (2 << 20) * (2 << 20)
+        job = f"psd{os.environ.get('MASTER_PORT', '0')}_{EmulatedArena._generation(rank_ctx)}"
+        name = f"{job}_{self.rank}"
+        try:
+            self._own = shared_memory.SharedMemory(name=name, create=True, size=nbytes)      # new segments are zero-filled
+        except FileExistsError:                                 # left behind by a run that was killed
+            stale = shared_memory.SharedMemory(name=name)
+            stale.close()
+            stale.unlink()
+            self._own = shared_memory.SharedMemory(name=name, create=True, size=nbytes)
+        rank_ctx.barrier()
+        self._segs = [self._own if p == self.rank else shared_memory.SharedMemory(name=f"{job}_{p}")
+                      for p in range(self.world)]
+        tensors = [torch.frombuffer(seg.buf, dtype=torch.uint8, count=nbytes) for seg in self._segs]
+        self.buf = tensors[self.rank]
+        self.base_ptrs = [t.data_ptr() for t in tensors]
+        for t in tensors:
+            EmulatedArena.mappings.append((t.data_ptr(), nbytes, t))
+        self.multicast_ptr = 0
+        self.offset = 0
+        self.nbytes = nbytes
+        rank_ctx.barrier()
+
+    _gen = 0
+
+    @staticmethod
+    def _generation(rank_ctx) -> int:
+        EmulatedArena._gen += 1            # every rank builds its arenas in the same order
+        return EmulatedArena._gen
+
+    def carve(self, nbytes: int) -> int:
+        off = self.offset
+        self.offset = (off + nbytes + 255) // 256 * 256
+        if self.offset > self.nbytes:
+            raise RuntimeError("symmetric arena exhausted")
+        return off
+
+    def view(self, off: int, shape, dtype) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= d
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        return self.buf[off: off + nbytes].view(dtype).view(*shape)
+
+    def peer_ptrs(self, off: int):
+        return [b + off for b in self.base_ptrs]
+
+    def mc_ptr(self, off: int) -> int:
+        return 0
+
+    def close(self):
+        EmulatedArena.mappings[:] = [m for m in EmulatedArena.mappings if m[0] not in self.base_ptrs]
+        self.buf = None
+        for seg in self._segs:
+            try:
+                seg.close()
+            except BufferError:
+                pass
+        try:
+            self._own.unlink()
+        except FileNotFoundError:
+            pass

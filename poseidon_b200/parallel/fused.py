@@ -20,6 +20,7 @@ src/caffe/svb_worker.cpp:19-179, ps/src/petuum_ps/thread/ssp_push_bg_worker.cpp:
 from __future__ import annotations
 
 import logging
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -37,6 +38,47 @@ _ALIGN = 256          # bytes; every arena segment starts on this boundary
 
 def _round_up(x, a):
     return (x + a - 1) // a * a
+
+
+class _NoCuda:
+    """Stand-ins for the CUDA stream API when the engine runs on the CPU emulation of the kernels (ops/emulate.py,
+    tests only): everything is synchronous there, so streams and events degenerate to no-ops."""
+
+    class Stream:
+        def __init__(self, *a, **k):
+            pass
+
+        def wait_stream(self, s):
+            pass
+
+    class Event:
+        def __init__(self, *a, **k):
+            pass
+
+        def record(self, s=None):
+            pass
+
+    @staticmethod
+    def current_stream(device=None):
+        return _NoCuda.Stream()
+
+    @staticmethod
+    def stream(s):
+        import contextlib
+        return contextlib.nullcontext()
+
+    @staticmethod
+    def synchronize(device=None):
+        pass
+
+    @staticmethod
+    def is_current_stream_capturing():
+        return False
+
+
+def _record_stream(t: torch.Tensor, s) -> None:
+    if t.is_cuda:
+        t.record_stream(s)
 
 
 class SymmetricArena:
@@ -93,7 +135,8 @@ class FusedBackend(Backend):
     def __init__(self, svb: bool = False, sfb_mode: str = "auto", grad_reduce: str = "sum",
                  one_shot_bytes: int = 256 * 1024, use_multimem: bool = True):
         self.svb, self.sfb_mode, self.reduce = svb, sfb_mode, grad_reduce
-        self.one_shot_bytes = one_shot_bytes
+        # buckets up to this size are reduced whole by every rank (one launch latency); larger ones are sharded
+        self.one_shot_bytes = int(os.environ.get("POSEIDON_ONE_SHOT_BYTES", one_shot_bytes))
         self.use_multimem = use_multimem
         self.arena: Optional[SymmetricArena] = None
         self.epoch = 0
@@ -106,8 +149,9 @@ class FusedBackend(Backend):
         super().setup(sync)
         rc = sync.rank_ctx
         self.world, self.rank, self.device = rc.world_size, rc.rank, rc.device
-        self.uses_comm_stream = self.world > 1
-        self.stream = torch.cuda.Stream(device=self.device, priority=-1) if self.world > 1 else None
+        self.cu = torch.cuda if self.device.type == "cuda" else _NoCuda
+        self.uses_comm_stream = self.world > 1 and self.device.type == "cuda"
+        self.stream = self.cu.Stream(device=self.device, priority=-1) if self.world > 1 else None
         self.k = sm100.K()
         net = sync.net
         # engine state for every learnable layer must exist before we re-home weights
@@ -172,7 +216,11 @@ class FusedBackend(Backend):
         for h in self.sfb_layers.values():
             total += h.arena_bytes(self.world)
         total += n_flag_blocks * _ALIGN * 2 + (1 << 20)
-        self.arena = SymmetricArena(total, sync.rank_ctx)
+        if self.device.type == "cuda":
+            self.arena = SymmetricArena(total, sync.rank_ctx)
+        else:
+            from ..ops.emulate import EmulatedArena          # host shared memory standing in for NVLink peer memory
+            self.arena = EmulatedArena(total, sync.rank_ctx)
         ar = self.arena
         self.flag_off = ar.carve(n_flag_blocks * _ALIGN)
         self._next_flag = 0
@@ -208,8 +256,8 @@ class FusedBackend(Backend):
             st = getattr(layer, "_sm100", None)
             if st is not None and not getattr(st, "row_mode", False) and id(layer.weight) in self.seg_of:
                 layer._grad_sink = self
-        torch.cuda.synchronize(self.device)
-        dist.barrier(device_ids=[self.device.index])
+        self.cu.synchronize(self.device)
+        sync.rank_ctx.barrier()
         self.refresh_shadows()
 
     def weight_buffer(self, layer, st) -> torch.Tensor:
@@ -298,7 +346,7 @@ class FusedBackend(Backend):
 
     def _launch_peer(self, bucket):
         ar = self.arena
-        cur = torch.cuda.current_stream()
+        cur = self.cu.current_stream()
         # stage gradients that were not produced directly inside the arena (biases, first-layer weights)
         for p, seg in zip(bucket.params, bucket.segs):
             if p.grad is None:
@@ -308,7 +356,7 @@ class FusedBackend(Backend):
                 gview.copy_(p.grad)
         self.stream.wait_stream(cur)
         self.epoch_of_bucket = self.epoch + 1
-        with torch.cuda.stream(self.stream):
+        with self.cu.stream(self.stream):
             for pi, (p, seg, lm, dm) in enumerate(zip(bucket.params, bucket.segs, bucket.lr_mult, bucket.decay_mult)):
                 if p.grad is None:
                     continue
@@ -326,7 +374,7 @@ class FusedBackend(Backend):
                 self.launches += 2
                 self.dense_bytes += n * 4
             if bucket.event is None:
-                bucket.event = torch.cuda.Event()
+                bucket.event = self.cu.Event()
             bucket.event.record(self.stream)
 
     def finish_iteration(self):
@@ -335,11 +383,11 @@ class FusedBackend(Backend):
         device is what lets a captured CUDA graph of the whole step be replayed."""
         self.epoch += 1
         if self.world > 1:
-            cur = torch.cuda.current_stream()
+            cur = self.cu.current_stream()
             self.stream.wait_stream(cur)
-            with torch.cuda.stream(self.stream):
+            with self.cu.stream(self.stream):
                 self.epoch_t.add_(1)
-            if torch.cuda.is_current_stream_capturing():
+            if self.cu.is_current_stream_capturing():
                 cur.wait_stream(self.stream)           # a capture must end with every forked stream joined
 
     def bytes_on_wire(self):
@@ -456,11 +504,11 @@ class FusedSFB:
         ar = be.arena
         P = be.world
         par = 0                      # single-buffered slots: peers acknowledge consumption on flag slot 4
-        cur = torch.cuda.current_stream()
+        cur = be.cu.current_stream()
         be.stream.wait_stream(cur)
-        with torch.cuda.stream(be.stream):
-            dy.record_stream(be.stream)
-            x2.record_stream(be.stream)
+        with be.cu.stream(be.stream):
+            _record_stream(dy, be.stream)
+            _record_stream(x2, be.stream)
             mc = be.use_multimem and ar.multicast_ptr != 0
             u_dst = self.u_off[par] + be.rank * self.u_slot
             v_dst = self.v_off[par] + be.rank * self.v_slot
@@ -482,13 +530,13 @@ class FusedSFB:
                 g = getattr(self, "_gbuf", None)
                 if g is None:
                     g = self._gbuf = torch.empty(self.N, self.K, device=w.device, dtype=torch.float32)
-                g.record_stream(be.stream)
+                _record_stream(g, be.stream)
                 k.sfb_outer_f32(u_ptrs, v_ptrs, M, self.N, self.K, g, 1.0, self.local_flags[par], 1, 0, 0, 0, be.epoch_t)
                 k.fused_update(w, g, h, st.wb, lr, mom, decay, rule, l1, delta, gscale, be.lr_t)
                 be.launches += 5
             k.peer_signal(flags, be.rank, 4, 1, be.epoch_t)      # "I have consumed every slot of this step"
             if self.event is None:
-                self.event = torch.cuda.Event()
+                self.event = be.cu.Event()
             self.event.record(be.stream)
         st.mark_updated(keep_wb=True)
         be.sfb_stats.sfb_bytes += M * (self.N + self.K) * 2

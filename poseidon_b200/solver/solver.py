@@ -245,7 +245,7 @@ class Solver:
         self.comm_name = comm
         if self.engine == "sm100" and comm in ("fused", "local"):
             from ..ops import sm100
-            if not sm100.active(self.device) or (rc.distributed and self.device.type != "cuda"):
+            if not sm100.active(self.device):
                 raise RuntimeError("the sm100 engine needs a CUDA device (B200)")
             from ..parallel.fused import FusedBackend
             self.comm_name = "fused"

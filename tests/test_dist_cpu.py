@@ -166,3 +166,37 @@ def test_sm100_engine_bounded_staleness(tmp_path, monkeypatch, single_sm100, com
     assert _rel(res[0], single_sm100) < 0.25              # and stay near the synchronous trajectory
     if "max_lag" in res[0]:
         assert int(res[0]["max_lag"]) <= 1
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The fused NVLink backend itself, ranks as processes: the symmetric arena is host shared memory, the peer ops are the
+# emulations of ops/emulate.py (same pointers-into-the-arena calling convention, same epoch / flag protocol as the
+# kernels).  What runs for real is parallel/fused.py: arena carving, re-homing of masters / histories / bf16 shadows,
+# gradient sinks, DWBP bucket launches, one- vs two-shot selection, SFB slots with consumed flags, epoch bookkeeping.
+@pytest.mark.parametrize("extra,sfb", [(["--comm", "fused"], False),
+                                       (["--comm", "fused", "--svb", "1", "--sfb_mode", "all"], True)])
+def test_fused_backend_two_ranks_on_emulated_peer_memory(tmp_path, monkeypatch, single_sm100, extra, sfb):
+    monkeypatch.setenv("POSEIDON_EMULATE", "1")
+    res = launch(2, str(tmp_path / "w"), ["--batch", "8", "--engine", "sm100"] + extra)
+    assert _rel(res[0], res[1]) == 0.0                     # every rank applies the same bits
+    assert _rel(res[0], single_sm100) < 1e-6               # == one process on the concatenated batch with lr x2
+    if sfb:
+        assert int(res[0]["wire_sfb_bytes"]) > 0
+        assert int(res[0]["wire_sfb_dense_equiv_bytes"]) > 8 * int(res[0]["wire_sfb_bytes"])
+    else:
+        assert int(res[0]["wire_sfb_bytes"]) == 0 and int(res[0]["wire_dense_allreduce_bytes"]) > 0
+
+
+def test_fused_backend_three_ranks_two_shot_equals_library_backend(tmp_path, monkeypatch):
+    """Sharded (two-shot) reduce + step + broadcast with a remainder shard (3 ranks), SFB on: same weights as the gloo
+    all-reduce backend on the same engine, and as the one-shot schedule."""
+    monkeypatch.setenv("POSEIDON_EMULATE", "1")
+    lib = launch(3, str(tmp_path / "g"), ["--batch", "8", "--engine", "sm100", "--comm", "gloo"])
+    monkeypatch.setenv("POSEIDON_ONE_SHOT_BYTES", "1024")
+    two = launch(3, str(tmp_path / "t"), ["--batch", "8", "--engine", "sm100", "--comm", "fused", "--svb", "1",
+                                         "--sfb_mode", "all"])
+    assert _rel(two[0], two[1]) == 0.0 and _rel(two[0], two[2]) == 0.0
+    assert _rel(two[0], lib[0]) < 1e-6
+    monkeypatch.setenv("POSEIDON_ONE_SHOT_BYTES", str(1 << 30))
+    one = launch(3, str(tmp_path / "o"), ["--batch", "8", "--engine", "sm100", "--comm", "fused"])
+    assert _rel(one[0], two[0]) < 1e-6
