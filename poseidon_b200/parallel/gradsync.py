@@ -438,6 +438,17 @@ class GradSync:
         if st is not None:
             st.mark_updated()
 
+    def weights_changed(self):
+        """The fp32 masters were rewritten wholesale (``.caffemodel`` load / restore, followed by the broadcast from rank
+        0): every rank re-derives its bf16 operands — including the arena-resident shadows that are otherwise only
+        written by the update kernels."""
+        for layer in self.net.layers:
+            st = getattr(layer, "_sm100", None)
+            if st is not None:
+                st.mark_updated()
+        if hasattr(self.backend, "refresh_shadows"):
+            self.backend.refresh_shadows()
+
     def finish_iteration(self):
         """Launch buckets whose grads never materialised this step (unused layers) — none in
         practice — and let the backend close the clock.  Does *not* host-sync."""

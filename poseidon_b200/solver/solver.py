@@ -578,14 +578,16 @@ class Solver:
         model_file = base + ".caffemodel"
         state_file = base + ".solverstate"
         per_rank = self.comm_name == "ssp"
+        if hasattr(self.sync.backend, "gather_history"):
+            # a collective (two-shot buckets keep the optimizer history sharded by rank): EVERY rank takes part, not
+            # only the one that writes the file
+            self.sync.backend.gather_history()
         if self.rank_ctx.is_root:
             netp = self.net.to_proto(bool(self.param.snapshot_diff))
             log.info("Snapshotting to %s", model_file)
             P.write_binary(model_file, netp)
         if self.rank_ctx.is_root or per_rank:
             st = P.SolverState(iter=self.iter, learned_net=model_file)
-            if hasattr(self.sync.backend, "gather_history"):
-                self.sync.backend.gather_history()
             for h, (layer, j) in zip(self.sync.history_tensors(), self.net.param_owner):
                 st.history.append(P.array_to_blob(layer.export_blob(j, h)))
             fn = state_file + (f".{self.rank_ctx.rank}.0" if per_rank else "")

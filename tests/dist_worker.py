@@ -31,6 +31,9 @@ def main():
     ap.add_argument("--delay_rank", type=int, default=-1)
     ap.add_argument("--solver_type", default="SGD")
     ap.add_argument("--aggr_fraction", type=float, default=0.1)
+    ap.add_argument("--snapshot_prefix", default="", help="write <prefix>_iter_N.{caffemodel,solverstate} after the last step")
+    ap.add_argument("--restore", default="", help="resume from this .solverstate; --steps counts the steps still to run")
+    ap.add_argument("--total_steps", type=int, default=0, help="with --restore: length of the uninterrupted run (data order)")
     args = ap.parse_args()
     rc = init_rank_context(args.device)
     M, W = args.batch, rc.world_size
@@ -42,10 +45,17 @@ def main():
     s = get_solver(sp, rank_ctx=rc, engine=args.engine, comm=args.comm, svb=bool(args.svb), sfb_mode=args.sfb_mode,
                    staleness=args.staleness, grad_reduce=args.grad_reduce, aggr_fraction=args.aggr_fraction,
                    dtype=torch.float32 if args.engine == "torch" else None)
-    x, y = make_data(M * W * args.steps, hw=args.hw)
+    total = args.total_steps or args.steps
+    first = total - args.steps if args.restore else 0
+    x, y = make_data(M * W * total, hw=args.hw)
     # global batch t = samples [t*M*W, (t+1)*M*W); this rank takes the slice [r*M, (r+1)*M) of it
-    idx = torch.cat([torch.arange(t * M * W + rc.rank * M, t * M * W + (rc.rank + 1) * M) for t in range(args.steps)])
+    idx = torch.cat([torch.arange(t * M * W + rc.rank * M, t * M * W + (rc.rank + 1) * M)
+                     for t in range(first, first + args.steps)])
     feed(s, x[idx], y[idx])
+    if args.snapshot_prefix:
+        sp.snapshot_prefix = args.snapshot_prefix
+    if args.restore:
+        s.restore(args.restore)
     if args.delay_rank == rc.rank and hasattr(s.sync.backend, "delay_hook"):
         import time
         s.sync.backend.delay_hook = lambda clock: time.sleep(0.05)
@@ -56,6 +66,9 @@ def main():
     if rc.device.type == "cuda":
         torch.cuda.synchronize()
     rc.barrier()
+    if args.snapshot_prefix:
+        s.snapshot()
+        rc.barrier()
     w = {f"{n}.{j}": l.export_blob(j) for n, l in zip(s.net.layer_names, s.net.layers) for j in range(len(l.blobs))}
     extra = {}
     if hasattr(s.sync.backend, "max_observed_lag"):
