@@ -202,3 +202,28 @@ def test_launcher_restarts_from_latest_snapshot(tmp_path):
     assert "lenet_iter_4.solverstate" in second                     # resumed from the newest snapshot
     assert os.path.exists(tmp_path / "lenet_iter_8.caffemodel")
     assert launch.latest_solverstate(solver).endswith("lenet_iter_8.solverstate")
+
+
+def test_launcher_fused_backend_lenet_with_restart_on_emulation(tmp_path):
+    """Everything at once, on the CPU: tools.launch starts 2 ranks of caffe_main with the sm100 engine (kernels
+    emulated), the fused backend on shared-memory peer arenas, LeNet (channel-padded layers), SFB on, test phases and
+    snapshots; rank 1 is killed before iteration 5; the supervisor restarts both from lenet_iter_4.solverstate."""
+    from poseidon_b200 import proto as P
+    from poseidon_b200.tools import launch
+    solver, hosts = _lenet_job(tmp_path, 8)
+    sp = P.read_solver(solver)
+    sp.snapshot, sp.test_interval = 2, 4
+    sp.test_iter = [2]
+    P.write_text(solver, sp)
+    run = str(tmp_path / "run")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rc = launch.main(["train", "--hostfile", hosts, "--solver", solver, "--run_dir", run, "--workdir", root,
+                      "--max_restarts", "1", "--env", "POSEIDON_EMULATE=1", "--env", "OMP_NUM_THREADS=2",
+                      "--env", "POSEIDON_FAULT=kill:rank=1,step=5,attempt=0",
+                      "--", "--engine=sm100", "--comm=fused", "--svb=true"])
+    first = open(os.path.join(run, "client_0.log")).read()
+    second = open(os.path.join(run, "client_0.restart1.log")).read()
+    assert rc == 0, (first[-1500:], second[-1500:])
+    assert "engine=sm100, comm=fused" in first and "Test net output #0: accuracy" in first
+    assert "Restored solver state from" in second and "lenet_iter_4.solverstate" in second
+    assert "Optimization Done" in second and os.path.exists(tmp_path / "lenet_iter_8.caffemodel")
