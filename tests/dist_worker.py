@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--delay_rank", type=int, default=-1)
     ap.add_argument("--solver_type", default="SGD")
     ap.add_argument("--aggr_fraction", type=float, default=0.1)
+    ap.add_argument("--freeze", default="", help="comma separated layers whose blobs get blobs_lr 0 (finetuning)")
     ap.add_argument("--snapshot_prefix", default="", help="write <prefix>_iter_N.{caffemodel,solverstate} after the last step")
     ap.add_argument("--restore", default="", help="resume from this .solverstate; --steps counts the steps still to run")
     ap.add_argument("--total_steps", type=int, default=0, help="with --restore: length of the uninterrupted run (data order)")
@@ -38,6 +39,9 @@ def main():
     rc = init_rank_context(args.device)
     M, W = args.batch, rc.world_size
     net = small_net(batch=M, hw=args.hw)
+    for l in net.layers:
+        if l.name in args.freeze.split(","):
+            l.blobs_lr = [0.0, 0.0]
     sp = small_solver_param(net, base_lr=args.base_lr, max_iter=args.steps, solver_type=args.solver_type,
                             momentum=0.0 if args.solver_type == "ADAGRAD" else 0.9)
     if rc.device.type == "cpu":

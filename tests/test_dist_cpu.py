@@ -217,3 +217,16 @@ def test_multi_rank_snapshot_and_resume_is_exact(tmp_path, monkeypatch, comm):
                                                  str(tmp_path / "snap_iter_2.solverstate")])
     assert _rel(res[0], res[1]) == 0.0
     assert _rel(res[0], full[0]) < 1e-6
+
+
+def test_fused_backend_with_frozen_layers_equals_library_backend(tmp_path, monkeypatch):
+    """Finetuning shape: blobs_lr 0 on a convolution and an inner product (no gradient, no bucket, no arena segment)."""
+    monkeypatch.setenv("POSEIDON_EMULATE", "1")
+    fz = ["--batch", "8", "--engine", "sm100", "--freeze", "conv2,fc4"]
+    lib = launch(2, str(tmp_path / "g"), fz + ["--comm", "gloo"])
+    fused = launch(2, str(tmp_path / "f"), fz + ["--comm", "fused", "--svb", "1", "--sfb_mode", "all"])
+    start = launch(2, str(tmp_path / "z"), fz + ["--comm", "gloo", "--steps", "1"])
+    assert _rel(fused[0], fused[1]) == 0.0 and _rel(fused[0], lib[0]) < 1e-6
+    for k in ("conv2.0", "conv2.1", "fc4.0", "fc4.1"):                 # frozen blobs did not move between step 1 and 3
+        assert np.array_equal(fused[0][k], start[0][k]), k
+    assert not np.array_equal(fused[0]["conv3.0"], start[0]["conv3.0"])
