@@ -456,6 +456,13 @@ class EmulatedArena:
         rank_ctx.barrier()
         self._segs = [self._own if p == self.rank else shared_memory.SharedMemory(name=f"{job}_{p}")
                       for p in range(self.world)]
+        try:                                                    # attaching registers the peer's segment with OUR resource
+            from multiprocessing import resource_tracker        # tracker too (Python < 3.13), which then tries to unlink it
+            for p, seg in enumerate(self._segs):                # a second time at exit: only the creator cleans up
+                if p != self.rank:
+                    resource_tracker.unregister(seg._name, "shared_memory")
+        except Exception:
+            pass
         tensors = [torch.frombuffer(seg.buf, dtype=torch.uint8, count=nbytes) for seg in self._segs]
         self.buf = tensors[self.rank]
         self.base_ptrs = [t.data_ptr() for t in tensors]

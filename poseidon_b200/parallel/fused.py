@@ -390,6 +390,14 @@ class FusedBackend(Backend):
             if self.cu.is_current_stream_capturing():
                 cur.wait_stream(self.stream)           # a capture must end with every forked stream joined
 
+    def close(self):
+        """Release host-side resources of the arena (the emulated shared-memory segments; the CUDA arena lives as long
+        as its tensors)."""
+        ar = self.arena
+        if ar is not None and hasattr(ar, "close"):
+            self.arena = None
+            ar.close()
+
     def bytes_on_wire(self):
         return {"dense_allreduce_bytes": self.dense_bytes, "sfb_bytes": self.sfb_stats.sfb_bytes,
                 "sfb_dense_equiv_bytes": self.sfb_stats.dense_equiv_bytes}

@@ -636,6 +636,8 @@ class Solver:
         self.net.close()
         for t in self.test_nets:
             t.close()
+        if hasattr(self.sync.backend, "close"):
+            self.sync.backend.close()
 
 
 class SGDSolver(Solver):

@@ -199,3 +199,32 @@ def test_lint_is_clean():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(root, "scripts", "lint.py")], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout[-3000:]
+
+
+def test_bench_harness_two_ranks_on_emulated_fused_backend():
+    """bench.py's multi-rank control flow (torchrun env, max over ranks, wire counters, e2e leg) with the sm100 engine
+    and the fused backend, kernels and peer memory emulated — numbers are meaningless, keys and plumbing are checked."""
+    import json
+    import os
+    import socket
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    env = dict(os.environ, POSEIDON_EMULATE="1", OMP_NUM_THREADS="2")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(root, "bench.py"),
+                          "--gpus", "2", "--steps", "2", "--warmup", "3", "--allow-cpu", "--model", "lenet"],
+                         capture_output=True, text=True, timeout=600, cwd=root, env=env)
+    assert out.returncode == 0, out.stderr[-3000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1                                              # rank 0 only
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["config"]["global_batch"] == 128 and d["config"]["parallelism"].startswith("dp2+dwbp")
+    assert d["config"]["engine"] == "sm100" and d["config"]["comm"] == "fused"
+    assert d["config"]["wire_bytes_total"]["dense_allreduce_bytes"] > 0 and d["gpu_launches"] > 0
+    assert d["e2e"]["value"] > 0 and d["e2e"]["d2h_bytes_per_step"] == 4
+    assert "resource_tracker" not in out.stderr
