@@ -283,19 +283,7 @@ class EmulatedKernels:
                 "fused_update: layout mismatch"
         if lr_dev is not None:
             lr = lr * float(lr_dev[0])
-        g = g.float() * gscale
-        if decay != 0:
-            g = g + decay * (torch.sign(w) if l1 else w)
-        if rule == 0:
-            h.mul_(momentum).add_(g, alpha=lr)
-            w.sub_(h)
-        elif rule == 1:
-            h_old = h.clone()
-            h.mul_(momentum).add_(g, alpha=lr)
-            w.sub_((1.0 + momentum) * h - momentum * h_old)
-        else:
-            h.add_(g * g)
-            w.sub_(lr * g / (h.sqrt() + delta))
+        self._step(w, g.float(), h, lr, momentum, decay, rule, l1, delta, gscale)
         if wb is not None:
             wb.view(-1).copy_(_storage_order_flat(w))
 
