@@ -88,7 +88,9 @@ class NativeDBSource:
                 pdb = os.path.join(path, "data.mdb")
             elif not os.path.isfile(pdb) and os.path.isfile(os.path.join(path, "CURRENT")):
                 pdb = path                          # LevelDB directory
-        threads = threads or max(2, min(16, (os.cpu_count() or 4) // 2))
+        # decode threads per rank: half the cores of this rank's share of the host (torchrun exports LOCAL_WORLD_SIZE)
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+        threads = threads or max(2, min(16, (os.cpu_count() or 4) // (2 * local_world)))
         self.loader = m.BatchLoader(pdb, batch, offset, max(1, stride), threads)
         n = self.loader.num_records()
         if rand_skip:
