@@ -432,7 +432,8 @@ class EmulatedArena:
         from multiprocessing import shared_memory
         self.rank, self.world, self.device = rank_ctx.rank, rank_ctx.world_size, rank_ctx.device
         nbytes = (nbytes + (2 << 20) - 1) // (2 << 20) * (2 << 20)
-        job = f"psd{os.environ.get('MASTER_PORT', '0')}_{EmulatedArena._generation(rank_ctx)}"
+        job = f"psd{os.environ.get('MASTER_PORT', '0')}_{EmulatedArena._generation(rank_ctx)}" \
+              f"_n{getattr(rank_ctx, 'node_id', 0)}"              # emulated "nodes" share one /dev/shm
         name = f"{job}_{self.rank}"
         try:
             self._own = shared_memory.SharedMemory(name=name, create=True, size=nbytes)      # new segments are zero-filled

@@ -87,7 +87,8 @@ class SymmetricArena:
         self.rank, self.world = rank_ctx.rank, rank_ctx.world_size
         self.device = rank_ctx.device
         nbytes = _round_up(nbytes, 2 << 20)
-        group_name = dist.group.WORLD.group_name
+        group = getattr(rank_ctx, "group", None) or dist.group.WORLD      # the node-local group on multi-node jobs
+        group_name = group.group_name
         try:
             symm.enable_symm_mem_for_group(group_name)      # required on some builds, deprecated no-op on others
         except Exception:
@@ -101,7 +102,7 @@ class SymmetricArena:
         self.offset = 0
         self.nbytes = nbytes
         torch.cuda.synchronize(self.device)
-        dist.barrier(device_ids=[self.device.index])
+        rank_ctx.barrier()
 
     def carve(self, nbytes: int) -> int:
         off = self.offset
@@ -128,6 +129,20 @@ class _Seg:
     __slots__ = ("param", "numel", "g_off", "w_off", "wb_off", "hist")
 
 
+class _NodeContext:
+    """The ranks of one node as seen by the arena: local rank / world, the node's process group, a group barrier."""
+    distributed = True
+
+    def __init__(self, rank: int, world_size: int, device, group, node_id: int):
+        self.rank, self.world_size, self.device, self.group, self.node_id = rank, world_size, device, group, node_id
+
+    def barrier(self):
+        if self.device.type == "cuda":
+            dist.barrier(group=self.group, device_ids=[self.device.index])
+        else:
+            dist.barrier(group=self.group)
+
+
 class FusedBackend(Backend):
     manages_operands = True        # its kernels rewrite the bf16 operands next to the fp32 masters
     name = "fused"
@@ -148,7 +163,29 @@ class FusedBackend(Backend):
     def setup(self, sync):
         super().setup(sync)
         rc = sync.rank_ctx
-        self.world, self.rank, self.device = rc.world_size, rc.rank, rc.device
+        self.device = rc.device
+        # Topology.  The NVLink arena spans ONE node: `world` / `rank` below are node-local (they address arena slots and
+        # shards); `gworld` is the size of the whole job.  Across nodes every rank first all-reduces its gradient with
+        # the ranks of equal local index on the other nodes (library collective over the network), then the node-local
+        # kernel reduces over NVLink, steps and broadcasts: sum_r sum_n g[n][r] is the global sum on every node.
+        self.gworld, self.grank = rc.world_size, rc.rank
+        lw = int(os.environ.get("LOCAL_WORLD_SIZE", self.gworld)) if rc.distributed else 1
+        if lw <= 0 or self.gworld % lw:
+            lw = self.gworld
+        self.nnodes = self.gworld // lw
+        self.node, self.cross_group = rc, None
+        self.world, self.rank = self.gworld, self.grank
+        self.inter_node_bytes = 0
+        if self.nnodes > 1:
+            if lw == 1:
+                raise RuntimeError("the fused NVLink backend needs more than one GPU per node; use --comm nccl")
+            node_id = self.grank // lw
+            self.world, self.rank = lw, self.grank % lw
+            # every rank creates every group, in the same order
+            node_groups = [dist.new_group(list(range(n * lw, (n + 1) * lw))) for n in range(self.nnodes)]
+            cross_groups = [dist.new_group([n * lw + r for n in range(self.nnodes)]) for r in range(lw)]
+            self.node = _NodeContext(self.rank, lw, rc.device, node_groups[node_id], node_id)
+            self.cross_group = cross_groups[self.rank]
         self.cu = torch.cuda if self.device.type == "cuda" else _NoCuda
         self.uses_comm_stream = self.world > 1 and self.device.type == "cuda"
         self.stream = self.cu.Stream(device=self.device, priority=-1) if self.world > 1 else None
@@ -184,8 +221,8 @@ class FusedBackend(Backend):
             ok_shape = (N % 8 == 0 and Kd % 8 == 0)
             if P == 1:
                 use = ok_shape
-            elif not self.svb or self.sfb_mode == "none":
-                use = False
+            elif not self.svb or self.sfb_mode == "none" or self.nnodes > 1:
+                use = False                   # (across nodes the factors would have to travel the network too: dense)
             else:
                 use = ok_shape and (self.sfb_mode == "all" or sfb_wins(M, N, Kd, P))
             self.sfb_stats.layers[name] = "sfb" if use else "dense"
@@ -217,10 +254,10 @@ class FusedBackend(Backend):
             total += h.arena_bytes(self.world)
         total += n_flag_blocks * _ALIGN * 2 + (1 << 20)
         if self.device.type == "cuda":
-            self.arena = SymmetricArena(total, sync.rank_ctx)
+            self.arena = SymmetricArena(total, self.node)
         else:
             from ..ops.emulate import EmulatedArena          # host shared memory standing in for NVLink peer memory
-            self.arena = EmulatedArena(total, sync.rank_ctx)
+            self.arena = EmulatedArena(total, self.node)
         ar = self.arena
         self.flag_off = ar.carve(n_flag_blocks * _ALIGN)
         self._next_flag = 0
@@ -257,7 +294,7 @@ class FusedBackend(Backend):
             if st is not None and not getattr(st, "row_mode", False) and id(layer.weight) in self.seg_of:
                 layer._grad_sink = self
         self.cu.synchronize(self.device)
-        sync.rank_ctx.barrier()
+        self.node.barrier()
         self.refresh_shadows()
 
     def weight_buffer(self, layer, st) -> torch.Tensor:
@@ -307,7 +344,7 @@ class FusedBackend(Backend):
 
     def _hyper_args(self, lm, dm):
         hy = self.sync.hyper
-        ws = self.world
+        ws = self.gworld
         decay = hy.weight_decay * dm * (ws if self.reduce == "sum" else 1.0)
         gscale = 1.0 if self.reduce == "sum" else 1.0 / ws
         # lr here is only the per-blob multiplier; the kernels multiply by lr_t[0]
@@ -364,6 +401,9 @@ class FusedBackend(Backend):
                 one_shot = n * 4 <= self.one_shot_bytes
                 lr, mom, decay, rule, l1, delta, gscale = self._hyper_args(lm, dm)
                 use_mc = self.use_multimem and ar.multicast_ptr != 0
+                if self.cross_group is not None:
+                    dist.all_reduce(ar.view(seg.g_off, (n,), torch.float32), group=self.cross_group)
+                    self.inter_node_bytes += n * 4
                 self.k.allreduce_sgd(ar.peer_ptrs(seg.g_off), ar.peer_ptrs(seg.w_off), ar.peer_ptrs(seg.wb_off),
                                      ar.peer_ptrs(bucket.flag_off + 64 * pi),
                                      ar.mc_ptr(seg.g_off) if use_mc else 0,
@@ -399,7 +439,8 @@ class FusedBackend(Backend):
             ar.close()
 
     def bytes_on_wire(self):
-        return {"dense_allreduce_bytes": self.dense_bytes, "sfb_bytes": self.sfb_stats.sfb_bytes,
+        return {"dense_allreduce_bytes": self.dense_bytes, "inter_node_allreduce_bytes": self.inter_node_bytes,
+                "sfb_bytes": self.sfb_stats.sfb_bytes,
                 "sfb_dense_equiv_bytes": self.sfb_stats.dense_equiv_bytes}
 
     # optimizer-state plumbing for snapshots: history of a two-shot bucket is sharded by rank
@@ -417,7 +458,7 @@ class FusedBackend(Backend):
                 hi = min(n, lo + per)
                 mine = torch.zeros(per, dtype=torch.float32, device=self.device)
                 mine[: hi - lo] = seg.hist[lo:hi]
-                dist.all_gather_into_tensor(padded, mine)
+                dist.all_gather_into_tensor(padded, mine, group=getattr(self.node, "group", None))
                 seg.hist.copy_(padded[:n])
 
 

@@ -239,7 +239,8 @@ class Solver:
             elif self.staleness > 0:
                 comm = "ssp"
             elif self.engine == "sm100":
-                comm = "fused"
+                # NVLink arena per node (+ a library all-reduce across nodes); one GPU per node has no NVLink peer
+                comm = "fused" if int(os.environ.get("LOCAL_WORLD_SIZE", rc.world_size)) > 1 else "nccl"
             else:
                 comm = "nccl"
         self.comm_name = comm

@@ -19,12 +19,14 @@ def _free_port():
     return p
 
 
-def launch(world, out, extra, device="cpu", timeout=300):
+def launch(world, out, extra, device="cpu", timeout=300, local_world=None):
+    """``local_world``: ranks per simulated node (torchrun's LOCAL_WORLD_SIZE / LOCAL_RANK layout, node-major)."""
     port = _free_port()
     procs = []
+    lw = local_world or world
     for r in range(world):
-        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
-                   MASTER_PORT=str(port), OMP_NUM_THREADS="2")
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r % lw), LOCAL_WORLD_SIZE=str(lw), WORLD_SIZE=str(world),
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2")
         cmd = [sys.executable, os.path.join(HERE, "dist_worker.py"), "--out", out] + extra
         if device:
             cmd += ["--device", device]
@@ -230,3 +232,22 @@ def test_fused_backend_with_frozen_layers_equals_library_backend(tmp_path, monke
     for k in ("conv2.0", "conv2.1", "fc4.0", "fc4.1"):                 # frozen blobs did not move between step 1 and 3
         assert np.array_equal(fused[0][k], start[0][k]), k
     assert not np.array_equal(fused[0]["conv3.0"], start[0]["conv3.0"])
+
+
+def test_fused_backend_two_nodes_hierarchical(tmp_path, monkeypatch):
+    """2 simulated nodes x 2 ranks: NVLink arena per node (node-local process group), gradients all-reduced across
+    nodes by the library among ranks of equal local index, then the node-local reduce + step + broadcast kernel.
+    Same weights as the flat gloo all-reduce on 4 ranks; snapshot (history gathered per node) + resume is exact."""
+    monkeypatch.setenv("POSEIDON_EMULATE", "1")
+    monkeypatch.setenv("POSEIDON_ONE_SHOT_BYTES", "1024")
+    base = ["--batch", "4", "--engine", "sm100"]
+    lib = launch(4, str(tmp_path / "g"), base + ["--comm", "gloo", "--steps", "4"])
+    full = launch(4, str(tmp_path / "f"), base + ["--comm", "fused", "--svb", "1", "--steps", "4"], local_world=2)
+    assert all(_rel(full[0], full[i]) == 0.0 for i in (1, 2, 3))
+    assert _rel(full[0], lib[0]) < 1e-6
+    assert int(full[0]["wire_inter_node_allreduce_bytes"]) > 0 and int(full[0]["wire_sfb_bytes"]) == 0
+    launch(4, str(tmp_path / "B"), base + ["--comm", "fused", "--steps", "2", "--total_steps", "4",
+                                            "--snapshot_prefix", str(tmp_path / "snap")], local_world=2)
+    res = launch(4, str(tmp_path / "C"), base + ["--comm", "fused", "--steps", "2", "--total_steps", "4", "--restore",
+                                                 str(tmp_path / "snap_iter_2.solverstate")], local_world=2)
+    assert _rel(res[3], full[0]) < 1e-6
