@@ -92,6 +92,18 @@ def init_rank_context(device: Optional[str] = None, hostfile: Optional[str] = No
             os.environ.setdefault("MASTER_ADDR", hosts[0][1])
             os.environ.setdefault("MASTER_PORT", str(hosts[0][2]))
             local_rank = sum(1 for (i, ip, _) in hosts if ip == hosts[rank][1] and i < rank)
+            # node layout for the NVLink arena (parallel/fused.py): lines of one host must be contiguous and every host
+            # must list the same number of processes — what torchrun's node-major rank order guarantees
+            ips = [ip for (_, ip, _) in hosts]
+            per_host = ips.count(ips[rank])
+            blocks_ok = all(ips[i] == ips[i - i % per_host] for i in range(world)) and world % per_host == 0 and \
+                len(set(ips)) * per_host == world
+            if blocks_ok:
+                os.environ.setdefault("LOCAL_WORLD_SIZE", str(per_host))
+                os.environ.setdefault("LOCAL_RANK", str(local_rank))
+            elif len(set(ips)) > 1:
+                raise ValueError("hostfile: list the processes of each host on consecutive lines, the same number per "
+                                 "host (needed to form the per-node NVLink groups)")
     use_cuda = torch.cuda.is_available() and (device is None or str(device).startswith("cuda"))
     if use_cuda:
         if device is not None and ":" in str(device) and world == 1:

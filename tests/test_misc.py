@@ -228,3 +228,24 @@ def test_bench_harness_two_ranks_on_emulated_fused_backend():
     assert d["config"]["wire_bytes_total"]["dense_allreduce_bytes"] > 0 and d["gpu_launches"] > 0
     assert d["e2e"]["value"] > 0 and d["e2e"]["d2h_bytes_per_step"] == 4
     assert "resource_tracker" not in out.stderr
+
+
+def test_hostfile_node_layout(tmp_path, monkeypatch):
+    """Hostfile mode derives LOCAL_WORLD_SIZE / LOCAL_RANK (the per-node NVLink groups) from runs of equal hosts."""
+    import os
+    import pytest
+    from poseidon_b200.parallel import context
+    monkeypatch.setattr(context.dist, "init_process_group", lambda **kw: None)
+    monkeypatch.setattr(context.dist, "is_initialized", lambda: False)
+    for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK", "LOCAL_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        monkeypatch.delenv(k, raising=False)
+    hf = tmp_path / "hosts"
+    hf.write_text("0 10.0.0.1 9000\n1 10.0.0.1 9001\n2 10.0.0.2 9000\n3 10.0.0.2 9001\n")
+    rc = context.init_rank_context("cpu", str(hf), client_id=3)
+    assert (rc.rank, rc.world_size, rc.local_rank) == (3, 4, 1)
+    assert os.environ["LOCAL_WORLD_SIZE"] == "2" and os.environ["LOCAL_RANK"] == "1" and os.environ["MASTER_ADDR"] == "10.0.0.1"
+    for k in ("LOCAL_RANK", "LOCAL_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        monkeypatch.delenv(k, raising=False)
+    hf.write_text("0 10.0.0.1 9000\n1 10.0.0.2 9000\n2 10.0.0.1 9001\n3 10.0.0.2 9001\n")       # interleaved hosts
+    with pytest.raises(ValueError, match="consecutive lines"):
+        context.init_rank_context("cpu", str(hf), client_id=0)
