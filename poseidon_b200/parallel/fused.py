@@ -402,8 +402,15 @@ class FusedBackend(Backend):
                 lr, mom, decay, rule, l1, delta, gscale = self._hyper_args(lm, dm)
                 use_mc = self.use_multimem and ar.multicast_ptr != 0
                 if self.cross_group is not None:
-                    dist.all_reduce(ar.view(seg.g_off, (n,), torch.float32), group=self.cross_group)
-                    self.inter_node_bytes += n * 4
+                    gseg = ar.view(seg.g_off, (n,), torch.float32)
+                    if getattr(self, "wire_bf16", False):  # bf16 over the network, fp32 in the arena
+                        wire = gseg.to(torch.bfloat16)
+                        dist.all_reduce(wire, group=self.cross_group)
+                        gseg.copy_(wire)
+                        self.inter_node_bytes += n * 2
+                    else:
+                        dist.all_reduce(gseg, group=self.cross_group)
+                        self.inter_node_bytes += n * 4
                 self.k.allreduce_sgd(ar.peer_ptrs(seg.g_off), ar.peer_ptrs(seg.w_off), ar.peer_ptrs(seg.wb_off),
                                      ar.peer_ptrs(bucket.flag_off + 64 * pi),
                                      ar.mc_ptr(seg.g_off) if use_mc else 0,

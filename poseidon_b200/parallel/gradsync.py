@@ -168,8 +168,14 @@ class TorchDistBackend(Backend):
         grads = {}
         if red:
             flat = torch.cat([p.grad.reshape(-1) for p in red]) if len(red) > 1 else red[0].grad.reshape(-1)
-            dist.all_reduce(flat)
-            self.dense_bytes += flat.numel() * flat.element_size()
+            if getattr(self, "wire_bf16", False):          # DenseFloat16-style wire format: half the bytes, fp32 at rest
+                wire = flat.to(torch.bfloat16)
+                dist.all_reduce(wire)
+                self.dense_bytes += wire.numel() * wire.element_size()
+                flat = wire.float()
+            else:
+                dist.all_reduce(flat)
+                self.dense_bytes += flat.numel() * flat.element_size()
             off = 0
             for p in red:
                 grads[id(p)] = flat[off:off + p.numel()].view_as(p)

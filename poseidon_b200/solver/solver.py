@@ -92,7 +92,8 @@ class Solver:
     def __init__(self, param, rank_ctx: Optional[RankContext] = None, engine: str = "torch",
                  comm: str = "auto", staleness: int = 0, svb: bool = False, grad_reduce: str = "sum",
                  dtype=None, model_dir: Optional[str] = None, data_shape_hint=None,
-                 snapshot_dir: Optional[str] = None, sfb_mode: str = "auto", aggr_fraction: float = 0.1):
+                 snapshot_dir: Optional[str] = None, sfb_mode: str = "auto", aggr_fraction: float = 0.1,
+                 wire_dtype: Optional[str] = None):
         if isinstance(param, str):
             model_dir = model_dir or os.path.dirname(os.path.abspath(param))
             param = P.read_solver(param)
@@ -110,6 +111,11 @@ class Solver:
         self.engine = engine
         self.staleness = int(staleness)
         self.aggr_fraction = float(aggr_fraction)
+        # gradients on the network as bf16 (the reference's DenseFloat16 row oplogs: fp16 on the wire, fp32 at rest);
+        # applies to the library all-reduce and to the fused engine's inter-node hop, never to NVLink traffic
+        self.wire_dtype = (wire_dtype or os.environ.get("POSEIDON_WIRE_DTYPE", "fp32")).lower()
+        if self.wire_dtype not in ("fp32", "bf16"):
+            raise ValueError(f"wire_dtype must be fp32 or bf16, got '{self.wire_dtype}'")
         self.svb = bool(svb)
         self.iter = 0
         self.display_counter = 0
@@ -250,7 +256,9 @@ class Solver:
                 raise RuntimeError("the sm100 engine needs a CUDA device (B200)")
             from ..parallel.fused import FusedBackend
             self.comm_name = "fused"
-            return GradSync(self.net, rc, self.hyper, FusedBackend(self.svb, sfb_mode, grad_reduce))
+            backend = FusedBackend(self.svb, sfb_mode, grad_reduce)
+            backend.wire_bf16 = self.wire_dtype == "bf16"
+            return GradSync(self.net, rc, self.hyper, backend)
         if comm == "local":
             backend = LocalBackend()
         elif comm in ("nccl", "gloo", "torchdist"):
@@ -261,6 +269,7 @@ class Solver:
             backend = SSPAggrBackend(self.staleness, self.aggr_fraction)
         else:
             raise ValueError(f"unknown comm backend '{comm}' for engine '{self.engine}'")
+        backend.wire_bf16 = self.wire_dtype == "bf16"
         sync = GradSync(self.net, rc, self.hyper, backend)
         if self.svb and rc.distributed:
             from ..parallel.sfb import enable_sfb

@@ -61,6 +61,8 @@ def make_parser():
     ap.add_argument("--comm", default="auto", choices=["auto", "fused", "nccl", "gloo", "ssp", "ssp_aggr", "local"])
     ap.add_argument("--aggr_fraction", type=float, default=0.1,
                     help="SSPAggr: fraction of the pending update sent per clock (the rest waits, bounded by --table_staleness)")
+    ap.add_argument("--wire_dtype", default="", choices=["", "fp32", "bf16"],
+                    help="gradients on the network as bf16 (= --row_oplog_type=3, the reference's DenseFloat16 oplogs)")
     ap.add_argument("--sfb_mode", default="auto", choices=["auto", "all", "none"])
     ap.add_argument("--grad_reduce", default="sum", choices=["sum", "mean"])
     ap.add_argument("--synthetic_shape", default="", help="CxHxW of stand-in data when a DB is absent")
@@ -84,7 +86,7 @@ def parse_args(argv=None):
     elif args.comm == "auto" and cm == "ssp" and args.table_staleness > 0:
         args.comm = "ssp"
     ignored = [f for f in _PS_FLAGS if getattr(args, f) is not None and
-               f not in ("stats_path", "num_rows_per_table", "consistency_model")]
+               f not in ("stats_path", "num_rows_per_table", "consistency_model", "row_oplog_type")]
     args.ignored_ps_flags = ignored
     return args
 
@@ -138,7 +140,8 @@ def cmd_train(args) -> int:
     solver = get_solver(sp, rank_ctx=rc, engine=_engine(args, rc.device), comm=args.comm,
                         staleness=args.table_staleness, svb=_bool(args.svb), grad_reduce=args.grad_reduce,
                         model_dir=os.path.dirname(os.path.abspath(args.solver)), data_shape_hint=hint,
-                        sfb_mode=args.sfb_mode, aggr_fraction=args.aggr_fraction)
+                        sfb_mode=args.sfb_mode, aggr_fraction=args.aggr_fraction,
+                        wire_dtype=args.wire_dtype or ("bf16" if str(args.row_oplog_type) == "3" else None))
     if rc.is_root:
         log.info("Starting Optimization (world_size=%d, engine=%s, comm=%s, svb=%s, staleness=%d)",
                  rc.world_size, solver.engine, solver.comm_name, _bool(args.svb), args.table_staleness)

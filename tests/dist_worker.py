@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--delay_rank", type=int, default=-1)
     ap.add_argument("--solver_type", default="SGD")
     ap.add_argument("--aggr_fraction", type=float, default=0.1)
+    ap.add_argument("--wire_dtype", default=None)
     ap.add_argument("--freeze", default="", help="comma separated layers whose blobs get blobs_lr 0 (finetuning)")
     ap.add_argument("--snapshot_prefix", default="", help="write <prefix>_iter_N.{caffemodel,solverstate} after the last step")
     ap.add_argument("--restore", default="", help="resume from this .solverstate; --steps counts the steps still to run")
@@ -48,6 +49,7 @@ def main():
         sp.solver_mode = "CPU"
     s = get_solver(sp, rank_ctx=rc, engine=args.engine, comm=args.comm, svb=bool(args.svb), sfb_mode=args.sfb_mode,
                    staleness=args.staleness, grad_reduce=args.grad_reduce, aggr_fraction=args.aggr_fraction,
+                   wire_dtype=args.wire_dtype,
                    dtype=torch.float32 if args.engine == "torch" else None)
     total = args.total_steps or args.steps
     first = total - args.steps if args.restore else 0

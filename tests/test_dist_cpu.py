@@ -251,3 +251,20 @@ def test_fused_backend_two_nodes_hierarchical(tmp_path, monkeypatch):
     res = launch(4, str(tmp_path / "C"), base + ["--comm", "fused", "--steps", "2", "--total_steps", "4", "--restore",
                                                  str(tmp_path / "snap_iter_2.solverstate")], local_world=2)
     assert _rel(res[3], full[0]) < 1e-6
+
+
+def test_bf16_wire_format_halves_network_bytes(tmp_path, monkeypatch, single):
+    """--wire_dtype bf16 (the reference's DenseFloat16 row oplogs): gradients cross the network as bf16, masters and
+    the reduction result stay fp32.  Half the bytes, weights within bf16 rounding of the fp32-wire run; on the fused
+    engine only the inter-node hop is affected."""
+    fp = launch(2, str(tmp_path / "a"), ["--batch", "8", "--comm", "gloo"])
+    bf = launch(2, str(tmp_path / "b"), ["--batch", "8", "--comm", "gloo", "--wire_dtype", "bf16"])
+    assert int(bf[0]["wire_dense_allreduce_bytes"]) * 2 == int(fp[0]["wire_dense_allreduce_bytes"])
+    assert _rel(bf[0], bf[1]) < 1e-7 and 0 < _rel(bf[0], fp[0]) < 0.02
+    monkeypatch.setenv("POSEIDON_EMULATE", "1")
+    base = ["--batch", "4", "--engine", "sm100", "--comm", "fused"]
+    f32 = launch(4, str(tmp_path / "c"), base, local_world=2)
+    f16 = launch(4, str(tmp_path / "d"), base + ["--wire_dtype", "bf16"], local_world=2)
+    assert int(f16[0]["wire_inter_node_allreduce_bytes"]) * 2 == int(f32[0]["wire_inter_node_allreduce_bytes"])
+    assert int(f16[0]["wire_dense_allreduce_bytes"]) == int(f32[0]["wire_dense_allreduce_bytes"])       # NVLink part
+    assert all(_rel(f16[0], f16[i]) == 0.0 for i in (1, 2, 3)) and 0 < _rel(f16[0], f32[0]) < 0.02
