@@ -402,15 +402,7 @@ class FusedBackend(Backend):
                 lr, mom, decay, rule, l1, delta, gscale = self._hyper_args(lm, dm)
                 use_mc = self.use_multimem and ar.multicast_ptr != 0
                 if self.cross_group is not None:
-                    gseg = ar.view(seg.g_off, (n,), torch.float32)
-                    if getattr(self, "wire_bf16", False):  # bf16 over the network, fp32 in the arena
-                        wire = gseg.to(torch.bfloat16)
-                        dist.all_reduce(wire, group=self.cross_group)
-                        gseg.copy_(wire)
-                        self.inter_node_bytes += n * 2
-                    else:
-                        dist.all_reduce(gseg, group=self.cross_group)
-                        self.inter_node_bytes += n * 4
+                    self._inter_node_reduce(ar.view(seg.g_off, (n,), torch.float32), n, one_shot)
                 self.k.allreduce_sgd(ar.peer_ptrs(seg.g_off), ar.peer_ptrs(seg.w_off), ar.peer_ptrs(seg.wb_off),
                                      ar.peer_ptrs(bucket.flag_off + 64 * pi),
                                      ar.mc_ptr(seg.g_off) if use_mc else 0,
@@ -423,6 +415,45 @@ class FusedBackend(Backend):
             if bucket.event is None:
                 bucket.event = self.cu.Event()
             bucket.event.record(self.stream)
+
+    def _network_all_reduce(self, t: torch.Tensor) -> torch.Tensor:
+        """Sum ``t`` over the ranks of equal local index on all nodes; bf16 on the wire if asked for."""
+        if getattr(self, "wire_bf16", False):
+            wire = t.to(torch.bfloat16)
+            dist.all_reduce(wire, group=self.cross_group)
+            self.inter_node_bytes += wire.numel() * 2
+            return wire.float()
+        dist.all_reduce(t, group=self.cross_group)
+        self.inter_node_bytes += t.numel() * 4
+        return t
+
+    def _inter_node_reduce(self, gseg: torch.Tensor, n: int, one_shot: bool):
+        """Multi-node jobs, in front of the node-local kernel (same stream).  Small (one-shot) buckets: all-reduce the
+        whole segment across nodes.  Sharded (two-shot) buckets: reduce-scatter inside the node first, so that only
+        this rank's shard — 1 / (GPUs per node) of the bucket — crosses the network; the global shard sum is then put
+        back into this rank's segment with the rest zeroed, and the unchanged kernel (which sums shard r over the local
+        ranks, steps it and broadcasts it) produces the global result."""
+        if one_shot:
+            gseg.copy_(self._network_all_reduce(gseg))
+            return
+        W = self.world
+        per = ((n // 4 + W - 1) // W) * 4                       # the kernel's shard size (in floats)
+        lo = min(n, per * self.rank)
+        hi = min(n, lo + per)
+        if self.device.type == "cuda":
+            buf = torch.zeros(per * W, dtype=torch.float32, device=self.device)
+            buf[:n].copy_(gseg)
+            shard = torch.empty(per, dtype=torch.float32, device=self.device)
+            dist.reduce_scatter_tensor(shard, buf, group=self.node.group)
+            shard = shard[: hi - lo]
+        else:                                                    # gloo has no reduce-scatter
+            full = gseg.clone()
+            dist.all_reduce(full, group=self.node.group)
+            shard = full[lo:hi].clone()
+        if hi > lo:
+            shard = self._network_all_reduce(shard)
+        gseg.zero_()
+        gseg[lo:hi].copy_(shard)
 
     def finish_iteration(self):
         """Close the step: the device-resident epoch counter (read by every comm kernel of this step as
