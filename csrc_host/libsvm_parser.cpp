@@ -120,7 +120,37 @@ static py::tuple parse_libsvm(py::bytes data, bool feature_one_based, bool label
   return py::make_tuple(labels, indptr, indices, values);
 }
 
+// CRC-32C (Castagnoli), slicing-by-4 — the checksum of LevelDB blocks and log records (data/leveldb_writer.py).
+static uint32_t crc32c_update(uint32_t crc, const uint8_t* p, size_t n) {
+  static uint32_t table[4][256];
+  static bool init = false;
+  if (!init) {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      table[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int t = 1; t < 4; ++t) table[t][i] = (table[t - 1][i] >> 8) ^ table[0][table[t - 1][i] & 0xFF];
+    init = true;
+  }
+  crc = ~crc;
+  while (n >= 4) {
+    crc ^= static_cast<uint32_t>(p[0]) | (static_cast<uint32_t>(p[1]) << 8) | (static_cast<uint32_t>(p[2]) << 16) |
+           (static_cast<uint32_t>(p[3]) << 24);
+    crc = table[3][crc & 0xFF] ^ table[2][(crc >> 8) & 0xFF] ^ table[1][(crc >> 16) & 0xFF] ^ table[0][crc >> 24];
+    p += 4;
+    n -= 4;
+  }
+  while (n--) crc = table[0][(crc ^ *p++) & 0xFF] ^ (crc >> 8);
+  return ~crc;
+}
+
 void bind_ml(py::module_& m) {
+  m.def("crc32c", [](py::bytes data, uint32_t seed) {
+    const std::string s = data;
+    return crc32c_update(seed, reinterpret_cast<const uint8_t*>(s.data()), s.size());
+  }, py::arg("data"), py::arg("seed") = 0, "CRC-32C (Castagnoli) of a byte string, continuing from `seed`");
   m.def("parse_libsvm", &parse_libsvm, py::arg("data"), py::arg("feature_one_based") = false,
         py::arg("label_one_based") = false, py::arg("max_rows") = -1, py::arg("threads") = 0,
         "LibSVM text -> (labels int32, indptr int64, indices int32, values float32), parsed on a thread per slice");

@@ -46,8 +46,9 @@ def main(argv=None):
         random.shuffle(lines)
     n = 0
     backend = args.backend.lower()
-    if backend not in ("pdb", "lmdb"):
-        raise SystemExit("--backend must be pdb (native record store) or lmdb (export for stock Caffe / Poseidon)")
+    if backend not in ("pdb", "lmdb", "leveldb"):
+        raise SystemExit("--backend must be pdb (native record store), lmdb or leveldb (exports that stock Caffe / "
+                         "Poseidon read; leveldb is the reference's default)")
 
     def records():
         nonlocal n
@@ -66,6 +67,9 @@ def main(argv=None):
         # an LMDB environment (data.mdb) that the reference's DataLayer reads with `backend: LMDB`
         from ..data.lmdb_writer import write_lmdb
         write_lmdb(args.db, records())
+    elif backend == "leveldb":
+        from ..data.leveldb_writer import write_leveldb
+        write_leveldb(args.db, records())
     else:
         with RecordWriter(args.db) as w:
             for key, value in records():

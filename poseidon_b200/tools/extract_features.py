@@ -31,6 +31,8 @@ def main(argv=None):
     ap.add_argument("num_mini_batches", type=int)
     ap.add_argument("--gpu", default="")
     ap.add_argument("--engine", default="auto")
+    ap.add_argument("--backend", default="pdb", choices=["pdb", "leveldb"],
+                    help="feature databases: the framework's record store, or LevelDB directories like the reference writes")
     args = ap.parse_args(argv)
     rc = init_rank_context(None if args.gpu != "-1" else "cpu")
     engine = args.engine if args.engine != "auto" else ("sm100" if rc.device.type == "cuda" else "torch")
@@ -53,7 +55,11 @@ def main(argv=None):
     for b in blob_names:
         if b not in net.blob_shapes:
             raise SystemExit(f"Unknown feature blob name {b} in the network {args.model}")
-    writers = [RecordWriter(f"{d}_{rc.rank}_0") for d in db_names]
+    if args.backend == "leveldb":
+        from ..data.leveldb_writer import LevelDBWriter as Writer
+    else:
+        Writer = RecordWriter
+    writers = [Writer(f"{d}_{rc.rank}_0") for d in db_names]
     idx = [0] * len(blob_names)
     with torch.no_grad():
         for _ in range(args.num_mini_batches):
