@@ -25,5 +25,5 @@ echo "built $OUT ($MODE)"
 STD=$(gcc -print-file-name=libstdc++.so.6)
 POSEIDON_FUZZ_ITERS=${POSEIDON_FUZZ_ITERS:-200} POSEIDON_HOST_SO="$OUT" LD_PRELOAD="$RT $STD" ASAN_OPTIONS=detect_leaks=0:abort_on_error=0 UBSAN_OPTIONS=print_stacktrace=1 \
   TSAN_OPTIONS="report_signal_unsafe=0" \
-  python -m pytest tests/test_native_loader.py tests/test_lmdb_reader.py tests/test_leveldb_reader.py tests/test_ml_helpers.py tests/test_host_fuzz.py \
+  python -m pytest tests/test_native_loader.py tests/test_lmdb_reader.py tests/test_leveldb_reader.py tests/test_ml_helpers.py tests/test_host_fuzz.py tests/test_leveldb_writer.py \
     -q -x -p no:cacheprovider 2>&1 | grep -v 'python3.12+0x' | tail -25
