@@ -106,3 +106,20 @@ def test_tools_write_leveldb_like_the_reference(tmp_path):
     _, out = net.forward()
     assert out["data"].shape == (3, 3, 8, 8) and out["label"].reshape(-1).tolist() == [0, 1, 2]
     net.close()
+
+
+@pytest.mark.parametrize("backend", ["leveldb", "lmdb", "pdb"])
+def test_partition_data_writes_the_requested_backend(tmp_path, backend):
+    """tools.partition_data: LevelDB in, N round-robin shards out in the reference's formats (it only supports LevelDB)."""
+    from poseidon_b200.tools import partition_data
+    rng = np.random.RandomState(2)
+    recs = _records(10, rng)
+    src = str(tmp_path / "src_leveldb")
+    write_leveldb(src, recs)
+    assert partition_data.main([src, "--num_partitions", "3", "--backend", backend]) == 0
+    total = []
+    for k in range(3):
+        r = open_db(f"{src}_{k}", {"leveldb": "LEVELDB", "lmdb": "LMDB", "pdb": "LEVELDB"}[backend])
+        assert len(r) == (4, 3, 3)[k]
+        total += [(r.key(i), r.value(i)) for i in range(len(r))]
+    assert sorted(total) == recs
