@@ -587,7 +587,7 @@ class Solver:
         base = f"{self._snapshot_prefix()}_iter_{self.iter}"
         model_file = base + ".caffemodel"
         state_file = base + ".solverstate"
-        per_rank = self.comm_name == "ssp"
+        per_rank = self.comm_name in ("ssp", "ssp_aggr")        # per-worker momentum in the asynchronous modes
         if hasattr(self.sync.backend, "gather_history"):
             # a collective (two-shot buckets keep the optimizer history sharded by rank): EVERY rank takes part, not
             # only the one that writes the file

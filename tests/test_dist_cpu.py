@@ -270,3 +270,16 @@ def test_bf16_wire_format_halves_network_bytes(tmp_path, monkeypatch, single):
     assert int(f16[0]["wire_inter_node_allreduce_bytes"]) * 2 == int(f32[0]["wire_inter_node_allreduce_bytes"])
     assert int(f16[0]["wire_dense_allreduce_bytes"]) == int(f32[0]["wire_dense_allreduce_bytes"])       # NVLink part
     assert all(_rel(f16[0], f16[i]) == 0.0 for i in (1, 2, 3)) and 0 < _rel(f16[0], f32[0]) < 0.02
+
+
+def test_ssp_aggr_snapshot_is_per_worker(tmp_path, monkeypatch):
+    """Momentum is per worker in the asynchronous modes: SSPAggr writes one .solverstate.<rank>.0 per rank like SSP (the
+    reference's per-thread solverstate suffix), and a resumed job continues the uninterrupted trajectory."""
+    monkeypatch.setenv("POSEIDON_EMULATE", "1")
+    base = ["--batch", "8", "--engine", "sm100", "--comm", "ssp_aggr", "--staleness", "1"]
+    full = launch(2, str(tmp_path / "A"), base + ["--steps", "4"])
+    launch(2, str(tmp_path / "B"), base + ["--steps", "2", "--total_steps", "4", "--snapshot_prefix", str(tmp_path / "snap")])
+    assert os.path.exists(tmp_path / "snap_iter_2.solverstate.0.0") and os.path.exists(tmp_path / "snap_iter_2.solverstate.1.0")
+    res = launch(2, str(tmp_path / "C"), base + ["--steps", "2", "--total_steps", "4", "--restore",
+                                                 str(tmp_path / "snap_iter_2.solverstate")])
+    assert _rel(res[0], full[0]) < 1e-5
