@@ -189,6 +189,11 @@ def test_reference_example_solvers_load_unmodified():
     assert s.net.layer_by_name["fc8"].weight.shape == (1000, 4096)
     assert "POSEIDON_ROOT" not in s._snapshot_prefix.__func__(type("S", (), {"param": s.param, "model_dir": s.model_dir, "snapshot_dir": "/tmp"})())
     s.close()
+    for mref, n_ip in (("/root/reference/models/bvlc_googlenet/quick_solver.prototxt", 5),
+                       ("/root/reference/models/bvlc_reference_caffenet/solver.prototxt", 3)):
+        s = get_solver(P.read_solver(mref), engine="torch", model_dir=os.path.dirname(mref))
+        assert sum(1 for l in s.net.layers if l.type_name == "INNER_PRODUCT") == n_ip and len(s.test_nets) == 1
+        s.close()
 
 
 def test_lint_is_clean():
