@@ -510,3 +510,60 @@ def test_data_layer_hands_first_conv_its_layout(emu, tmp_path, k, stride, pad, c
         s.close()
     for a, b in zip(out["torch"], out["sm100"]):
         assert abs(a - b) <= 0.02 * max(1.0, abs(a)), out
+
+
+@pytest.mark.parametrize("engine", ["torch", "sm100"])
+def test_learns_a_separable_task(emu, engine):
+    """End-to-end sanity beyond "the loss goes down": a 4-class task (which quadrant holds the bright blob) is learnt to
+    > 95 % held-out accuracy in 150 SGD steps by both engines, through the TEST-phase accuracy layer."""
+    from poseidon_b200 import get_solver, proto as P
+    from poseidon_b200.models.zoo import NetBuilder
+
+    def data(n, seed):
+        rng = np.random.RandomState(seed)
+        y = rng.randint(0, 4, size=n)
+        x = rng.randn(n, 1, 12, 12).astype(np.float32) * 0.3
+        for i, c in enumerate(y):
+            r0, c0 = (c // 2) * 6, (c % 2) * 6
+            x[i, 0, r0 + 1: r0 + 5, c0 + 1: c0 + 5] += 1.5
+        return torch.from_numpy(x), torch.from_numpy(y.astype(np.float32))
+
+    b = NetBuilder("quadrants")
+    b.layer("data", "MEMORY_DATA", (), ("data", "label"),
+            memory_data_param={"batch_size": 32, "channels": 1, "height": 12, "width": 12})
+    g = {"type": "xavier"}
+    b.conv("conv1", "data", 8, 3, pad=1, wf=g, bf={"type": "constant", "value": 0.0})
+    b.relu("relu1", "conv1")
+    b.pool("pool1", "conv1", "MAX", 2, 2)
+    b.fc("ip1", "pool1", 16, wf=g, bf={"type": "constant", "value": 0.0})
+    b.relu("relu2", "ip1")
+    b.fc("ip2", "ip1", 4, wf=g, bf={"type": "constant", "value": 0.0})
+    b.accuracy("accuracy", "ip2")
+    b.softmax_loss("loss", "ip2")
+    sp = P.SolverParameter(base_lr=0.05, lr_policy="step", gamma=0.5, stepsize=60, momentum=0.9, weight_decay=1e-4,
+                           display=0, max_iter=150, snapshot=0, snapshot_after_train=False, random_seed=5,
+                           solver_mode="CPU", test_interval=1000)
+    sp.test_iter = [4]
+    sp.net_param = b.net
+    s = get_solver(sp, engine=engine, dtype=torch.float32 if engine == "torch" else None)
+    xtr, ytr = data(32 * 150, 1)
+    xte, yte = data(32 * 4, 2)
+    feed(s, xtr, ytr)
+    for layer in s.test_nets[0].layers:
+        if layer.type_name == "MEMORY_DATA":
+            layer.reset(xte, yte)
+    s.step(150)
+    scores = s.test(0) if hasattr(s, "test") else None
+    acc = None
+    if isinstance(scores, dict):
+        acc = scores.get("accuracy")
+    if acc is None:                                   # evaluate by hand through the shared-weight test net
+        net = s.test_nets[0]
+        hits = 0
+        with torch.no_grad():
+            for _ in range(4):
+                _, out = net.forward()
+                hits += float(out["accuracy"]) * 32
+        acc = hits / 128
+    assert acc > 0.95, acc
+    s.close()
