@@ -261,7 +261,7 @@ def test_inception_block_with_concat_and_dropout(emu):
     assert set(d.float().unique().tolist()) <= {0.0, 2.0} and not torch.equal(d, e)
 
 
-@pytest.mark.parametrize("name,steps", [("alexnet", 3), ("caffenet", 2), ("googlenet", 3)])
+@pytest.mark.parametrize("name,steps", [("alexnet", 3), ("caffenet", 2), ("googlenet", 3), ("vgg16", 2)])
 def test_zoo_models_follow_fp32_engine(emu, name, steps):
     """The reference's ImageNet models, full size (batch 2, synthetic data), dropout neutralised: the sm100 engine's
     loss trajectory (space-to-depth conv1, fused ReLU / LRN masks, CONCAT slices, auxiliary losses) tracks fp32."""
@@ -287,7 +287,9 @@ def test_zoo_models_follow_fp32_engine(emu, name, steps):
 
     l_sm, s = run("sm100")
     l_ref, _ = run("torch")
-    if name != "googlenet":
+    if name == "vgg16":
+        assert s.net.layer_by_name["conv1_1"]._sm100.pad8             # 3x3 / s1 first layer: image padded to 8 channels
+    elif name != "googlenet":
         assert s.net.layer_by_name["conv1"]._sm100.s2d
     for a, b in zip(l_ref, l_sm):
         assert abs(a - b) < 0.01 * abs(a), (l_ref, l_sm)
