@@ -200,9 +200,20 @@ def main(argv=None) -> int:
     ap.add_argument("--max_restarts", type=int, default=0,
                     help="restart a failed training job up to N times from its newest .solverstate")
     ap.add_argument("--force", action="store_true", help="kill: SIGKILL instead of SIGTERM")
+    ap.add_argument("--nproc_per_node", type=int, default=0,
+                    help="no hostfile needed: run N processes on this machine (writes run_dir/hostfile)")
     args = ap.parse_args(argv)
     if args.command == "kill":
         return cmd_kill(args)
+    if args.nproc_per_node > 0:
+        os.makedirs(args.run_dir, exist_ok=True)
+        args.hostfile = os.path.join(args.run_dir, "hostfile")
+        s0 = socket.socket()
+        s0.bind(("127.0.0.1", 0))
+        port = s0.getsockname()[1]
+        s0.close()
+        with open(args.hostfile, "w") as f:
+            f.write("".join(f"{i} 127.0.0.1 {port + i}\n" for i in range(args.nproc_per_node)))
     return cmd_train(args, extra)
 
 

@@ -135,6 +135,9 @@ def test_launcher_runs_one_process_per_hostfile_line(tmp_path, capsys):
     recs = json.load(open(os.path.join(run, "pids.json")))["clients"]
     assert [r["client"] for r in recs] == [0, 1] and all(r["local"] for r in recs)
     capsys.readouterr()
+    assert launch.main(["train", "--nproc_per_node", "3", "--solver", solver, "--dry_run", "--run_dir", run]) == 0
+    out3 = capsys.readouterr().out
+    assert out3.count("--client_id=") == 3 and len(open(os.path.join(run, "hostfile")).read().splitlines()) == 3
     (tmp_path / "remote").write_text("0 10.0.0.1 9999\n1 10.0.0.2 9999\n")
     assert launch.main(["train", "--hostfile", str(tmp_path / "remote"), "--solver", solver, "--dry_run",
                         "--run_dir", run, "--", "--table_staleness=1"]) == 0
