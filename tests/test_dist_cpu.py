@@ -191,17 +191,14 @@ def test_fused_backend_two_ranks_on_emulated_peer_memory(tmp_path, monkeypatch, 
 
 def test_fused_backend_three_ranks_two_shot_equals_library_backend(tmp_path, monkeypatch):
     """Sharded (two-shot) reduce + step + broadcast with a remainder shard (3 ranks), SFB on: same weights as the gloo
-    all-reduce backend on the same engine, and as the one-shot schedule."""
+    all-reduce backend on the same engine."""
     monkeypatch.setenv("POSEIDON_EMULATE", "1")
     lib = launch(3, str(tmp_path / "g"), ["--batch", "8", "--engine", "sm100", "--comm", "gloo"])
     monkeypatch.setenv("POSEIDON_ONE_SHOT_BYTES", "1024")
     two = launch(3, str(tmp_path / "t"), ["--batch", "8", "--engine", "sm100", "--comm", "fused", "--svb", "1",
                                          "--sfb_mode", "all"])
     assert _rel(two[0], two[1]) == 0.0 and _rel(two[0], two[2]) == 0.0
-    assert _rel(two[0], lib[0]) < 1e-6
-    monkeypatch.setenv("POSEIDON_ONE_SHOT_BYTES", str(1 << 30))
-    one = launch(3, str(tmp_path / "o"), ["--batch", "8", "--engine", "sm100", "--comm", "fused"])
-    assert _rel(one[0], two[0]) < 1e-6
+    assert _rel(two[0], lib[0]) < 1e-6           # (the one-shot schedule is compared with it in the 2-rank tests)
 
 
 @pytest.mark.parametrize("comm", [["--comm", "fused", "--svb", "1", "--sfb_mode", "all"], ["--comm", "gloo"]])
