@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 from . import schema
-from .message import DecodeError, Message, get_class, parse_text, to_text
+from .message import DecodeError, Message, ParseError, get_class, parse_text, to_text
 
 SVProto = get_class("SVProto")
 BlobProto = get_class("BlobProto")

@@ -652,10 +652,19 @@ def _finalize_pending(msg: Message):
                 _finalize_pending(val)
 
 
+class ParseError(ValueError):
+    """Malformed protobuf text (.prototxt) input."""
+
+
 def parse_text(text: str, msg_or_cls):
     msg = msg_or_cls() if isinstance(msg_or_cls, type) else msg_or_cls
-    _TextParser(text).parse_message(msg, None)
-    _finalize_pending(msg)
+    try:
+        _TextParser(text).parse_message(msg, None)
+        _finalize_pending(msg)
+    except ParseError:
+        raise
+    except (ValueError, TypeError, IndexError, KeyError, AttributeError, OverflowError, RecursionError) as e:
+        raise ParseError(f"{type(msg).__name__}: {e}") from e
     return msg
 
 

@@ -139,3 +139,22 @@ def test_malformed_wire_data_raises_decode_error():
         except P.DecodeError:
             seen["err"] += 1
     assert seen["err"] > 100 and seen["ok"] > 50, seen
+
+
+def test_malformed_prototxt_raises_parse_error():
+    import numpy as np
+    from poseidon_b200.models import zoo
+    from test_host_fuzz import _mutations
+    txt = P.to_text(zoo.lenet(batch=4, test_batch=4)).encode()
+    rng = np.random.RandomState(0)
+    seen = {"ok": 0, "err": 0}
+    for mut in _mutations(txt, rng, 500):
+        try:
+            P.parse_text(mut.decode("utf-8", "replace"), P.NetParameter)
+            seen["ok"] += 1
+        except P.ParseError as e:
+            assert "NetParameter" in str(e)
+            seen["err"] += 1
+    assert seen["err"] > 300, seen
+    with pytest.raises(P.ParseError, match="bogus_field|unknown|no field"):
+        P.parse_text('name: "x" bogus_field: 3', P.NetParameter)
