@@ -181,6 +181,7 @@ def measure_e2e(args, solver, rc, batch, world):
 
 def main():
     args = parse_args()
+    os.environ.setdefault("POSEIDON_SYNTHETIC_DATA", "1")     # the benchmark runs on stand-in data by contract (no datasets)
     if args.impl == "reference":
         reference_unavailable()
         return 0

@@ -27,6 +27,10 @@ def bench(fn):
 
 
 flops = 2.0 * M * N * Kd
+import os
+PAIR = int(os.environ.get("PSD_PAIR", "1"))
+K.set_pair_cta(PAIR)
+print(f"== cta_group::{2 if PAIR else 1} kernels ==", flush=True)
 for a_mn in (False, True):
     for b_mn in (False, True):
         if a_mn and not b_mn:

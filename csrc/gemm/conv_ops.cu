@@ -29,17 +29,20 @@ static int g_conv_im2col = 1;      // TMA im2col-mode operand fetch where the ge
 
 static int g_conv_cluster = 1;     // CTAs per cluster sharing the TMA operand by multicast (1 = off; measured slower at 2 on B200, kept as an option)
 
-template <int BN, bool A_MN, bool B_MN, int EPI, int GATHER>
+int pair_cta_enabled();
+
+template <int BN, bool A_MN, bool B_MN, int EPI, int GATHER, int CG = 1>
 static void launch_conv(const TmapSet& tm, const GemmParams& p, const ConvGeom& cg, int grid, cudaStream_t stream) {
-  auto kern = umma_gemm_kernel<BN, A_MN, B_MN, EPI, GATHER>;
-  constexpr int smem = GemmSmem<BN>::kTotal;
+  auto kern = umma_gemm_kernel<BN, A_MN, B_MN, EPI, GATHER, CG>;
+  constexpr int smem = GemmSmem<BN, CG>::kTotal;
   static bool configured = false;
   if (!configured) {
     C10_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   constexpr int threads = kNumThreads + (has_gather_warps(GATHER) ? kGatherThreads : 0);
-  if (p.cluster <= 1) {
+  const int cluster = CG == 2 ? 2 : p.cluster;
+  if (cluster <= 1) {
     kern<<<grid, threads, smem, stream>>>(tm, p, cg);
   } else {
     cudaLaunchConfig_t cfg{};
@@ -49,7 +52,7 @@ static void launch_conv(const TmapSet& tm, const GemmParams& p, const ConvGeom& 
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = p.cluster;
+    attr[0].val.clusterDim.x = cluster;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -57,6 +60,12 @@ static void launch_conv(const TmapSet& tm, const GemmParams& p, const ConvGeom& 
     C10_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm, p, cg));
   }
   C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+// Grid of a paired-CTA launch: one CTA pair per pair-tile, at most sms/2 pairs.
+static int pair_grid(long m_blocks, long n_blocks, long split, int sms) {
+  const long pair_tiles = ((m_blocks + 1) / 2) * n_blocks * split;
+  return static_cast<int>(2 * std::max<long>(1, std::min<long>(pair_tiles, sms / 2)));
 }
 
 // cluster size to use for a tile space of `tiles_along` blocks along the cluster dimension, and the grid
@@ -213,6 +222,18 @@ at::Tensor conv_fprop(const at::Tensor& x, const at::Tensor& wb, const c10::opti
     p.relu_slope = static_cast<float>(slope);
     p.alpha = 1.f;
     if (cl == 1 && try_im2col_map(&tm.a[0], cg, BLOCK_M)) {
+      if (pair_cta_enabled() && m_blocks >= 2) {
+        // paired CTAs: two pixel blocks share every weight tile; each CTA stages BN/2 weight rows
+        encode_tmap_bf16_2d(&tm.b[0], wptr, cg.K, Cout_g, cg.K, BLOCK_K, bn / 2);
+        const int pgrid = pair_grid(m_blocks, n_blocks, 1, sms);
+        switch (bn) {
+          case 64: launch_conv<64, false, false, EPI_BF16, IM2COL_A, 2>(tm, p, cg, pgrid, stream); break;
+          case 128: launch_conv<128, false, false, EPI_BF16, IM2COL_A, 2>(tm, p, cg, pgrid, stream); break;
+          case 192: launch_conv<192, false, false, EPI_BF16, IM2COL_A, 2>(tm, p, cg, pgrid, stream); break;
+          default: launch_conv<256, false, false, EPI_BF16, IM2COL_A, 2>(tm, p, cg, pgrid, stream); break;
+        }
+        continue;
+      }
       switch (bn) {
         case 64: launch_conv<64, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
         case 128: launch_conv<128, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
@@ -280,6 +301,17 @@ at::Tensor conv_dgrad(const at::Tensor& dy, const at::Tensor& wt, at::IntArrayRe
     p.alpha = 1.f;
     (void)mask_pitch;
     if (cl == 1 && try_im2col_map(&tm.a[0], cg, BLOCK_M)) {
+      if (pair_cta_enabled() && m_blocks >= 2) {
+        encode_tmap_bf16_2d(&tm.b[0], wptr, cg.K, Cg, cg.K, BLOCK_K, bn / 2);
+        const int pgrid = pair_grid(m_blocks, n_blocks, 1, sms);
+        switch (bn) {
+          case 64: launch_conv<64, false, false, EPI_BF16, IM2COL_A, 2>(tm, p, cg, pgrid, stream); break;
+          case 128: launch_conv<128, false, false, EPI_BF16, IM2COL_A, 2>(tm, p, cg, pgrid, stream); break;
+          case 192: launch_conv<192, false, false, EPI_BF16, IM2COL_A, 2>(tm, p, cg, pgrid, stream); break;
+          default: launch_conv<256, false, false, EPI_BF16, IM2COL_A, 2>(tm, p, cg, pgrid, stream); break;
+        }
+        continue;
+      }
       switch (bn) {
         case 64: launch_conv<64, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
         case 128: launch_conv<128, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
@@ -345,6 +377,14 @@ void conv_wgrad(const at::Tensor& x, const at::Tensor& dy, at::Tensor dw, at::In
     p.atomic = 1;
     p.alpha = static_cast<float>(alpha);
     if (cl == 1 && try_im2col_map(&tm.b[0], cg, BLOCK_K)) {
+      const long m_blocks = (Cout_g + BLOCK_M - 1) / BLOCK_M;
+      if (pair_cta_enabled() && m_blocks >= 2 && m_blocks % 2 == 0 && (bn == 128 || bn == 256)) {
+        // paired CTAs along Cout (even block counts only: a phantom block would waste a third of conv3's MMA work)
+        const int pgrid = pair_grid(m_blocks, n_blocks, split, sms);
+        if (bn == 128) launch_conv<128, true, true, EPI_F32, IM2COL_B, 2>(tm, p, cg, pgrid, stream);
+        else launch_conv<256, true, true, EPI_F32, IM2COL_B, 2>(tm, p, cg, pgrid, stream);
+        continue;
+      }
       switch (bn) {
         case 64: launch_conv<64, true, true, EPI_F32, IM2COL_B>(tm, p, cg, grid, stream); break;
         case 128: launch_conv<128, true, true, EPI_F32, IM2COL_B>(tm, p, cg, grid, stream); break;

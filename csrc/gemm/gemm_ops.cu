@@ -73,25 +73,63 @@ void encode_tmap_im2col_bf16(CUtensorMap* map, const void* base, int64_t C, int6
               " N=", N, " lower=", lower_w, ",", lower_h, " upper=", upper_w, ",", upper_h);
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+static int g_pair_cta = 1;        // cta_group::2 (paired CTAs) where the tile space allows it; 0 = single-CTA kernels only
+int pair_cta_enabled() { return g_pair_cta; }
+
+// Launch on a (CG,1,1) cluster.  grid is a multiple of CG.
+template <typename Kern>
+static void launch_clustered(Kern kern, int grid, int threads, int smem, int cluster, cudaStream_t stream, const TmapSet& tm,
+                             const GemmParams& p, const ConvGeom& cg) {
+  if (cluster <= 1) {
+    kern<<<grid, threads, smem, stream>>>(tm, p, cg);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    C10_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm, p, cg));
+  }
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI, int CG>
 static void launch(const TmapSet& tm, const GemmParams& p, int grid, cudaStream_t stream) {
-  auto kern = umma_gemm_kernel<BN, A_MN, B_MN, EPI>;
-  constexpr int smem = GemmSmem<BN>::kTotal;
+  auto kern = umma_gemm_kernel<BN, A_MN, B_MN, EPI, GATHER_NONE, CG>;
+  constexpr int smem = GemmSmem<BN, CG>::kTotal;
   static bool configured = false;
   if (!configured) {
     C10_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  kern<<<grid, kNumThreads, smem, stream>>>(tm, p, ConvGeom{});
-  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  launch_clustered(kern, grid, kNumThreads, smem, CG, stream, tm, p, ConvGeom{});
 }
 
 template <bool A_MN, bool B_MN, int EPI>
-static void dispatch_bn(int bn, const TmapSet& tm, const GemmParams& p, int grid, cudaStream_t s) {
+static void dispatch_bn(int bn, int cg, const TmapSet& tm, const GemmParams& p, int grid, cudaStream_t s) {
+  if (cg == 2) {
+    switch (bn) {
+      case 64:
+        if constexpr (!B_MN) launch<64, A_MN, B_MN, EPI, 2>(tm, p, grid, s);
+        else TORCH_CHECK(false, "paired CTAs with an MN-major B need BLOCK_N >= 128");
+        break;
+      case 128: launch<128, A_MN, B_MN, EPI, 2>(tm, p, grid, s); break;
+      case 256: launch<256, A_MN, B_MN, EPI, 2>(tm, p, grid, s); break;
+      default: TORCH_CHECK(false, "unsupported BLOCK_N ", bn);
+    }
+    return;
+  }
   switch (bn) {
-    case 64: launch<64, A_MN, B_MN, EPI>(tm, p, grid, s); break;
-    case 128: launch<128, A_MN, B_MN, EPI>(tm, p, grid, s); break;
-    case 256: launch<256, A_MN, B_MN, EPI>(tm, p, grid, s); break;
+    case 64: launch<64, A_MN, B_MN, EPI, 1>(tm, p, grid, s); break;
+    case 128: launch<128, A_MN, B_MN, EPI, 1>(tm, p, grid, s); break;
+    case 256: launch<256, A_MN, B_MN, EPI, 1>(tm, p, grid, s); break;
     default: TORCH_CHECK(false, "unsupported BLOCK_N ", bn);
   }
 }
@@ -119,11 +157,15 @@ void gemm_launch(const std::vector<int64_t>& a_ptrs, bool a_mn, int64_t lda, con
   const auto* prop = at::cuda::getCurrentDeviceProperties();
   const int sms = prop->multiProcessorCount;
   if (bn <= 0) bn = pick_bn(M, N, sms);
+  const int64_t m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+  // Paired CTAs (cta_group::2): two m-blocks share every B tile.  Needs >= 2 m-blocks, an even CTA budget, and — for an
+  // MN-major B — a half tile made of whole 64-column chunks.
+  int cgp = (g_pair_cta && m_blocks >= 2 && (!b_mn || bn >= 128) && (max_ctas <= 0 || max_ctas >= 2)) ? 2 : 1;
   TmapSet tm;
   for (int s = 0; s < nsrc; ++s) {
     if (!a_mn) encode_tmap_bf16_2d(&tm.a[s], reinterpret_cast<void*>(a_ptrs[s]), K, M, lda, BLOCK_K, BLOCK_M);
     else       encode_tmap_bf16_2d(&tm.a[s], reinterpret_cast<void*>(a_ptrs[s]), M, K, lda, 64, BLOCK_K);
-    if (!b_mn) encode_tmap_bf16_2d(&tm.b[s], reinterpret_cast<void*>(b_ptrs[s]), K, N, ldb, BLOCK_K, bn);
+    if (!b_mn) encode_tmap_bf16_2d(&tm.b[s], reinterpret_cast<void*>(b_ptrs[s]), K, N, ldb, BLOCK_K, bn / cgp);
     else       encode_tmap_bf16_2d(&tm.b[s], reinterpret_cast<void*>(b_ptrs[s]), N, K, ldb, 64, BLOCK_K);
   }
   p.M = static_cast<int>(M);
@@ -132,19 +174,21 @@ void gemm_launch(const std::vector<int64_t>& a_ptrs, bool a_mn, int64_t lda, con
   p.num_src = nsrc;
   if (p.split_k < 1) p.split_k = 1;
   p.split_k = std::min(p.split_k, p.kb_per_src * nsrc);
-  const int64_t tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + bn - 1) / bn) * p.split_k;
-  int grid = static_cast<int>(std::min<int64_t>(tiles, max_ctas > 0 ? max_ctas : sms));
+  const int64_t m_units = cgp == 2 ? (m_blocks + 1) / 2 : m_blocks;
+  const int64_t tiles = m_units * ((N + bn - 1) / bn) * p.split_k;          // CTA (or CTA-pair) tiles
+  const int budget = (max_ctas > 0 ? max_ctas : sms) / cgp;
+  int grid = static_cast<int>(std::min<int64_t>(tiles, budget)) * cgp;
   if (!a_mn && !b_mn) {
-    if (epi == EPI_BF16) dispatch_bn<false, false, EPI_BF16>(bn, tm, p, grid, stream);
-    else if (epi == EPI_F32) dispatch_bn<false, false, EPI_F32>(bn, tm, p, grid, stream);
+    if (epi == EPI_BF16) dispatch_bn<false, false, EPI_BF16>(bn, cgp, tm, p, grid, stream);
+    else if (epi == EPI_F32) dispatch_bn<false, false, EPI_F32>(bn, cgp, tm, p, grid, stream);
     else TORCH_CHECK(false, "EPI_SGD requires MN-major operands");
   } else if (!a_mn && b_mn) {
-    if (epi == EPI_BF16) dispatch_bn<false, true, EPI_BF16>(bn, tm, p, grid, stream);
-    else if (epi == EPI_F32) dispatch_bn<false, true, EPI_F32>(bn, tm, p, grid, stream);
+    if (epi == EPI_BF16) dispatch_bn<false, true, EPI_BF16>(bn, cgp, tm, p, grid, stream);
+    else if (epi == EPI_F32) dispatch_bn<false, true, EPI_F32>(bn, cgp, tm, p, grid, stream);
     else TORCH_CHECK(false, "K-major x MN-major supports the bf16 / fp32 epilogues");
   } else if (a_mn && b_mn) {
-    if (epi == EPI_F32) dispatch_bn<true, true, EPI_F32>(bn, tm, p, grid, stream);
-    else if (epi == EPI_SGD) dispatch_bn<true, true, EPI_SGD>(bn, tm, p, grid, stream);
+    if (epi == EPI_F32) dispatch_bn<true, true, EPI_F32>(bn, cgp, tm, p, grid, stream);
+    else if (epi == EPI_SGD) dispatch_bn<true, true, EPI_SGD>(bn, cgp, tm, p, grid, stream);
     else TORCH_CHECK(false, "MN-major x MN-major supports fp32 / SGD epilogues");
   } else {
     TORCH_CHECK(false, "MN-major A with K-major B is not instantiated");
@@ -310,9 +354,12 @@ void sfb_outer_f32(std::vector<int64_t> u_ptrs, std::vector<int64_t> v_ptrs, int
               at::cuda::getCurrentCUDAStream());
 }
 
+void set_pair_cta(int64_t on) { g_pair_cta = on != 0; }
+
 }  // namespace psd
 
 TORCH_LIBRARY_FRAGMENT(poseidon, m) {
+  m.def("set_pair_cta(int on) -> ()", &psd::set_pair_cta);
   m.def("sfb_outer_f32(int[] u_ptrs, int[] v_ptrs, int Mb, int N, int K, Tensor(a!) out, float alpha, Tensor? flags, "
         "int epoch, int src_rot, int bn, int max_ctas, Tensor? epoch_dev) -> ()", &psd::sfb_outer_f32);
   m.def("gemm_bf16(Tensor a, bool a_mn, Tensor b, bool b_mn, Tensor? bias, bool relu, float slope, Tensor? mask, "

@@ -77,16 +77,18 @@ struct GemmParams {
   const uint32_t* epoch_dev;   // optional device-resident step counter added to `epoch` (CUDA-graph replays)
 };
 
-template <int BN>
+// CG = CTAs per UMMA (1, or 2 = paired CTAs: each CTA stages its own 128 rows of A but only BN/2 rows of B).
+template <int BN, int CG = 1>
 struct GemmSmem {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;     // 16 KB
-  static constexpr int kBBytes = BN * BLOCK_K * 2;
+  static constexpr int kBBytes = (BN / CG) * BLOCK_K * 2;   // this CTA's share of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN >= 192) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kStages = CG == 2 ? (BN >= 192 ? 6 : 8) : ((BN >= 192) ? 4 : (BN >= 128 ? 6 : 8));
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);   // power of two >= 2 accumulators
   static constexpr int kBarBytes = 256;
   static constexpr int kEpiStageBytes = kEpiWarps * 32 * 33 * 4;    // per epilogue warp: 32x32 fp32 transpose tile (+1 pad)
   static constexpr int kTotal = kStages * kStageBytes + kBarBytes + kEpiStageBytes + 1024;  // +1024 alignment slack
+  static_assert(kTotal <= 232448, "shared memory budget (227 KB per CTA)");
 };
 
 __device__ __forceinline__ float sgd_apply(float acc, float& w, float& h, const GemmParams& p, float lr) {
@@ -234,31 +236,40 @@ __device__ __forceinline__ void sgd_rows_from_slab(const GemmParams& p, const fl
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 
-// Producer policy: both operands via TMA.
-template <int BN, bool A_MN, bool B_MN>
+// Producer policy: both operands via TMA.  CG == 2: the loads complete on the LEADER CTA's full barrier (`bar` is then its
+// shared::cluster address with the rank bit cleared) and this CTA fetches only its half of the B tile (rows / columns
+// [crank * BN/2, (crank + 1) * BN/2) of the tile).
+template <int CG>
+__device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  if constexpr (CG == 2) tma_load_2d_cg2(dst, map, bar, x, y);
+  else tma_load_2d_u32(dst, map, bar, x, y);
+}
+template <int BN, bool A_MN, bool B_MN, int CG = 1>
 struct TmaProducer {
-  __device__ static void load_a(const TmapSet& tm, int src, int kb, int m_blk, uint8_t* sa, uint64_t* full) {
+  static_assert(CG == 1 || !B_MN || (BN / CG) % 64 == 0, "MN-major B: each CTA's share must be whole 64-column chunks");
+  __device__ static void load_a(const TmapSet& tm, int src, int kb, int m_blk, uint32_t sa, uint32_t bar) {
     const int k0 = kb * BLOCK_K;
     if constexpr (!A_MN) {
-      tma_load_2d(sa, &tm.a[src], full, k0, m_blk * BLOCK_M);
+      tma_2d<CG>(sa, &tm.a[src], bar, k0, m_blk * BLOCK_M);
     } else {
 #pragma unroll
-      for (int c = 0; c < BLOCK_M / 64; ++c) tma_load_2d(sa + c * 8192, &tm.a[src], full, m_blk * BLOCK_M + 64 * c, k0);
+      for (int c = 0; c < BLOCK_M / 64; ++c) tma_2d<CG>(sa + c * 8192, &tm.a[src], bar, m_blk * BLOCK_M + 64 * c, k0);
     }
   }
-  __device__ static void load_b(const TmapSet& tm, int src, int kb, int n_blk, uint8_t* sb, uint64_t* full) {
+  __device__ static void load_b(const TmapSet& tm, int src, int kb, int n_blk, int crank, uint32_t sb, uint32_t bar) {
     const int k0 = kb * BLOCK_K;
+    const int n0 = n_blk * BN + crank * (BN / CG);
     if constexpr (!B_MN) {
-      tma_load_2d(sb, &tm.b[src], full, k0, n_blk * BN);
+      tma_2d<CG>(sb, &tm.b[src], bar, k0, n0);                 // tensor-map box: BN / CG rows
     } else {
 #pragma unroll
-      for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &tm.b[src], full, n_blk * BN + 64 * c, k0);
+      for (int c = 0; c < BN / CG / 64; ++c) tma_2d<CG>(sb + c * 8192, &tm.b[src], bar, n0 + 64 * c, k0);
     }
   }
-  __device__ static void load_stage(const TmapSet& tm, int src, int kb, int m_blk, int n_blk, uint8_t* sa,
-                                    uint8_t* sb, uint64_t* full) {
-    load_a(tm, src, kb, m_blk, sa, full);
-    load_b(tm, src, kb, n_blk, sb, full);
+  __device__ static void load_stage(const TmapSet& tm, int src, int kb, int m_blk, int n_blk, int crank, uint32_t sa,
+                                    uint32_t sb, uint32_t bar) {
+    load_a(tm, src, kb, m_blk, sa, bar);
+    load_b(tm, src, kb, n_blk, crank, sb, bar);
   }
 };
 
@@ -295,14 +306,38 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int m_blocks, int n_block
   return tc;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, int GATHER = GATHER_NONE>
+// Paired CTAs: the pair walks (pair of m-blocks, n-block, split) tiles; CTA `crank` of the pair owns m-block 2*mp + crank.
+// A phantom m-block past the edge (odd m_blocks) is harmless: its loads are out of range (zero-filled) and its
+// epilogue rows are skipped.
+template <bool NFAST>
+__device__ __forceinline__ TileCoord tile_coord_pair(int t, int m_pairs, int n_blocks, int crank) {
+  TileCoord tc;
+  int mp;
+  if (NFAST) {
+    tc.n_blk = t % n_blocks;
+    const int rest = t / n_blocks;
+    mp = rest % m_pairs;
+    tc.split = rest / m_pairs;
+  } else {
+    mp = t % m_pairs;
+    const int rest = t / m_pairs;
+    tc.n_blk = rest % n_blocks;
+    tc.split = rest / n_blocks;
+  }
+  tc.m_blk = 2 * mp + crank;
+  return tc;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI, int GATHER = GATHER_NONE, int CG = 1>
 __global__ void __launch_bounds__(kNumThreads + (has_gather_warps(GATHER) ? kGatherThreads : 0), 1)
 umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const ConvGeom cg) {
+  static_assert(CG == 1 || CG == 2, "one CTA or a CTA pair per UMMA");
+  static_assert(CG == 1 || !has_gather_warps(GATHER), "paired CTAs need TMA producers (cp.async cannot signal the leader)");
   static_assert(GATHER != GATHER_A || !A_MN, "gathered A is produced K-major");
   static_assert(GATHER != GATHER_B || B_MN, "gathered B is produced MN-major");
   static_assert(GATHER != IM2COL_A || !A_MN, "im2col A is K-major");
   static_assert(GATHER != IM2COL_B || B_MN, "im2col B is MN-major");
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, CG>;
   constexpr int kStages = S::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -320,12 +355,19 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
   const int m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int n_blocks = (p.N + BN - 1) / BN;
   const int total_kb = p.kb_per_src * p.num_src;
-  const int C = (has_gather_warps(GATHER) && p.cluster > 1) ? p.cluster : 1;
-  const int crank = C > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int C = (CG == 1 && has_gather_warps(GATHER) && p.cluster > 1) ? p.cluster : 1;
+  const int crank = (C > 1 || CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+  const bool leader = CG == 1 || crank == 0;            // CG == 2: cluster rank 0 issues the MMAs for the pair
   const uint16_t cmask = static_cast<uint16_t>((1u << C) - 1);
   // cluster-level tile space and stride
-  const int num_tiles = (GATHER == GATHER_B ? m_blocks * ((n_blocks + C - 1) / C) : ((m_blocks + C - 1) / C) * n_blocks) * p.split_k;
-  const int tile0 = blockIdx.x / C, tile_step = gridDim.x / C;
+  const int m_pairs = (m_blocks + 1) / 2;
+  const int num_tiles = CG == 2 ? m_pairs * n_blocks * p.split_k
+                                : (GATHER == GATHER_B ? m_blocks * ((n_blocks + C - 1) / C) : ((m_blocks + C - 1) / C) * n_blocks) * p.split_k;
+  const int tile0 = blockIdx.x / (C * CG), tile_step = gridDim.x / (C * CG);
+  auto coord = [&](int t) -> TileCoord {
+    if constexpr (CG == 2) return tile_coord_pair<EPI == EPI_SGD>(t, m_pairs, n_blocks, crank);
+    else return tile_coord<GATHER, EPI == EPI_SGD>(t, m_blocks, n_blocks, C, crank);
+  };
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.num_src; ++s) {
@@ -335,22 +377,26 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1 + (has_gather_warps(GATHER) ? kGatherThreads : 0));
+      mbar_init(&full_bar[s], 1 + (has_gather_warps(GATHER) ? kGatherThreads : 0));   // CG == 2: only the leader's is used
       mbar_init(&empty_bar[s], C);        // released by the MMA thread of every CTA sharing the multicast operand
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], kEpiWarps);   // one arrive per epilogue warp
+      mbar_init(&tmem_empty[s], kEpiWarps * CG);   // one arrive per epilogue warp (CG == 2: of both CTAs, on the leader's)
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, S::kTmemCols);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc_cg2(tmem_slot, S::kTmemCols);
+    } else {
+      tmem_alloc(tmem_slot, S::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (C > 1) cluster_sync_all();        // peers' barriers are initialised before any remote arrive / multicast
+  if (C > 1 || CG == 2) cluster_sync_all();   // peers' barriers / TMEM exist before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -364,7 +410,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const TileCoord tc = tile_coord<GATHER, EPI == EPI_SGD>(tile, m_blocks, n_blocks, C, crank);
+        const TileCoord tc = coord(tile);
         const int m_blk = tc.m_blk, n_blk = tc.n_blk, split = tc.split;
         const int g0 = static_cast<int>(static_cast<long>(total_kb) * split / p.split_k);
         const int g1 = static_cast<int>(static_cast<long>(total_kb) * (split + 1) / p.split_k);
@@ -372,8 +418,8 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
         [[maybe_unused]] int im_w = 0, im_h = 0, im_n = 0;
         [[maybe_unused]] const int im_org_w = cg.off_w - (cg.dr < 0 ? cg.S - 1 : 0);
         [[maybe_unused]] const int im_org_h = cg.off_h - (cg.dr < 0 ? cg.R - 1 : 0);
-        [[maybe_unused]] int im_c0[BN / 64];
-        [[maybe_unused]] uint16_t im_offw[BN / 64], im_offh[BN / 64];
+        [[maybe_unused]] int im_c0[BN / CG / 64 > 0 ? BN / CG / 64 : 1];
+        [[maybe_unused]] uint16_t im_offw[BN / CG / 64 > 0 ? BN / CG / 64 : 1], im_offh[BN / CG / 64 > 0 ? BN / CG / 64 : 1];
         if constexpr (GATHER == IM2COL_A) {
           const uint32_t m0 = static_cast<uint32_t>(m_blk) * BLOCK_M;
           const uint32_t n_img = fdiv(m0, cg.div_ohow);
@@ -386,8 +432,8 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
         }
         if constexpr (GATHER == IM2COL_B) {
 #pragma unroll
-          for (int c = 0; c < BN / 64; ++c) {
-            int kc = n_blk * BN + c * 64;
+          for (int c = 0; c < BN / CG / 64; ++c) {
+            int kc = n_blk * BN + crank * (BN / CG) + c * 64;
             if (kc >= cg.K) kc = 0;                      // columns past K are dropped by the epilogue: load anything valid
             const int tap = static_cast<int>(fdiv(static_cast<uint32_t>(kc), cg.div_cg));
             im_c0[c] = kc - tap * cg.Cgk;
@@ -415,9 +461,12 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kStageBytes;
           if (elect_one()) {
+          // completion barrier of this stage's loads: own full barrier, or (paired CTAs) the leader's
+          const uint32_t fbar = CG == 2 ? (smem_u32(&full_bar[stage]) & kPeerBitMask) : smem_u32(&full_bar[stage]);
+          const uint32_t sa32 = smem_u32(sa), sb32 = sa32 + S::kABytes;
           if constexpr (GATHER == GATHER_NONE) {
-            mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
-            TmaProducer<BN, A_MN, B_MN>::load_stage(tm, src, kb, m_blk, n_blk, sa, sa + S::kABytes, &full_bar[stage]);
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], CG * S::kStageBytes);
+            TmaProducer<BN, A_MN, B_MN, CG>::load_stage(tm, src, kb, m_blk, n_blk, crank, sa32, sb32, fbar);
           } else if constexpr (GATHER == IM2COL_A) {
             // A tile = 128 output pixels x 64 channels of tap (r, s): one im2col-mode TMA instruction
             const int k0 = g * BLOCK_K;
@@ -427,29 +476,39 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
             const int sx = tap - r * cg.S;
             const bool in_k = k0 < cg.K;
             const int offw = cg.dr > 0 ? sx : cg.S - 1 - sx, offh = cg.dr > 0 ? r : cg.R - 1 - r;
-            mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], CG * S::kStageBytes);
             // k-blocks past K (K % 64 != 0 never happens here: C_g % 64 == 0) — keep the guard cheap
-            tma_load_im2col_4d(smem_u32(sa), &tm.a[0], smem_u32(&full_bar[stage]), in_k ? c0 : 0, im_w, im_h, im_n,
-                               static_cast<uint16_t>(in_k ? offw : 0), static_cast<uint16_t>(in_k ? offh : 0));
-            TmaProducer<BN, A_MN, B_MN>::load_b(tm, src, kb, n_blk, sa + S::kABytes, &full_bar[stage]);
+            if constexpr (CG == 2)
+              tma_load_im2col_4d_cg2(sa32, &tm.a[0], fbar, in_k ? c0 : 0, im_w, im_h, im_n,
+                                     static_cast<uint16_t>(in_k ? offw : 0), static_cast<uint16_t>(in_k ? offh : 0));
+            else
+              tma_load_im2col_4d(sa32, &tm.a[0], fbar, in_k ? c0 : 0, im_w, im_h, im_n,
+                                 static_cast<uint16_t>(in_k ? offw : 0), static_cast<uint16_t>(in_k ? offh : 0));
+            TmaProducer<BN, A_MN, B_MN, CG>::load_b(tm, src, kb, n_blk, crank, sb32, fbar);
           } else if constexpr (GATHER == IM2COL_B) {
-            // B tile = BN/64 chunks of [64 reduction pixels][64 channels of one tap]; the pixels advance with g
+            // B tile = BN/64 chunks of [64 reduction pixels][64 channels of one tap]; the pixels advance with g.
+            // Paired CTAs: this CTA fetches chunks [crank * BN/128, (crank + 1) * BN/128) of the tile.
             const uint32_t m0 = static_cast<uint32_t>(g) * BLOCK_K;
             const uint32_t n_img = fdiv(m0, cg.div_ohow);
             const uint32_t rem = m0 - n_img * static_cast<uint32_t>(cg.OH * cg.OW);
             const uint32_t oh = fdiv(rem, cg.div_ow);
             const uint32_t ow = rem - oh * static_cast<uint32_t>(cg.OW);
             const int bw = static_cast<int>(ow) * cg.sw + im_org_w, bh = static_cast<int>(oh) * cg.sh + im_org_h;
-            mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], CG * S::kStageBytes);
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              tma_load_im2col_4d(smem_u32(sa + S::kABytes + c * 8192), &tm.b[0], smem_u32(&full_bar[stage]), im_c0[c], bw, bh,
-                                 static_cast<int>(n_img), im_offw[c], im_offh[c]);
-            TmaProducer<BN, A_MN, B_MN>::load_a(tm, src, kb, m_blk, sa, &full_bar[stage]);
+            for (int c = 0; c < BN / CG / 64; ++c) {
+              if constexpr (CG == 2)
+                tma_load_im2col_4d_cg2(sb32 + c * 8192, &tm.b[0], fbar, im_c0[c], bw, bh, static_cast<int>(n_img), im_offw[c],
+                                       im_offh[c]);
+              else
+                tma_load_im2col_4d(sb32 + c * 8192, &tm.b[0], fbar, im_c0[c], bw, bh, static_cast<int>(n_img), im_offw[c],
+                                   im_offh[c]);
+            }
+            TmaProducer<BN, A_MN, B_MN, CG>::load_a(tm, src, kb, m_blk, sa32, fbar);
           } else if constexpr (GATHER == GATHER_A) {
             mbar_arrive_expect_tx(&full_bar[stage], S::kBBytes);     // the whole B tile lands here (C slices)
             if (C == 1) {
-              TmaProducer<BN, A_MN, B_MN>::load_b(tm, src, kb, n_blk, sa + S::kABytes, &full_bar[stage]);
+              TmaProducer<BN, A_MN, B_MN>::load_b(tm, src, kb, n_blk, 0, sb32, fbar);
             } else {
               // this CTA fetches rows [crank*BN/C, (crank+1)*BN/C) of the K-major weight tile for the whole cluster
               const int rows = BN / C;
@@ -459,7 +518,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], S::kABytes);
             if (C == 1) {
-              TmaProducer<BN, A_MN, B_MN>::load_a(tm, src, kb, m_blk, sa, &full_bar[stage]);
+              TmaProducer<BN, A_MN, B_MN>::load_a(tm, src, kb, m_blk, sa32, fbar);
             } else {
               // dY^T tile (MN-major: 2 chunks of [64 k-rows][64 cout]); CTA `crank` fetches k-rows [crank*64/C, ...)
               const int krows = BLOCK_K / C;
@@ -480,15 +539,15 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+  } else if (warp == 1 && leader) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues; paired CTAs: leader only) ==========
     {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, A_MN, B_MN);
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M * CG, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
-        const int split = tile_coord<GATHER, EPI == EPI_SGD>(tile, m_blocks, n_blocks, C, crank).split;
+        const int split = coord(tile).split;
         const int g0 = static_cast<int>(static_cast<long>(total_kb) * split / p.split_k);
         const int g1 = static_cast<int>(static_cast<long>(total_kb) * (split + 1) / p.split_k);
         const int as = it & 1;
@@ -507,17 +566,26 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
                                        : make_smem_desc(a_addr + k * (UMMA_K * 2), 16, 1024);
               const uint64_t db = B_MN ? make_smem_desc(b_addr + k * (UMMA_K * 128), 8192, 1024)
                                        : make_smem_desc(b_addr + k * (UMMA_K * 2), 16, 1024);
-              umma_bf16(d_tmem, da, db, idesc, (g > g0 || k > 0) ? 1u : 0u);
+              if constexpr (CG == 2) umma_bf16_cg2(d_tmem, da, db, idesc, (g > g0 || k > 0) ? 1u : 0u);
+              else umma_bf16(d_tmem, da, db, idesc, (g > g0 || k > 0) ? 1u : 0u);
             }
-            // frees the smem slot when these MMAs retire — in every CTA that shares the multicast operand
-            if (C == 1) umma_commit(&empty_bar[stage]);
-            else umma_commit_mcast(&empty_bar[stage], cmask);
-            if (g == g1 - 1) umma_commit(&tmem_full[as]);      // accumulator complete -> epilogue
+            // frees the smem slot when these MMAs retire — in every CTA that shares the multicast operand / the pair
+            if constexpr (CG == 2) {
+              umma_commit_cg2(&empty_bar[stage], 0x3);
+              if (g == g1 - 1) umma_commit_cg2(&tmem_full[as], 0x3);   // accumulator complete -> both CTAs' epilogues
+            } else {
+              if (C == 1) umma_commit(&empty_bar[stage]);
+              else umma_commit_mcast(&empty_bar[stage], cmask);
+              if (g == g1 - 1) umma_commit(&tmem_full[as]);      // accumulator complete -> epilogue
+            }
           }
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        if (g0 >= g1 && elect_one()) umma_commit(&tmem_full[as]);      // (never: every split owns >= 1 k-block)
+        if (g0 >= g1 && elect_one()) {                                  // (never: every split owns >= 1 k-block)
+          if constexpr (CG == 2) umma_commit_cg2(&tmem_full[as], 0x3);
+          else umma_commit(&tmem_full[as]);
+        }
       }
     }
   } else if (has_gather_warps(GATHER) && warp >= kGatherWarp0) {
@@ -530,7 +598,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-      const TileCoord tc = tile_coord<GATHER, EPI == EPI_SGD>(tile, m_blocks, n_blocks, C, crank);
+      const TileCoord tc = coord(tile);
       const int m_blk = tc.m_blk, n_blk = tc.n_blk, split = tc.split;
       const int g0 = static_cast<int>(static_cast<long>(total_kb) * split / p.split_k);
       const int g1 = static_cast<int>(static_cast<long>(total_kb) * (split + 1) / p.split_k);
@@ -601,7 +669,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
     constexpr bool kSgdPrefetch = false;
     auto prefetch_sgd_tile = [&](int t) {
       if (EPI != EPI_SGD || t >= num_tiles || (p.N & 3) != 0 || (p.ldc & 3) != 0) return;
-      const TileCoord pc = tile_coord<GATHER, EPI == EPI_SGD>(t, m_blocks, n_blocks, C, crank);
+      const TileCoord pc = coord(t);
       const int te = (warp - kEpiWarp0) * 32 + lane;      // 0..255: row = te >> 1, W or H = te & 1
       const int row = pc.m_blk * BLOCK_M + (te >> 1);
       const int col = pc.n_blk * BN;
@@ -614,7 +682,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
     };
     if (kSgdPrefetch) prefetch_sgd_tile(tile0);
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
-      const TileCoord tc = tile_coord<GATHER, EPI == EPI_SGD>(tile, m_blocks, n_blocks, C, crank);
+      const TileCoord tc = coord(tile);
       const int m_blk = tc.m_blk, n_blk = tc.n_blk;
       const int as = it & 1;
       if (kSgdPrefetch) prefetch_sgd_tile(tile + tile_step);
@@ -651,16 +719,20 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tmem_empty[as]);
+        else mbar_arrive_remote(&tmem_empty[as], 0);      // the pair's accumulator buffer is released on the leader
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (C > 1) cluster_sync_all();        // no CTA leaves while peers may still arrive on its barriers
+  if (C > 1 || CG == 2) cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer may still touch it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, S::kTmemCols);
+    if constexpr (CG == 2) tmem_dealloc_cg2(tmem_base, S::kTmemCols);
+    else tmem_dealloc(tmem_base, S::kTmemCols);
   }
 }
 

@@ -16,7 +16,8 @@ from .. import proto as P
 
 
 class DataTransformer:
-    def __init__(self, tp, phase, device="cpu", seed: Optional[int] = None, model_dir=None):
+    def __init__(self, tp, phase, device="cpu", seed: Optional[int] = None, model_dir=None,
+                 allow_missing_mean: bool = False):
         self.scale = float(tp.scale)
         self.mirror = bool(tp.mirror)
         self.crop = int(tp.crop_size)
@@ -30,10 +31,14 @@ class DataTransformer:
             if os.path.exists(path):
                 blob = P.read_binary(path, P.BlobProto)
                 self.mean = torch.from_numpy(P.blob_to_array(blob)[0].copy()).to(self.device)
-            else:
+            elif os.environ.get("POSEIDON_SYNTHETIC_DATA", "0") == "1" or allow_missing_mean:
                 import logging
                 logging.getLogger("poseidon_b200").warning(
-                    "mean_file %s not found; using zero mean", path)
+                    "mean_file %s not found; using zero mean (synthetic data explicitly allowed)", path)
+            else:
+                # reference: data_transformer.cpp:19-27 CHECKs that the mean file can be read
+                raise IOError(f"mean_file {path} not found (set POSEIDON_SYNTHETIC_DATA=1 / --synthetic_shape to run "
+                              "without it on stand-in data)")
         if len(tp.mean_value):
             if tp.has("mean_file"):
                 raise ValueError("Cannot specify mean_file and mean_value at the same time")

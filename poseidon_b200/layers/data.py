@@ -27,6 +27,21 @@ def _resolve(ctx, path):
     return resolve(path, ctx.model_dir)
 
 
+def synthetic_allowed(ctx) -> bool:
+    """Stand-in data is an explicit request, never a silent fallback: ``--synthetic_shape`` / ``data_shape_hint=`` or
+    ``POSEIDON_SYNTHETIC_DATA=1`` (set by bench.py, smoke() and the test-suite).  Otherwise an unopenable source is
+    fatal, like the reference's LOG(FATAL) (src/caffe/layers/data_layer.cpp:118-141)."""
+    return ctx.data_shape_hint is not None or os.environ.get("POSEIDON_SYNTHETIC_DATA", "0") == "1"
+
+
+def _no_source(ctx, layer_name, what):
+    if not synthetic_allowed(ctx):
+        raise IOError(f"data layer '{layer_name}': {what}. Refusing to train on synthetic data; pass "
+                      "--synthetic_shape CxHxW (or set POSEIDON_SYNTHETIC_DATA=1) to request stand-in data explicitly")
+    if ctx.rank == 0:
+        log.warning("data layer '%s': %s -> synthetic data (explicitly allowed)", layer_name, what)
+
+
 def _guess_shape(ctx, source: str, crop: int):
     """Shape of synthetic stand-in data when the named DB is not present on this box."""
     if ctx.data_shape_hint is not None:
@@ -55,7 +70,8 @@ class BasePrefetchingDataLayer(Layer):
 
     def setup(self, bottom_shapes):
         self.transformer = DataTransformer(self.lp.transform_param, self.ctx.phase, self.ctx.device,
-                                           seed=self.ctx.seed, model_dir=self.ctx.model_dir)
+                                           seed=self.ctx.seed, model_dir=self.ctx.model_dir,
+                                           allow_missing_mean=synthetic_allowed(self.ctx))
         self.source = self.make_source()
         x, y = self.source.next_batch()
         self._first = (x, y)
@@ -129,9 +145,8 @@ class DataLayer(BasePrefetchingDataLayer):
         try:
             reader = open_db(path, dp.enum_name("backend"))
         except (IOError, OSError) as e:
+            _no_source(self.ctx, self.layer_name, f"cannot open {path}: {e}")
             shape, ncls = _guess_shape(self.ctx, src, int(self.lp.transform_param.crop_size))
-            if self.ctx.rank == 0:
-                log.warning("DATA layer '%s': %s -> synthetic %s uint8 data", self.layer_name, e, shape)
             return SyntheticSource(batch, shape, ncls, seed=1234 + self.ctx.rank)
         off, stride = shard_indices(len(reader), shared, nclients, client, nthreads, thread)
         from ..data.lmdb_reader import LMDBFile
@@ -160,8 +175,7 @@ class ImageDataLayer(BasePrefetchingDataLayer):
             shape, ncls = _guess_shape(self.ctx, src, int(self.lp.transform_param.crop_size))
             if ip.new_height and ip.new_width:
                 shape = (3, int(ip.new_height), int(ip.new_width))
-            if self.ctx.rank == 0:
-                log.warning("IMAGE_DATA layer '%s': list %s missing -> synthetic %s", self.layer_name, src, shape)
+            _no_source(self.ctx, self.layer_name, f"image list {src!r} missing")
             return SyntheticSource(batch, shape, ncls, seed=4321 + self.ctx.rank)
         from ..data.images import ImageListSource
         nthreads = getattr(self.ctx, "threads_per_client", 1)
@@ -182,8 +196,7 @@ class WindowDataLayer(BasePrefetchingDataLayer):
         src = _resolve(self.ctx, wp.source)
         crop = int(self.lp.transform_param.crop_size)
         if not src or not os.path.exists(src):
-            if self.ctx.rank == 0:
-                log.warning("WINDOW_DATA layer '%s': window file missing -> synthetic", self.layer_name)
+            _no_source(self.ctx, self.layer_name, f"window file {src!r} missing")
             return SyntheticSource(int(wp.batch_size), (3, crop or 227, crop or 227), 21, seed=99 + self.ctx.rank)
         from ..data.images import WindowSource
         return WindowSource(src, int(wp.batch_size), crop, float(wp.fg_threshold), float(wp.bg_threshold),

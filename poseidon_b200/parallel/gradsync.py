@@ -98,10 +98,10 @@ def apply_rule(hyper: Hyper, w, g, h, lr_mult, decay_mult, decay_scale=1.0):
             R.adagrad_step(w, g, h, lr, hyper.delta, wd, hyper.l1)
 
 
-def compute_update(hyper: Hyper, w, g, h, lr_mult, decay_mult):
+def compute_update(hyper: Hyper, w, g, h, lr_mult, decay_mult, decay_scale=1.0):
     """Return the step Δ (so that w_new = w − Δ) and advance the history, without touching w."""
     lr = hyper.lr * lr_mult
-    wd = hyper.weight_decay * decay_mult
+    wd = hyper.weight_decay * decay_mult * decay_scale
     with torch.no_grad():
         if wd:
             g = g + wd * (torch.sign(w) if hyper.l1 else w)
@@ -208,6 +208,16 @@ class TorchDistBackend(Backend):
         return out
 
 
+def _apply_global_grad_step(sync, hyper, p, h, lr_mult, decay_mult):
+    """Step a parameter whose gradient is already the global sum (library SFB): equals the sum of the per-worker
+    updates the SSP backends would otherwise exchange (decay × world size, like TorchDistBackend's `sum` mode)."""
+    ws = sync.rank_ctx.world_size
+    delta = compute_update(hyper, p.data, p.grad, h, lr_mult, decay_mult, decay_scale=float(ws))
+    with torch.no_grad():
+        p.data.sub_(delta)
+    sync.invalidate_operands(p)
+
+
 class SSPBackend(Backend):
     """Stale-synchronous-parallel async SGD without a server.
 
@@ -237,6 +247,11 @@ class SSPBackend(Backend):
     def launch(self, bucket):
         hy = self.sync.hyper
         for p, h, lm, dm in zip(bucket.params, bucket.history, bucket.lr_mult, bucket.decay_mult):
+            if getattr(p, "_grad_is_global", False):
+                # sufficient-factor weights: .grad is already Σ_p u_pᵀv_p on every rank (parallel/sfb.py), so the summed
+                # update Σ_p Δ_p is one local step on it with the decay counted once per worker — nothing to exchange
+                _apply_global_grad_step(self.sync, hy, p, h, lm, dm)
+                continue
             delta = compute_update(hy, p.data, p.grad, h, lm, dm)
             with torch.no_grad():
                 p.data.sub_(delta)                       # read-my-writes
@@ -311,6 +326,9 @@ class SSPAggrBackend(Backend):
     def launch(self, bucket):
         hy = self.sync.hyper
         for p, h, lm, dm in zip(bucket.params, bucket.history, bucket.lr_mult, bucket.decay_mult):
+            if getattr(p, "_grad_is_global", False):
+                _apply_global_grad_step(self.sync, hy, p, h, lm, dm)      # see SSPBackend.launch
+                continue
             delta = compute_update(hy, p.data, p.grad, h, lm, dm)
             with torch.no_grad():
                 p.data.sub_(delta)                                   # read-my-writes

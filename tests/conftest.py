@@ -3,6 +3,7 @@ import sys
 
 import pytest
 
+os.environ.setdefault("POSEIDON_SYNTHETIC_DATA", "1")     # the suite trains on stand-in data; production refuses to
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 

@@ -86,6 +86,17 @@ def test_ssp_staleness_zero_is_bsp_with_summed_updates(tmp_path, single):
     _assert_close(res[0], single, 5e-5)
 
 
+@pytest.mark.parametrize("comm", ["ssp", "ssp_aggr"])
+def test_ssp_with_sufficient_factors_at_staleness_zero_is_bsp(tmp_path, single, comm):
+    """--svb=true with a bounded-staleness backend (the caffe_main usage example): SFB weights carry the GLOBAL gradient,
+    so they are stepped locally and never exchanged again (round-1 advisor finding: they used to get world x the update)."""
+    extra = ["--aggr_fraction", "1.0"] if comm == "ssp_aggr" else []
+    res = launch(2, str(tmp_path / "w"), ["--batch", "8", "--comm", comm, "--staleness", "0", "--svb", "1", "--sfb_mode", "all"]
+                 + extra)
+    _assert_close(res[0], res[1], 1e-6)
+    _assert_close(res[0], single, 5e-5)
+
+
 def test_ssp_bounded_staleness_converges_to_same_table(tmp_path):
     res = launch(2, str(tmp_path / "w"), ["--batch", "8", "--comm", "ssp", "--staleness", "2", "--steps", "6",
                                             "--delay_rank", "1"])
