@@ -45,6 +45,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--graph", type=int, default=-1, help="CUDA-graph the step (default: on for the sm100 engine)")
     ap.add_argument("--vendor-dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-exposed-comm", action="store_true",
+                    help="skip the compute-only arm (N > 1) that exposed_comm_ms is measured against")
+    ap.add_argument("--require-nvls", action="store_true", help="fail if the arena has no NVLS multicast mapping")
     return ap.parse_args()
 
 
@@ -105,6 +108,22 @@ def reference_unavailable():
            "leveldb, lmdb, hdf5, opencv, protobuf-dev), cuDNN R2/R3 APIs removed since cuDNN 8, and sm_20..sm_50 "
            "gencodes rejected by nvcc 12.9; `pip install /root/reference` has no setup.py/pyproject (see DESIGN.md)")
     print(json.dumps({"impl": "reference", "unavailable": why}))
+
+
+def measure_compute_only(args, rc):
+    """The same per-GPU step with communication removed: every rank trains its own replica (world-size-1 context, local
+    fused update) at the same time as its peers, so power and clocks match the N-GPU run.  exposed_comm_ms is the N-GPU
+    step time minus this one."""
+    from poseidon_b200.parallel.context import RankContext
+    solo = RankContext(0, 1, rc.local_rank, rc.device)
+    solver = build_solver(args, solo, device_resident=True)
+    if args.engine == "sm100" or args.graph == 1:
+        solver.enable_cuda_graph(warmup=2)
+    for _ in range(max(3, args.warmup)):
+        solver.step(1)
+    ms, _ = timed_steps(solver, rc, args.steps, read_loss=False)      # rc: barrier + max over the REAL ranks
+    solver.close()
+    return ms / args.steps
 
 
 def build_solver(args, rank_ctx, device_resident: bool):
@@ -194,6 +213,10 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), __file__] + sys.argv[1:]
         return subprocess.call(cmd)
+    if args.require_nvls:
+        os.environ["POSEIDON_REQUIRE_NVLS"] = "1"
+    if args.engine == "torch" and "--svb" not in " ".join(sys.argv):
+        args.svb = 0          # vendor baseline: dense NCCL all-reduce (DDP-style), no sufficient factors
     rc = init_rank_context("cpu" if (args.allow_cpu and not torch.cuda.is_available()) else None)
     if rc.device.type != "cuda":
         if not args.allow_cpu:
@@ -215,6 +238,8 @@ def main():
     # CUDA-graph the step: sm100 engine on one GPU, or on several with the fused NVLink backend (device-side epochs)
     use_graph = (args.graph == 1) or (args.graph < 0 and args.engine == "sm100" and
                                        (world == 1 or (solver.comm_name == "fused" and args.staleness == 0)))
+    if rc.device.type != "cuda":
+        use_graph = False
     if use_graph:
         try:
             solver.enable_cuda_graph(warmup=2)
@@ -235,6 +260,7 @@ def main():
     value = batch * world * args.steps / (ms / 1e3)
     wire = solver.sync.backend.bytes_on_wire() if hasattr(solver.sync.backend, "bytes_on_wire") else {}
     sfb_layers = getattr(getattr(solver.sync.backend, "sfb_stats", None), "layers", {})
+    comm_profile = solver.sync.backend.comm_profile() if hasattr(solver.sync.backend, "comm_profile") else {}
     # ---------------- end-to-end through the public API: pinned H2D of every batch + D2H of every loss
     e2e = None
     if not args.no_e2e:
@@ -243,6 +269,16 @@ def main():
         except Exception as exc:      # never lose the device-timed result to a failure of the end-to-end leg
             e2e = {"error": f"{type(exc).__name__}: {exc}"}
     solver.close()
+    # ---------------- exposed communication time: N-GPU step minus the same step with communication removed
+    exposed = None
+    if world > 1 and not args.no_exposed_comm and rc.device.type == "cuda":
+        try:
+            ms_solo = measure_compute_only(args, rc)
+            exposed = {"exposed_comm_ms": ms / args.steps - ms_solo, "compute_only_ms_per_step": ms_solo,
+                       "how": "same step, every rank on its own replica (world-size-1 context, local fused update), all "
+                              "ranks running concurrently; device-timed, max over ranks"}
+        except Exception as exc:
+            exposed = {"error": f"{type(exc).__name__}: {exc}"}
     if rc.is_root:
         shape = solver.net.blob_shapes[solver.net.top_names[0][0]]
         out = {
@@ -262,8 +298,14 @@ def main():
                              "inputs rotate over 4 batches",
                        "sfb_layers": sfb_layers, "wire_bytes_total": wire,
                        "baseline_ref": "133 img/s per K20 derived in BASELINE.md §1 (reference publishes no img/s)"},
-            "clocks": clocks, "gpu_launches": launches, "impl": "ours",
+            "clocks": clocks, "gpu_launches": launches,
+            "impl": "ours" if args.engine == "sm100" else
+                    "vendor_baseline (cuDNN/cuBLAS via PyTorch + NCCL; constructed, NOT the reference)",
+            "sfb_layers": sfb_layers, "wire_bytes": comm_profile, "multimem": comm_profile.get("multimem"),
         }
+        if exposed is not None:
+            out["exposed_comm_ms"] = exposed.get("exposed_comm_ms")
+            out["exposed_comm"] = exposed
         if e2e is not None:
             out["e2e"] = e2e
         print(json.dumps(out))

@@ -19,7 +19,9 @@ if os.environ.get('PSD_CONV_IM2COL') == '0':
     sm100.K().set_conv_im2col(0)
 PAIR = int(os.environ.get("PSD_PAIR", "1"))
 sm100.K().set_pair_cta(PAIR)
-print(f"== cta_group::{2 if PAIR else 1} kernels ==", flush=True)
+MC = int(os.environ.get("PSD_MCAST", "2"))
+sm100.K().set_conv_mcast(MC)
+print(f"== cta_group::{2 if PAIR else 1} kernels, im2col multicast cluster {MC} ==", flush=True)
 which = sys.argv[1].split(",") if len(sys.argv) > 1 else list(CASES)
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 for name in which:

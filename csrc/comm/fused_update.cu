@@ -187,10 +187,12 @@ allreduce_sgd_kernel(PeerPtrs pp, float* __restrict__ h, long n, int rank, int w
     if (pp.g_mc != nullptr) {
       gv = multimem_ld_reduce_f32x4(pp.g_mc + 4 * i);
     } else {
-      gv = reinterpret_cast<const float4*>(pp.g[rank])[i];
+      // ONE_SHOT: fixed order 0..world-1 (every rank sums the same bucket: identical order = bit-identical replicas);
+      // two-shot: staggered from the own rank so the links are used evenly (one owner per shard: order is irrelevant)
+      gv = reinterpret_cast<const float4*>(pp.g[ONE_SHOT ? 0 : rank])[i];
 #pragma unroll 1
       for (int q = 1; q < world; ++q) {
-        const int p = (rank + q) % world;           // stagger peers so links are used evenly
+        const int p = ONE_SHOT ? q : (rank + q) % world;
         const float4 t = reinterpret_cast<const float4*>(pp.g[p])[i];
         gv.x += t.x; gv.y += t.y; gv.z += t.z; gv.w += t.w;
       }
@@ -265,6 +267,176 @@ void allreduce_sgd(std::vector<int64_t> g_ptrs, std::vector<int64_t> w_ptrs, std
   else
     allreduce_sgd_kernel<false><<<grid, 512, 0, stream>>>(pp, h.data_ptr<float>(), n, static_cast<int>(rank), world,
                                                           static_cast<uint32_t>(epoch), hp, dc, lrp, edp);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------ one launch per BUCKET
+// Round 2: the per-tensor launch above cost two system-scope flag barriers and a separate zero_() launch per parameter
+// tensor (weight and bias separately) — the fixed multi-GPU tax the 1 -> 2 GPU step showed.  This
+// form reduces + steps + broadcasts up to kMaxSegs tensors of a layer behind ONE barrier pair, and re-arms the gradient
+// staging inside the kernel:
+//   * two-shot segments: only the OWNER of a shard ever reads it, so the owner writes zeros back over the shard in
+//     every rank's G right after reading it (one multimem.st through the switch, or P2P stores) — made data-dependent on
+//     the loaded value so the store cannot overtake the load;
+//   * one-shot segments: every rank reads every rank's G, so each rank zeroes ITS OWN copy after the closing barrier
+//     (the last CTA; these segments are <= 256 KB).
+constexpr int kMaxSegs = 4;
+struct SegSet {
+  long g_off[kMaxSegs], w_off[kMaxSegs], wb_off[kMaxSegs];    // byte offsets inside the (symmetric) arena
+  float* h[kMaxSegs];                                         // local optimizer history (sharded by rank for two-shot)
+  long n[kMaxSegs];                                           // floats, multiple of 4
+  float lr[kMaxSegs], decay[kMaxSegs];
+  int one_shot[kMaxSegs];
+  int nseg;
+};
+struct ArenaPtrs {
+  char* base[kMaxRanks];
+  char* mc;                       // multicast mapping of the arena (0 = none: P2P loads / stores)
+  uint32_t* flags[kMaxRanks];     // this bucket's flag block on every rank
+};
+
+__device__ __forceinline__ void multimem_st_b64(void* mc, uint2 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(mc), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y))
+               : "memory");
+}
+// 0.0f that the hardware cannot produce before `v` has been loaded
+__device__ __forceinline__ float dependent_zero(float v) {
+  uint32_t z;
+  asm volatile("and.b32 %0, %1, 0;" : "=r"(z) : "r"(__float_as_uint(v)));
+  return __uint_as_float(z);
+}
+
+__global__ void __launch_bounds__(512)
+allreduce_sgd_multi_kernel(ArenaPtrs ap, SegSet ss, int rank, int world, uint32_t epoch, UpdateHyper hp,
+                           unsigned int* __restrict__ done_counter, const float* __restrict__ lr_dev,
+                           const uint32_t* __restrict__ epoch_dev) {
+  const float lr_glob = lr_dev != nullptr ? __ldg(lr_dev) : 1.f;
+  if (epoch_dev != nullptr) epoch += *reinterpret_cast<const volatile uint32_t*>(epoch_dev);
+  PeerPtrs fl{};
+  for (int p = 0; p < world; ++p) fl.flags[p] = ap.flags[p];
+  peer_barrier(fl, rank, world, 0, epoch);
+  for (int s = 0; s < ss.nseg; ++s) {
+    UpdateHyper h = hp;
+    h.lr = ss.lr[s] * lr_glob;
+    h.decay = ss.decay[s];
+    const bool one = ss.one_shot[s] != 0;
+    const long n4 = ss.n[s] >> 2;
+    long lo = 0, hi = n4;
+    if (!one) {
+      const long per = (n4 + world - 1) / world;
+      lo = min(n4, per * rank);
+      hi = min(n4, lo + per);
+    }
+    float4* wl = reinterpret_cast<float4*>(ap.base[rank] + ss.w_off[s]);
+    float4* hl = reinterpret_cast<float4*>(ss.h[s]);
+    const bool has_wb = ss.wb_off[s] >= 0;
+    for (long i = lo + blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < hi;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+      float4 gv;
+      if (ap.mc != nullptr) {
+        gv = multimem_ld_reduce_f32x4(reinterpret_cast<const float*>(ap.mc + ss.g_off[s]) + 4 * i);
+      } else {
+        // fixed peer order 0..world-1: identical fp32 summation order on every rank, so one-shot replicas stay
+        // bit-identical (the rank-staggered order let them drift for world > 2)
+        gv = reinterpret_cast<const float4*>(ap.base[0] + ss.g_off[s])[i];
+#pragma unroll 1
+        for (int q = 1; q < world; ++q) {
+          const float4 t = reinterpret_cast<const float4*>(ap.base[q] + ss.g_off[s])[i];
+          gv.x += t.x; gv.y += t.y; gv.z += t.z; gv.w += t.w;
+        }
+      }
+      if (!one) {
+        // re-arm the shard in every rank's staging buffer (only this rank reads it)
+        const float z = dependent_zero(gv.x + gv.y + gv.z + gv.w);
+        const float4 zv = make_float4(z, z, z, z);
+        if (ap.mc != nullptr) {
+          multimem_st_f32x4(reinterpret_cast<float*>(ap.mc + ss.g_off[s]) + 4 * i, zv);
+        } else {
+#pragma unroll 1
+          for (int q = 0; q < world; ++q) reinterpret_cast<float4*>(ap.base[(rank + q) % world] + ss.g_off[s])[i] = zv;
+        }
+      }
+      float4 wv = wl[i], hv = hl[i];
+      step_rule(gv.x, wv.x, hv.x, h);
+      step_rule(gv.y, wv.y, hv.y, h);
+      step_rule(gv.z, wv.z, hv.z, h);
+      step_rule(gv.w, wv.w, hv.w, h);
+      hl[i] = hv;
+      const uint2 b = pack_bf16x4(wv);
+      if (one) {
+        wl[i] = wv;
+        if (has_wb) reinterpret_cast<uint2*>(ap.base[rank] + ss.wb_off[s])[i] = b;
+      } else if (ap.mc != nullptr) {
+        multimem_st_f32x4(reinterpret_cast<float*>(ap.mc + ss.w_off[s]) + 4 * i, wv);
+        if (has_wb) multimem_st_b64(reinterpret_cast<uint2*>(ap.mc + ss.wb_off[s]) + i, b);
+      } else {
+#pragma unroll 1
+        for (int q = 0; q < world; ++q) {
+          const int p = (rank + q) % world;
+          reinterpret_cast<float4*>(ap.base[p] + ss.w_off[s])[i] = wv;
+          if (has_wb) reinterpret_cast<uint2*>(ap.base[p] + ss.wb_off[s])[i] = b;
+        }
+      }
+    }
+  }
+  // ---- everyone finished reading my G and (two-shot) writing my W
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last) {
+    if (threadIdx.x == 0) *done_counter = 0;
+    peer_barrier(fl, rank, world, 1, epoch);
+    for (int s = 0; s < ss.nseg; ++s) {
+      if (!ss.one_shot[s]) continue;
+      float4* gl = reinterpret_cast<float4*>(ap.base[rank] + ss.g_off[s]);
+      for (long i = threadIdx.x; i < (ss.n[s] >> 2); i += blockDim.x) gl[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+void allreduce_sgd_multi(std::vector<int64_t> base_ptrs, int64_t mc_base, std::vector<int64_t> flag_ptrs,
+                         std::vector<int64_t> g_offs, std::vector<int64_t> w_offs, std::vector<int64_t> wb_offs,
+                         std::vector<at::Tensor> hists, std::vector<int64_t> ns, std::vector<int64_t> one_shots,
+                         std::vector<double> lrs, std::vector<double> decays, int64_t rank, int64_t epoch,
+                         at::Tensor done_counter, double momentum, int64_t rule, bool l1, double delta, double gscale,
+                         int64_t max_ctas, const c10::optional<at::Tensor>& lr_dev, const c10::optional<at::Tensor>& epoch_dev) {
+  const int world = static_cast<int>(base_ptrs.size());
+  const int nseg = static_cast<int>(g_offs.size());
+  TORCH_CHECK(world >= 1 && world <= kMaxRanks && flag_ptrs.size() == base_ptrs.size(), "allreduce_sgd_multi: 1..8 ranks");
+  TORCH_CHECK(nseg >= 1 && nseg <= kMaxSegs && w_offs.size() == g_offs.size() && wb_offs.size() == g_offs.size() &&
+              hists.size() == g_offs.size() && ns.size() == g_offs.size() && one_shots.size() == g_offs.size() &&
+              lrs.size() == g_offs.size() && decays.size() == g_offs.size(), "allreduce_sgd_multi: 1..4 segments");
+  TORCH_CHECK(done_counter.scalar_type() == at::kInt && done_counter.numel() >= 1);
+  c10::cuda::CUDAGuard guard(done_counter.device());
+  ArenaPtrs ap{};
+  for (int p = 0; p < world; ++p) {
+    ap.base[p] = reinterpret_cast<char*>(base_ptrs[p]);
+    ap.flags[p] = reinterpret_cast<uint32_t*>(flag_ptrs[p]);
+  }
+  ap.mc = reinterpret_cast<char*>(mc_base);
+  SegSet ss{};
+  ss.nseg = nseg;
+  long work4 = 0;
+  for (int s = 0; s < nseg; ++s) {
+    TORCH_CHECK(hists[s].is_cuda() && hists[s].scalar_type() == at::kFloat && hists[s].numel() >= ns[s] && ns[s] % 4 == 0);
+    TORCH_CHECK(g_offs[s] % 16 == 0 && w_offs[s] % 16 == 0 && (wb_offs[s] < 0 || wb_offs[s] % 8 == 0), "segment alignment");
+    ss.g_off[s] = g_offs[s]; ss.w_off[s] = w_offs[s]; ss.wb_off[s] = wb_offs[s];
+    ss.h[s] = hists[s].data_ptr<float>();
+    ss.n[s] = ns[s];
+    ss.lr[s] = static_cast<float>(lrs[s]);
+    ss.decay[s] = static_cast<float>(decays[s]);
+    ss.one_shot[s] = one_shots[s] ? 1 : 0;
+    work4 = std::max<long>(work4, one_shots[s] ? ns[s] / 4 : (ns[s] / 4 + world - 1) / world);
+  }
+  UpdateHyper hp = make_hyper(1.0, momentum, 0.0, rule, l1, delta, gscale);
+  const int grid = static_cast<int>(std::max<long>(1, std::min<long>((work4 + 511) / 512, max_ctas > 0 ? max_ctas : 64)));
+  allreduce_sgd_multi_kernel<<<grid, 512, 0, at::cuda::getCurrentCUDAStream()>>>(
+      ap, ss, static_cast<int>(rank), world, static_cast<uint32_t>(epoch), hp,
+      reinterpret_cast<unsigned int*>(done_counter.data_ptr()), lr_dev.has_value() ? lr_dev->data_ptr<float>() : nullptr,
+      epoch_dev.has_value() ? reinterpret_cast<const uint32_t*>(epoch_dev->data_ptr()) : nullptr);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
@@ -356,6 +528,10 @@ TORCH_LIBRARY_FRAGMENT(poseidon, m) {
   m.def("allreduce_sgd(int[] g_ptrs, int[] w_ptrs, int[] wb_ptrs, int[] flag_ptrs, int g_mc, int w_mc, Tensor(a!) h, int n, "
         "int rank, int epoch, bool one_shot, Tensor(b!) done_counter, float lr, float momentum, float decay, int rule, "
         "bool l1, float delta, float gscale, int max_ctas, Tensor? lr_dev, Tensor? epoch_dev) -> ()", &psd::allreduce_sgd);
+  m.def("allreduce_sgd_multi(int[] base_ptrs, int mc_base, int[] flag_ptrs, int[] g_offs, int[] w_offs, int[] wb_offs, "
+        "Tensor[] hists, int[] ns, int[] one_shots, float[] lrs, float[] decays, int rank, int epoch, Tensor(a!) done_counter, "
+        "float momentum, int rule, bool l1, float delta, float gscale, int max_ctas, Tensor? lr_dev, Tensor? epoch_dev) -> ()",
+        &psd::allreduce_sgd_multi);
   m.def("peer_push(Tensor src, int[] dst_ptrs, int dst_mc, int[] flag_ptrs, int rank, int slot, int epoch, bool signal, "
         "Tensor(a!) done_counter, int wait_slot, Tensor? epoch_dev) -> ()", &psd::peer_push);
   m.def("peer_signal(int[] flag_ptrs, int rank, int slot, int epoch, Tensor? epoch_dev) -> ()", &psd::peer_signal);

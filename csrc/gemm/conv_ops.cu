@@ -68,6 +68,49 @@ static int pair_grid(long m_blocks, long n_blocks, long split, int sms) {
   return static_cast<int>(2 * std::max<long>(1, std::min<long>(pair_tiles, sms / 2)));
 }
 
+static int g_conv_mcast = 2;       // CTAs per cluster sharing the im2col operand by TMA multicast (1 = off)
+
+// Launch the im2col-A kernel (fprop / dgrad) for tile width bn; CG = 2: paired CTAs, else cluster multicast (p.cluster).
+template <int CG>
+static void launch_im2col_a(int bn, const TmapSet& tm, const GemmParams& p, const ConvGeom& cg, int grid, cudaStream_t stream) {
+  switch (bn) {
+    case 32:
+      if constexpr (CG == 1) launch_conv<32, false, false, EPI_BF16, IM2COL_A, 1>(tm, p, cg, grid, stream);
+      else TORCH_CHECK(false, "paired CTAs: BLOCK_N >= 64");
+      break;
+    case 64: launch_conv<64, false, false, EPI_BF16, IM2COL_A, CG>(tm, p, cg, grid, stream); break;
+    case 96:
+      if constexpr (CG == 1) launch_conv<96, false, false, EPI_BF16, IM2COL_A, 1>(tm, p, cg, grid, stream);
+      else TORCH_CHECK(false, "paired CTAs: BLOCK_N 96 is not instantiated");
+      break;
+    case 128: launch_conv<128, false, false, EPI_BF16, IM2COL_A, CG>(tm, p, cg, grid, stream); break;
+    case 192: launch_conv<192, false, false, EPI_BF16, IM2COL_A, CG>(tm, p, cg, grid, stream); break;
+    case 256: launch_conv<256, false, false, EPI_BF16, IM2COL_A, CG>(tm, p, cg, grid, stream); break;
+    default: TORCH_CHECK(false, "unsupported conv BLOCK_N ", bn);
+  }
+}
+
+// Multicast plan for an im2col-A convolution with n_cols output columns: the cluster's C CTAs take C consecutive column
+// blocks of the SAME pixel tile and each fetches 128 / C of its pixel rows.  The tile width is the narrowest
+// instantiated one that covers n_cols / C (the TMA time per k-block is ~815 / C cycles, the MMA time 2 * bn: narrow
+// tiles cost nothing while the TMA engine is the bound).  Returns C (1 = no multicast) and sets *bn, *grid.
+static int plan_im2col_mcast(long n_cols, long m_blocks, int sms, int* bn, int* grid) {
+  int c = g_conv_mcast;
+  if (c <= 1 || n_cols < 32) return 1;
+  while (c > 1 && n_cols < 32L * c) c >>= 1;
+  if (c <= 1) return 1;
+  const long want = (n_cols + c - 1) / c;
+  int w = 256;
+  for (int cand : {256, 192, 128, 96, 64, 32})
+    if (cand >= want) w = cand;
+  *bn = w;
+  const long n_blocks = (n_cols + w - 1) / w;
+  const long cluster_tiles = m_blocks * ((n_blocks + c - 1) / c);
+  const int usable = c >= 4 ? ((sms / 4) * 4 - 16) : (sms / c) * c;       // size-4 clusters strand ~16 SMs (GPC shapes)
+  *grid = static_cast<int>(std::max<long>(c, std::min<long>(cluster_tiles * c, (usable / c) * c)));
+  return c;
+}
+
 // cluster size to use for a tile space of `tiles_along` blocks along the cluster dimension, and the grid
 static int pick_cluster(long tiles_along, long tiles_total, int sms, int* grid) {
   int c = g_conv_cluster;
@@ -222,24 +265,23 @@ at::Tensor conv_fprop(const at::Tensor& x, const at::Tensor& wb, const c10::opti
     p.relu_slope = static_cast<float>(slope);
     p.alpha = 1.f;
     if (cl == 1 && try_im2col_map(&tm.a[0], cg, BLOCK_M)) {
-      if (pair_cta_enabled() && m_blocks >= 2) {
-        // paired CTAs: two pixel blocks share every weight tile; each CTA stages BN/2 weight rows
-        encode_tmap_bf16_2d(&tm.b[0], wptr, cg.K, Cout_g, cg.K, BLOCK_K, bn / 2);
-        const int pgrid = pair_grid(m_blocks, n_blocks, 1, sms);
-        switch (bn) {
-          case 64: launch_conv<64, false, false, EPI_BF16, IM2COL_A, 2>(tm, p, cg, pgrid, stream); break;
-          case 128: launch_conv<128, false, false, EPI_BF16, IM2COL_A, 2>(tm, p, cg, pgrid, stream); break;
-          case 192: launch_conv<192, false, false, EPI_BF16, IM2COL_A, 2>(tm, p, cg, pgrid, stream); break;
-          default: launch_conv<256, false, false, EPI_BF16, IM2COL_A, 2>(tm, p, cg, pgrid, stream); break;
-        }
+      int mbn = bn, mgrid = grid;
+      const int mc = plan_im2col_mcast(Cout_g, m_blocks, sms, &mbn, &mgrid);
+      if (mc > 1) {
+        // cluster multicast of the im2col operand: every CTA fetches 128 / mc pixel rows of the shared A tile
+        TORCH_CHECK(try_im2col_map(&tm.a[0], cg, BLOCK_M / mc), "im2col map");
+        encode_tmap_bf16_2d(&tm.b[0], wptr, cg.K, Cout_g, cg.K, BLOCK_K, mbn);
+        p.cluster = mc;
+        launch_im2col_a<1>(mbn, tm, p, cg, mgrid, stream);
         continue;
       }
-      switch (bn) {
-        case 64: launch_conv<64, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
-        case 128: launch_conv<128, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
-        case 192: launch_conv<192, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
-        default: launch_conv<256, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
+      if (pair_cta_enabled() && m_blocks >= 2 && bn >= 64) {
+        // paired CTAs: two pixel blocks share every weight tile; each CTA stages BN/2 weight rows
+        encode_tmap_bf16_2d(&tm.b[0], wptr, cg.K, Cout_g, cg.K, BLOCK_K, bn / 2);
+        launch_im2col_a<2>(bn, tm, p, cg, pair_grid(m_blocks, n_blocks, 1, sms), stream);
+        continue;
       }
+      launch_im2col_a<1>(bn, tm, p, cg, grid, stream);
       continue;
     }
     TORCH_CHECK(cg.Cgk == cg.Cg, "conv_fprop: channel-padded operand needs the TMA im2col path");
@@ -301,23 +343,21 @@ at::Tensor conv_dgrad(const at::Tensor& dy, const at::Tensor& wt, at::IntArrayRe
     p.alpha = 1.f;
     (void)mask_pitch;
     if (cl == 1 && try_im2col_map(&tm.a[0], cg, BLOCK_M)) {
-      if (pair_cta_enabled() && m_blocks >= 2) {
-        encode_tmap_bf16_2d(&tm.b[0], wptr, cg.K, Cg, cg.K, BLOCK_K, bn / 2);
-        const int pgrid = pair_grid(m_blocks, n_blocks, 1, sms);
-        switch (bn) {
-          case 64: launch_conv<64, false, false, EPI_BF16, IM2COL_A, 2>(tm, p, cg, pgrid, stream); break;
-          case 128: launch_conv<128, false, false, EPI_BF16, IM2COL_A, 2>(tm, p, cg, pgrid, stream); break;
-          case 192: launch_conv<192, false, false, EPI_BF16, IM2COL_A, 2>(tm, p, cg, pgrid, stream); break;
-          default: launch_conv<256, false, false, EPI_BF16, IM2COL_A, 2>(tm, p, cg, pgrid, stream); break;
-        }
+      int mbn = bn, mgrid = grid;
+      const int mc = plan_im2col_mcast(Cg, m_blocks, sms, &mbn, &mgrid);
+      if (mc > 1) {
+        TORCH_CHECK(try_im2col_map(&tm.a[0], cg, BLOCK_M / mc), "im2col map");
+        encode_tmap_bf16_2d(&tm.b[0], wptr, cg.K, Cg, cg.K, BLOCK_K, mbn);
+        p.cluster = mc;
+        launch_im2col_a<1>(mbn, tm, p, cg, mgrid, stream);
         continue;
       }
-      switch (bn) {
-        case 64: launch_conv<64, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
-        case 128: launch_conv<128, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
-        case 192: launch_conv<192, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
-        default: launch_conv<256, false, false, EPI_BF16, IM2COL_A>(tm, p, cg, grid, stream); break;
+      if (pair_cta_enabled() && m_blocks >= 2 && bn >= 64) {
+        encode_tmap_bf16_2d(&tm.b[0], wptr, cg.K, Cg, cg.K, BLOCK_K, bn / 2);
+        launch_im2col_a<2>(bn, tm, p, cg, pair_grid(m_blocks, n_blocks, 1, sms), stream);
+        continue;
       }
+      launch_im2col_a<1>(bn, tm, p, cg, grid, stream);
       continue;
     }
     TORCH_CHECK(cg.Cgk == cg.Cg, "conv_dgrad: channel-padded operand needs the TMA im2col path");
@@ -378,6 +418,20 @@ void conv_wgrad(const at::Tensor& x, const at::Tensor& dy, at::Tensor dw, at::In
     p.alpha = static_cast<float>(alpha);
     if (cl == 1 && try_im2col_map(&tm.b[0], cg, BLOCK_K)) {
       const long m_blocks = (Cout_g + BLOCK_M - 1) / BLOCK_M;
+      if (g_conv_mcast > 1 && m_blocks >= 2 && bn >= 128) {
+        // cluster along Cout: its CTAs need the same im2col B tile (bn / 64 boxes of 64 pixels x 64 channels per k-block,
+        // ~6 cycles per pixel row on the TMA engine) — each fetches every C-th box and multicasts it
+        const int mc = (m_blocks % 3 == 0 && bn >= 192) ? 3 : 2;
+        const long ctiles = ((m_blocks + mc - 1) / mc) * n_blocks * split;
+        p.cluster = mc;
+        const int mgrid = static_cast<int>(std::max<long>(1, std::min<long>(ctiles, sms / mc))) * mc;
+        switch (bn) {
+          case 128: launch_conv<128, true, true, EPI_F32, IM2COL_B>(tm, p, cg, mgrid, stream); break;
+          case 192: launch_conv<192, true, true, EPI_F32, IM2COL_B>(tm, p, cg, mgrid, stream); break;
+          default: launch_conv<256, true, true, EPI_F32, IM2COL_B>(tm, p, cg, mgrid, stream); break;
+        }
+        continue;
+      }
       if (pair_cta_enabled() && m_blocks >= 2 && m_blocks % 2 == 0 && (bn == 128 || bn == 256)) {
         // paired CTAs along Cout (even block counts only: a phantom block would waste a third of conv3's MMA work)
         const int pgrid = pair_grid(m_blocks, n_blocks, split, sms);
@@ -466,6 +520,10 @@ at::Tensor conv_pack_padded(const at::Tensor& wb, int64_t Cout, int64_t RS, int6
 
 namespace psd {
 void set_conv_im2col(int64_t on) { g_conv_im2col = on != 0; }
+void set_conv_mcast(int64_t c) {
+  TORCH_CHECK(c == 1 || c == 2 || c == 4, "im2col multicast cluster size must be 1, 2 or 4");
+  g_conv_mcast = static_cast<int>(c);
+}
 void set_conv_cluster(int64_t c) {
   TORCH_CHECK(c == 1 || c == 2 || c == 4, "cluster size must be 1, 2 or 4");
   g_conv_cluster = static_cast<int>(c);
@@ -475,6 +533,7 @@ void set_conv_cluster(int64_t c) {
 TORCH_LIBRARY_FRAGMENT(poseidon, m) {
   m.def("set_conv_cluster(int c) -> ()", &psd::set_conv_cluster);
   m.def("set_conv_im2col(int on) -> ()", &psd::set_conv_im2col);
+  m.def("set_conv_mcast(int c) -> ()", &psd::set_conv_mcast);
   m.def("conv_fprop(Tensor x, Tensor wb, Tensor? bias, int[] kernel, int[] stride, int[] pad, int groups, int mode, "
         "int OH, int OW, bool relu, float slope, Tensor? out) -> Tensor", &psd::conv_fprop);
   m.def("conv_dgrad(Tensor dy, Tensor wt, int[] kernel, int[] pad, int groups, int H, int W, Tensor? mask, float slope) "

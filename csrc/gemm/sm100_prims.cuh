@@ -78,6 +78,17 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t byte
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes) : "memory");
 }
 
+// Bulk-async (TMA) store of one contiguous row segment: shared -> global, 16-byte aligned, size a multiple of 16.
+__device__ __forceinline__ void bulk_store_row(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(gdst)),
+               "r"(smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+// Close the thread's bulk group and wait until its SOURCE (shared memory) has been read — not for the global writes.
+__device__ __forceinline__ void bulk_commit_wait_read() {
+  asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // (Measured: letting only lane 0 poll in the warp-uniform role loops and parking the other lanes on __syncwarp is much
 //  slower — AlexNet 80 k -> 62 k img/s — so all 32 lanes execute mbar_wait together.)
 
@@ -113,6 +124,21 @@ __device__ __forceinline__ void tma_load_im2col_4d(uint32_t smem_dst, const CUte
       " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w),
       "h"(off_h)
+      : "memory");
+}
+
+// im2col-mode load multicast to every CTA of `cta_mask` (same smem offset, same mbarrier offset in each of them).
+// Measured on B200 (profiles/r2_conv_ncu_summary.md): the TMA engine delivers an im2col box at ~6 cycles per 128-byte
+// pixel row — 815 cycles for a 128-pixel A tile, more than the 512 cycles of the widest UMMA — so the convolution
+// kernels were bound by their OWN TMA engine, not by bytes.  CTAs of a cluster that need the same pixel tile (they differ
+// in the output-channel block) therefore each fetch 1/C of its rows and multicast them.
+__device__ __forceinline__ void tma_load_im2col_4d_mcast(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c, int w,
+                                                         int h, int n, uint16_t off_w, uint16_t off_h, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w),
+      "h"(off_h), "h"(cta_mask)
       : "memory");
 }
 

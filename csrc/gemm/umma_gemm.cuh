@@ -83,10 +83,13 @@ struct GemmSmem {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;     // 16 KB
   static constexpr int kBBytes = (BN / CG) * BLOCK_K * 2;   // this CTA's share of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = CG == 2 ? (BN >= 192 ? 6 : 8) : ((BN >= 192) ? 4 : (BN >= 128 ? 6 : 8));
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);   // power of two >= 2 accumulators
   static constexpr int kBarBytes = 256;
   static constexpr int kEpiStageBytes = kEpiWarps * 32 * 33 * 4;    // per epilogue warp: 32x32 fp32 transpose tile (+1 pad)
+  // as many ring stages as fit beside the barriers and the epilogue staging (at most 8: 4 @ BN 256, 6 @ 128, 8 @ <= 64;
+  // paired CTAs: 6 @ 256, 8 @ 128)
+  static constexpr int kFit = (232448 - 1024 - kBarBytes - kEpiStageBytes) / kStageBytes;
+  static constexpr int kStages = kFit > 8 ? 8 : kFit;
   static constexpr int kTotal = kStages * kStageBytes + kBarBytes + kEpiStageBytes + 1024;  // +1024 alignment slack
   static_assert(kTotal <= 232448, "shared memory budget (227 KB per CTA)");
 };
@@ -290,7 +293,7 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int m_blocks, int n_block
     const int rest = t / n_blocks;
     tc.m_blk = rest % m_blocks;
     tc.split = rest / m_blocks;
-  } else if (GATHER == GATHER_B) {
+  } else if (GATHER == GATHER_B || GATHER == IM2COL_A) {
     const int n_groups = (n_blocks + C - 1) / C;
     tc.m_blk = t % m_blocks;
     const int rest = t / m_blocks;
@@ -355,18 +358,25 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
   const int m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int n_blocks = (p.N + BN - 1) / BN;
   const int total_kb = p.kb_per_src * p.num_src;
-  const int C = (CG == 1 && has_gather_warps(GATHER) && p.cluster > 1) ? p.cluster : 1;
+  // CTAs per cluster sharing one operand by TMA multicast (CG == 1 only): the cp.async gather modes share the TMA (weight /
+  // dY) operand; the im2col-TMA modes share the IM2COL operand itself — its delivery rate, not its bytes, is what bounds
+  // the convolution kernels, so each CTA of the cluster fetches 1/C of the pixel rows for everybody.
+  const int C = (CG == 1 && GATHER != GATHER_NONE && p.cluster > 1) ? p.cluster : 1;
   const int crank = (C > 1 || CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
   const bool leader = CG == 1 || crank == 0;            // CG == 2: cluster rank 0 issues the MMAs for the pair
   const uint16_t cmask = static_cast<uint16_t>((1u << C) - 1);
   // cluster-level tile space and stride
   const int m_pairs = (m_blocks + 1) / 2;
   const int num_tiles = CG == 2 ? m_pairs * n_blocks * p.split_k
-                                : (GATHER == GATHER_B ? m_blocks * ((n_blocks + C - 1) / C) : ((m_blocks + C - 1) / C) * n_blocks) * p.split_k;
+                                : ((GATHER == GATHER_B || GATHER == IM2COL_A) ? m_blocks * ((n_blocks + C - 1) / C)
+                                                                              : ((m_blocks + C - 1) / C) * n_blocks) * p.split_k;
   const int tile0 = blockIdx.x / (C * CG), tile_step = gridDim.x / (C * CG);
+  // n fastest for the epilogues that stream whole fp32 rows (optimizer step; plain fp32 output of the inner-product weight
+  // gradient): the CTAs running at the same time then cover complete rows — one contiguous region of memory
+  constexpr bool kNFast = EPI == EPI_SGD || (EPI == EPI_F32 && GATHER == GATHER_NONE);
   auto coord = [&](int t) -> TileCoord {
-    if constexpr (CG == 2) return tile_coord_pair<EPI == EPI_SGD>(t, m_pairs, n_blocks, crank);
-    else return tile_coord<GATHER, EPI == EPI_SGD>(t, m_blocks, n_blocks, C, crank);
+    if constexpr (CG == 2) return tile_coord_pair<kNFast>(t, m_pairs, n_blocks, crank);
+    else return tile_coord<GATHER, kNFast>(t, m_blocks, n_blocks, C, crank);
   };
 
   if (warp == 0 && lane == 0) {
@@ -421,7 +431,8 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
         [[maybe_unused]] int im_c0[BN / CG / 64 > 0 ? BN / CG / 64 : 1];
         [[maybe_unused]] uint16_t im_offw[BN / CG / 64 > 0 ? BN / CG / 64 : 1], im_offh[BN / CG / 64 > 0 ? BN / CG / 64 : 1];
         if constexpr (GATHER == IM2COL_A) {
-          const uint32_t m0 = static_cast<uint32_t>(m_blk) * BLOCK_M;
+          // first base pixel this CTA fetches: the tile's, or (cluster multicast) that of its 128 / C pixel slice
+          const uint32_t m0 = static_cast<uint32_t>(m_blk) * BLOCK_M + static_cast<uint32_t>(crank * (BLOCK_M / C));
           const uint32_t n_img = fdiv(m0, cg.div_ohow);
           const uint32_t rem = m0 - n_img * static_cast<uint32_t>(cg.OH * cg.OW);
           const uint32_t oh = fdiv(rem, cg.div_ow);
@@ -481,6 +492,9 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
             if constexpr (CG == 2)
               tma_load_im2col_4d_cg2(sa32, &tm.a[0], fbar, in_k ? c0 : 0, im_w, im_h, im_n,
                                      static_cast<uint16_t>(in_k ? offw : 0), static_cast<uint16_t>(in_k ? offh : 0));
+            else if (C > 1)       // this CTA's 128 / C pixel rows of the shared A tile, delivered to the whole cluster
+              tma_load_im2col_4d_mcast(sa32 + crank * (BLOCK_M / C) * 128, &tm.a[0], fbar, in_k ? c0 : 0, im_w, im_h, im_n,
+                                       static_cast<uint16_t>(in_k ? offw : 0), static_cast<uint16_t>(in_k ? offh : 0), cmask);
             else
               tma_load_im2col_4d(sa32, &tm.a[0], fbar, in_k ? c0 : 0, im_w, im_h, im_n,
                                  static_cast<uint16_t>(in_k ? offw : 0), static_cast<uint16_t>(in_k ? offh : 0));
@@ -497,12 +511,18 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], CG * S::kStageBytes);
 #pragma unroll
             for (int c = 0; c < BN / CG / 64; ++c) {
-              if constexpr (CG == 2)
+              if constexpr (CG == 2) {
                 tma_load_im2col_4d_cg2(sb32 + c * 8192, &tm.b[0], fbar, im_c0[c], bw, bh, static_cast<int>(n_img), im_offw[c],
                                        im_offh[c]);
-              else
+              } else if (C > 1) {
+                // cluster along Cout sharing the im2col B tile: chunk c is fetched by CTA (c % C) for everybody
+                if (c % C == crank)
+                  tma_load_im2col_4d_mcast(sb32 + c * 8192, &tm.b[0], fbar, im_c0[c], bw, bh, static_cast<int>(n_img),
+                                           im_offw[c], im_offh[c], cmask);
+              } else {
                 tma_load_im2col_4d(sb32 + c * 8192, &tm.b[0], fbar, im_c0[c], bw, bh, static_cast<int>(n_img), im_offw[c],
                                    im_offh[c]);
+              }
             }
             TmaProducer<BN, A_MN, B_MN, CG>::load_a(tm, src, kb, m_blk, sa32, fbar);
           } else if constexpr (GATHER == GATHER_A) {
@@ -626,7 +646,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
         // B tile (MN-major): BN/64 chunk-columns of [64 reduction rows (m)][64 k-columns]; the k-columns are
         // fixed per tile (decode the taps once), the rows advance with the reduction index g — their row-table
         // entries for k-block g+1 are fetched before waiting for the slot of k-block g
-        constexpr int kChunks = BN / 64;
+        constexpr int kChunks = BN / 64 > 0 ? BN / 64 : 1;      // (BN < 64 is never instantiated with gather warps)
         constexpr int kRows = 64 / kRowStep;
         ChunkOff taps[kChunks];
 #pragma unroll
@@ -681,6 +701,8 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
       }
     };
     if (kSgdPrefetch) prefetch_sgd_tile(tile0);
+    [[maybe_unused]] const bool bulk_f32 = EPI == EPI_F32 && !p.atomic && p.col_cgk == 0 && (p.N & 3) == 0 && (p.ldc & 3) == 0 &&
+                                           (reinterpret_cast<uintptr_t>(p.c_f32) & 15) == 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
       const TileCoord tc = coord(tile);
       const int m_blk = tc.m_blk, n_blk = tc.n_blk;
@@ -709,12 +731,59 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
           epi_bar_sync();                                 // slab free for the next quadrant
         }
       } else {
+        bool stored = false;
+        if constexpr (EPI == EPI_F32) {
+          // Plain fp32 output (inner-product weight gradients, the SFB reconstruct in its two-pass form): pure HBM
+          // streaming — a 128 x BN tile is 128 KB of output for as little as 4 k-blocks of MMA.  The per-warp 32x32 walk
+          // of epilogue_tile32 issues isolated 128-byte stores and measured 33 % of the HBM copy rate
+          // (profiles/r1_roofline.md).  Here a TMEM lane quadrant (32 rows x BN columns) is laid down in ONE shared slab
+          // (row pitch BN + 4 floats: 16-byte aligned rows, conflict-free float4 stores from the lane = row layout) and
+          // leaves as 32 bulk-async (TMA) row stores of up to 1 KB each; the issuing lanes only wait until the copy
+          // engine has READ the slab, so the global writes of one quadrant overlap the fill of the next.
+          if (bulk_f32) {
+            constexpr int LDS = BN + 4;
+            static_assert(32 * LDS * 4 <= S::kEpiStageBytes, "fp32 slab must fit the epilogue staging buffer");
+            constexpr int RW = 32 / kEpiWarps;
+            const int col0 = n_blk * BN;
+            const int ncols = min(BN, p.N - col0);
 #pragma unroll 1
-        for (int c = half; c < BN / 32; c += kEpiWarps / 4) {
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, r);
-          tmem_ld_wait();
-          epilogue_tile32<EPI>(p, r, epi_stage + e * (32 * 33), lane, row0, n_blk * BN + c * 32);
+            for (int qq = 0; qq < 4; ++qq) {
+              if (q == qq) {
+#pragma unroll 1
+                for (int c = half; c < BN / 32; c += kEpiWarps / 4) {
+                  uint32_t r[32];
+                  tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, r);
+                  tmem_ld_wait();
+                  float4* dst = reinterpret_cast<float4*>(epi_stage + lane * LDS + c * 32);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    dst[j] = make_float4(__uint_as_float(r[4 * j]) * p.alpha, __uint_as_float(r[4 * j + 1]) * p.alpha,
+                                         __uint_as_float(r[4 * j + 2]) * p.alpha, __uint_as_float(r[4 * j + 3]) * p.alpha);
+                }
+                fence_proxy_async_smem();               // generic-proxy writes -> visible to the bulk-copy engine
+              }
+              epi_bar_sync();
+              if (lane < RW) {
+                const int rr = e * RW + lane;
+                const int row = m_blk * BLOCK_M + qq * 32 + rr;
+                if (row < p.M && ncols > 0)
+                  bulk_store_row(p.c_f32 + static_cast<long>(row) * p.ldc + col0, epi_stage + rr * LDS,
+                                 static_cast<uint32_t>(ncols) * 4u);
+                bulk_commit_wait_read();                 // the slab may be overwritten once the engine has read it
+              }
+              epi_bar_sync();
+            }
+            stored = true;
+          }
+        }
+        if (!stored) {
+#pragma unroll 1
+          for (int c = half; c < BN / 32; c += kEpiWarps / 4) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, r);
+            tmem_ld_wait();
+            epilogue_tile32<EPI>(p, r, epi_stage + e * (32 * 33), lane, row0, n_blk * BN + c * 32);
+          }
         }
       }
       tc_fence_before();
@@ -724,6 +793,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
         else mbar_arrive_remote(&tmem_empty[as], 0);      // the pair's accumulator buffer is released on the leader
       }
     }
+    if constexpr (EPI == EPI_F32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // bulk row stores have landed
   }
 
   tc_fence_before();

@@ -156,6 +156,11 @@ def set_filler_seed(seed: Optional[int]):
         _FILL_GEN.manual_seed(int(seed))
 
 
+def _caffe_num(t: torch.Tensor) -> int:
+    """`num` of the Caffe blob holding this tensor: blobs are 4-D, lower-rank tensors are left-padded with ones."""
+    return t.shape[0] if t.dim() == 4 else 1
+
+
 def fill(t: torch.Tensor, filler=None) -> torch.Tensor:
     typ = filler.type if filler is not None else "constant"
     g = _FILL_GEN
@@ -174,11 +179,16 @@ def fill(t: torch.Tensor, filler=None) -> torch.Tensor:
                 mask = torch.bernoulli(torch.full_like(t, non_zero_p), generator=g)
                 t.mul_(mask)
         elif typ == "positive_unitball":
+            # the reference normalises each of the blob's `num` slices (filler.hpp:138-204); an inner-product weight is
+            # the 4-D blob (1, 1, N, K), i.e. ONE slice of N*K elements
             t.uniform_(0, 1, generator=g)
-            flat = t.view(t.shape[0], -1)
+            flat = t.view(_caffe_num(t), -1)
             flat.div_(flat.sum(dim=1, keepdim=True))
         elif typ == "xavier":
-            fan_in = t.numel() // t.shape[0]
+            # fan_in = count / num of the 4-D blob (filler.hpp:210-275): Cin*kh*kw for a convolution, but N*K for an
+            # inner-product weight (blob (1,1,N,K)) and N for its bias — kept for parity with nets tuned on the reference
+            # (GoogLeNet's classifiers), although it is not the layer's true fan-in
+            fan_in = t.numel() // _caffe_num(t)
             scale = math.sqrt(3.0 / fan_in)
             t.uniform_(-scale, scale, generator=g)
         else:

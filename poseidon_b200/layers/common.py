@@ -167,7 +167,7 @@ class EltwiseLayer(Layer):
         return [tuple(bottom_shapes[0])]
 
     def forward(self, *xs):
-        return (ops.reference.eltwise(xs, self.op, self.coeffs or None),)
+        return (ops.get(self.ctx).eltwise(xs, self.op, self.coeffs or None),)
 
 
 @register("ARGMAX")
@@ -197,7 +197,7 @@ class MVNLayer(Layer):
         return [tuple(bottom_shapes[0])]
 
     def forward(self, x):
-        return (ops.reference.mvn(x, self.nv, self.ac),)
+        return (ops.get(self.ctx).mvn(x, self.nv, self.ac),)
 
 
 @register("SILENCE")

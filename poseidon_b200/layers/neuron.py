@@ -6,7 +6,6 @@ cuDNN variants (:372, :459, :548) collapse into the engine switch.
 """
 from __future__ import annotations
 
-import torch
 
 from .. import ops
 from .base import Layer, register
@@ -40,7 +39,7 @@ class SigmoidLayer(NeuronLayer):
     """reference: src/caffe/layers/sigmoid_layer.cu."""
 
     def forward(self, x):
-        return (torch.sigmoid(x),)
+        return (ops.get(self.ctx).sigmoid(x),)
 
 
 @register("TANH")
@@ -48,7 +47,7 @@ class TanHLayer(NeuronLayer):
     """reference: src/caffe/layers/tanh_layer.cu."""
 
     def forward(self, x):
-        return (torch.tanh(x),)
+        return (ops.get(self.ctx).tanh(x),)
 
 
 @register("ABSVAL")
@@ -56,7 +55,7 @@ class AbsValLayer(NeuronLayer):
     """reference: src/caffe/layers/absval_layer.cpp."""
 
     def forward(self, x):
-        return (torch.abs(x),)
+        return (ops.get(self.ctx).absval(x),)
 
 
 @register("BNLL")
@@ -64,7 +63,7 @@ class BNLLLayer(NeuronLayer):
     """reference: src/caffe/layers/bnll_layer.cpp:19-20."""
 
     def forward(self, x):
-        return (ops.reference.bnll(x),)
+        return (ops.get(self.ctx).bnll(x),)
 
 
 @register("POWER")
@@ -76,7 +75,7 @@ class PowerLayer(NeuronLayer):
         self.power, self.scale, self.shift = float(p.power), float(p.scale), float(p.shift)
 
     def forward(self, x):
-        return (ops.reference.power(x, self.power, self.scale, self.shift),)
+        return (ops.get(self.ctx).power(x, self.power, self.scale, self.shift),)
 
 
 @register("THRESHOLD")
@@ -88,7 +87,7 @@ class ThresholdLayer(NeuronLayer):
         self.threshold = float(self.lp.threshold_param.threshold)
 
     def forward(self, x):
-        return ((x > self.threshold).to(x.dtype),)
+        return (ops.get(self.ctx).threshold(x, self.threshold),)
 
 
 @register("DROPOUT")

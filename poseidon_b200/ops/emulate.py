@@ -52,6 +52,9 @@ class EmulatedKernels:
     def set_conv_im2col(self, on):
         return None
 
+    def set_pair_cta(self, on):              # csrc/gemm/gemm_ops.cu (cta_group::2 on/off: no numerical effect)
+        return None
+
     # ------------------------------------------------------------------------------------------ GEMM
     def gemm_bf16(self, a, a_mn, b, b_mn, bias, relu, slope, mask, out, bn):
         """C[M,N] bf16 = act(A·Bᵀ + bias), A = a ([M,K]) or aᵀ, B = b ([N,K]) or bᵀ (csrc/gemm/gemm_ops.cu:173-240)."""
@@ -258,6 +261,132 @@ class EmulatedKernels:
         (dx,) = torch.autograd.grad(y, xf, dy.float())
         return _nhwc(dx.to(BF16))
 
+    # ------------------------------------------------------------------------------------------ layer kernels (round 2)
+    @staticmethod
+    def _like(ref, v):
+        """bf16 result with the strides of ``ref`` (the kernels write storage order)."""
+        out = torch.empty_like(ref, dtype=BF16)
+        out.copy_(v)
+        return out
+
+    def unary_fwd(self, x, op, a, b, c):
+        """csrc/ops/neuron.cu: 0 sigmoid, 1 tanh, 2 abs, 3 bnll, 4 power(a; scale b, shift c), 5 threshold(a)."""
+        xf = x.float()
+        y = [torch.sigmoid, torch.tanh, torch.abs, R.bnll, lambda t: R.power(t, a, b, c), lambda t: (t > a).float()][op](xf)
+        return self._like(x, y)
+
+    def unary_bwd(self, saved, dy, op, a, b, c):
+        s, g = saved.float(), dy.float()
+        if op == 0:
+            d = g * s * (1 - s)
+        elif op == 1:
+            d = g * (1 - s * s)
+        elif op == 2:
+            d = g * torch.sign(s)
+        elif op == 3:
+            e = torch.exp(s.clamp_max(50.0))
+            d = g * e / (e + 1)
+        elif op == 4:
+            v = c + b * s
+            d = g * b if a == 1 else (g * 2 * b * v if a == 2 else g * a * b * v.pow(a - 1))
+        else:
+            d = torch.zeros_like(g)
+        return self._like(dy, d)
+
+    def eltwise_fwd(self, xs, op, coeffs, want_mask):
+        fs = [x.float() for x in xs]
+        mask = torch.empty(0, dtype=torch.uint8)
+        if op == 0:
+            y = fs[0]
+            for t in fs[1:]:
+                y = y * t
+        elif op == 1:
+            cs = coeffs or [1.0] * len(fs)
+            y = sum(c * t for c, t in zip(cs, fs))
+        else:
+            st = torch.stack(fs)
+            y, arg = st.max(0)
+            if want_mask:
+                mask = arg.to(torch.uint8)
+        return self._like(xs[0], y), mask
+
+    def eltwise_bwd(self, xs, dy, mask, op, coeffs, need):
+        g = dy.float()
+        outs = []
+        for j in range(len(xs)):
+            if not need[j]:
+                outs.append(torch.empty(0, dtype=BF16))
+                continue
+            if op == 0:
+                d = g
+                for q, x in enumerate(xs):
+                    if q != j:
+                        d = d * x.float()
+            elif op == 1:
+                d = g * (coeffs[j] if coeffs else 1.0)
+            else:
+                d = g * (mask == j)
+            outs.append(self._like(dy, d))
+        return outs
+
+    def softmax_fwd(self, x):
+        return self._like(x, torch.softmax(x.float(), 1))
+
+    def softmax_bwd(self, y, dy):
+        yf, g = y.float(), dy.float()
+        return self._like(y, yf * (g - (g * yf).sum(1, keepdim=True)))
+
+    def mvn_fwd(self, x, nv, ac):
+        xf = x.float()
+        n, c = x.shape[:2]
+        v = xf.reshape(n, 1, -1) if ac else xf.reshape(n, c, -1)
+        mean = v.mean(2)
+        var = ((v * v).mean(2) - mean * mean).clamp_min(0)
+        inv = 1.0 / (var.sqrt() + 1e-10) if nv else torch.ones_like(mean)
+        stats = torch.stack([mean.expand(n, c), inv.expand(n, c)], 2).contiguous()
+        y = (xf - stats[:, :, 0].view(n, c, 1, 1)) * stats[:, :, 1].view(n, c, 1, 1)
+        return _nhwc(y.to(BF16)), stats
+
+    def mvn_bwd(self, y, dy, stats, nv, ac):
+        g, yf = dy.float(), y.float()
+        n, c = y.shape[:2]
+        dims = (1, 2, 3) if ac else (2, 3)
+        d = g - g.mean(dims, keepdim=True)
+        if nv:
+            d = (d - yf * (g * yf).mean(dims, keepdim=True)) * stats[:, :, 1].view(n, c, 1, 1)
+        return _nhwc(d.to(BF16))
+
+    def lrn_within_fwd(self, x, size, alpha, beta):
+        return _nhwc(R.lrn_within(x.float(), size, alpha, beta).to(BF16))
+
+    def lrn_within_bwd(self, x, dy, size, alpha, beta):
+        xf = x.float().detach().requires_grad_(True)
+        with torch.enable_grad():
+            y = R.lrn_within(xf, size, alpha, beta)
+        (dx,) = torch.autograd.grad(y, xf, dy.float())
+        return _nhwc(dx.to(BF16))
+
+    def stochastic_pool_fwd(self, x, k, s, oh, ow, train, seed, iter_dev):
+        """(y, idx): idx is opaque to the caller (fed back to pool_bwd), so the emulation stores the plane index like
+        its pool_fwd does (csrc/ops/lrn_within.cu: the kernel stores the in-window tap)."""
+        xf = x.float()
+        cols, oh2, ow2 = R._pool_windows(xf, tuple(k), tuple(s))
+        assert (oh2, ow2) == (oh, ow)
+        ssum = cols.sum(-1)
+        if not train:
+            y = (cols * cols).sum(-1) / ssum.clamp_min(torch.finfo(torch.float32).tiny)
+            return _nhwc(y.to(BF16)), torch.empty(0, dtype=torch.int64)
+        it = int(iter_dev.item()) if iter_dev is not None else 0
+        g = torch.Generator().manual_seed((int(seed) ^ (it * 0x9E3779B97F4A7C15)) & 0x7FFFFFFFFFFFFFFF)
+        thr = torch.rand(ssum.shape, generator=g) * ssum
+        tap = (cols.cumsum(-1) < thr.unsqueeze(-1)).sum(-1).clamp_max(cols.shape[-1] - 1)
+        y = cols.gather(-1, tap.unsqueeze(-1)).squeeze(-1)
+        n, c, h, w = x.shape
+        ohs = torch.arange(oh).view(1, 1, oh, 1) * s[0] + tap // k[1]
+        ows = torch.arange(ow).view(1, 1, 1, ow) * s[1] + tap % k[1]
+        idx = (ohs.clamp_max(h - 1) * w + ows.clamp_max(w - 1)).contiguous()
+        return _nhwc(y.to(BF16)), idx
+
     # ------------------------------------------------------------------------------------------ loss
     def softmax_xent(self, x, label, grad_scale, want_grad, want_prob):
         """(loss[1] fp32, dx like x, prob fp32): mean NLL over rows, dx = (p - onehot)·grad_scale/rows
@@ -371,6 +500,40 @@ class EmulatedKernels:
             if wb_ptrs:
                 self._mem(wb_ptrs[p], n * 2, BF16)[sl] = w.to(BF16)
         self._peer_barrier(flag_ptrs, rank, 1, ep)
+
+    def allreduce_sgd_multi(self, base_ptrs, mc_base, flag_ptrs, g_offs, w_offs, wb_offs, hists, ns, one_shots, lrs, decays,
+                            rank, epoch, done_counter, momentum, rule, l1, delta, gscale, max_ctas, lr_dev, epoch_dev):
+        """One launch per bucket: up to 4 segments behind one barrier pair; the kernel re-arms (zeroes) the gradient
+        staging it consumed — the shard owner in every rank's arena for two-shot segments, each rank its own copy after
+        the closing barrier for one-shot segments (csrc/comm/fused_update.cu: allreduce_sgd_multi_kernel)."""
+        world = len(base_ptrs)
+        ep = self._epoch(epoch, epoch_dev)
+        lr_glob = float(lr_dev[0]) if lr_dev is not None else 1.0
+        self._peer_barrier(flag_ptrs, rank, 0, ep)
+        for g_off, w_off, wb_off, h, n, one_shot, lr, decay in zip(g_offs, w_offs, wb_offs, hists, ns, one_shots, lrs, decays):
+            n4 = n // 4
+            lo, hi = 0, n4
+            if not one_shot:
+                per = (n4 + world - 1) // world
+                lo = min(n4, per * rank)
+                hi = min(n4, lo + per)
+            sl = slice(4 * lo, 4 * hi)
+            g = self._mem(base_ptrs[0] + g_off, n * 4, torch.float32)[sl].clone()
+            for q in range(1, world):
+                g += self._mem(base_ptrs[q] + g_off, n * 4, torch.float32)[sl]
+            if not one_shot:
+                for q in range(world):
+                    self._mem(base_ptrs[q] + g_off, n * 4, torch.float32)[sl] = 0.0
+            w = self._mem(base_ptrs[rank] + w_off, n * 4, torch.float32)[sl].clone()
+            self._step(w, g, h[:n][sl], lr * lr_glob, momentum, decay, rule, l1, delta, gscale)
+            for p in ([rank] if one_shot else range(world)):
+                self._mem(base_ptrs[p] + w_off, n * 4, torch.float32)[sl] = w
+                if wb_off >= 0:
+                    self._mem(base_ptrs[p] + wb_off, n * 2, BF16)[sl] = w.to(BF16)
+        self._peer_barrier(flag_ptrs, rank, 1, ep)
+        for g_off, n, one_shot in zip(g_offs, ns, one_shots):
+            if one_shot:
+                self._mem(base_ptrs[rank] + g_off, n * 4, torch.float32).zero_()
 
     def peer_push(self, src, dst_ptrs, dst_mc, flag_ptrs, rank, slot, epoch, signal, done_counter, wait_slot, epoch_dev):
         """Payload into every rank's arena, then (optionally) this rank's epoch flag on every peer

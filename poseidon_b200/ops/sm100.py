@@ -571,8 +571,66 @@ def lrn_across(x, size, alpha, beta, mask_input=False):
     return _LRNFn.apply(x, size, alpha, beta, mask_input)
 
 
-lrn_within = R.lrn_within
-stochastic_pool = R.stochastic_pool
+def _cl_dense(x: torch.Tensor) -> bool:
+    return x.dim() == 4 and x.is_contiguous(memory_format=CL)
+
+
+class _LRNWithinFn(torch.autograd.Function):
+    """One kernel forward, two backward (the reference composes five layers: lrn_layer.cpp:20-69)."""
+
+    @staticmethod
+    def forward(ctx, x, size, alpha, beta):
+        x = as_kernel_input(x)
+        ctx.save_for_backward(x)
+        ctx.args = (size, alpha, beta)
+        return K().lrn_within_fwd(x, size, alpha, beta)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        size, alpha, beta = ctx.args
+        return K().lrn_within_bwd(x, as_kernel_input(dy), size, alpha, beta), None, None, None
+
+
+def lrn_within(x, size, alpha, beta):
+    if not _on(x) or x.dim() != 4 or x.shape[1] % 8:
+        return R.lrn_within(x, size, alpha, beta)
+    return _LRNWithinFn.apply(x, int(size), float(alpha), float(beta))
+
+
+class _StoPoolFn(torch.autograd.Function):
+    """Stochastic pooling, training phase: the sampled tap index is stored in MAX pooling's arg-max format, so the
+    backward is pool_bwd's gather (reference: pooling_layer.cu:81-118 forward, :295-330 backward)."""
+
+    @staticmethod
+    def forward(ctx, x, kernel, stride, seed):
+        x = as_kernel_input(x)
+        oh = R.pool_out_size(x.shape[2], kernel[0], stride[0], 0)
+        ow = R.pool_out_size(x.shape[3], kernel[1], stride[1], 0)
+        y, idx = K().stochastic_pool_fwd(x, list(kernel), list(stride), oh, ow, True, seed, iteration_seed(x.device))
+        ctx.save_for_backward(idx)
+        ctx.args = (tuple(x.shape[2:]), kernel, stride)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        in_hw, kernel, stride = ctx.args
+        dx = K().pool_bwd(as_kernel_input(dy), idx, True, list(in_hw), list(kernel), list(stride), [0, 0])
+        return dx, None, None, None
+
+
+def stochastic_pool(x, kernel, stride, train: bool, generator=None):
+    if not _on(x) or x.dim() != 4 or x.shape[1] % 8 or kernel[0] * kernel[1] > 255:
+        return R.stochastic_pool(x, kernel, stride, train, generator)
+    if not train:
+        x = as_kernel_input(x)
+        oh = R.pool_out_size(x.shape[2], kernel[0], stride[0], 0)
+        ow = R.pool_out_size(x.shape[3], kernel[1], stride[1], 0)
+        return K().stochastic_pool_fwd(x, list(kernel), list(stride), oh, ow, False, 0, None)[0]
+    _dropout_counter[0] += 1
+    seed = (torch.initial_seed() * 1000003 + _dropout_counter[0] * 7919 + 17) & 0x7FFFFFFFFFFFFFFF
+    return _StoPoolFn.apply(x, tuple(kernel), tuple(stride), int(seed))
 
 
 class _PoolFn(torch.autograd.Function):
@@ -705,7 +763,146 @@ def softmax_loss(x, label, return_prob=False):
     return loss
 
 
-softmax = R.softmax
+class _SoftmaxFn(torch.autograd.Function):
+    """Channel softmax: with NHWC memory every (n, h, w) position is one contiguous row (softmax_layer.cu:14-149)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        y = K().softmax_fwd(x)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = dy if dy.dtype == torch.bfloat16 else dy.to(torch.bfloat16)
+        dy = as_kernel_input(dy) if dy.dim() == 4 else (dy if dy.stride(1) == 1 else dy.contiguous())
+        return K().softmax_bwd(y, dy)
+
+
+def softmax(x):
+    if not _on(x) or x.dtype != torch.bfloat16 or x.dim() not in (2, 4):
+        return R.softmax(x)
+    if x.dim() == 4:
+        x = as_kernel_input(x)
+    elif x.stride(1) != 1:
+        x = x.contiguous()
+    return _SoftmaxFn.apply(x)
+
+
+# ---- elementwise neurons: Sigmoid / TanH / AbsVal / BNLL / Power / Threshold ------------------------------------------
+U_SIGMOID, U_TANH, U_ABSVAL, U_BNLL, U_POWER, U_THRESHOLD = range(6)
+
+
+def _unary_ok(x: torch.Tensor) -> bool:
+    dense = x.is_contiguous() or _cl_dense(x)
+    return _on(x) and x.dtype == torch.bfloat16 and dense and x.data_ptr() % 16 == 0
+
+
+class _UnaryFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, op, a, b, c):
+        y = K().unary_fwd(x, op, a, b, c)
+        ctx.args = (op, a, b, c)
+        ctx.save_for_backward(y if op in (U_SIGMOID, U_TANH) else x)       # what the reference's backward reads
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (s,) = ctx.saved_tensors
+        op, a, b, c = ctx.args
+        if op == U_THRESHOLD:
+            return None, None, None, None, None
+        dy = dy if dy.dtype == torch.bfloat16 else dy.to(torch.bfloat16)
+        if dy.stride() != s.stride():
+            dy = torch.empty_like(s).copy_(dy)
+        return K().unary_bwd(s, dy, op, a, b, c), None, None, None, None
+
+
+def _unary(x, op, a=0.0, b=0.0, c=0.0, fallback=None):
+    if not _unary_ok(x):
+        return fallback(x)
+    return _UnaryFn.apply(x, op, float(a), float(b), float(c))
+
+
+def sigmoid(x):
+    return _unary(x, U_SIGMOID, fallback=torch.sigmoid)
+
+
+def tanh(x):
+    return _unary(x, U_TANH, fallback=torch.tanh)
+
+
+def absval(x):
+    return _unary(x, U_ABSVAL, fallback=torch.abs)
+
+
+def bnll(x):
+    return _unary(x, U_BNLL, fallback=R.bnll)
+
+
+def power(x, pw, scale, shift):
+    return _unary(x, U_POWER, pw, scale, shift, fallback=lambda t: R.power(t, pw, scale, shift))
+
+
+def threshold(x, t):
+    return _unary(x, U_THRESHOLD, t, fallback=lambda v: (v > t).to(v.dtype))
+
+
+# ---- Eltwise ---------------------------------------------------------------------------------------------------------
+_ELT = {"PROD": 0, "SUM": 1, "MAX": 2}
+
+
+class _EltwiseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, op, coeffs, *xs):
+        need_grad = any(x.requires_grad for x in xs)
+        y, mask = K().eltwise_fwd(list(xs), op, list(coeffs), need_grad)
+        ctx.op, ctx.coeffs = op, coeffs
+        ctx.save_for_backward(mask, *(xs if op == 0 else xs[:1]))       # PROD reads its bottoms again; SUM / MAX do not
+        ctx.n = len(xs)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        mask, *saved = ctx.saved_tensors
+        ref = saved[0]
+        dy = dy if dy.dtype == torch.bfloat16 else dy.to(torch.bfloat16)
+        if dy.stride() != ref.stride():
+            dy = torch.empty_like(ref).copy_(dy)
+        xs = saved if ctx.op == 0 else [ref] * ctx.n
+        need = [1 if g else 0 for g in ctx.needs_input_grad[2:]]
+        outs = K().eltwise_bwd(list(xs), dy, mask, ctx.op, list(ctx.coeffs), need)
+        return (None, None) + tuple(o if n else None for o, n in zip(outs, need))
+
+
+def eltwise(xs, op="SUM", coeffs=None):
+    ok = 2 <= len(xs) <= 8 and all(_unary_ok(x) and x.stride() == xs[0].stride() for x in xs) and xs[0].numel() % 8 == 0
+    if not ok:
+        return R.eltwise(xs, op, coeffs)
+    return _EltwiseFn.apply(_ELT[op], tuple(float(c) for c in (coeffs or [])), *xs)
+
+
+# ---- MVN ---------------------------------------------------------------------------------------------------------------
+class _MVNFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, nv, ac):
+        y, stats = K().mvn_fwd(x, nv, ac)
+        ctx.save_for_backward(y, stats)
+        ctx.args = (nv, ac)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, stats = ctx.saved_tensors
+        nv, ac = ctx.args
+        return K().mvn_bwd(y, as_kernel_input(dy), stats, nv, ac), None, None
+
+
+def mvn(x, normalize_variance=True, across_channels=False):
+    if not _on(x) or x.dim() != 4 or x.shape[1] % 8 or x.dtype != torch.bfloat16:
+        return R.mvn(x, normalize_variance, across_channels)
+    return _MVNFn.apply(as_kernel_input(x), bool(normalize_variance), bool(across_channels))
 
 
 def concat(xs, dim):

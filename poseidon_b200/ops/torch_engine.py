@@ -15,6 +15,17 @@ lrn_within = R.lrn_within
 relu = R.relu
 softmax = R.softmax
 softmax_loss = R.softmax_loss
+sigmoid = torch.sigmoid
+tanh = torch.tanh
+absval = torch.abs
+bnll = R.bnll
+power = R.power
+eltwise = R.eltwise
+mvn = R.mvn
+
+
+def threshold(x, t):
+    return (x > t).to(x.dtype)
 
 
 def conv2d(x, w, b, stride, pad, groups, relu_slope=None, layer=None):

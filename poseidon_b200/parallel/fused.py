@@ -101,6 +101,13 @@ class SymmetricArena:
         self.multicast_ptr = int(mc)
         self.offset = 0
         self.nbytes = nbytes
+        # Which branch the comm kernels will take is decided here and nowhere else: a non-zero multicast pointer means
+        # multimem.ld_reduce / multimem.st through the NVSwitch (NVLS); zero means per-peer P2P loads / stores.
+        if self.rank == 0:
+            log.info("symmetric arena: %d MiB per rank, %d ranks, NVLS multicast %s", nbytes >> 20, self.world,
+                     f"mapped at {self.multicast_ptr:#x}" if self.multicast_ptr else "UNAVAILABLE (P2P loads/stores)")
+        if os.environ.get("POSEIDON_REQUIRE_NVLS", "0") == "1" and not self.multicast_ptr:
+            raise RuntimeError("POSEIDON_REQUIRE_NVLS=1 but the symmetric-memory rendezvous returned no multicast mapping")
         torch.cuda.synchronize(self.device)
         rank_ctx.barrier()
 
@@ -152,7 +159,10 @@ class FusedBackend(Backend):
         self.svb, self.sfb_mode, self.reduce = svb, sfb_mode, grad_reduce
         # buckets up to this size are reduced whole by every rank (one launch latency); larger ones are sharded
         self.one_shot_bytes = int(os.environ.get("POSEIDON_ONE_SHOT_BYTES", one_shot_bytes))
-        self.use_multimem = use_multimem
+        self.use_multimem = use_multimem and os.environ.get("POSEIDON_MULTIMEM", "1") != "0"
+        # SFB reconstruct: optimizer step fused into the outer-product kernel's epilogue (1), or the two-pass form
+        # "P-source outer product -> fp32 buffer (bulk row stores), then the streaming update kernel" (0)
+        self.fuse_sfb_sgd = os.environ.get("POSEIDON_SFB_FUSED_SGD", "1") != "0"
         self.arena: Optional[SymmetricArena] = None
         self.epoch = 0
         self.dense_bytes = 0
@@ -394,24 +404,29 @@ class FusedBackend(Backend):
         self.stream.wait_stream(cur)
         self.epoch_of_bucket = self.epoch + 1
         with self.cu.stream(self.stream):
-            for pi, (p, seg, lm, dm) in enumerate(zip(bucket.params, bucket.segs, bucket.lr_mult, bucket.decay_mult)):
-                if p.grad is None:
-                    continue
-                n = seg.numel
-                one_shot = n * 4 <= self.one_shot_bytes
-                lr, mom, decay, rule, l1, delta, gscale = self._hyper_args(lm, dm)
+            live = [(p, seg, lm, dm) for p, seg, lm, dm in zip(bucket.params, bucket.segs, bucket.lr_mult, bucket.decay_mult)
+                    if p.grad is not None]
+            if live:
                 use_mc = self.use_multimem and ar.multicast_ptr != 0
-                if self.cross_group is not None:
-                    self._inter_node_reduce(ar.view(seg.g_off, (n,), torch.float32), n, one_shot)
-                self.k.allreduce_sgd(ar.peer_ptrs(seg.g_off), ar.peer_ptrs(seg.w_off), ar.peer_ptrs(seg.wb_off),
-                                     ar.peer_ptrs(bucket.flag_off + 64 * pi),
-                                     ar.mc_ptr(seg.g_off) if use_mc else 0,
-                                     ar.mc_ptr(seg.w_off) if (use_mc and not one_shot) else 0,
-                                     seg.hist, n, self.rank, 1, one_shot, self.done_counter,
-                                     lr, mom, decay, rule, l1, delta, gscale, 64, self.lr_t, self.epoch_t)
-                ar.view(seg.g_off, (n,), torch.float32).zero_()
-                self.launches += 2
-                self.dense_bytes += n * 4
+                g_offs, w_offs, wb_offs, hists, ns, ones, lrs, decays = [], [], [], [], [], [], [], []
+                hy = None
+                for p, seg, lm, dm in live:
+                    n = seg.numel
+                    one_shot = n * 4 <= self.one_shot_bytes
+                    lr, mom, decay, rule, l1, delta, gscale = hy = self._hyper_args(lm, dm)
+                    if self.cross_group is not None:
+                        self._inter_node_reduce(ar.view(seg.g_off, (n,), torch.float32), n, one_shot)
+                    g_offs.append(seg.g_off); w_offs.append(seg.w_off); wb_offs.append(seg.wb_off)
+                    hists.append(seg.hist); ns.append(n); ones.append(1 if one_shot else 0)
+                    lrs.append(lr); decays.append(decay)
+                    self.dense_bytes += n * 4
+                _, mom, _, rule, l1, delta, gscale = hy
+                # ONE launch per bucket (weight + bias behind one barrier pair); the kernel also re-arms (zeroes) the
+                # gradient staging it consumed, so no memset launch follows
+                self.k.allreduce_sgd_multi(ar.base_ptrs, ar.multicast_ptr if use_mc else 0, ar.peer_ptrs(bucket.flag_off),
+                                           g_offs, w_offs, wb_offs, hists, ns, ones, lrs, decays, self.rank, 1,
+                                           self.done_counter, mom, rule, l1, delta, gscale, 64, self.lr_t, self.epoch_t)
+                self.launches += 1
             if bucket.event is None:
                 bucket.event = self.cu.Event()
             bucket.event.record(self.stream)
@@ -475,6 +490,25 @@ class FusedBackend(Backend):
         if ar is not None and hasattr(ar, "close"):
             self.arena = None
             ar.close()
+
+    def comm_profile(self) -> Dict:
+        """Static description of one step's communication (valid under CUDA-graph replay, where the Python-side byte
+        counters stand still): per rank, bytes of dense gradients entering the in-kernel all-reduce, bytes of sufficient
+        factors published, and the dense bytes those SFB layers would have cost; plus which NVLink path the kernels use."""
+        dense = sfb = sfb_equiv = 0
+        if self.world > 1:
+            for b in self.sync.buckets:
+                for p, seg in zip(b.params, getattr(b, "segs", [])):
+                    if id(p) in b.self_updating:
+                        continue
+                    dense += seg.numel * 4
+            for h in self.sfb_layers.values():
+                sfb += h.M * (h.N + h.K) * 2
+                sfb_equiv += h.N * h.K * 4
+        mc = bool(self.arena is not None and getattr(self.arena, "multicast_ptr", 0) and self.use_multimem)
+        return {"dense_allreduce_bytes_per_step": dense, "sfb_factor_bytes_per_step": sfb,
+                "sfb_dense_equiv_bytes_per_step": sfb_equiv, "multimem": mc,
+                "nvlink_path": ("nvls_multicast" if mc else "p2p") if self.world > 1 else "none"}
 
     def bytes_on_wire(self):
         return {"dense_allreduce_bytes": self.dense_bytes, "inter_node_allreduce_bytes": self.inter_node_bytes,

@@ -116,9 +116,47 @@ def compute_update(hyper: Hyper, w, g, h, lr_mult, decay_mult, decay_scale=1.0):
         return lr * g / (h.sqrt() + hyper.delta)
 
 
+def foreach_sgd_step(hyper: Hyper, entries, lr_t: torch.Tensor, decay_scale=1.0, gscale=1.0):
+    """Caffe's SGD rule (h <- mom*h + lr*(g + wd*w); w <- w - h) over many tensors with ``torch._foreach`` kernels and a
+    DEVICE-resident learning rate, so the step can sit inside a captured CUDA graph.  This is the optimizer of the
+    constructed vendor baseline (cuDNN/cuBLAS through PyTorch + foreach SGD); the product fuses the step into its
+    reduce / wgrad kernels instead.  ``entries``: (param, grad, history, lr_mult, decay_mult); grads are consumed."""
+    if hyper.solver_type != SGD or hyper.l1:
+        raise RuntimeError("the foreach (CUDA-graph) optimizer of the library backends implements SGD with L2 decay")
+    groups: Dict[tuple, list] = {}
+    for e in entries:
+        groups.setdefault((float(e[3]), float(e[4])), []).append(e)
+    with torch.no_grad():
+        for (lm, dm), es in groups.items():
+            ws = [e[0].data for e in es]
+            gs = [e[1] if e[1].dtype == e[0].dtype else e[1].to(e[0].dtype) for e in es]
+            hs = [e[2] for e in es]
+            if gscale != 1.0:
+                torch._foreach_mul_(gs, gscale)
+            wd = hyper.weight_decay * dm * decay_scale
+            if wd:
+                torch._foreach_add_(gs, ws, alpha=wd)
+            torch._foreach_mul_(gs, lr_t * lm if lm != 1.0 else lr_t)
+            torch._foreach_mul_(hs, hyper.momentum)
+            torch._foreach_add_(hs, gs)
+            torch._foreach_sub_(ws, hs)
+
+
 class Backend:
     name = "base"
     uses_comm_stream = False
+    deferred_step = False     # library backends: reduce per bucket (DWBP), ONE foreach optimizer step at the end of the iteration
+    lr_t: Optional[torch.Tensor] = None
+
+    def enable_deferred_step(self, device):
+        """Switch to the CUDA-graph-safe optimizer: learning rate on the device, one foreach step per iteration."""
+        self.deferred_step = True
+        self.lr_t = torch.zeros((), dtype=torch.float32, device=device)
+        self._deferred = []
+
+    def set_lr(self, lr: float):
+        if self.lr_t is not None:
+            self.lr_t.fill_(float(lr))
 
     def setup(self, sync: "GradSync"):
         self.sync = sync
@@ -138,8 +176,17 @@ class LocalBackend(Backend):
 
     def launch(self, bucket):
         hy = self.sync.hyper
+        if self.deferred_step:
+            self._deferred += [(p, p.grad, h, lm, dm) for p, h, lm, dm in
+                               zip(bucket.params, bucket.history, bucket.lr_mult, bucket.decay_mult)]
+            return
         for p, h, lm, dm in zip(bucket.params, bucket.history, bucket.lr_mult, bucket.decay_mult):
             apply_rule(hy, p.data, p.grad, h, lm, dm)
+
+    def finish_iteration(self):
+        if self.deferred_step and self._deferred:
+            foreach_sgd_step(self.sync.hyper, self._deferred, self.lr_t)
+            self._deferred = []
 
 
 class TorchDistBackend(Backend):
@@ -180,11 +227,27 @@ class TorchDistBackend(Backend):
             for p in red:
                 grads[id(p)] = flat[off:off + p.numel()].view_as(p)
                 off += p.numel()
+        if self.deferred_step:
+            # DDP-style: the reduction overlaps backward (comm stream), the optimizer runs once at the end of the step
+            self._deferred += [(p, grads.get(id(p), p.grad), h, lm, dm) for p, h, lm, dm in
+                               zip(bucket.params, bucket.history, bucket.lr_mult, bucket.decay_mult)]
+            return
         for p, h, lm, dm in zip(bucket.params, bucket.history, bucket.lr_mult, bucket.decay_mult):
             g = grads.get(id(p), p.grad)
             if self.reduce == "mean":
                 g = g / ws
             apply_rule(hy, p.data, g, h, lm, dm, decay_scale=float(ws) if self.reduce == "sum" else 1.0)
+
+    def finish_iteration(self):
+        if not (self.deferred_step and self._deferred):
+            return
+        ws = self.sync.rank_ctx.world_size
+        if self.cuda:
+            torch.cuda.current_stream().wait_stream(self.stream)      # every bucket's all-reduce has been issued there
+        foreach_sgd_step(self.sync.hyper, self._deferred, self.lr_t,
+                         decay_scale=float(ws) if self.reduce == "sum" else 1.0,
+                         gscale=1.0 / ws if self.reduce == "mean" else 1.0)
+        self._deferred = []
 
     def launch(self, bucket):
         if not self.cuda:

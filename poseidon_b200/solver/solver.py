@@ -286,6 +286,47 @@ class Solver:
             self._train_iteration()
 
     # ---- CUDA-graph execution: the whole step (forward, backward, DWBP hooks, fused updates) is one graph ----
+    GRAPH_WARMUP = 2
+
+    def _graph_wanted(self) -> bool:
+        """``solve()`` (i.e. ``caffe_main train`` and ``CaffeEngine.start``) replays the training step as one CUDA graph
+        whenever that is possible: sm100 engine on a GPU with the fused backend (one GPU, or many with BSP).  The library
+        backends can be graphed on request (``use_cuda_graph=True`` / POSEIDON_CUDA_GRAPH=1).  Eager otherwise."""
+        mode = getattr(self, "use_cuda_graph", None)
+        env = os.environ.get("POSEIDON_CUDA_GRAPH", "")
+        if env in ("0", "1"):
+            mode = env == "1"
+        if mode is False or self.device.type != "cuda" or bool(self.param.debug_info):
+            return False
+        name = type(self.sync.backend).__name__
+        if name == "FusedBackend":
+            from ..ops import sm100
+            return not sm100.emulating()
+        return bool(mode) and name in ("LocalBackend", "TorchDistBackend")
+
+    def _graph_window_ok(self, max_iter: int) -> bool:
+        """Capturing runs GRAPH_WARMUP eager iterations plus the captured one inside ``enable_cuda_graph``: start only
+        where none of them is a snapshot / test boundary and the captured one is not a display iteration."""
+        sp, w = self.param, self.GRAPH_WARMUP
+        if self.iter + w + 1 > max_iter:
+            return False
+        for interval in (int(sp.snapshot or 0), int(sp.test_interval or 0)):
+            if interval and (self.iter + w) // interval != self.iter // interval:
+                return False
+        return not (sp.display and (self.iter + w) % int(sp.display) == 0)
+
+    def _try_enable_graph(self) -> bool:
+        try:
+            self.enable_cuda_graph(warmup=self.GRAPH_WARMUP)
+            if self.rank_ctx.is_root:
+                log.info("Training step captured as one CUDA graph (%d kernels of this framework per replay)",
+                         getattr(self, "graph_launches", 0))
+            return True
+        except Exception as exc:          # deterministic across ranks (same net, same backend): everyone falls back together
+            self._graph = None
+            log.warning("CUDA-graph capture failed (%s: %s); continuing with eager launches", type(exc).__name__, exc)
+            return False
+
     def read_loss_async(self):
         """Start a device->host copy of the latest step's loss into page-locked memory and return a handle whose
         ``.value()`` blocks only on that copy.  Reading the handle one step later keeps the copy off the critical
@@ -300,9 +341,16 @@ class Solver:
         see fresh values, and so does the fused NVLink backend's epoch counter (multi-GPU replays stay in lock step
         through the in-kernel flag protocol)."""
         fused_comm = type(self.sync.backend).__name__ == "FusedBackend"
-        if self.engine != "sm100" or self.device.type != "cuda" or (self.rank_ctx.distributed and not fused_comm):
-            raise RuntimeError("CUDA-graph steps need the sm100 engine (multi-GPU: with the fused NVLink backend, whose "
-                               "epoch counter lives on the device)")
+        library = type(self.sync.backend).__name__ in ("LocalBackend", "TorchDistBackend")
+        if self.device.type != "cuda":
+            raise RuntimeError("CUDA-graph steps need a CUDA device")
+        if not fused_comm and not library:
+            raise RuntimeError("CUDA-graph steps need the fused NVLink backend (device-side epochs) or the all-reduce "
+                               "library backend; the bounded-staleness library backends schedule on the host")
+        if library:
+            # the constructed vendor baseline (any engine): per-bucket all-reduce from the hooks + one foreach SGD step,
+            # learning rate in device memory
+            self.sync.backend.enable_deferred_step(self.device)
         from ..ops import sm100
         net = self.net
         k = net.num_leading_data_layers()
@@ -327,6 +375,9 @@ class Solver:
                 h.event = None
         self._g_first = k
         self.sync.begin_iteration(learning_rate(self.param, self.iter))
+        if self.rank_ctx.distributed and library:
+            for b in self.sync.buckets:
+                b.event = None
         graph = torch.cuda.CUDAGraph()
         from ..ops import counting
         n0 = counting.total()
@@ -472,12 +523,16 @@ class Solver:
         self.rank_ctx.barrier()
         self.t0 = time.time()
         max_iter = int(sp.max_iter or 0)
+        want_graph = self._graph_wanted()
         while self.iter < max_iter:
             if sp.snapshot and self.iter > int(getattr(self, "_start_iter", 0)) and self.iter % sp.snapshot == 0:
                 self.snapshot()
             if sp.test_interval and self.iter % sp.test_interval == 0 and \
                     (self.iter > 0 or sp.test_initialization):
                 self.test_all()
+            if want_graph and getattr(self, "_graph", None) is None and self._graph_window_ok(max_iter):
+                want_graph = self._try_enable_graph()          # runs GRAPH_WARMUP + 1 real iterations
+                continue
             self._train_iteration()
         self.sync.wait_all()
         if hasattr(self.sync.backend, "drain"):
@@ -507,6 +562,8 @@ class Solver:
         sp = self.param
         net = self.test_nets[test_net_id]
         self.sync.wait_all()
+        if hasattr(self.sync.backend, "drain"):
+            self.sync.backend.drain()          # evaluate the table all workers agree on (see snapshot())
         world = self.rank_ctx.world_size
         n_iters = max(1, int(math.ceil(float(sp.test_iter[test_net_id]) / world)))
         scores: List[float] = []
@@ -582,6 +639,10 @@ class Solver:
         momentum is per-worker and every rank writes its own suffixed file like the reference.
         reference: src/caffe/solver.cpp:632-667, 990-997."""
         self.sync.wait_all()
+        if hasattr(self.sync.backend, "drain"):
+            # bounded-staleness backends: fold in the peers' in-flight deltas / flush unsent residuals first, so that the
+            # rank-0 .caffemodel is the table every worker agrees on (a collective: every rank snapshots at the same iter)
+            self.sync.backend.drain()
         if self.device.type == "cuda":
             torch.cuda.synchronize(self.device)
         base = f"{self._snapshot_prefix()}_iter_{self.iter}"

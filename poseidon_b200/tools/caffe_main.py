@@ -66,6 +66,8 @@ def make_parser():
     ap.add_argument("--sfb_mode", default="auto", choices=["auto", "all", "none"])
     ap.add_argument("--grad_reduce", default="sum", choices=["sum", "mean"])
     ap.add_argument("--synthetic_shape", default="", help="CxHxW of stand-in data when a DB is absent")
+    ap.add_argument("--cuda_graph", default="auto", choices=["auto", "0", "1"],
+                    help="replay the training step as one CUDA graph (auto: sm100 engine with the fused backend)")
     ap.add_argument("--stats_json", default="")
     ap.add_argument("--log_level", default="INFO")
     for f in _PS_FLAGS:
@@ -142,6 +144,8 @@ def cmd_train(args) -> int:
                         model_dir=os.path.dirname(os.path.abspath(args.solver)), data_shape_hint=hint,
                         sfb_mode=args.sfb_mode, aggr_fraction=args.aggr_fraction,
                         wire_dtype=args.wire_dtype or ("bf16" if str(args.row_oplog_type) == "3" else None))
+    if args.cuda_graph != "auto":
+        solver.use_cuda_graph = args.cuda_graph == "1"
     if rc.is_root:
         log.info("Starting Optimization (world_size=%d, engine=%s, comm=%s, svb=%s, staleness=%d)",
                  rc.world_size, solver.engine, solver.comm_name, _bool(args.svb), args.table_staleness)

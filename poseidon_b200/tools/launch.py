@@ -74,10 +74,13 @@ def latest_solverstate(solver_path: str):
     prefix = expand_placeholder(sp.snapshot_prefix or "snapshot", os.path.dirname(os.path.abspath(solver_path)),
                                 must_exist=False)
     best = (-1, None)
-    for f in glob.glob(glob.escape(prefix) + "_iter_*.solverstate"):
-        m = re.search(r"_iter_(\d+)\.solverstate$", f)
-        if m and int(m.group(1)) > best[0]:
-            best = (int(m.group(1)), f)
+    # synchronous modes write one `<prefix>_iter_N.solverstate`; the bounded-staleness modes write per-worker files
+    # `<prefix>_iter_N.solverstate.<rank>.0` (momentum is per worker there) — Solver.restore takes the UNSUFFIXED base name
+    # and picks its own rank's file, so that is what is returned in both cases
+    for f in glob.glob(glob.escape(prefix) + "_iter_*.solverstate*"):
+        m = re.search(r"^(.*_iter_(\d+)\.solverstate)(\.\d+\.\d+)?$", f)
+        if m and int(m.group(2)) > best[0]:
+            best = (int(m.group(2)), m.group(1))
     return best[1]
 
 

@@ -117,3 +117,66 @@ def test_googlenet_small_batch_step(ext):
     assert 8 < first < 22, first
     assert loss == loss and loss < 60, loss
     s.close()
+
+
+def test_solve_replays_the_step_as_a_cuda_graph(ext, tmp_path):
+    """``Solver.solve`` — the path behind ``caffe_main train`` and ``CaffeEngine.start`` — captures the step as a CUDA
+    graph by itself (display / snapshot boundaries included) and ends where the eager run ends."""
+    from poseidon_b200 import get_solver
+
+    def run(graph, sub):
+        net = small_net(batch=16)
+        sp = small_solver_param(net, max_iter=12)
+        sp.display = 5
+        sp.snapshot = 10
+        sp.snapshot_prefix = str(tmp_path / sub / "small")
+        (tmp_path / sub).mkdir()
+        s = get_solver(sp, engine="sm100")
+        s.use_cuda_graph = graph
+        x, y = make_data(16 * 12)
+        feed(s, x, y)
+        s.solve()
+        torch.cuda.synchronize()
+        out = {n: l.export_blob(0) for n, l in zip(s.net.layer_names, s.net.layers) if len(l.blobs)}
+        graphed = getattr(s, "_graph", None) is not None
+        rows = [r[0] for r in s.train_table.rows]
+        s.close()
+        return out, graphed, rows
+
+    import numpy as np
+    import os
+    w_e, g_e, rows_e = run(False, "eager")
+    w_g, g_g, rows_g = run(None, "graph")                 # None = auto
+    assert not g_e and g_g
+    assert rows_e == rows_g == [0, 5, 10]                  # every display iteration was displayed in both modes
+    assert os.path.exists(tmp_path / "graph" / "small_iter_10.solverstate")
+    for n in w_e:
+        d = np.abs(w_e[n] - w_g[n]).max()
+        assert d <= 0.02 * np.abs(w_e[n]).max() + 1e-4, (n, d)
+
+
+def test_vendor_arm_cuda_graph_matches_eager(ext):
+    """The constructed vendor baseline (torch engine: cuDNN/cuBLAS + foreach SGD with a device-side learning rate)
+    can be replayed as one CUDA graph and follows its own eager trajectory."""
+    from poseidon_b200 import get_solver
+
+    def run(graph):
+        net = small_net(batch=16)
+        sp = small_solver_param(net, max_iter=8)
+        s = get_solver(sp, engine="torch", dtype=torch.float32)
+        x, y = make_data(16 * 8)
+        feed(s, x, y)
+        if graph:
+            s.enable_cuda_graph(warmup=2)
+            s.step(5)
+        else:
+            s.step(8)
+        torch.cuda.synchronize()
+        out = {n: l.export_blob(0) for n, l in zip(s.net.layer_names, s.net.layers) if len(l.blobs)}
+        s.close()
+        return out
+
+    import numpy as np
+    w_e, w_g = run(False), run(True)
+    for n in w_e:
+        assert np.allclose(w_e[n], w_g[n], atol=2e-4, rtol=1e-3), n

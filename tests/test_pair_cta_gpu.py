@@ -27,6 +27,18 @@ def mode(ext, request):
     ext.set_pair_cta(1)
 
 
+@pytest.fixture(params=[(2, 1), (4, 1), (1, 1), (1, 0)], ids=["mcast2", "mcast4", "pair", "single"])
+def conv_mode(ext, request):
+    """Convolution schedules: cluster multicast of the im2col operand (2 or 4 CTAs per cluster, each fetching a slice
+    of the shared pixel tile), paired CTAs, plain single-CTA."""
+    mc, pair = request.param
+    ext.set_conv_mcast(mc)
+    ext.set_pair_cta(pair)
+    yield request.param
+    ext.set_conv_mcast(2)
+    ext.set_pair_cta(1)
+
+
 @pytest.mark.parametrize("M,N,K", [(256, 256, 64), (384, 256, 512), (1000, 320, 200), (4096, 1024, 1024), (640, 96, 576),
                                    (130, 4096, 256)])
 @pytest.mark.parametrize("bn", [0, 64, 128, 256])
@@ -82,11 +94,14 @@ CONV = [
     (3, 128, 7, 9, 256, 3, 1, 1, 1),       # odd spatial extent: ragged last m-block and a phantom block
     (2, 192, 28, 28, 64, 1, 1, 0, 1),      # 1x1
     (2, 512, 14, 14, 512, 3, 1, 1, 1),     # VGG conv4/5 shape: Cout 512 -> wgrad pairs along Cout
+    (2, 64, 28, 28, 96, 3, 1, 1, 1),       # Cout 96: multicast tiles of 64 (+32 valid) / 32 columns
+    (2, 128, 14, 14, 48, 1, 1, 0, 1),      # Cout 48: narrowest tiles
+    (2, 192, 14, 14, 320, 3, 1, 1, 1),     # Cout 320 -> 2 x 192 / 4 x 96 (phantom columns)
 ]
 
 
 @pytest.mark.parametrize("case", CONV)
-def test_conv_im2col(ext, mode, case):
+def test_conv_im2col(ext, conv_mode, case):
     from poseidon_b200.ops import sm100
     from test_ops_gpu import _FakeLayer, _nhwc
     n, cin, h, w, cout, k, stride, pad, group = case

@@ -190,3 +190,27 @@ def test_jsonl_metrics(tmp_path, monkeypatch):
     assert "images_per_sec_per_rank" not in rows[0] and rows[1]["images_per_sec_per_rank"] > 0
     assert rows[2]["world_size"] == 1 and "loss" in rows[2]["outputs"]
     s.close()
+
+
+def test_foreach_deferred_step_matches_per_tensor_rule():
+    """The CUDA-graph-safe optimizer of the library backends (device-resident lr, torch._foreach kernels, one step per
+    iteration) is Caffe's SGD rule exactly: same weights / history as gradsync.apply_rule, incl. lr / decay multipliers."""
+    import torch
+    from poseidon_b200.parallel import gradsync as G
+    torch.manual_seed(3)
+    hy = G.Hyper(G.SGD, momentum=0.9, weight_decay=5e-4)
+    hy.lr = 0.01
+    ws = [torch.randn(7, 5), torch.randn(5), torch.randn(3, 2, 2, 2)]
+    gs = [torch.randn_like(w) for w in ws]
+    hs = [torch.rand_like(w) * 0.1 for w in ws]
+    mults = [(1.0, 1.0), (2.0, 0.0), (1.0, 1.0)]
+    ref_w, ref_h = [w.clone() for w in ws], [h.clone() for h in hs]
+    for w, g, h, (lm, dm) in zip(ref_w, gs, ref_h, mults):
+        G.apply_rule(hy, w, g.clone(), h, lm, dm, decay_scale=2.0)
+    params = [torch.nn.Parameter(w.clone()) for w in ws]
+    hist = [h.clone() for h in hs]
+    lr_t = torch.tensor(0.01)
+    G.foreach_sgd_step(hy, [(p, g.clone(), h, lm, dm) for p, g, h, (lm, dm) in zip(params, gs, hist, mults)], lr_t,
+                       decay_scale=2.0)
+    for p, h, rw, rh in zip(params, hist, ref_w, ref_h):
+        assert torch.allclose(p.data, rw, atol=1e-6) and torch.allclose(h, rh, atol=1e-6)
