@@ -237,7 +237,7 @@ def main():
     batch = solver.net.blob_shapes[solver.net.top_names[0][0]][0]
     # CUDA-graph the step: sm100 engine on one GPU, or on several with the fused NVLink backend (device-side epochs)
     use_graph = (args.graph == 1) or (args.graph < 0 and args.engine == "sm100" and
-                                       (world == 1 or (solver.comm_name == "fused" and args.staleness == 0)))
+                                       (world == 1 or solver.comm_name == "fused"))
     if rc.device.type != "cuda":
         use_graph = False
     if use_graph:

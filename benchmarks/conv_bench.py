@@ -18,8 +18,8 @@ if os.environ.get('PSD_CONV_IM2COL') == '0':
     os.environ['POSEIDON_PAD_K'] = '0'
     sm100.K().set_conv_im2col(0)
 PAIR = int(os.environ.get("PSD_PAIR", "1"))
-sm100.K().set_pair_cta(PAIR)
-MC = int(os.environ.get("PSD_MCAST", "2"))
+sm100.K().set_conv_pair(PAIR)
+MC = int(os.environ.get("PSD_MCAST", "1"))
 sm100.K().set_conv_mcast(MC)
 print(f"== cta_group::{2 if PAIR else 1} kernels, im2col multicast cluster {MC} ==", flush=True)
 which = sys.argv[1].split(",") if len(sys.argv) > 1 else list(CASES)

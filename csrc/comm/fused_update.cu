@@ -440,6 +440,229 @@ void allreduce_sgd_multi(std::vector<int64_t> base_ptrs, int64_t mc_base, std::v
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
+// ------------------------------------------------------------------------------------ bounded staleness (SSP) on the arena
+// Bösen's SSP / SSPPush consistency (ps/src/petuum_ps/consistency/ssp_push_consistency_controller.cpp:70-115,
+// ssp_consistency_controller.cpp:37-161; src/caffe/solver.cpp:441-443 "clock") without a server, a host thread or NCCL:
+//
+//   clock c, rank p, per bucket:
+//     ssp_delta   Δ_p(c) = optimizer step on the LOCAL gradient (own momentum history, like the reference's workers);
+//                 applied to the local weights at once (read-my-writes), stored in slot c % R of p's delta ring inside the
+//                 symmetric arena (R = s + 1), gradient staging re-armed; then "ready" flag c+1 raised on every peer.
+//                 Before overwriting slot c % R the kernel waits until every peer has CONSUMED Δ_p(c - R) — which is
+//                 exactly the SSP blocking rule: nobody runs more than s clocks ahead of the slowest reader.
+//                 The last CTA then PLANS the fold: for each peer q it must fold q's clocks <= c - s (waits for them) and
+//                 may fold whatever q has published beyond that (opportunistic freshness) — one decision per launch, so all
+//                 CTAs of the fold kernel act on the same clock ranges.
+//     ssp_fold    W_p -= Σ_q Σ_{c' in plan(q)} Δ_q(c')  read straight from the peers' rings over NVLink (P2P loads), bf16
+//                 shadow refreshed; then "consumed" counters raised on the producers.  Every delta is folded exactly once
+//                 by every peer; s = 0 degenerates to BSP with summed per-worker updates.
+// All clocks live in device memory (the step counter that also drives the BSP kernels), so the whole step — including the
+// waits — is one CUDA graph.
+constexpr int kSspReadySlot = 5, kSspConsumedSlot = 6;
+
+struct SspSegs {
+  long g_off[kMaxSegs], w_off[kMaxSegs], wb_off[kMaxSegs], d_off[kMaxSegs];   // byte offsets in the arena; d_off = slot 0 of the ring
+  float* h[kMaxSegs];          // local (per-worker) optimizer history
+  long n[kMaxSegs];            // floats, multiple of 4
+  float lr[kMaxSegs], decay[kMaxSegs];
+  int nseg;
+};
+struct SspState {
+  uint32_t* folded;      // [kMaxRanks] clocks of peer q already folded into my weights
+  uint32_t* plan;        // [kMaxRanks] fold up to (exclusive) this clock in the next ssp_fold
+  uint32_t* max_lag;     // [1] largest number of a peer's clocks (<= my clock) left unfolded after planning
+};
+
+__global__ void __launch_bounds__(512)
+ssp_delta_kernel(ArenaPtrs ap, SspSegs ss, long ring_stride, int rank, int world, int R, int staleness, UpdateHyper hp,
+                 unsigned int* __restrict__ done_counter, const float* __restrict__ lr_dev, const uint32_t* __restrict__ clock_dev,
+                 SspState st) {
+  const float lr_glob = lr_dev != nullptr ? __ldg(lr_dev) : 1.f;
+  const uint32_t c = *reinterpret_cast<const volatile uint32_t*>(clock_dev);
+  // slot reuse: every peer has folded my clock c - R
+  if (c >= static_cast<uint32_t>(R)) {
+    if (threadIdx.x < world && static_cast<int>(threadIdx.x) != rank)
+      wait_flag_ge(ap.flags[rank] + kSspConsumedSlot * kMaxRanks + threadIdx.x, c - R + 1);
+    __syncthreads();
+  }
+  const long slot_off = static_cast<long>(c % R) * ring_stride;
+  for (int s = 0; s < ss.nseg; ++s) {
+    UpdateHyper h = hp;
+    h.lr = ss.lr[s] * lr_glob;
+    h.decay = ss.decay[s];
+    const long n4 = ss.n[s] >> 2;
+    float4* gl = reinterpret_cast<float4*>(ap.base[rank] + ss.g_off[s]);
+    float4* wl = reinterpret_cast<float4*>(ap.base[rank] + ss.w_off[s]);
+    uint2* bl = reinterpret_cast<uint2*>(ap.base[rank] + ss.wb_off[s]);
+    float4* hl = reinterpret_cast<float4*>(ss.h[s]);
+    float4* dl = reinterpret_cast<float4*>(ap.base[rank] + ss.d_off[s] + slot_off);
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<long>(gridDim.x) * blockDim.x) {
+      const float4 gv = gl[i];
+      gl[i] = make_float4(0.f, 0.f, 0.f, 0.f);                       // re-arm the gradient staging
+      float4 wv = wl[i], hv = hl[i];
+      const float4 w0 = wv;
+      step_rule(gv.x, wv.x, hv.x, h);
+      step_rule(gv.y, wv.y, hv.y, h);
+      step_rule(gv.z, wv.z, hv.z, h);
+      step_rule(gv.w, wv.w, hv.w, h);
+      hl[i] = hv;
+      wl[i] = wv;                                                     // read-my-writes
+      bl[i] = pack_bf16x4(wv);
+      dl[i] = make_float4(w0.x - wv.x, w0.y - wv.y, w0.z - wv.z, w0.w - wv.w);
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x == 0) *done_counter = 0;
+  __threadfence_system();
+  if (threadIdx.x < world && static_cast<int>(threadIdx.x) != rank) {
+    const int q = threadIdx.x;
+    st_release_sys(ap.flags[q] + kSspReadySlot * kMaxRanks + rank, c + 1);            // Δ_rank(c) is readable
+    // plan the fold of q's deltas: clocks [0, must) are due now, anything q has published beyond is folded if it is there
+    const uint32_t lo = st.folded[q];
+    const uint32_t must = (c + 1 > static_cast<uint32_t>(staleness)) ? c + 1 - staleness : 0u;
+    const uint32_t* ready = ap.flags[rank] + kSspReadySlot * kMaxRanks + q;
+    if (must > lo) wait_flag_ge(ready, must);
+    const uint32_t avail = ld_acquire_sys(ready);
+    uint32_t hi = avail > lo ? avail : lo;
+    if (hi > lo + static_cast<uint32_t>(R)) hi = lo + R;              // (cannot happen: q blocks on my consumption)
+    st.plan[q] = hi;
+    atomicMax(st.max_lag, (c + 1 > hi) ? c + 1 - hi : 0u);
+  }
+}
+
+__global__ void __launch_bounds__(512)
+ssp_fold_kernel(ArenaPtrs ap, SspSegs ss, long ring_stride, int rank, int world, int R, unsigned int* __restrict__ done_counter,
+                SspState st, int drain) {
+  __shared__ uint32_t lo_s[kMaxRanks], hi_s[kMaxRanks];
+  if (threadIdx.x < kMaxRanks) {
+    const int q = threadIdx.x;
+    uint32_t lo = 0, hi = 0;
+    if (q < world && q != rank) {
+      lo = st.folded[q];
+      // drain: the host barrier guarantees that every rank has published its last clock — the flag is final, so every
+      // CTA reads the same value
+      hi = drain ? ld_acquire_sys(ap.flags[rank] + kSspReadySlot * kMaxRanks + q) : st.plan[q];
+      if (hi < lo) hi = lo;
+    }
+    lo_s[q] = lo;
+    hi_s[q] = hi;
+  }
+  __syncthreads();
+  bool any = false;
+  for (int q = 0; q < world; ++q) any = any || hi_s[q] > lo_s[q];
+  if (any) {
+    for (int s = 0; s < ss.nseg; ++s) {
+      const long n4 = ss.n[s] >> 2;
+      float4* wl = reinterpret_cast<float4*>(ap.base[rank] + ss.w_off[s]);
+      uint2* bl = reinterpret_cast<uint2*>(ap.base[rank] + ss.wb_off[s]);
+      for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<long>(gridDim.x) * blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < world; ++q) {
+          for (uint32_t cc = lo_s[q]; cc < hi_s[q]; ++cc) {
+            const float4 d = reinterpret_cast<const float4*>(ap.base[q] + ss.d_off[s] + static_cast<long>(cc % R) * ring_stride)[i];
+            acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
+          }
+        }
+        float4 wv = wl[i];
+        wv.x -= acc.x; wv.y -= acc.y; wv.z -= acc.z; wv.w -= acc.w;
+        wl[i] = wv;
+        bl[i] = pack_bf16x4(wv);
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x == 0) *done_counter = 0;
+  if (threadIdx.x < world && static_cast<int>(threadIdx.x) != rank) {
+    const int q = threadIdx.x;
+    st.folded[q] = hi_s[q];
+    st_release_sys(ap.flags[q] + kSspConsumedSlot * kMaxRanks + rank, hi_s[q]);       // q may reuse the slots I have read
+  }
+}
+
+static void fill_ssp(ArenaPtrs& ap, SspSegs& ss, const std::vector<int64_t>& base_ptrs, const std::vector<int64_t>& flag_ptrs,
+                     const std::vector<int64_t>& g_offs, const std::vector<int64_t>& w_offs, const std::vector<int64_t>& wb_offs,
+                     const std::vector<int64_t>& d_offs, const std::vector<at::Tensor>& hists, const std::vector<int64_t>& ns,
+                     const std::vector<double>& lrs, const std::vector<double>& decays, long* work4) {
+  const int world = static_cast<int>(base_ptrs.size());
+  const int nseg = static_cast<int>(g_offs.size());
+  TORCH_CHECK(world >= 1 && world <= kMaxRanks && flag_ptrs.size() == base_ptrs.size(), "ssp: 1..8 ranks");
+  TORCH_CHECK(nseg >= 1 && nseg <= kMaxSegs && w_offs.size() == g_offs.size() && wb_offs.size() == g_offs.size() &&
+              d_offs.size() == g_offs.size() && ns.size() == g_offs.size(), "ssp: 1..4 segments");
+  for (int p = 0; p < world; ++p) {
+    ap.base[p] = reinterpret_cast<char*>(base_ptrs[p]);
+    ap.flags[p] = reinterpret_cast<uint32_t*>(flag_ptrs[p]);
+  }
+  ap.mc = nullptr;
+  ss.nseg = nseg;
+  *work4 = 0;
+  for (int s = 0; s < nseg; ++s) {
+    TORCH_CHECK(ns[s] % 4 == 0 && g_offs[s] % 16 == 0 && w_offs[s] % 16 == 0 && wb_offs[s] % 8 == 0 && d_offs[s] % 16 == 0,
+                "ssp: segment alignment");
+    ss.g_off[s] = g_offs[s]; ss.w_off[s] = w_offs[s]; ss.wb_off[s] = wb_offs[s]; ss.d_off[s] = d_offs[s];
+    ss.n[s] = ns[s];
+    if (!hists.empty()) {
+      TORCH_CHECK(hists[s].is_cuda() && hists[s].scalar_type() == at::kFloat && hists[s].numel() >= ns[s]);
+      ss.h[s] = hists[s].data_ptr<float>();
+      ss.lr[s] = static_cast<float>(lrs[s]);
+      ss.decay[s] = static_cast<float>(decays[s]);
+    }
+    *work4 = std::max<long>(*work4, ns[s] / 4);
+  }
+}
+
+static SspState ssp_state(at::Tensor& state) {
+  TORCH_CHECK(state.is_cuda() && state.scalar_type() == at::kInt && state.numel() >= 2 * kMaxRanks + 1, "ssp: state tensor");
+  auto* p = reinterpret_cast<uint32_t*>(state.data_ptr());
+  return SspState{p, p + kMaxRanks, p + 2 * kMaxRanks};
+}
+
+void ssp_delta(std::vector<int64_t> base_ptrs, std::vector<int64_t> flag_ptrs, std::vector<int64_t> g_offs,
+               std::vector<int64_t> w_offs, std::vector<int64_t> wb_offs, std::vector<int64_t> d_offs, int64_t ring_stride,
+               std::vector<at::Tensor> hists, std::vector<int64_t> ns, std::vector<double> lrs, std::vector<double> decays,
+               int64_t rank, int64_t ring, int64_t staleness, at::Tensor done_counter, at::Tensor state, double momentum,
+               int64_t rule, bool l1, double delta, double gscale, int64_t max_ctas, const c10::optional<at::Tensor>& lr_dev,
+               const at::Tensor& clock_dev) {
+  c10::cuda::CUDAGuard guard(done_counter.device());
+  ArenaPtrs ap{};
+  SspSegs ss{};
+  long work4 = 0;
+  fill_ssp(ap, ss, base_ptrs, flag_ptrs, g_offs, w_offs, wb_offs, d_offs, hists, ns, lrs, decays, &work4);
+  TORCH_CHECK(ring >= 1 && ring == staleness + 1 && ring_stride % 16 == 0, "ssp: ring = staleness + 1 slots");
+  UpdateHyper hp = make_hyper(1.0, momentum, 0.0, rule, l1, delta, gscale);
+  const int grid = static_cast<int>(std::max<long>(1, std::min<long>((work4 + 511) / 512, max_ctas > 0 ? max_ctas : 96)));
+  ssp_delta_kernel<<<grid, 512, 0, at::cuda::getCurrentCUDAStream()>>>(
+      ap, ss, ring_stride, static_cast<int>(rank), static_cast<int>(base_ptrs.size()), static_cast<int>(ring),
+      static_cast<int>(staleness), hp, reinterpret_cast<unsigned int*>(done_counter.data_ptr()),
+      lr_dev.has_value() ? lr_dev->data_ptr<float>() : nullptr, reinterpret_cast<const uint32_t*>(clock_dev.data_ptr()),
+      ssp_state(state));
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void ssp_fold(std::vector<int64_t> base_ptrs, std::vector<int64_t> flag_ptrs, std::vector<int64_t> w_offs,
+              std::vector<int64_t> wb_offs, std::vector<int64_t> d_offs, int64_t ring_stride, std::vector<int64_t> ns, int64_t rank,
+              int64_t ring, at::Tensor done_counter, at::Tensor state, bool drain, int64_t max_ctas) {
+  c10::cuda::CUDAGuard guard(done_counter.device());
+  ArenaPtrs ap{};
+  SspSegs ss{};
+  long work4 = 0;
+  fill_ssp(ap, ss, base_ptrs, flag_ptrs, w_offs, w_offs, wb_offs, d_offs, {}, ns, {}, {}, &work4);
+  const int grid = static_cast<int>(std::max<long>(1, std::min<long>((work4 + 511) / 512, max_ctas > 0 ? max_ctas : 96)));
+  ssp_fold_kernel<<<grid, 512, 0, at::cuda::getCurrentCUDAStream()>>>(
+      ap, ss, ring_stride, static_cast<int>(rank), static_cast<int>(base_ptrs.size()), static_cast<int>(ring),
+      reinterpret_cast<unsigned int*>(done_counter.data_ptr()), ssp_state(state), drain ? 1 : 0);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
 // Publish a payload (sufficient factors) into EVERY rank's arena at the same offset — one multimem.st through
 // the NVSwitch when a multicast mapping exists, P2P stores otherwise — then (optionally) raise this rank's
 // epoch flag on every peer.  The payload crosses NVLink exactly once per peer; consumers read it locally.
@@ -532,6 +755,12 @@ TORCH_LIBRARY_FRAGMENT(poseidon, m) {
         "Tensor[] hists, int[] ns, int[] one_shots, float[] lrs, float[] decays, int rank, int epoch, Tensor(a!) done_counter, "
         "float momentum, int rule, bool l1, float delta, float gscale, int max_ctas, Tensor? lr_dev, Tensor? epoch_dev) -> ()",
         &psd::allreduce_sgd_multi);
+  m.def("ssp_delta(int[] base_ptrs, int[] flag_ptrs, int[] g_offs, int[] w_offs, int[] wb_offs, int[] d_offs, int ring_stride, "
+        "Tensor[] hists, int[] ns, float[] lrs, float[] decays, int rank, int ring, int staleness, Tensor(a!) done_counter, "
+        "Tensor(b!) state, float momentum, int rule, bool l1, float delta, float gscale, int max_ctas, Tensor? lr_dev, "
+        "Tensor clock_dev) -> ()", &psd::ssp_delta);
+  m.def("ssp_fold(int[] base_ptrs, int[] flag_ptrs, int[] w_offs, int[] wb_offs, int[] d_offs, int ring_stride, int[] ns, "
+        "int rank, int ring, Tensor(a!) done_counter, Tensor(b!) state, bool drain, int max_ctas) -> ()", &psd::ssp_fold);
   m.def("peer_push(Tensor src, int[] dst_ptrs, int dst_mc, int[] flag_ptrs, int rank, int slot, int epoch, bool signal, "
         "Tensor(a!) done_counter, int wait_slot, Tensor? epoch_dev) -> ()", &psd::peer_push);
   m.def("peer_signal(int[] flag_ptrs, int rank, int slot, int epoch, Tensor? epoch_dev) -> ()", &psd::peer_signal);

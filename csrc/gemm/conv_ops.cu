@@ -68,7 +68,9 @@ static int pair_grid(long m_blocks, long n_blocks, long split, int sms) {
   return static_cast<int>(2 * std::max<long>(1, std::min<long>(pair_tiles, sms / 2)));
 }
 
-static int g_conv_mcast = 2;       // CTAs per cluster sharing the im2col operand by TMA multicast (1 = off)
+static int g_conv_mcast = 1;       // CTAs per cluster sharing the im2col operand by TMA multicast (1 = off, the default:
+                                   // measured no faster on B200 — every SM still ingests the whole tile, profiles/r2_conv_ncu_summary.md)
+static int g_conv_pair = 0;        // paired CTAs for the convolution kernels (measured equal to single-CTA; opt-in)
 
 // Launch the im2col-A kernel (fprop / dgrad) for tile width bn; CG = 2: paired CTAs, else cluster multicast (p.cluster).
 template <int CG>
@@ -275,7 +277,7 @@ at::Tensor conv_fprop(const at::Tensor& x, const at::Tensor& wb, const c10::opti
         launch_im2col_a<1>(mbn, tm, p, cg, mgrid, stream);
         continue;
       }
-      if (pair_cta_enabled() && m_blocks >= 2 && bn >= 64) {
+      if (g_conv_pair && pair_cta_enabled() && m_blocks >= 2 && bn >= 64) {
         // paired CTAs: two pixel blocks share every weight tile; each CTA stages BN/2 weight rows
         encode_tmap_bf16_2d(&tm.b[0], wptr, cg.K, Cout_g, cg.K, BLOCK_K, bn / 2);
         launch_im2col_a<2>(bn, tm, p, cg, pair_grid(m_blocks, n_blocks, 1, sms), stream);
@@ -352,7 +354,7 @@ at::Tensor conv_dgrad(const at::Tensor& dy, const at::Tensor& wt, at::IntArrayRe
         launch_im2col_a<1>(mbn, tm, p, cg, mgrid, stream);
         continue;
       }
-      if (pair_cta_enabled() && m_blocks >= 2 && bn >= 64) {
+      if (g_conv_pair && pair_cta_enabled() && m_blocks >= 2 && bn >= 64) {
         encode_tmap_bf16_2d(&tm.b[0], wptr, cg.K, Cg, cg.K, BLOCK_K, bn / 2);
         launch_im2col_a<2>(bn, tm, p, cg, pair_grid(m_blocks, n_blocks, 1, sms), stream);
         continue;
@@ -432,7 +434,7 @@ void conv_wgrad(const at::Tensor& x, const at::Tensor& dy, at::Tensor dw, at::In
         }
         continue;
       }
-      if (pair_cta_enabled() && m_blocks >= 2 && m_blocks % 2 == 0 && (bn == 128 || bn == 256)) {
+      if (g_conv_pair && pair_cta_enabled() && m_blocks >= 2 && m_blocks % 2 == 0 && (bn == 128 || bn == 256)) {
         // paired CTAs along Cout (even block counts only: a phantom block would waste a third of conv3's MMA work)
         const int pgrid = pair_grid(m_blocks, n_blocks, split, sms);
         if (bn == 128) launch_conv<128, true, true, EPI_F32, IM2COL_B, 2>(tm, p, cg, pgrid, stream);
@@ -520,6 +522,7 @@ at::Tensor conv_pack_padded(const at::Tensor& wb, int64_t Cout, int64_t RS, int6
 
 namespace psd {
 void set_conv_im2col(int64_t on) { g_conv_im2col = on != 0; }
+void set_conv_pair(int64_t on) { g_conv_pair = on != 0; }
 void set_conv_mcast(int64_t c) {
   TORCH_CHECK(c == 1 || c == 2 || c == 4, "im2col multicast cluster size must be 1, 2 or 4");
   g_conv_mcast = static_cast<int>(c);
@@ -534,6 +537,7 @@ TORCH_LIBRARY_FRAGMENT(poseidon, m) {
   m.def("set_conv_cluster(int c) -> ()", &psd::set_conv_cluster);
   m.def("set_conv_im2col(int on) -> ()", &psd::set_conv_im2col);
   m.def("set_conv_mcast(int c) -> ()", &psd::set_conv_mcast);
+  m.def("set_conv_pair(int on) -> ()", &psd::set_conv_pair);
   m.def("conv_fprop(Tensor x, Tensor wb, Tensor? bias, int[] kernel, int[] stride, int[] pad, int groups, int mode, "
         "int OH, int OW, bool relu, float slope, Tensor? out) -> Tensor", &psd::conv_fprop);
   m.def("conv_dgrad(Tensor dy, Tensor wt, int[] kernel, int[] pad, int groups, int H, int W, Tensor? mask, float slope) "

@@ -364,6 +364,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
   const int C = (CG == 1 && GATHER != GATHER_NONE && p.cluster > 1) ? p.cluster : 1;
   const int crank = (C > 1 || CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
   const bool leader = CG == 1 || crank == 0;            // CG == 2: cluster rank 0 issues the MMAs for the pair
+  const int prank = CG == 2 ? crank : 0;                // which half of the B tile this CTA stages (paired CTAs only)
   const uint16_t cmask = static_cast<uint16_t>((1u << C) - 1);
   // cluster-level tile space and stride
   const int m_pairs = (m_blocks + 1) / 2;
@@ -432,7 +433,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
         [[maybe_unused]] uint16_t im_offw[BN / CG / 64 > 0 ? BN / CG / 64 : 1], im_offh[BN / CG / 64 > 0 ? BN / CG / 64 : 1];
         if constexpr (GATHER == IM2COL_A) {
           // first base pixel this CTA fetches: the tile's, or (cluster multicast) that of its 128 / C pixel slice
-          const uint32_t m0 = static_cast<uint32_t>(m_blk) * BLOCK_M + static_cast<uint32_t>(crank * (BLOCK_M / C));
+          const uint32_t m0 = static_cast<uint32_t>(m_blk) * BLOCK_M + (C > 1 ? static_cast<uint32_t>(crank * (BLOCK_M / C)) : 0u);
           const uint32_t n_img = fdiv(m0, cg.div_ohow);
           const uint32_t rem = m0 - n_img * static_cast<uint32_t>(cg.OH * cg.OW);
           const uint32_t oh = fdiv(rem, cg.div_ow);
@@ -444,7 +445,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
         if constexpr (GATHER == IM2COL_B) {
 #pragma unroll
           for (int c = 0; c < BN / CG / 64; ++c) {
-            int kc = n_blk * BN + crank * (BN / CG) + c * 64;
+            int kc = n_blk * BN + prank * (BN / CG) + c * 64;
             if (kc >= cg.K) kc = 0;                      // columns past K are dropped by the epilogue: load anything valid
             const int tap = static_cast<int>(fdiv(static_cast<uint32_t>(kc), cg.div_cg));
             im_c0[c] = kc - tap * cg.Cgk;
@@ -477,7 +478,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
           const uint32_t sa32 = smem_u32(sa), sb32 = sa32 + S::kABytes;
           if constexpr (GATHER == GATHER_NONE) {
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], CG * S::kStageBytes);
-            TmaProducer<BN, A_MN, B_MN, CG>::load_stage(tm, src, kb, m_blk, n_blk, crank, sa32, sb32, fbar);
+            TmaProducer<BN, A_MN, B_MN, CG>::load_stage(tm, src, kb, m_blk, n_blk, prank, sa32, sb32, fbar);
           } else if constexpr (GATHER == IM2COL_A) {
             // A tile = 128 output pixels x 64 channels of tap (r, s): one im2col-mode TMA instruction
             const int k0 = g * BLOCK_K;
@@ -498,7 +499,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
             else
               tma_load_im2col_4d(sa32, &tm.a[0], fbar, in_k ? c0 : 0, im_w, im_h, im_n,
                                  static_cast<uint16_t>(in_k ? offw : 0), static_cast<uint16_t>(in_k ? offh : 0));
-            TmaProducer<BN, A_MN, B_MN, CG>::load_b(tm, src, kb, n_blk, crank, sb32, fbar);
+            TmaProducer<BN, A_MN, B_MN, CG>::load_b(tm, src, kb, n_blk, prank, sb32, fbar);
           } else if constexpr (GATHER == IM2COL_B) {
             // B tile = BN/64 chunks of [64 reduction pixels][64 channels of one tap]; the pixels advance with g.
             // Paired CTAs: this CTA fetches chunks [crank * BN/128, (crank + 1) * BN/128) of the tile.

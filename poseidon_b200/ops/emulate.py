@@ -52,6 +52,12 @@ class EmulatedKernels:
     def set_conv_im2col(self, on):
         return None
 
+    def set_conv_mcast(self, c):
+        return None
+
+    def set_conv_pair(self, on):
+        return None
+
     def set_pair_cta(self, on):              # csrc/gemm/gemm_ops.cu (cta_group::2 on/off: no numerical effect)
         return None
 
@@ -125,8 +131,12 @@ class EmulatedKernels:
         cop = wt.shape[1] // (r * s)
         w = wt.reshape(groups, cg, r, s, cop)[..., :cout_g].float()           # g, ci, r, s, co
         w4 = w.permute(0, 4, 1, 2, 3).reshape(cout, cg, r, s)                  # conv weight [Cout, Cg, R, S]
-        dx = F.conv_transpose2d(dy.float(), w4, None, 1, tuple(pad), 0, groups)
-        assert tuple(dx.shape[2:]) == (H, W)
+        # out[t] = sum_j dy[t - j] w[j], t in [0, OH + R - 1);  dx[i] = sum_j dy[i + pad - j] w[j] = out[i + pad], i < H —
+        # the output extent is the caller's (the strided data gradient asks for one phase of dX: fewer or more rows than
+        # the natural transposed-convolution size, the excess being zero)
+        full = F.conv_transpose2d(dy.float(), w4, None, 1, 0, 0, groups)
+        full = F.pad(full, (0, max(0, pad[1] + W - full.shape[3]), 0, max(0, pad[0] + H - full.shape[2])))
+        dx = full[:, :, pad[0]: pad[0] + H, pad[1]: pad[1] + W]
         if mask is not None:
             dx = torch.where(mask.float() > 0, dx, dx * slope)
         return _nhwc(dx.to(BF16))
@@ -534,6 +544,71 @@ class EmulatedKernels:
         for g_off, n, one_shot in zip(g_offs, ns, one_shots):
             if one_shot:
                 self._mem(base_ptrs[rank] + g_off, n * 4, torch.float32).zero_()
+
+    # ---- bounded staleness on the arena (csrc/comm/fused_update.cu: ssp_delta_kernel / ssp_fold_kernel) ----------------
+    _SSP_READY, _SSP_CONSUMED = 5, 6
+
+    def ssp_delta(self, base_ptrs, flag_ptrs, g_offs, w_offs, wb_offs, d_offs, ring_stride, hists, ns, lrs, decays, rank, ring,
+                  staleness, done_counter, state, momentum, rule, l1, delta, gscale, max_ctas, lr_dev, clock_dev):
+        """Own optimizer step on the local gradient (applied at once), the step itself stored in slot clock % ring of this
+        rank's delta ring; then the fold of the peers' deltas is planned: clocks <= clock - staleness are due (waited
+        for), anything a peer has published beyond that is taken along."""
+        world, KM = len(base_ptrs), self._K_MAX_RANKS
+        c = int(clock_dev[0]) & 0xFFFFFFFF
+        lr_glob = float(lr_dev[0]) if lr_dev is not None else 1.0
+        mine = self._flags(flag_ptrs[rank])
+        if c >= ring:
+            for q in range(world):
+                if q != rank:
+                    self._wait_ge(mine[self._SSP_CONSUMED * KM + q], c - ring + 1, f"rank {q} consuming my clock {c - ring}")
+        for g_off, w_off, wb_off, d_off, h, n, lr, decay in zip(g_offs, w_offs, wb_offs, d_offs, hists, ns, lrs, decays):
+            g = self._mem(base_ptrs[rank] + g_off, n * 4, torch.float32)
+            w = self._mem(base_ptrs[rank] + w_off, n * 4, torch.float32)
+            w0 = w.clone()
+            wn = w.clone()
+            self._step(wn, g.clone(), h[:n], lr * lr_glob, momentum, decay, rule, l1, delta, gscale)
+            g.zero_()
+            w.copy_(wn)
+            self._mem(base_ptrs[rank] + wb_off, n * 2, BF16).copy_(wn.to(BF16))
+            self._mem(base_ptrs[rank] + d_off + (c % ring) * ring_stride, n * 4, torch.float32).copy_(w0 - wn)
+        for q in range(world):
+            if q == rank:
+                continue
+            self._flags(flag_ptrs[q])[self._SSP_READY * KM + rank] = c + 1
+            lo = int(state[q])
+            must = max(c + 1 - staleness, 0)
+            if must > lo:
+                self._wait_ge(mine[self._SSP_READY * KM + q], must, f"delta of rank {q} for clock {must - 1}")
+            avail = int(mine[self._SSP_READY * KM + q]) & 0xFFFFFFFF
+            hi = min(max(avail, lo), lo + ring)
+            state[KM + q] = hi
+            state[2 * KM] = max(int(state[2 * KM]), max(c + 1 - hi, 0))
+
+    def ssp_fold(self, base_ptrs, flag_ptrs, w_offs, wb_offs, d_offs, ring_stride, ns, rank, ring, done_counter, state, drain,
+                 max_ctas):
+        """W -= sum of the planned (or, draining, of all published) peer deltas, read from the peers' rings; then the
+        producers are told how far their rings have been consumed."""
+        world, KM = len(base_ptrs), self._K_MAX_RANKS
+        mine = self._flags(flag_ptrs[rank])
+        rng = {}
+        for q in range(world):
+            if q == rank:
+                continue
+            lo = int(state[q])
+            hi = (int(mine[self._SSP_READY * KM + q]) & 0xFFFFFFFF) if drain else int(state[KM + q])
+            rng[q] = (lo, max(hi, lo))
+        if any(hi > lo for lo, hi in rng.values()):
+            for w_off, wb_off, d_off, n in zip(w_offs, wb_offs, d_offs, ns):
+                w = self._mem(base_ptrs[rank] + w_off, n * 4, torch.float32)
+                acc = torch.zeros(n)
+                for q, (lo, hi) in rng.items():
+                    for cc in range(lo, hi):
+                        acc += self._mem(base_ptrs[q] + d_off + (cc % ring) * ring_stride, n * 4, torch.float32)
+                w.sub_(acc)
+                self._mem(base_ptrs[rank] + wb_off, n * 2, BF16).copy_(w.to(BF16))
+        for q, (lo, hi) in rng.items():
+            state[q] = hi
+            self._flags(flag_ptrs[q])[self._SSP_CONSUMED * KM + rank] = hi
 
     def peer_push(self, src, dst_ptrs, dst_mc, flag_ptrs, rank, slot, epoch, signal, done_counter, wait_slot, epoch_dev):
         """Payload into every rank's arena, then (optionally) this rank's epoch flag on every peer

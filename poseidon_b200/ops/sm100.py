@@ -393,16 +393,65 @@ class _ConvFn(torch.autograd.Function):
             k.colsum(dy, dy.shape[0] * dy.shape[2] * dy.shape[3], st.Coutp, pitch, db, 1.0, False)
             db = db[: st.Cout]
         if ctx.needs_input_grad[0]:
-            if (st.row_mode and not st.pad8) or stride != (1, 1):
-                raise NotImplementedError(f"sm100 conv '{layer.layer_name}': data gradient is implemented for "
-                                          "stride-1 convolutions (first / strided layers never need it in the "
-                                          "supported model families)")
-            mask = xin if st.mask_input else None
-            dx = k.conv_dgrad(dy, st.dgrad_pack(), [st.R, st.S], list(layer.pad), st.groups, xin.shape[2],
-                              xin.shape[3], mask, 0.0)
+            if st.row_mode and not st.pad8:
+                raise NotImplementedError(f"sm100 conv '{layer.layer_name}': ROW-mode (<= 4 channel) layers are image "
+                                          "layers; their data gradient is never needed")
+            if tuple(stride) != (1, 1):
+                dx = _strided_dgrad(k, st, layer, dy, xin)
+            else:
+                mask = xin if st.mask_input else None
+                dx = k.conv_dgrad(dy, st.dgrad_pack(), [st.R, st.S], list(layer.pad), st.groups, xin.shape[2],
+                                  xin.shape[3], mask, 0.0)
             if st.pad8 and st.Cp != st.cin_logical:
                 dx = dx[:, : st.cin_logical]
         return dx, dw, db, None, None
+
+
+def _strided_dgrad(k, st: "ConvState", layer, dy: torch.Tensor, xin: torch.Tensor) -> torch.Tensor:
+    """Data gradient of a strided convolution as sh * sw stride-1 problems (reference: any stride through col2im,
+    src/caffe/layers/conv_layer.cu:84-119 + util/im2col.cu:74-113).
+
+    Input row ih = a + sh * i' (phase a) only receives taps r = r0 + sh * j with r0 = (a + ph) mod sh, and then
+        oh = (ih + ph - r) / sh = i' + q - j,          q = (a + ph - r0) / sh   (an integer >= 0),
+    i.e. the pixels of one phase are a stride-1 data gradient over dY with the sub-filter W[:, :, r0::sh, s0::sw] and
+    padding (q_h, q_w): the same tcgen05 dgrad kernel, one launch per phase, each writing one interleaved sub-grid of dX.
+    No atomics, no col2im scatter."""
+    sh, sw = layer.stride
+    ph, pw = layer.pad
+    n, _, H, W = xin.shape
+    cin = st.Cp
+    dx = torch.empty(n, cin, H, W, device=dy.device, dtype=torch.bfloat16).contiguous(memory_format=CL)
+    w4 = layer.weight.data.permute(0, 2, 3, 1)                       # [Cout, R, S, Cg] (physical order of the master)
+    if st.pad8:
+        w4 = torch.nn.functional.pad(w4, (0, st.Cp - st.cin_logical))
+    cg = w4.shape[3]
+    packs = getattr(st, "_phase_packs", None)
+    if packs is None or st.dirty_wt:
+        packs = st._phase_packs = {}
+    for a in range(sh):
+        r0 = (a + ph) % sh
+        qh = (a + ph - r0) // sh
+        ha = len(range(a, H, sh))
+        for b in range(sw):
+            s0 = (b + pw) % sw
+            qw = (b + pw - s0) // sw
+            wb_ = len(range(b, W, sw))
+            if ha == 0 or wb_ == 0:
+                continue
+            sub = w4[:, r0::sh, s0::sw, :]
+            rs, ss = sub.shape[1], sub.shape[2]
+            if rs == 0 or ss == 0:
+                dx[:, :, a::sh, b::sw] = 0                              # no tap reaches this phase (stride > kernel)
+                continue
+            key = (a, b)
+            if key not in packs:
+                packs[key] = k.conv_pack_dgrad(sub.contiguous().reshape(-1), st.Cout, rs * ss, cg, st.groups, None, 0)
+            part = k.conv_dgrad(dy, packs[key], [rs, ss], [qh, qw], st.groups, ha, wb_, None, 0.0)
+            dx[:, :, a::sh, b::sw] = part
+    st.dirty_wt = False
+    if st.mask_input:
+        dx = k.relu_bwd(xin, dx, 0.0)                                   # the producer's ReLU, fused on the stride-1 path
+    return dx
 
 
 def conv2d(x, w, b, stride, pad, groups, relu_slope=None, layer=None):

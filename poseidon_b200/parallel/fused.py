@@ -133,7 +133,7 @@ class SymmetricArena:
 
 
 class _Seg:
-    __slots__ = ("param", "numel", "g_off", "w_off", "wb_off", "hist")
+    __slots__ = ("param", "numel", "g_off", "w_off", "wb_off", "hist", "d_off")
 
 
 class _NodeContext:
@@ -155,8 +155,13 @@ class FusedBackend(Backend):
     name = "fused"
 
     def __init__(self, svb: bool = False, sfb_mode: str = "auto", grad_reduce: str = "sum",
-                 one_shot_bytes: int = 256 * 1024, use_multimem: bool = True):
+                 one_shot_bytes: int = 256 * 1024, use_multimem: bool = True, staleness: int = 0):
         self.svb, self.sfb_mode, self.reduce = svb, sfb_mode, grad_reduce
+        # staleness > 0: bounded-staleness (SSP) async SGD on the same arena — per-worker deltas in a ring of s + 1 slots,
+        # folded by the peers at most s clocks late (ssp_delta / ssp_fold kernels); no SFB, no sharded history
+        self.staleness = int(staleness)
+        self.ssp = self.staleness > 0 or os.environ.get("POSEIDON_FUSED_SSP", "0") == "1"
+        self.per_worker_state = False
         # buckets up to this size are reduced whole by every rank (one launch latency); larger ones are sharded
         self.one_shot_bytes = int(os.environ.get("POSEIDON_ONE_SHOT_BYTES", one_shot_bytes))
         self.use_multimem = use_multimem and os.environ.get("POSEIDON_MULTIMEM", "1") != "0"
@@ -207,6 +212,7 @@ class FusedBackend(Backend):
         self._choose_sfb(net, sync)
         if self.world > 1:
             self._build_arena(net, sync)
+        self.per_worker_state = self.ssp and self.world > 1
         self.done_counter = torch.zeros(4, dtype=torch.int32, device=self.device)
         self.lr_t = torch.zeros(1, dtype=torch.float32, device=self.device)     # global lr, read by the kernels
         self.epoch_t = torch.zeros(1, dtype=torch.int32, device=self.device)    # step counter, read by the comm kernels
@@ -231,8 +237,9 @@ class FusedBackend(Backend):
             ok_shape = (N % 8 == 0 and Kd % 8 == 0)
             if P == 1:
                 use = ok_shape
-            elif not self.svb or self.sfb_mode == "none" or self.nnodes > 1:
-                use = False                   # (across nodes the factors would have to travel the network too: dense)
+            elif not self.svb or self.sfb_mode == "none" or self.nnodes > 1 or self.ssp:
+                use = False                   # (across nodes the factors would have to travel the network too: dense;
+                                              #  under SSP every worker steps on its own gradient: nothing to reconstruct)
             else:
                 use = ok_shape and (self.sfb_mode == "all" or sfb_wins(M, N, Kd, P))
             self.sfb_stats.layers[name] = "sfb" if use else "dense"
@@ -256,10 +263,11 @@ class FusedBackend(Backend):
         segs: List[_Seg] = []
         total = 0
         n_flag_blocks = len(sync.buckets) + len(self.sfb_layers) + 4
+        ring = self.staleness + 1 if self.ssp else 0
         for b in sync.buckets:
             for p in b.params:
                 n4 = _round_up(p.numel(), 4)
-                total += _round_up(n4 * 4, _ALIGN) * 2 + _round_up(n4 * 2, _ALIGN)
+                total += _round_up(n4 * 4, _ALIGN) * (2 + ring) + _round_up(n4 * 2, _ALIGN)
         for h in self.sfb_layers.values():
             total += h.arena_bytes(self.world)
         total += n_flag_blocks * _ALIGN * 2 + (1 << 20)
@@ -297,6 +305,15 @@ class FusedBackend(Backend):
                 self.seg_of[id(p)] = s
                 b.segs.append(s)
                 self._bind_shadow(p, s)
+            if self.ssp:
+                # delta ring of the bucket: `ring` slots, each holding the bucket's segments back to back
+                b.ring_stride = sum(_round_up(sg.numel * 4, _ALIGN) for sg in b.segs)
+                base = ar.carve(b.ring_stride * ring)
+                off = 0
+                for sg in b.segs:
+                    sg.d_off = base + off
+                    off += _round_up(sg.numel * 4, _ALIGN)
+                b.ssp_state = torch.zeros(2 * K_MAX_RANKS + 1, dtype=torch.int32, device=self.device)
         for h in self.sfb_layers.values():
             h.alloc(ar, self._alloc_flag_block())
         for layer in net.layers:
@@ -406,7 +423,9 @@ class FusedBackend(Backend):
         with self.cu.stream(self.stream):
             live = [(p, seg, lm, dm) for p, seg, lm, dm in zip(bucket.params, bucket.segs, bucket.lr_mult, bucket.decay_mult)
                     if p.grad is not None]
-            if live:
+            if live and self.ssp:
+                self._launch_ssp(bucket, live)
+            elif live:
                 use_mc = self.use_multimem and ar.multicast_ptr != 0
                 g_offs, w_offs, wb_offs, hists, ns, ones, lrs, decays = [], [], [], [], [], [], [], []
                 hy = None
@@ -430,6 +449,57 @@ class FusedBackend(Backend):
             if bucket.event is None:
                 bucket.event = self.cu.Event()
             bucket.event.record(self.stream)
+
+    def _launch_ssp(self, bucket, live):
+        """Bounded staleness on the arena (csrc/comm/fused_update.cu: ssp_delta / ssp_fold): own step now, the peers'
+        deltas folded at most `staleness` clocks late, exactly once, read over NVLink from their rings."""
+        ar, hy = self.arena, self.sync.hyper
+        if self.cross_group is not None:
+            raise RuntimeError("fused SSP spans one NVLink node; use --comm ssp across nodes")
+        g_offs = [seg.g_off for _, seg, _, _ in live]
+        w_offs = [seg.w_off for _, seg, _, _ in live]
+        wb_offs = [seg.wb_off for _, seg, _, _ in live]
+        d_offs = [seg.d_off for _, seg, _, _ in live]
+        ns = [seg.numel for _, seg, _, _ in live]
+        hists = [seg.hist for _, seg, _, _ in live]
+        lrs = [lm for _, _, lm, _ in live]
+        # every worker steps on ITS gradient with the plain decay; the sum of the P deltas is what BSP-sum applies at once
+        decays = [hy.weight_decay * dm for _, _, _, dm in live]
+        flags = ar.peer_ptrs(bucket.flag_off)
+        ring = self.staleness + 1
+        self.k.ssp_delta(ar.base_ptrs, flags, g_offs, w_offs, wb_offs, d_offs, bucket.ring_stride, hists, ns, lrs, decays,
+                         self.rank, ring, self.staleness, self.done_counter, bucket.ssp_state, hy.momentum, hy.solver_type,
+                         hy.l1, hy.delta, 1.0, 0, self.lr_t, self.epoch_t)
+        self.k.ssp_fold(ar.base_ptrs, flags, w_offs, wb_offs, d_offs, bucket.ring_stride, ns, self.rank, ring,
+                        self.done_counter, bucket.ssp_state, False, 0)
+        self.launches += 2
+        self.ssp_delta_bytes = getattr(self, "ssp_delta_bytes", 0) + sum(ns) * 4
+
+    def drain(self):
+        """Fold every delta that is still in flight (end of training, before a snapshot or a test pass): afterwards all
+        replicas hold the same table.  A collective: every rank calls it at the same iteration."""
+        if not self.ssp or self.world == 1:
+            return
+        self.cu.synchronize(self.device)
+        self.node.barrier()                        # every rank has published its last clock
+        ar = self.arena
+        with self.cu.stream(self.stream):
+            for b in self.sync.buckets:
+                segs = getattr(b, "segs", [])
+                if not segs:
+                    continue
+                self.k.ssp_fold(ar.base_ptrs, ar.peer_ptrs(b.flag_off), [sg.w_off for sg in segs], [sg.wb_off for sg in segs],
+                                [sg.d_off for sg in segs], b.ring_stride, [sg.numel for sg in segs], self.rank,
+                                self.staleness + 1, self.done_counter, b.ssp_state, True, 0)
+        self.cu.synchronize(self.device)
+        self.node.barrier()                        # nobody publishes again before everyone has drained
+
+    @property
+    def max_observed_lag(self) -> int:
+        """Largest number of a peer's clocks that were still unfolded right after a fold was planned (<= staleness)."""
+        if not self.ssp:
+            return 0
+        return max([int(b.ssp_state[2 * K_MAX_RANKS].item()) for b in self.sync.buckets if hasattr(b, "ssp_state")] + [0])
 
     def _network_all_reduce(self, t: torch.Tensor) -> torch.Tensor:
         """Sum ``t`` over the ranks of equal local index on all nodes; bf16 on the wire if asked for."""
@@ -512,12 +582,12 @@ class FusedBackend(Backend):
 
     def bytes_on_wire(self):
         return {"dense_allreduce_bytes": self.dense_bytes, "inter_node_allreduce_bytes": self.inter_node_bytes,
-                "sfb_bytes": self.sfb_stats.sfb_bytes,
+                "ssp_delta_bytes": getattr(self, "ssp_delta_bytes", 0), "sfb_bytes": self.sfb_stats.sfb_bytes,
                 "sfb_dense_equiv_bytes": self.sfb_stats.dense_equiv_bytes}
 
     # optimizer-state plumbing for snapshots: history of a two-shot bucket is sharded by rank
     def gather_history(self):
-        if self.world == 1:
+        if self.world == 1 or self.ssp:            # SSP: momentum is per worker and never sharded
             return
         for b in self.sync.buckets:
             for seg in getattr(b, "segs", []):

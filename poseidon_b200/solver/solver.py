@@ -239,11 +239,12 @@ class Solver:
 
     def _make_sync(self, comm, grad_reduce, sfb_mode):
         rc = self.rank_ctx
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", rc.world_size))
         if comm == "auto":
             if not rc.distributed:
                 comm = "local"
-            elif self.staleness > 0:
-                comm = "ssp"
+            elif self.staleness > 0 and not (self.engine == "sm100" and 1 < local_world == rc.world_size):
+                comm = "ssp"                     # library bounded staleness (torch engine / multi-node jobs)
             elif self.engine == "sm100":
                 # NVLink arena per node (+ a library all-reduce across nodes); one GPU per node has no NVLink peer
                 comm = "fused" if int(os.environ.get("LOCAL_WORLD_SIZE", rc.world_size)) > 1 else "nccl"
@@ -256,7 +257,7 @@ class Solver:
                 raise RuntimeError("the sm100 engine needs a CUDA device (B200)")
             from ..parallel.fused import FusedBackend
             self.comm_name = "fused"
-            backend = FusedBackend(self.svb, sfb_mode, grad_reduce)
+            backend = FusedBackend(self.svb, sfb_mode, grad_reduce, staleness=self.staleness)
             backend.wire_bf16 = self.wire_dtype == "bf16"
             return GradSync(self.net, rc, self.hyper, backend)
         if comm == "local":
@@ -648,7 +649,8 @@ class Solver:
         base = f"{self._snapshot_prefix()}_iter_{self.iter}"
         model_file = base + ".caffemodel"
         state_file = base + ".solverstate"
-        per_rank = self.comm_name in ("ssp", "ssp_aggr")        # per-worker momentum in the asynchronous modes
+        # per-worker momentum in the asynchronous modes (library ssp / ssp_aggr, or the fused engine's SSP kernels)
+        per_rank = self.comm_name in ("ssp", "ssp_aggr") or getattr(self.sync.backend, "per_worker_state", False)
         if hasattr(self.sync.backend, "gather_history"):
             # a collective (two-shot buckets keep the optimizer history sharded by rank): EVERY rank takes part, not
             # only the one that writes the file

@@ -200,6 +200,38 @@ def test_fused_backend_two_ranks_on_emulated_peer_memory(tmp_path, monkeypatch, 
         assert int(res[0]["wire_sfb_bytes"]) == 0 and int(res[0]["wire_dense_allreduce_bytes"]) > 0
 
 
+def test_fused_ssp_staleness_zero_is_bsp_with_summed_updates(tmp_path, monkeypatch, single_sm100):
+    """The fused engine's SSP kernels (ssp_delta / ssp_fold on the arena's delta rings, no library collective) at
+    staleness 0: every worker's delta of clock c is folded before clock c + 1 starts = BSP with summed per-worker updates
+    = one process on the concatenated batch with lr x 2."""
+    monkeypatch.setenv("POSEIDON_EMULATE", "1")
+    monkeypatch.setenv("POSEIDON_FUSED_SSP", "1")
+    res = launch(2, str(tmp_path / "w"), ["--batch", "8", "--engine", "sm100", "--comm", "fused", "--staleness", "0"])
+    lib = launch(2, str(tmp_path / "l"), ["--batch", "8", "--engine", "sm100", "--comm", "ssp", "--staleness", "0"])
+    assert _rel(res[0], res[1]) < 1e-6
+    assert _rel(res[0], lib[0]) < 1e-6                # the library SSP backend is the oracle: same update, same order of magnitude of rounding
+    assert _rel(res[0], single_sm100) < 2e-2          # (w - d_p) - d_q vs w - (d_p + d_q): last-bit differences that bf16 operands amplify
+    assert int(res[0]["max_lag"]) == 0 and int(res[0]["wire_ssp_delta_bytes"]) > 0
+
+
+@pytest.mark.parametrize("world,staleness", [(2, 1), (3, 2)])
+def test_fused_ssp_bounded_staleness_with_a_straggler(tmp_path, monkeypatch, single_sm100, world, staleness):
+    """A delayed rank (POSEIDON_FAULT) under the fused SSP kernels: nobody observes a peer more than `staleness` clocks
+    behind, every delta is folded exactly once everywhere (after the final drain all replicas hold the same table), and
+    the trajectory stays near the synchronous one.  Same contract as the library SSP backend."""
+    monkeypatch.setenv("POSEIDON_EMULATE", "1")
+    monkeypatch.setenv("POSEIDON_FAULT", "delay:rank=1,step=2,ms=400")
+    res = launch(world, str(tmp_path / "w"), ["--batch", "8", "--engine", "sm100", "--comm", "fused", "--staleness",
+                                               str(staleness), "--steps", "6"])
+    for r in res[1:]:
+        assert _rel(res[0], r) < 1e-5
+    assert all(int(r["max_lag"]) <= staleness for r in res)
+    assert np.isfinite(res[0]["loss"])
+    lib = launch(world, str(tmp_path / "l"), ["--batch", "8", "--engine", "sm100", "--comm", "ssp", "--staleness", str(staleness),
+                                               "--steps", "6"])
+    assert _rel(res[0], lib[0]) < 0.2          # both are async trajectories of the same job: close, not equal
+
+
 def test_fused_backend_three_ranks_two_shot_equals_library_backend(tmp_path, monkeypatch):
     """Sharded (two-shot) reduce + step + broadcast with a remainder shard (3 ranks), SFB on: same weights as the gloo
     all-reduce backend on the same engine."""

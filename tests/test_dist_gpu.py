@@ -58,3 +58,30 @@ def test_two_gpu_snapshot_and_resume(tmp_path, monkeypatch, comm):
     res = launch(2, str(tmp_path / "C"), base + ["--steps", "2", "--total_steps", "4", "--restore", state], device=None)
     _close(res[0], res[1], 1e-6 if comm[1] != "ssp" else 0.05)
     _close(res[0], full[0], 0.02 if comm[1] != "ssp" else 0.2)
+
+
+def test_fused_ssp_two_ranks_staleness_zero_matches_library_ssp(tmp_path, monkeypatch):
+    """The SSP kernels on the NVLink arena (ssp_delta / ssp_fold: per-worker deltas in a ring, folded by the peers over
+    P2P loads, no NCCL on the path) at staleness 0 = BSP with summed per-worker updates = the library SSP backend."""
+    monkeypatch.setenv("POSEIDON_FUSED_SSP", "1")
+    base = ["--batch", "8", "--engine", "sm100", "--hw", "35"]
+    res = launch(2, str(tmp_path / "f"), base + ["--comm", "fused", "--staleness", "0"], device=None)
+    lib = launch(2, str(tmp_path / "l"), base + ["--comm", "ssp", "--staleness", "0"], device=None)
+    _close(res[0], res[1], 1e-5)
+    _close(res[0], lib[0], 0.03)
+    assert int(res[0]["max_lag"]) == 0 and int(res[0]["wire_ssp_delta_bytes"]) > 0
+
+
+@pytest.mark.parametrize("staleness", [1, 2])
+def test_fused_ssp_straggler_stays_within_the_staleness_bound(tmp_path, monkeypatch, staleness):
+    """An injected straggler (POSEIDON_FAULT delay on rank 1): no worker ever sees a peer more than `staleness` clocks
+    behind, every delta is folded exactly once (replicas agree after the drain), training stays finite and near the
+    library SSP trajectory."""
+    monkeypatch.setenv("POSEIDON_FAULT", "delay:rank=1,step=2,ms=300")
+    base = ["--batch", "8", "--engine", "sm100", "--hw", "35", "--steps", "6", "--staleness", str(staleness)]
+    res = launch(2, str(tmp_path / "f"), base + ["--comm", "fused"], device=None)
+    _close(res[0], res[1], 1e-4)
+    assert all(int(r["max_lag"]) <= staleness for r in res)
+    assert np.isfinite(res[0]["loss"])
+    lib = launch(2, str(tmp_path / "l"), base + ["--comm", "ssp"], device=None)
+    _close(res[0], lib[0], 0.3)

@@ -67,7 +67,16 @@ def test_threshold(ext):
 def test_eltwise(ext, op, coeffs, shape):
     from poseidon_b200.ops import sm100
     xs = [_x(shape, 10 + i) for i in range(3)]
-    _check(lambda *t: sm100.eltwise(t, op, coeffs), lambda *t: R.eltwise(t, op, coeffs), xs)
+
+    def ref(*t):
+        if op != "MAX":
+            return R.eltwise(t, op, coeffs)
+        # the reference routes the gradient of a tie to the EARLIER bottom (eltwise_layer.cu:11-34: strict '>' against the
+        # running maximum); torch.maximum would split it, and bf16 inputs do tie
+        st = torch.stack(t)
+        arg = st.argmax(0)              # first maximal index
+        return st.gather(0, arg.unsqueeze(0)).squeeze(0)
+    _check(lambda *t: sm100.eltwise(t, op, coeffs), ref, xs)
 
 
 @pytest.mark.parametrize("shape", [(64, 1000), (4, 21, 13, 11), (2, 1000, 1, 1), (8, 2048)])

@@ -149,6 +149,10 @@ CONV_CASES = [
     (2, 96, 28, 28, 128, 3, 1, 1, 1),      # GoogLeNet 3x3 after a 96-channel reduce: channel-padded im2col (96 -> 128)
     (2, 480, 14, 14, 208, 1, 1, 0, 1),     # 1x1 on 480 channels (-> 512), Cout 208 (dgrad slots 208 -> 256)
     (2, 160, 14, 14, 320, 3, 1, 1, 1),     # 160 -> 192
+    (2, 64, 28, 28, 128, 3, 2, 1, 1),      # strided convolutions inside a net: dgrad = sh*sw stride-1 phase problems
+    (2, 192, 15, 13, 64, 1, 2, 0, 1),
+    (2, 64, 14, 14, 64, 5, 2, 2, 1),
+    (2, 128, 12, 12, 128, 2, 3, 0, 2),     # stride > kernel (phases without taps), grouped
 ]
 
 

@@ -33,10 +33,10 @@ def conv_mode(ext, request):
     of the shared pixel tile), paired CTAs, plain single-CTA."""
     mc, pair = request.param
     ext.set_conv_mcast(mc)
-    ext.set_pair_cta(pair)
+    ext.set_conv_pair(pair)
     yield request.param
-    ext.set_conv_mcast(2)
-    ext.set_pair_cta(1)
+    ext.set_conv_mcast(1)
+    ext.set_conv_pair(0)
 
 
 @pytest.mark.parametrize("M,N,K", [(256, 256, 64), (384, 256, 512), (1000, 320, 200), (4096, 1024, 1024), (640, 96, 576),

@@ -570,3 +570,34 @@ def test_learns_a_separable_task(emu, engine):
         acc = hits / 128
     assert acc > 0.95, acc
     s.close()
+
+
+@pytest.mark.parametrize("k,stride,pad,hw,groups", [(3, 2, 1, (9, 11), 1), (5, 2, 2, (12, 10), 1), (2, 2, 0, (8, 8), 1),
+                                                     (1, 2, 0, (7, 9), 1), (3, 3, 1, (10, 10), 2), (7, 2, 3, (14, 14), 1),
+                                                     (2, 3, 0, (9, 9), 1)])
+def test_strided_conv_data_gradient(emu, k, stride, pad, hw, groups):
+    """Strided convolutions inside a net (not only as first layer): the data gradient is assembled from sh * sw stride-1
+    phase problems (ops/sm100.py::_strided_dgrad) and equals autograd through F.conv2d, also when the stride exceeds the
+    kernel (phases without taps) and with groups."""
+    from test_ops_gpu import _FakeLayer
+    torch.manual_seed(k * 10 + stride)
+    cin, cout = 16, 32
+    layer = _FakeLayer.__new__(_FakeLayer)
+    layer.layer_name, layer.num_output, layer.kernel, layer.stride, layer.pad = "conv", cout, (k, k), (stride, stride), (pad, pad)
+    layer.group, layer.bias_term, layer.in_hw = groups, True, hw
+    layer.weight = torch.nn.Parameter(torch.randn(cout, cin // groups, k, k) * 0.1)
+    layer.bias = torch.nn.Parameter(torch.randn(cout) * 0.1)
+    x = torch.randn(2, cin, *hw).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    xs = x.clone().requires_grad_(True)
+    y = emu.conv2d(xs, layer.weight, layer.bias, layer.stride, layer.pad, groups, relu_slope=None, layer=layer)
+    xr = x.float().requires_grad_(True)
+    wr = layer.weight.detach().to(torch.bfloat16).float().requires_grad_(True)
+    yr = torch.nn.functional.conv2d(xr, wr, layer.bias.detach(), stride, pad, 1, groups)
+    assert tuple(y.shape) == tuple(yr.shape)
+    dy = torch.randn_like(yr).to(torch.bfloat16)
+    y.backward(dy.contiguous(memory_format=torch.channels_last))
+    yr.backward(dy.float())
+    err = (xs.grad.float() - xr.grad).abs().max().item()
+    assert err <= 2e-2 * xr.grad.abs().max().item() + 1e-3, err
+    werr = (layer.weight.grad.float() - wr.grad).abs().max().item()
+    assert werr <= 3e-2 * wr.grad.abs().max().item() + 1e-3, werr
