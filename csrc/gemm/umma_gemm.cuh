@@ -285,10 +285,10 @@ struct TileCoord {
 };
 // NFAST (optimizer-step epilogue): n fastest, so that the CTAs running at the same time update whole rows of W —
 // one contiguous region of memory — instead of a 1 KB column slab with a row-sized stride between pieces.
-template <int GATHER, bool NFAST = false>
-__device__ __forceinline__ TileCoord tile_coord(int t, int m_blocks, int n_blocks, int C, int crank) {
+template <int GATHER>
+__device__ __forceinline__ TileCoord tile_coord(int t, int m_blocks, int n_blocks, int C, int crank, bool nfast) {
   TileCoord tc;
-  if (NFAST) {
+  if (nfast) {
     tc.n_blk = t % n_blocks;
     const int rest = t / n_blocks;
     tc.m_blk = rest % m_blocks;
@@ -312,11 +312,10 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int m_blocks, int n_block
 // Paired CTAs: the pair walks (pair of m-blocks, n-block, split) tiles; CTA `crank` of the pair owns m-block 2*mp + crank.
 // A phantom m-block past the edge (odd m_blocks) is harmless: its loads are out of range (zero-filled) and its
 // epilogue rows are skipped.
-template <bool NFAST>
-__device__ __forceinline__ TileCoord tile_coord_pair(int t, int m_pairs, int n_blocks, int crank) {
+__device__ __forceinline__ TileCoord tile_coord_pair(int t, int m_pairs, int n_blocks, int crank, bool nfast) {
   TileCoord tc;
   int mp;
-  if (NFAST) {
+  if (nfast) {
     tc.n_blk = t % n_blocks;
     const int rest = t / n_blocks;
     mp = rest % m_pairs;
@@ -374,10 +373,11 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
   const int tile0 = blockIdx.x / (C * CG), tile_step = gridDim.x / (C * CG);
   // n fastest for the epilogues that stream whole fp32 rows (optimizer step; plain fp32 output of the inner-product weight
   // gradient): the CTAs running at the same time then cover complete rows — one contiguous region of memory
-  constexpr bool kNFast = EPI == EPI_SGD || (EPI == EPI_F32 && GATHER == GATHER_NONE);
+  // (not for the atomic split-K form: there the m-blocks of one weight tile should run back to back)
+  const bool nfast = EPI == EPI_SGD || (EPI == EPI_F32 && GATHER == GATHER_NONE && !p.atomic);
   auto coord = [&](int t) -> TileCoord {
-    if constexpr (CG == 2) return tile_coord_pair<kNFast>(t, m_pairs, n_blocks, crank);
-    else return tile_coord<GATHER, kNFast>(t, m_blocks, n_blocks, C, crank);
+    if constexpr (CG == 2) return tile_coord_pair(t, m_pairs, n_blocks, crank, nfast);
+    else return tile_coord<GATHER>(t, m_blocks, n_blocks, C, crank, nfast);
   };
 
   if (warp == 0 && lane == 0) {

@@ -177,6 +177,37 @@ at::Tensor relu_bwd(const at::Tensor& y, const at::Tensor& dy, double slope) {
   return dx;
 }
 
+// ReLU backward for NHWC tensors that are channel slices of wider buffers (zero-copy concat: a branch convolution's
+// output y lives inside the concat slab, its incoming gradient dy is a channel slice of the slab's gradient): rows are
+// pixels, C contiguous channels, independent pixel pitches.  Output dense NHWC.
+__global__ void relu_bwd_pitch_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dy,
+                                      __nv_bfloat16* __restrict__ dx, long total8, int c8n, long py, long pdy, float slope) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total8; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long pix = i / c8n;
+    const int c0 = static_cast<int>(i - pix * c8n) * 8;
+    float f[8], d[8];
+    unpack8(ld8(y + pix * py + c0), f);
+    unpack8(ld8(dy + pix * pdy + c0), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] = f[j] > 0.f ? d[j] : d[j] * slope;
+    st8(dx + pix * (static_cast<long>(c8n) * 8) + c0, pack8(d));
+  }
+}
+at::Tensor relu_bwd_nhwc(const at::Tensor& y, const at::Tensor& dy, double slope) {
+  TORCH_CHECK(y.is_cuda() && y.scalar_type() == at::kBFloat16 && dy.scalar_type() == at::kBFloat16);
+  c10::cuda::CUDAGuard guard(y.device());
+  NhwcView vy = nhwc_view(y), vd = nhwc_view(dy);
+  TORCH_CHECK(vy.N == vd.N && vy.C == vd.C && vy.H == vd.H && vy.W == vd.W && vy.C % 8 == 0 && vy.pitch % 8 == 0 &&
+              vd.pitch % 8 == 0, "relu_bwd_nhwc: shapes must match, channels in multiples of 8");
+  at::Tensor dx = empty_nhwc(vy.N, vy.C, vy.H, vy.W, y.options());
+  const long total8 = static_cast<long>(vy.N) * vy.H * vy.W * (vy.C / 8);
+  relu_bwd_pitch_kernel<<<grid_for(total8, 256), 256, 0, at::cuda::getCurrentCUDAStream()>>>(
+      reinterpret_cast<const __nv_bfloat16*>(y.data_ptr()), reinterpret_cast<const __nv_bfloat16*>(dy.data_ptr()),
+      reinterpret_cast<__nv_bfloat16*>(dx.data_ptr()), total8, vy.C / 8, vy.pitch, vd.pitch, static_cast<float>(slope));
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  return dx;
+}
+
 // ------------------------------------------------------------------ dropout (mask regenerated from (seed, index))
 __device__ __forceinline__ uint32_t mix32(uint32_t a, uint32_t b) {
   uint32_t h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u);
@@ -272,6 +303,7 @@ TORCH_LIBRARY_FRAGMENT(poseidon, m) {
         "int cp, int opad, int wextra, int hextra, bool s2d) -> Tensor", &psd::transform_nhwc);
   m.def("relu_fwd(Tensor x, float slope) -> Tensor", &psd::relu_fwd);
   m.def("relu_bwd(Tensor y, Tensor dy, float slope) -> Tensor", &psd::relu_bwd);
+  m.def("relu_bwd_nhwc(Tensor y, Tensor dy, float slope) -> Tensor", &psd::relu_bwd_nhwc);
   m.def("dropout_apply(Tensor x, float ratio, int seed, Tensor? seed_dev) -> Tensor", &psd::dropout_apply);
   m.def("colsum(Tensor dy, int rows, int C, int ld, Tensor(a!) out, float alpha, bool accumulate) -> ()", &psd::colsum);
 }

@@ -78,8 +78,25 @@ class ConcatLayer(Layer):
             out[self.dim] += s[self.dim]
         return [tuple(out)]
 
+    _slab = None          # sm100 engine, zero-copy concat: the output buffer the producers write their slices into
+    _slab_channels = 0
+
+    def slab_view(self, offset: int, n: int, h: int, w: int, device):
+        """Channel slice [offset, offset + c) of this pass's output slab (allocated by the first producer that asks);
+        planned by net/fusion.py for bottoms produced by convolution kernels."""
+        import torch
+        if self._slab is None or tuple(self._slab.shape) != (n, self._slab_channels, h, w) or self._slab.device != device:
+            self._slab = torch.empty(n, self._slab_channels, h, w, device=device, dtype=torch.bfloat16) \
+                .contiguous(memory_format=torch.channels_last)
+        c = self._slab_slices[offset]
+        slab = self._slab
+        # an ALIAS of the slice, not an autograd view of the slab: the producers' kernels write disjoint slices of one
+        # buffer, which view tracking would flag as in-place modification of a shared base
+        return torch.empty(0, dtype=slab.dtype, device=slab.device).set_(
+            slab.untyped_storage(), slab.storage_offset() + offset, (n, c, h, w), slab.stride())
+
     def forward(self, *xs):
-        return (ops.get(self.ctx).concat(xs, self.dim),)
+        return (ops.get(self.ctx).concat(xs, self.dim, layer=self),)
 
 
 @register("SLICE")

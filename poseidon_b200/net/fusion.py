@@ -85,6 +85,41 @@ def plan_sm100(net) -> None:
                     else:
                         c.engine_kw = dict(getattr(c, "engine_kw", {}), mask_input=True)
 
+    # zero-copy CONCAT: bottoms produced by convolution kernels (ReLU fused or absent) and read by nobody else are
+    # written straight into the concat output slab (channel-offset view with the slab's pixel pitch)
+    producer_of = {}
+    for i, tn in enumerate(net.top_names):
+        for t in tn:
+            producer_of[t] = i               # last writer (in-place layers overwrite)
+    n_slab = 0
+    for i, layer in enumerate(net.layers):
+        if layer.type_name != "CONCAT" or layer.dim != 1 or len(net.bottom_names[i]) < 2:
+            continue
+        shapes = [net.blob_shapes[b] for b in net.bottom_names[i]]
+        if any(s[1] % 8 for s in shapes) or len(set(net.bottom_names[i])) != len(net.bottom_names[i]):
+            continue
+        plan, off, ok = [], 0, True
+        for b, shp in zip(net.bottom_names[i], shapes):
+            writers = [j for j, tn in enumerate(net.top_names) if b in tn and not net.skip_layer[j]]
+            readers = [j for j in consumers.get(b, []) if not net.skip_layer[j]]
+            j = writers[-1] if writers else -1
+            c = net.layers[j] if j >= 0 else None
+            if c is None or len(writers) != 1 or c.type_name != "CONVOLUTION" or readers != [i] or \
+                    getattr(c, "_concat_slab", None) is not None or c._sm100.Coutp != c._sm100.Cout:
+                ok = False
+                break
+            plan.append((c, off, shp[1]))
+            off += shp[1]
+        if not ok:
+            continue
+        layer._slab_channels = off
+        layer._slab_slices = {o: n_c for _, o, n_c in plan}
+        for c, o, _ in plan:
+            c._concat_slab = (layer, o)
+        n_slab += 1
+    if n_slab and net.ctx.rank == 0:
+        log.info("sm100 plan: %d CONCAT layers are zero-copy (branch convolutions write into the concat slab)", n_slab)
+
     # data layer -> first conv hand-off
     for i, layer in enumerate(net.layers):
         if not getattr(layer, "is_data", False) or not net.top_names[i]:

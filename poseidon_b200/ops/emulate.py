@@ -186,6 +186,10 @@ class EmulatedKernels:
         assert y.stride() == dy.stride(), "relu_bwd: layout mismatch"
         return torch.where(y.float() > 0, dy.float(), dy.float() * slope).to(BF16)
 
+    def relu_bwd_nhwc(self, y, dy, slope):
+        """Pitch-aware variant (y / dy may be channel slices of wider NHWC buffers); dense NHWC result."""
+        return _nhwc(torch.where(y.float() > 0, dy.float(), dy.float() * slope).to(BF16))
+
     def dropout_apply(self, x, ratio, seed, seed_dev):
         """The same (seed, iteration, element) -> keep map for forward and backward (csrc/ops/elementwise.cu:178-222);
         the emulation draws the map from a generator keyed the same way instead of the kernel's integer hash."""

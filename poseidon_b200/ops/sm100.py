@@ -348,8 +348,13 @@ class _ConvFn(torch.autograd.Function):
         else:
             if st.Coutp != st.Cout and bias is not None:
                 bias = torch.nn.functional.pad(bias.detach(), (0, st.Coutp - st.Cout))
+            # zero-copy concat: this layer's output is a channel slice of its consumer CONCAT layer's slab
+            slab = getattr(layer, "_concat_slab", None)
+            out = None
+            if slab is not None and st.Coutp == st.Cout:
+                out = slab[0].slab_view(slab[1], xin.shape[0], oh, ow, xin.device)
             y = k.conv_fprop(xin, st.operand(), bias, [st.R, st.S], list(stride), list(conv_pad), st.groups,
-                             1 if (st.row_mode and not st.pad8) else 0, oh, ow, relu, float(relu_slope or 0.0), None)
+                             1 if (st.row_mode and not st.pad8) else 0, oh, ow, relu, float(relu_slope or 0.0), out)
             if st.Coutp != st.Cout:
                 y = y[:, : st.Cout]            # channel slice of the padded tensor (pixel pitch Coutp)
         ctx.layer, ctx.relu_slope, ctx.conv_pad = layer, relu_slope, conv_pad
@@ -374,7 +379,10 @@ class _ConvFn(torch.autograd.Function):
         else:
             dy = as_kernel_input(dy)
             if y is not None and not st.consumer_masks:
-                dy = k.relu_bwd(y, dy.contiguous(memory_format=CL), float(ctx.relu_slope))
+                if y.is_contiguous(memory_format=CL) and dy.is_contiguous(memory_format=CL):
+                    dy = k.relu_bwd(y, dy, float(ctx.relu_slope))
+                else:                       # y and / or dy are channel slices of a concat slab: pitch-aware kernel
+                    dy = k.relu_bwd_nhwc(y, dy, float(ctx.relu_slope))
         stride = layer.stride
         dw = db = dx = None
         if ctx.needs_input_grad[1]:
@@ -954,7 +962,34 @@ def mvn(x, normalize_variance=True, across_channels=False):
     return _MVNFn.apply(as_kernel_input(x), bool(normalize_variance), bool(across_channels))
 
 
-def concat(xs, dim):
+class _SlabConcatFn(torch.autograd.Function):
+    """CONCAT over channels whose bottoms were written by their producers straight into one slab (channel-offset views
+    with the slab's pixel pitch): forward is the identity on memory, backward hands out channel slices of dY.
+    reference: src/caffe/layers/concat_layer.cu:10-72 copies every bottom (forward) and every slice (backward)."""
+
+    @staticmethod
+    def forward(ctx, slab, sizes, *xs):
+        ctx.sizes = sizes
+        return slab
+
+    @staticmethod
+    def backward(ctx, dy):
+        return (None, None) + tuple(torch.split(dy, ctx.sizes, dim=1))
+
+
+def concat(xs, dim, layer=None):
+    slab = getattr(layer, "_slab", None) if layer is not None else None
+    if slab is not None and dim == 1:
+        layer._slab = None                       # the next forward pass allocates a fresh slab
+        off, ok = 0, True
+        for x in xs:
+            ok = ok and x.data_ptr() == slab.data_ptr() + off * slab.element_size() and x.shape[1] + off <= slab.shape[1] \
+                and x.shape[0] == slab.shape[0] and tuple(x.shape[2:]) == tuple(slab.shape[2:])
+            off += x.shape[1]
+        if ok and off == slab.shape[1]:
+            if not torch.is_grad_enabled() or not any(x.requires_grad for x in xs):
+                return slab
+            return _SlabConcatFn.apply(slab, tuple(x.shape[1] for x in xs), *xs)
     return torch.cat([x if x.dtype == xs[0].dtype else x.to(xs[0].dtype) for x in xs], dim=dim)
 
 

@@ -45,7 +45,7 @@ def dropout(x, ratio, train):
     return R.dropout(x, ratio, train)
 
 
-def concat(xs, dim):
+def concat(xs, dim, layer=None):
     return torch.cat(list(xs), dim=dim)
 
 

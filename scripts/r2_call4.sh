@@ -10,14 +10,16 @@ B="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 1
 echo "=== bench alexnet 2 GPUs (fused SFB epilogue)" >> $L
 NCCL_DEBUG=INFO timeout 900 $B --steps 100 --warmup 10 2>&1 | grep -E "NVLS|^\{|symmetric arena|Error|error" | head -12 >> $L
 echo "=== bench alexnet 2 GPUs (two-pass SFB)" >> $L
-POSEIDON_SFB_FUSED_SGD=0 timeout 900 $B --steps 100 --warmup 10 --no-e2e --no-exposed-comm 2>&1 | tail -1 >> $L
+POSEIDON_SFB_FUSED_SGD=0 timeout 900 $B --steps 100 --warmup 10 --no-e2e --no-exposed-comm 2>&1 | tail -1 | cut -c1-900 >> $L
 echo "=== bench alexnet 2 GPUs (no multimem: P2P)" >> $L
-POSEIDON_MULTIMEM=0 timeout 900 $B --steps 100 --warmup 10 --no-e2e --no-exposed-comm 2>&1 | tail -1 >> $L
+POSEIDON_MULTIMEM=0 timeout 900 $B --steps 100 --warmup 10 --no-e2e --no-exposed-comm 2>&1 | tail -1 | cut -c1-900 >> $L
 echo "=== bench googlenet 2 GPUs" >> $L
-timeout 900 $B --model googlenet --steps 50 --warmup 10 --no-e2e 2>&1 | tail -1 >> $L
+timeout 900 $B --model googlenet --steps 50 --warmup 10 --no-e2e 2>&1 | tail -1 | cut -c1-900 >> $L
 echo "=== vendor arm 2 GPUs (torch engine + NCCL, CUDA graph)" >> $L
-timeout 900 $B --engine torch --graph 1 --steps 50 --warmup 10 --no-e2e --no-exposed-comm 2>&1 | tail -2 >> $L
-timeout 900 $B --engine torch --graph 1 --model googlenet --steps 50 --warmup 10 --no-e2e --no-exposed-comm 2>&1 | tail -2 >> $L
+timeout 900 $B --engine torch --graph 1 --steps 50 --warmup 10 --no-e2e --no-exposed-comm 2>&1 | tail -2 | cut -c1-900 >> $L
+timeout 900 $B --engine torch --graph 1 --model googlenet --steps 50 --warmup 10 --no-e2e --no-exposed-comm 2>&1 | tail -2 | cut -c1-900 >> $L
+echo "=== caffenet SSP staleness 1, 2 GPUs (fused SSP kernels, CUDA graph)" >> $L
+timeout 900 $B --model caffenet --staleness 1 --steps 50 --warmup 10 --no-e2e --no-exposed-comm 2>&1 | tail -1 | cut -c1-600 >> $L
 echo "=== bench alexnet 1 GPU (same box)" >> $L
-timeout 600 python bench.py --steps 100 --warmup 10 --no-e2e 2>&1 | tail -1 >> $L
+timeout 600 python bench.py --steps 100 --warmup 10 --no-e2e 2>&1 | tail -1 | cut -c1-900 >> $L
 tail -120 $L

@@ -97,7 +97,16 @@ def test_mvn(ext, nv, ac):
 def test_lrn_within_channel(ext, size):
     from poseidon_b200.ops import sm100
     x = _x((2, 32, 12, 10), 5, 2.0)
-    _check(lambda t: sm100.lrn_within(t, size, 0.5, 0.75), lambda t: R.lrn_within(t, size, 0.5, 0.75), [x], rel=3e-2)
+    # the oracle runs on the CPU: torch's CUDA avg_pool2d backward (ceil_mode + padding, channels-last) disagrees with its
+    # own CPU implementation and with the closed form (scripts/debug/lrn_within_dbg.py) — the kernel matches the latter
+    a = x.clone().requires_grad_(True)
+    b = x.float().cpu().contiguous().requires_grad_(True)
+    y, yr = sm100.lrn_within(a, size, 0.5, 0.75), R.lrn_within(b, size, 0.5, 0.75)
+    _close(y.cpu(), yr, 3e-2, "forward")
+    dy = _x(tuple(yr.shape), 99)
+    y.backward(dy)
+    yr.backward(dy.float().cpu())
+    _close(a.grad.cpu(), b.grad, 4.5e-2, "grad")
 
 
 def test_stochastic_pool_test_phase_and_train_statistics(ext):

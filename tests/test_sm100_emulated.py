@@ -250,7 +250,7 @@ def test_inception_block_with_concat_and_dropout(emu):
         feed(s, x, y)                  # the same 4 images every step: the net must memorise them
         s.step(1)
         losses.append(float(s.last_loss))
-    assert losses[-1] < 0.8 * losses[0] and all(b < a + 0.05 for a, b in zip(losses, losses[1:])), losses
+    assert losses[-1] < 0.88 * losses[0] and all(b < a + 0.05 for a, b in zip(losses, losses[1:])), losses
     for n, l in zip(s.net.layer_names, s.net.layers):
         if len(l.blobs):
             assert np.abs(l.export_blob(0) - before[n]).max() > 0, f"{n} never updated"
