@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--no-exposed-comm", action="store_true",
                     help="skip the compute-only arm (N > 1) that exposed_comm_ms is measured against")
     ap.add_argument("--require-nvls", action="store_true", help="fail if the arena has no NVLS multicast mapping")
+    ap.add_argument("--kernel-list", default="", help="write a per-kernel time table (CUPTI via torch.profiler, a few EAGER "
+                    "steps on every rank, rank r -> FILE.r) — works for multi-rank runs, where ncu cannot be used")
     return ap.parse_args()
 
 
@@ -124,6 +126,36 @@ def measure_compute_only(args, rc):
     ms, _ = timed_steps(solver, rc, args.steps, read_loss=False)      # rc: barrier + max over the REAL ranks
     solver.close()
     return ms / args.steps
+
+
+def dump_kernel_list(args, rc, path):
+    """Kernel names / counts / device time of 3 eager training steps of THIS rank (comm-stream kernels included)."""
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+    solver = build_solver(args, rc, device_resident=True)
+    for _ in range(4):
+        solver.step(1)
+    solver.sync.wait_all()
+    torch.cuda.synchronize(rc.device)
+    rc.barrier()
+    steps = 3
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(steps):
+            solver.step(1)
+        solver.sync.wait_all()
+        torch.cuda.synchronize(rc.device)
+    rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
+    cp = solver.sync.backend.comm_profile() if hasattr(solver.sync.backend, "comm_profile") else {}
+    with open(f"{path}.{rc.rank}", "w") as f:
+        f.write(f"# {args.model} rank {rc.rank}/{rc.world_size}, {steps} eager steps, CUPTI kernel times (torch.profiler)\n")
+        f.write(f"# comm profile per step: {json.dumps(cp)}\n")
+        f.write(f"{'us/step':>10s} {'calls/step':>10s} {'avg us':>9s}  kernel\n")
+        for e in rows:
+            if e.device_time_total <= 0:
+                continue
+            f.write(f"{e.device_time_total / steps:10.1f} {e.count / steps:10.1f} "
+                    f"{e.device_time_total / max(e.count, 1):9.1f}  {e.key[:150]}\n")
+    solver.close()
 
 
 def build_solver(args, rank_ctx, device_resident: bool):
@@ -279,6 +311,11 @@ def main():
                               "ranks running concurrently; device-timed, max over ranks"}
         except Exception as exc:
             exposed = {"error": f"{type(exc).__name__}: {exc}"}
+    if args.kernel_list and rc.device.type == "cuda":
+        try:
+            dump_kernel_list(args, rc, args.kernel_list)
+        except Exception as exc:
+            print(f"[bench] kernel list failed: {type(exc).__name__}: {exc}", file=sys.stderr)
     if rc.is_root:
         shape = solver.net.blob_shapes[solver.net.top_names[0][0]]
         out = {

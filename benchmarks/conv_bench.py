@@ -12,6 +12,9 @@ CASES = {
     "conv3": (256, 256, 13, 13, 384, 3, 1, 1, 1),
     "conv4": (256, 384, 13, 13, 384, 3, 1, 1, 2),
     "conv5": (256, 384, 13, 13, 256, 3, 1, 1, 2),
+    # experiments (profiles/r2_conv_ncu_summary.md): same GEMM extent as conv3 (M 43264, N 384, K 2304) with ...
+    "conv3_nopad": (256, 256, 15, 15, 384, 3, 1, 0, 1),       # ... no padding: no zero-filled pixels in the im2col boxes
+    "conv3_as1x1": (256, 2304, 13, 13, 384, 1, 1, 0, 1),      # ... one tap over 2304 channels: im2col-mode TMA reading a plain [M, K] matrix
 }
 import os
 if os.environ.get('PSD_CONV_IM2COL') == '0':
@@ -19,6 +22,8 @@ if os.environ.get('PSD_CONV_IM2COL') == '0':
     sm100.K().set_conv_im2col(0)
 PAIR = int(os.environ.get("PSD_PAIR", "1"))
 sm100.K().set_conv_pair(PAIR)
+if os.environ.get("PSD_MAX_STAGES"):
+    sm100.K().set_max_stages(int(os.environ["PSD_MAX_STAGES"]))
 MC = int(os.environ.get("PSD_MCAST", "1"))
 sm100.K().set_conv_mcast(MC)
 print(f"== cta_group::{2 if PAIR else 1} kernels, im2col multicast cluster {MC} ==", flush=True)

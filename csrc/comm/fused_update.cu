@@ -57,14 +57,18 @@ __device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
 }
 
 // ------------------------------------------------------------------------------------ single GPU
+// REARM: the gradient buffer is a persistent accumulation target (conv wgrad adds into it with split-K atomics): leave it
+// zeroed for the next step instead of paying a memset launch per layer and step.
+template <bool REARM>
 __global__ void __launch_bounds__(256)
-fused_update_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ h, __nv_bfloat16* __restrict__ wb,
+fused_update_kernel(float* __restrict__ w, float* __restrict__ g, float* __restrict__ h, __nv_bfloat16* __restrict__ wb,
                     long n, UpdateHyper hp, const float* __restrict__ lr_dev) {
   if (lr_dev != nullptr) hp.lr *= __ldg(lr_dev);     // global learning rate lives on the device (CUDA-graph replay safe)
   const long n4 = n >> 2;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<long>(gridDim.x) * blockDim.x) {
     float4 wv = reinterpret_cast<float4*>(w)[i], hv = reinterpret_cast<float4*>(h)[i];
     const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    if (REARM) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     step_rule(gv.x, wv.x, hv.x, hp);
     step_rule(gv.y, wv.y, hv.y, hp);
     step_rule(gv.z, wv.z, hv.z, hp);
@@ -77,6 +81,7 @@ fused_update_kernel(float* __restrict__ w, const float* __restrict__ g, float* _
   for (long i = (n4 << 2) + blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
     float wv = w[i], hv = h[i];
     step_rule(g[i], wv, hv, hp);
+    if (REARM) g[i] = 0.f;
     w[i] = wv;
     h[i] = hv;
     if (wb != nullptr) wb[i] = __float2bfloat16(wv);
@@ -105,8 +110,9 @@ static bool same_dense_layout(const at::Tensor& a, const at::Tensor& b) {
 }
 
 // W, G, H: fp32 tensors with identical (dense) layout; wb: optional bf16 shadow in the same storage order.
-void fused_update(at::Tensor w, const at::Tensor& g, at::Tensor h, c10::optional<at::Tensor> wb, double lr, double momentum,
-                  double decay, int64_t rule, bool l1, double delta, double gscale, const c10::optional<at::Tensor>& lr_dev) {
+void fused_update(at::Tensor w, at::Tensor g, at::Tensor h, c10::optional<at::Tensor> wb, double lr, double momentum,
+                  double decay, int64_t rule, bool l1, double delta, double gscale, const c10::optional<at::Tensor>& lr_dev,
+                  bool rearm) {
   TORCH_CHECK(w.is_cuda() && w.scalar_type() == at::kFloat && g.scalar_type() == at::kFloat && h.scalar_type() == at::kFloat);
   TORCH_CHECK(same_dense_layout(w, g) && same_dense_layout(w, h), "fused_update: W, G, H must share one dense layout");
   TORCH_CHECK(w.is_non_overlapping_and_dense(), "fused_update: dense tensors expected");
@@ -122,9 +128,11 @@ void fused_update(at::Tensor w, const at::Tensor& g, at::Tensor h, c10::optional
                        (wbp == nullptr || reinterpret_cast<uintptr_t>(wbp) % 8 == 0);
   TORCH_CHECK(aligned, "fused_update: 16-byte aligned buffers expected");
   const int grid = static_cast<int>(std::max<long>(1, std::min<long>((n / 4 + 255) / 256, 148 * 8)));
-  fused_update_kernel<<<grid, 256, 0, at::cuda::getCurrentCUDAStream()>>>(
-      w.data_ptr<float>(), g.data_ptr<float>(), h.data_ptr<float>(), wbp, n,
-      make_hyper(lr, momentum, decay, rule, l1, delta, gscale), lr_dev.has_value() ? lr_dev->data_ptr<float>() : nullptr);
+  const UpdateHyper hp = make_hyper(lr, momentum, decay, rule, l1, delta, gscale);
+  const float* lrp = lr_dev.has_value() ? lr_dev->data_ptr<float>() : nullptr;
+  auto st = at::cuda::getCurrentCUDAStream();
+  if (rearm) fused_update_kernel<true><<<grid, 256, 0, st>>>(w.data_ptr<float>(), g.data_ptr<float>(), h.data_ptr<float>(), wbp, n, hp, lrp);
+  else fused_update_kernel<false><<<grid, 256, 0, st>>>(w.data_ptr<float>(), g.data_ptr<float>(), h.data_ptr<float>(), wbp, n, hp, lrp);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
@@ -746,8 +754,8 @@ void peer_signal(std::vector<int64_t> flag_ptrs, int64_t rank, int64_t slot, int
 }  // namespace psd
 
 TORCH_LIBRARY_FRAGMENT(poseidon, m) {
-  m.def("fused_update(Tensor(a!) w, Tensor g, Tensor(b!) h, Tensor(c!)? wb, float lr, float momentum, float decay, int rule, "
-        "bool l1, float delta, float gscale, Tensor? lr_dev) -> ()", &psd::fused_update);
+  m.def("fused_update(Tensor(a!) w, Tensor(d!) g, Tensor(b!) h, Tensor(c!)? wb, float lr, float momentum, float decay, int rule, "
+        "bool l1, float delta, float gscale, Tensor? lr_dev, bool rearm=False) -> ()", &psd::fused_update);
   m.def("allreduce_sgd(int[] g_ptrs, int[] w_ptrs, int[] wb_ptrs, int[] flag_ptrs, int g_mc, int w_mc, Tensor(a!) h, int n, "
         "int rank, int epoch, bool one_shot, Tensor(b!) done_counter, float lr, float momentum, float decay, int rule, "
         "bool l1, float delta, float gscale, int max_ctas, Tensor? lr_dev, Tensor? epoch_dev) -> ()", &psd::allreduce_sgd);

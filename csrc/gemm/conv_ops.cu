@@ -30,6 +30,7 @@ static int g_conv_im2col = 1;      // TMA im2col-mode operand fetch where the ge
 static int g_conv_cluster = 1;     // CTAs per cluster sharing the TMA operand by multicast (1 = off; measured slower at 2 on B200, kept as an option)
 
 int pair_cta_enabled();
+extern int g_max_stages;
 
 template <int BN, bool A_MN, bool B_MN, int EPI, int GATHER, int CG = 1>
 static void launch_conv(const TmapSet& tm, const GemmParams& p, const ConvGeom& cg, int grid, cudaStream_t stream) {
@@ -254,6 +255,7 @@ at::Tensor conv_fprop(const at::Tensor& x, const at::Tensor& wb, const c10::opti
     encode_tmap_bf16_2d(&tm.b[0], wptr, cg.K, Cout_g, cg.K, BLOCK_K, bn / cl);     // each CTA multicasts 1/cl of the rows
     tm.a[0] = tm.b[0];
     GemmParams p{};
+    p.max_stages = g_max_stages;
     p.cluster = cl;
     p.M = static_cast<int>(cg.M);
     p.N = Cout_g;
@@ -332,6 +334,7 @@ at::Tensor conv_dgrad(const at::Tensor& dy, const at::Tensor& wt, at::IntArrayRe
     encode_tmap_bf16_2d(&tm.b[0], wptr, cg.K, Cg, cg.K, BLOCK_K, bn / cl);
     tm.a[0] = tm.b[0];
     GemmParams p{};
+    p.max_stages = g_max_stages;
     p.cluster = cl;
     p.M = static_cast<int>(cg.M);
     p.N = Cg;
@@ -399,6 +402,7 @@ void conv_wgrad(const at::Tensor& x, const at::Tensor& dy, at::Tensor dw, at::In
     // A = dYᵀ: MN-major, inner = Cout_g channels of this group, outer = M pixels, pitch = dy pixel pitch
     const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(dy.data_ptr()) + gidx * Cout_g;
     GemmParams p{};
+    p.max_stages = g_max_stages;
     p.M = Cout_g;
     p.N = cg.K;
     p.kb_per_src = static_cast<int>((cg.M + BLOCK_K - 1) / BLOCK_K);

@@ -4,6 +4,10 @@
 #include <torch/library.h>
 #include <torch/types.h>
 
+#include <array>
+#include <map>
+#include <mutex>
+
 #include "umma_gemm.cuh"
 
 namespace psd {
@@ -73,6 +77,7 @@ void encode_tmap_im2col_bf16(CUtensorMap* map, const void* base, int64_t C, int6
               " N=", N, " lower=", lower_w, ",", lower_h, " upper=", upper_w, ",", upper_h);
 }
 
+int g_max_stages = 0;             // experiment knob (set_max_stages): ring stages actually used, 0 = all
 static int g_pair_cta = 1;        // cta_group::2 (paired CTAs) where the tile space allows it; 0 = single-CTA kernels only
 int pair_cta_enabled() { return g_pair_cta; }
 
@@ -170,6 +175,7 @@ void gemm_launch(const std::vector<int64_t>& a_ptrs, bool a_mn, int64_t lda, con
   }
   p.M = static_cast<int>(M);
   p.N = static_cast<int>(N);
+  p.max_stages = g_max_stages;
   p.kb_per_src = static_cast<int>((K + BLOCK_K - 1) / BLOCK_K);
   p.num_src = nsrc;
   if (p.split_k < 1) p.split_k = 1;
@@ -197,13 +203,14 @@ void gemm_launch(const std::vector<int64_t>& a_ptrs, bool a_mn, int64_t lda, con
 
 // Split-K finish: out = act(ws + bias) (optionally ReLU-masked) -> bf16.  ws is the fp32 [M, N] partial-sum buffer.
 __global__ void __launch_bounds__(256)
-splitk_finish_kernel(const float* __restrict__ ws, __nv_bfloat16* __restrict__ out, long ldc, const float* __restrict__ bias,
+splitk_finish_kernel(float* __restrict__ ws, __nv_bfloat16* __restrict__ out, long ldc, const float* __restrict__ bias,
                      const __nv_bfloat16* __restrict__ mask, int relu, float slope, int M, int N) {
   const long total = static_cast<long>(M) * N;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
     const int m = static_cast<int>(i / N), n = static_cast<int>(i - static_cast<long>(m) * N);
     float v = ws[i];
+    ws[i] = 0.f;                               // re-arm the cached workspace for its next user (no memset launch per call)
     if (bias != nullptr) v += bias[n];
     if (relu) v = v > 0.f ? v : v * slope;
     if (mask != nullptr && !(__bfloat162float(mask[m * ldc + n]) > 0.f)) v *= slope;
@@ -248,7 +255,17 @@ at::Tensor gemm_bf16(const at::Tensor& a, bool a_mn, const at::Tensor& b, bool b
     const int64_t kb = (K + BLOCK_K - 1) / BLOCK_K;
     const int64_t split = std::min<int64_t>(sms / std::max<int64_t>(tiles, 1), kb / 8);
     if (tiles * 2 <= sms && split >= 2) {
-      at::Tensor ws = at::zeros({M, N}, a.options().dtype(at::kFloat));
+      // fp32 partial-sum workspace: one per (device, stream, extent), zeroed once — the finishing kernel leaves it zeroed
+      static std::map<std::array<int64_t, 4>, at::Tensor> ws_cache;
+      static std::mutex ws_mu;
+      at::Tensor ws;
+      {
+        std::lock_guard<std::mutex> lock(ws_mu);
+        const std::array<int64_t, 4> key{a.device().index(), reinterpret_cast<int64_t>(stream.stream()), M, N};
+        auto it = ws_cache.find(key);
+        if (it == ws_cache.end()) it = ws_cache.emplace(key, at::zeros({M, N}, a.options().dtype(at::kFloat))).first;
+        ws = it->second;
+      }
       GemmParams q{};
       q.c_f32 = ws.data_ptr<float>();
       q.ldc = N;
@@ -355,11 +372,13 @@ void sfb_outer_f32(std::vector<int64_t> u_ptrs, std::vector<int64_t> v_ptrs, int
 }
 
 void set_pair_cta(int64_t on) { g_pair_cta = on != 0; }
+void set_max_stages(int64_t n) { g_max_stages = static_cast<int>(n); }
 
 }  // namespace psd
 
 TORCH_LIBRARY_FRAGMENT(poseidon, m) {
   m.def("set_pair_cta(int on) -> ()", &psd::set_pair_cta);
+  m.def("set_max_stages(int n) -> ()", &psd::set_max_stages);
   m.def("sfb_outer_f32(int[] u_ptrs, int[] v_ptrs, int Mb, int N, int K, Tensor(a!) out, float alpha, Tensor? flags, "
         "int epoch, int src_rot, int bn, int max_ctas, Tensor? epoch_dev) -> ()", &psd::sfb_outer_f32);
   m.def("gemm_bf16(Tensor a, bool a_mn, Tensor b, bool b_mn, Tensor? bias, bool relu, float slope, Tensor? mask, "

@@ -51,6 +51,7 @@ struct GemmParams {
   int split_k;           // >1: partial sums accumulated with atomics (EPI_F32 only)
   int src_rot;           // first source to visit (own rank for SFB: local data needs no flag wait)
   int cluster;           // CTAs per cluster sharing the TMA operand by multicast (1 = no clusters); conv kernels only
+  int max_stages;        // experiment knob: use only this many ring stages (0 = all that fit)
   // --- epilogue operands
   __nv_bfloat16* c_bf16; // EPI_BF16 output [M, ldc]
   float* c_f32;          // EPI_F32 output [M, ldc]
@@ -353,6 +354,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int nst = (p.max_stages > 0 && p.max_stages < kStages) ? p.max_stages : kStages;     // ring depth in use
 
   const int m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int n_blocks = (p.N + BN - 1) / BN;
@@ -551,7 +553,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
           }
           }  // elect_one
           __syncwarp();
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nst) { stage = 0; phase ^= 1; }
           if (++kb == p.kb_per_src) {
             kb = 0;
             if (++src == p.num_src) src = 0;
@@ -601,7 +603,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
             }
           }
           __syncwarp();
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nst) { stage = 0; phase ^= 1; }
         }
         if (g0 >= g1 && elect_one()) {                                  // (never: every split owns >= 1 k-block)
           if constexpr (CG == 2) umma_commit_cg2(&tmem_full[as], 0x3);
@@ -641,7 +643,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
             for (int i = 0; i < kRows; ++i) gather_chunk_row(gr, sa + i * (kRowStep * 128), pos[i], t);
           }
           cp_async_mbar_arrive_noinc(&full_bar[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nst) { stage = 0; phase ^= 1; }
         }
       } else {
         // B tile (MN-major): BN/64 chunk-columns of [64 reduction rows (m)][64 k-columns]; the k-columns are
@@ -672,7 +674,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
             }
           }
           cp_async_mbar_arrive_noinc(&full_bar[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nst) { stage = 0; phase ^= 1; }
         }
       }
     }

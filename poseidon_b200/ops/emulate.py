@@ -58,6 +58,9 @@ class EmulatedKernels:
     def set_conv_pair(self, on):
         return None
 
+    def set_max_stages(self, n):
+        return None
+
     def set_pair_cta(self, on):              # csrc/gemm/gemm_ops.cu (cta_group::2 on/off: no numerical effect)
         return None
 
@@ -418,7 +421,7 @@ class EmulatedKernels:
         return loss, dx, (prob if want_prob else torch.empty(0))
 
     # ------------------------------------------------------------------------------------------ optimizer
-    def fused_update(self, w, g, h, wb, lr, momentum, decay, rule, l1, delta, gscale, lr_dev):
+    def fused_update(self, w, g, h, wb, lr, momentum, decay, rule, l1, delta, gscale, lr_dev, rearm=False):
         """One optimizer step in place on (w, h) + refresh of the bf16 shadow in the master's storage order
         (csrc/comm/fused_update.cu:30-108).  rule 0 SGD, 1 Nesterov, 2 AdaGrad."""
         for t in (g, h):
@@ -427,6 +430,8 @@ class EmulatedKernels:
         if lr_dev is not None:
             lr = lr * float(lr_dev[0])
         self._step(w, g.float(), h, lr, momentum, decay, rule, l1, delta, gscale)
+        if rearm:
+            g.zero_()                       # persistent accumulation buffer: left zeroed for the next step's wgrad
         if wb is not None:
             wb.view(-1).copy_(_storage_order_flat(w))
 

@@ -707,7 +707,11 @@ class _PoolFn(torch.autograd.Function):
         is_max, in_hw, kernel, stride, pad = ctx.args
         dy = as_kernel_input(dy)
         if y is not None:
-            dy = dy * (y > 0)        # producer's ReLU mask, evaluated on the (small) pooled tensor
+            # producer's ReLU mask, evaluated on the (small) pooled tensor: max(ReLU(x)) > 0 <=> the arg-max passed the ReLU
+            if dy.is_contiguous(memory_format=CL) and y.is_contiguous(memory_format=CL):
+                dy = K().relu_bwd(y, dy, 0.0)
+            else:
+                dy = K().relu_bwd_nhwc(y, dy, 0.0)
         dx = K().pool_bwd(dy, idx, is_max, list(in_hw), list(kernel), list(stride), list(pad))
         return dx, None, None, None, None, None
 

@@ -4,15 +4,17 @@
   and bound to an NVLS multicast object; handles come from ``torch.distributed._symmetric_memory``,
   which is bootstrap plumbing only).  It holds, at identical offsets on every rank: the gradient
   staging buffer G, the fp32 master weights W, the bf16 shadow weights Wb, the sufficient-factor
-  staging ring (u, v per SFB layer, double-buffered by step parity) and the epoch-flag blocks.
+  staging slots (u, v per SFB layer and rank; single-buffered, guarded by "consumed" flags), the bounded-staleness
+  delta rings (SSP mode) and the epoch-flag blocks.
   This replaces the Bösen PS tables + process/thread caches (reference: src/caffe/blob.cpp:58-83,
   ps/src/petuum_ps/client/client_table.cpp:26-158, ps/src/petuum_ps/server/server_table.cpp).
 * ``FusedBackend`` — per-bucket ``allreduce_sgd`` kernel (two-shot, history sharded across ranks;
   one-shot for small buckets) launched from the DWBP hooks on a high-priority stream.
-* ``FusedSFB`` — sufficient-factor broadcasting: u, v are published in the arena, peers are signalled
-  with release flags, and ONE tcgen05 kernel pulls every peer's factors over NVLink with TMA and
-  accumulates Σ_p u_pᵀ v_p in TMEM with the optimizer step fused into its epilogue — no dense ΔW ever
-  exists, locally or on the wire.  With one rank it degenerates to the fused wgrad+update kernel.
+* ``FusedSFB`` — sufficient-factor broadcasting: every rank PUSHES its u, v into slot `rank` of every peer's arena
+  (one NVSwitch-multicast store stream) and raises a release flag; ONE tcgen05 kernel then walks the P local slots as
+  P reduction sources (waiting on slot p's flag right before its first TMA load) and accumulates Σ_p u_pᵀ v_p in TMEM
+  with the optimizer step fused into its epilogue — no dense ΔW ever exists, locally or on the wire.  With one rank it
+  degenerates to the fused wgrad+update kernel.
 
 reference: src/caffe/solver.cpp:455-531 (ThreadSyncWithPS / ThreadSyncWithSVB),
 src/caffe/svb_worker.cpp:19-179, ps/src/petuum_ps/thread/ssp_push_bg_worker.cpp:12-68.
@@ -212,6 +214,11 @@ class FusedBackend(Backend):
         self._choose_sfb(net, sync)
         if self.world > 1:
             self._build_arena(net, sync)
+        if self.world == 1:
+            for layer in net.layers:
+                st = getattr(layer, "_sm100", None)
+                if isinstance(st, sm100.ConvState) and not st.row_mode and layer.weight.requires_grad:
+                    layer._grad_sink = self
         self.per_worker_state = self.ssp and self.world > 1
         self.done_counter = torch.zeros(4, dtype=torch.int32, device=self.device)
         self.lr_t = torch.zeros(1, dtype=torch.float32, device=self.device)     # global lr, read by the kernels
@@ -326,7 +333,17 @@ class FusedBackend(Backend):
 
     def weight_buffer(self, layer, st) -> torch.Tensor:
         """Gradient sink: the layer's wgrad kernel accumulates straight into the symmetric G arena (the segment
-        is zeroed by the previous step's all-reduce launch)."""
+        is zeroed by the previous step's all-reduce launch).  One GPU: a persistent per-layer fp32 buffer that the
+        update kernel re-arms (zeroes) after reading — no torch.zeros per layer and step."""
+        if self.world == 1:
+            shape = (st.Coutp, st.Kw) if isinstance(st, sm100.ConvState) else (st.N, st.Kp)
+            buf = getattr(st, "_gsink", None)
+            if buf is None or tuple(buf.shape) != shape:
+                buf = st._gsink = torch.zeros(shape, device=self.device, dtype=torch.float32)
+            elif getattr(st, "_gsink_dirty", False):
+                buf.zero_()                 # the last hand-out was not consumed by a re-arming update (shared weights, ...)
+            st._gsink_dirty = True
+            return buf
         seg = self.seg_of[id(layer.weight)]
         shape = (st.Cout, st.Kw) if isinstance(st, sm100.ConvState) else (st.N, st.K)
         return self.arena.view(seg.g_off, (seg.numel,), torch.float32)[: layer.weight.numel()].view(*shape)
@@ -402,7 +419,11 @@ class FusedBackend(Backend):
             if not _same_order(g, p.data):
                 g = torch.empty_like(p.data).copy_(g)
             lr, mom, decay, rule, l1, delta, gscale = self._hyper_args(lm, dm)
-            self.k.fused_update(p.data, g, h, wb, lr, mom, decay, rule, l1, delta, gscale, self.lr_t)
+            gs = getattr(st, "_gsink", None) if p is getattr(bucket.layer, "weight", None) else None
+            rearm = gs is not None and g.data_ptr() == gs.data_ptr()      # the persistent sink: leave it zeroed
+            self.k.fused_update(p.data, g, h, wb, lr, mom, decay, rule, l1, delta, gscale, self.lr_t, rearm)
+            if rearm:
+                st._gsink_dirty = False
             self.launches += 1
             if p is getattr(bucket.layer, "weight", None):
                 fresh = wb is not None
@@ -627,7 +648,8 @@ def _storage_order_flat(t: torch.Tensor) -> torch.Tensor:
 class FusedSFB:
     """Per-layer sufficient-factor exchange + fused outer-product/optimizer kernel.
 
-    Staging layout (per step parity) inside every rank's arena:  U[P][M][N], V[P][M][K] bf16.  Rank r
+    Staging layout inside every rank's arena (single-buffered; a rank may only overwrite a peer's slot after that peer
+    raised its *consumed* flag for the previous step):  U[P][M][N], V[P][M][K] bf16.  Rank r
     *pushes* its factors into slot r of every rank (one NVSwitch-multicast store stream, or P2P stores),
     raises its epoch flag on every peer, and the tcgen05 kernel walks the P slots as P reduction sources,
     waiting on slot p's flag right before its first TMA load of that slot — so the outer product of the

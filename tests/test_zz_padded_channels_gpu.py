@@ -10,11 +10,8 @@ import torch
 from smallnet import feed, make_data, small_solver_param
 from test_sm100_emulated import _odd_channel_net
 
-# Written after the GPU budget of round 1 was spent: these have never run on a B200.  Non-strict xfail keeps a first-run
-# failure from masking the validated suites (a pass is reported as XPASS); remove the marker after the first GPU run.
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(reason="first GPU run pending (added without GPU access; validated on the CPU emulation)",
-                                strict=False)]
+# (Green on a B200 since round 1's driver run and round 2's call 1: the provisional xfail marker is gone.)
+pytestmark = [pytest.mark.gpu]
 
 
 def _run(engine, net_fn, steps, batch, hw, classes):
