@@ -136,6 +136,103 @@ void fused_update(at::Tensor w, at::Tensor g, at::Tensor h, c10::optional<at::Te
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
+// ------------------------------------------------------------------------------------ single GPU, many tensors, one launch
+// GoogLeNet steps 128 parameter tensors, most of them a few KB: at ~3 us per launch the optimizer was 7 % of the step
+// (profiles/r2_kernels_googlenet_1gpu.txt).  One launch walks up to kMaxMulti tensors: every block owns a fixed-size
+// chunk of one tensor (block -> tensor through a prefix table in the kernel parameters).
+constexpr int kMaxMulti = 48;
+constexpr int kMultiChunk4 = 2048;          // float4 per block-chunk (32 KB of weights)
+struct MultiSeg {
+  float* w[kMaxMulti];
+  float* g[kMaxMulti];
+  float* h[kMaxMulti];
+  __nv_bfloat16* wb[kMaxMulti];
+  long n[kMaxMulti];
+  float lr[kMaxMulti], decay[kMaxMulti];
+  int first_block[kMaxMulti + 1];
+  unsigned char rearm[kMaxMulti];
+  int count;
+};
+
+__global__ void __launch_bounds__(256)
+fused_update_multi_kernel(const __grid_constant__ MultiSeg ms, UpdateHyper hp, const float* __restrict__ lr_dev) {
+  const float lr_glob = lr_dev != nullptr ? __ldg(lr_dev) : 1.f;
+  int s = 0;
+  while (s + 1 < ms.count && static_cast<int>(blockIdx.x) >= ms.first_block[s + 1]) ++s;
+  hp.lr = ms.lr[s] * lr_glob;
+  hp.decay = ms.decay[s];
+  float* __restrict__ w = ms.w[s];
+  float* __restrict__ g = ms.g[s];
+  float* __restrict__ h = ms.h[s];
+  __nv_bfloat16* __restrict__ wb = ms.wb[s];
+  const bool rearm = ms.rearm[s] != 0;
+  const long n = ms.n[s], n4 = n >> 2;
+  const long lo = static_cast<long>(blockIdx.x - ms.first_block[s]) * kMultiChunk4;
+  const long hi = min(n4, lo + kMultiChunk4);
+  for (long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    float4 wv = reinterpret_cast<float4*>(w)[i], hv = reinterpret_cast<float4*>(h)[i];
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    if (rearm) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    step_rule(gv.x, wv.x, hv.x, hp);
+    step_rule(gv.y, wv.y, hv.y, hp);
+    step_rule(gv.z, wv.z, hv.z, hp);
+    step_rule(gv.w, wv.w, hv.w, hp);
+    reinterpret_cast<float4*>(w)[i] = wv;
+    reinterpret_cast<float4*>(h)[i] = hv;
+    if (wb != nullptr) reinterpret_cast<uint2*>(wb)[i] = pack_bf16x4(wv);
+  }
+  if (hi == n4) {                               // the tensor's last chunk also takes its (< 4 element) tail
+    for (long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+      float wv = w[i], hv = h[i];
+      step_rule(g[i], wv, hv, hp);
+      if (rearm) g[i] = 0.f;
+      w[i] = wv;
+      h[i] = hv;
+      if (wb != nullptr) wb[i] = __float2bfloat16(wv);
+    }
+  }
+}
+
+// ws / gs / hs: fp32 tensors of pairwise identical dense layout, 16-byte aligned; wbs[i] may be undefined (numel 0).
+void fused_update_multi(std::vector<at::Tensor> ws, std::vector<at::Tensor> gs, std::vector<at::Tensor> hs,
+                        std::vector<at::Tensor> wbs, std::vector<double> lrs, std::vector<double> decays,
+                        std::vector<int64_t> rearms, double momentum, int64_t rule, bool l1, double delta, double gscale,
+                        const c10::optional<at::Tensor>& lr_dev) {
+  const size_t total = ws.size();
+  TORCH_CHECK(gs.size() == total && hs.size() == total && wbs.size() == total && lrs.size() == total && decays.size() == total &&
+              rearms.size() == total, "fused_update_multi: list lengths differ");
+  if (total == 0) return;
+  c10::cuda::CUDAGuard guard(ws[0].device());
+  auto st = at::cuda::getCurrentCUDAStream();
+  const float* lrp = lr_dev.has_value() ? lr_dev->data_ptr<float>() : nullptr;
+  const UpdateHyper hp = make_hyper(1.0, momentum, 0.0, rule, l1, delta, gscale);
+  for (size_t base = 0; base < total; base += kMaxMulti) {
+    MultiSeg ms{};
+    ms.count = static_cast<int>(std::min<size_t>(kMaxMulti, total - base));
+    int blocks = 0;
+    for (int i = 0; i < ms.count; ++i) {
+      const at::Tensor &w = ws[base + i], &g = gs[base + i], &h = hs[base + i], &wb = wbs[base + i];
+      TORCH_CHECK(w.is_cuda() && w.scalar_type() == at::kFloat && g.scalar_type() == at::kFloat && h.scalar_type() == at::kFloat);
+      TORCH_CHECK(same_dense_layout(w, g) && same_dense_layout(w, h) && w.is_non_overlapping_and_dense(),
+                  "fused_update_multi: W, G, H must share one dense layout");
+      ms.w[i] = w.data_ptr<float>(); ms.g[i] = g.data_ptr<float>(); ms.h[i] = h.data_ptr<float>();
+      ms.wb[i] = wb.numel() ? reinterpret_cast<__nv_bfloat16*>(wb.data_ptr()) : nullptr;
+      if (wb.numel()) TORCH_CHECK(wb.scalar_type() == at::kBFloat16 && wb.numel() == w.numel());
+      TORCH_CHECK((reinterpret_cast<uintptr_t>(ms.w[i]) | reinterpret_cast<uintptr_t>(ms.g[i]) | reinterpret_cast<uintptr_t>(ms.h[i])) % 16 == 0 &&
+                  reinterpret_cast<uintptr_t>(ms.wb[i]) % 8 == 0, "fused_update_multi: 16-byte aligned buffers expected");
+      ms.n[i] = w.numel();
+      ms.lr[i] = static_cast<float>(lrs[base + i]);
+      ms.decay[i] = static_cast<float>(decays[base + i]);
+      ms.rearm[i] = rearms[base + i] ? 1 : 0;
+      ms.first_block[i] = blocks;
+      blocks += static_cast<int>(std::max<long>(1, ((w.numel() >> 2) + kMultiChunk4 - 1) / kMultiChunk4));
+    }
+    ms.first_block[ms.count] = blocks;
+    fused_update_multi_kernel<<<blocks, 256, 0, st>>>(ms, hp, lrp);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+  }
+}
+
 // ------------------------------------------------------------------------------------ multi GPU
 struct PeerPtrs {
   const float* g[kMaxRanks];      // every rank's gradient bucket (symmetric)
@@ -161,13 +258,16 @@ __device__ __forceinline__ void multimem_st_f32x4(float* mc, float4 v) {
 }
 
 // Cross-rank barrier on this bucket's flag block.  phase 0/1 use separate words so epochs never alias.
-__device__ __forceinline__ void peer_barrier(const PeerPtrs& pp, int rank, int world, int phase, uint32_t epoch) {
+__device__ __forceinline__ void peer_barrier_flags(uint32_t* const* flags, int rank, int world, int phase, uint32_t epoch) {
   if (threadIdx.x < world) {
     // tell peer t that `rank` reached `epoch`
-    st_release_sys(pp.flags[threadIdx.x] + phase * kMaxRanks + rank, epoch);
+    st_release_sys(flags[threadIdx.x] + phase * kMaxRanks + rank, epoch);
   }
-  if (threadIdx.x < world) wait_flag_ge(pp.flags[rank] + phase * kMaxRanks + threadIdx.x, epoch);
+  if (threadIdx.x < world) wait_flag_ge(flags[rank] + phase * kMaxRanks + threadIdx.x, epoch);
   __syncthreads();
+}
+__device__ __forceinline__ void peer_barrier(const PeerPtrs& pp, int rank, int world, int phase, uint32_t epoch) {
+  peer_barrier_flags(pp.flags, rank, world, phase, epoch);
 }
 
 template <bool ONE_SHOT>
@@ -316,14 +416,12 @@ __device__ __forceinline__ float dependent_zero(float v) {
 }
 
 __global__ void __launch_bounds__(512)
-allreduce_sgd_multi_kernel(ArenaPtrs ap, SegSet ss, int rank, int world, uint32_t epoch, UpdateHyper hp,
+allreduce_sgd_multi_kernel(const __grid_constant__ ArenaPtrs ap, const __grid_constant__ SegSet ss, int rank, int world, uint32_t epoch, UpdateHyper hp,
                            unsigned int* __restrict__ done_counter, const float* __restrict__ lr_dev,
                            const uint32_t* __restrict__ epoch_dev) {
   const float lr_glob = lr_dev != nullptr ? __ldg(lr_dev) : 1.f;
   if (epoch_dev != nullptr) epoch += *reinterpret_cast<const volatile uint32_t*>(epoch_dev);
-  PeerPtrs fl{};
-  for (int p = 0; p < world; ++p) fl.flags[p] = ap.flags[p];
-  peer_barrier(fl, rank, world, 0, epoch);
+  peer_barrier_flags(ap.flags, rank, world, 0, epoch);
   for (int s = 0; s < ss.nseg; ++s) {
     UpdateHyper h = hp;
     h.lr = ss.lr[s] * lr_glob;
@@ -396,7 +494,7 @@ allreduce_sgd_multi_kernel(ArenaPtrs ap, SegSet ss, int rank, int world, uint32_
   __syncthreads();
   if (last) {
     if (threadIdx.x == 0) *done_counter = 0;
-    peer_barrier(fl, rank, world, 1, epoch);
+    peer_barrier_flags(ap.flags, rank, world, 1, epoch);
     for (int s = 0; s < ss.nseg; ++s) {
       if (!ss.one_shot[s]) continue;
       float4* gl = reinterpret_cast<float4*>(ap.base[rank] + ss.g_off[s]);
@@ -756,6 +854,8 @@ void peer_signal(std::vector<int64_t> flag_ptrs, int64_t rank, int64_t slot, int
 TORCH_LIBRARY_FRAGMENT(poseidon, m) {
   m.def("fused_update(Tensor(a!) w, Tensor(d!) g, Tensor(b!) h, Tensor(c!)? wb, float lr, float momentum, float decay, int rule, "
         "bool l1, float delta, float gscale, Tensor? lr_dev, bool rearm=False) -> ()", &psd::fused_update);
+  m.def("fused_update_multi(Tensor[] ws, Tensor[] gs, Tensor[] hs, Tensor[] wbs, float[] lrs, float[] decays, int[] rearms, "
+        "float momentum, int rule, bool l1, float delta, float gscale, Tensor? lr_dev) -> ()", &psd::fused_update_multi);
   m.def("allreduce_sgd(int[] g_ptrs, int[] w_ptrs, int[] wb_ptrs, int[] flag_ptrs, int g_mc, int w_mc, Tensor(a!) h, int n, "
         "int rank, int epoch, bool one_shot, Tensor(b!) done_counter, float lr, float momentum, float decay, int rule, "
         "bool l1, float delta, float gscale, int max_ctas, Tensor? lr_dev, Tensor? epoch_dev) -> ()", &psd::allreduce_sgd);

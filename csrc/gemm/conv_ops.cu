@@ -71,7 +71,8 @@ static int pair_grid(long m_blocks, long n_blocks, long split, int sms) {
 
 static int g_conv_mcast = 1;       // CTAs per cluster sharing the im2col operand by TMA multicast (1 = off, the default:
                                    // measured no faster on B200 — every SM still ingests the whole tile, profiles/r2_conv_ncu_summary.md)
-static int g_conv_pair = 0;        // paired CTAs for the convolution kernels (measured equal to single-CTA; opt-in)
+static int g_conv_pair = 1;        // paired CTAs for the im2col convolution kernels: A/B on one box (r2 call 13) AlexNet
+                                   // 3.298 -> 3.267 ms, VGG-16 10.49 -> 10.04 ms per step
 
 // Launch the im2col-A kernel (fprop / dgrad) for tile width bn; CG = 2: paired CTAs, else cluster multicast (p.cluster).
 template <int CG>

@@ -77,6 +77,7 @@ void encode_tmap_im2col_bf16(CUtensorMap* map, const void* base, int64_t C, int6
               " N=", N, " lower=", lower_w, ",", lower_h, " upper=", upper_w, ",", upper_h);
 }
 
+int g_no_bulk_epi = 0;
 int g_max_stages = 0;             // experiment knob (set_max_stages): ring stages actually used, 0 = all
 static int g_pair_cta = 1;        // cta_group::2 (paired CTAs) where the tile space allows it; 0 = single-CTA kernels only
 int pair_cta_enabled() { return g_pair_cta; }
@@ -176,6 +177,7 @@ void gemm_launch(const std::vector<int64_t>& a_ptrs, bool a_mn, int64_t lda, con
   p.M = static_cast<int>(M);
   p.N = static_cast<int>(N);
   p.max_stages = g_max_stages;
+  p.no_bulk_epi = g_no_bulk_epi;
   p.kb_per_src = static_cast<int>((K + BLOCK_K - 1) / BLOCK_K);
   p.num_src = nsrc;
   if (p.split_k < 1) p.split_k = 1;
@@ -201,16 +203,49 @@ void gemm_launch(const std::vector<int64_t>& a_ptrs, bool a_mn, int64_t lda, con
   }
 }
 
-// Split-K finish: out = act(ws + bias) (optionally ReLU-masked) -> bf16.  ws is the fp32 [M, N] partial-sum buffer.
+// Split-K finish: out = act(ws + bias) (optionally ReLU-masked) -> bf16, and the fp32 partial-sum workspace is left ZEROED
+// for its next user (the workspace is cached: no memset launch per call).  Four columns per thread (16-byte loads /
+// stores, 32-bit index math); the scalar form serves N or ldc that are not multiples of 4.
 __global__ void __launch_bounds__(256)
 splitk_finish_kernel(float* __restrict__ ws, __nv_bfloat16* __restrict__ out, long ldc, const float* __restrict__ bias,
                      const __nv_bfloat16* __restrict__ mask, int relu, float slope, int M, int N) {
+  if ((N & 3) == 0 && (ldc & 3) == 0) {
+    const uint32_t n4 = static_cast<uint32_t>(N) >> 2;
+    const uint32_t total4 = static_cast<uint32_t>(M) * n4;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+      const uint32_t m = i / n4, c = (i - m * n4) << 2;
+      float4 v = reinterpret_cast<float4*>(ws)[i];
+      reinterpret_cast<float4*>(ws)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias != nullptr) {
+        const float4 b = *reinterpret_cast<const float4*>(bias + c);
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+      }
+      if (relu) {
+        v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+        v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+      }
+      const long o = static_cast<long>(m) * ldc + c;
+      if (mask != nullptr) {
+        const uint2 mk = *reinterpret_cast<const uint2*>(mask + o);
+        if (!(__uint_as_float(mk.x << 16) > 0.f)) v.x *= slope;
+        if (!(__uint_as_float(mk.x & 0xffff0000u) > 0.f)) v.y *= slope;
+        if (!(__uint_as_float(mk.y << 16) > 0.f)) v.z *= slope;
+        if (!(__uint_as_float(mk.y & 0xffff0000u) > 0.f)) v.w *= slope;
+      }
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(out + o) = pk;
+    }
+    return;
+  }
   const long total = static_cast<long>(M) * N;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
     const int m = static_cast<int>(i / N), n = static_cast<int>(i - static_cast<long>(m) * N);
     float v = ws[i];
-    ws[i] = 0.f;                               // re-arm the cached workspace for its next user (no memset launch per call)
+    ws[i] = 0.f;
     if (bias != nullptr) v += bias[n];
     if (relu) v = v > 0.f ? v : v * slope;
     if (mask != nullptr && !(__bfloat162float(mask[m * ldc + n]) > 0.f)) v *= slope;
@@ -274,7 +309,7 @@ at::Tensor gemm_bf16(const at::Tensor& a, bool a_mn, const at::Tensor& b, bool b
       q.split_k = static_cast<int>(split);
       gemm_launch({reinterpret_cast<int64_t>(a.data_ptr())}, a_mn, a.stride(0),
                   {reinterpret_cast<int64_t>(b.data_ptr())}, b_mn, b.stride(0), M, N, K, EPI_F32, q, bn_s, 0, stream);
-      const long total = M * N;
+      const long total = (N % 4 == 0 && p.ldc % 4 == 0) ? M * N / 4 : M * N;
       const int grid = static_cast<int>(std::min<long>((total + 255) / 256, 148L * 8));
       splitk_finish_kernel<<<grid, 256, 0, stream>>>(ws.data_ptr<float>(), p.c_bf16, p.ldc, p.bias, p.mask, p.relu ? 1 : 0,
                                                      p.relu_slope, static_cast<int>(M), static_cast<int>(N));
@@ -373,12 +408,14 @@ void sfb_outer_f32(std::vector<int64_t> u_ptrs, std::vector<int64_t> v_ptrs, int
 
 void set_pair_cta(int64_t on) { g_pair_cta = on != 0; }
 void set_max_stages(int64_t n) { g_max_stages = static_cast<int>(n); }
+void set_bulk_epilogue(int64_t on) { g_no_bulk_epi = on ? 0 : 1; }
 
 }  // namespace psd
 
 TORCH_LIBRARY_FRAGMENT(poseidon, m) {
   m.def("set_pair_cta(int on) -> ()", &psd::set_pair_cta);
   m.def("set_max_stages(int n) -> ()", &psd::set_max_stages);
+  m.def("set_bulk_epilogue(int on) -> ()", &psd::set_bulk_epilogue);
   m.def("sfb_outer_f32(int[] u_ptrs, int[] v_ptrs, int Mb, int N, int K, Tensor(a!) out, float alpha, Tensor? flags, "
         "int epoch, int src_rot, int bn, int max_ctas, Tensor? epoch_dev) -> ()", &psd::sfb_outer_f32);
   m.def("gemm_bf16(Tensor a, bool a_mn, Tensor b, bool b_mn, Tensor? bias, bool relu, float slope, Tensor? mask, "

@@ -52,6 +52,7 @@ struct GemmParams {
   int src_rot;           // first source to visit (own rank for SFB: local data needs no flag wait)
   int cluster;           // CTAs per cluster sharing the TMA operand by multicast (1 = no clusters); conv kernels only
   int max_stages;        // experiment knob: use only this many ring stages (0 = all that fit)
+  int no_bulk_epi;       // experiment knob: 1 = plain fp32 epilogue through the per-warp 32x32 walk instead of bulk row stores
   // --- epilogue operands
   __nv_bfloat16* c_bf16; // EPI_BF16 output [M, ldc]
   float* c_f32;          // EPI_F32 output [M, ldc]
@@ -704,7 +705,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
       }
     };
     if (kSgdPrefetch) prefetch_sgd_tile(tile0);
-    [[maybe_unused]] const bool bulk_f32 = EPI == EPI_F32 && !p.atomic && p.col_cgk == 0 && (p.N & 3) == 0 && (p.ldc & 3) == 0 &&
+    [[maybe_unused]] const bool bulk_f32 = EPI == EPI_F32 && !p.atomic && !p.no_bulk_epi && p.col_cgk == 0 && (p.N & 3) == 0 && (p.ldc & 3) == 0 &&
                                            (reinterpret_cast<uintptr_t>(p.c_f32) & 15) == 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
       const TileCoord tc = coord(tile);

@@ -86,8 +86,9 @@ class ConcatLayer(Layer):
         planned by net/fusion.py for bottoms produced by convolution kernels."""
         import torch
         if self._slab is None or tuple(self._slab.shape) != (n, self._slab_channels, h, w) or self._slab.device != device:
-            self._slab = torch.empty(n, self._slab_channels, h, w, device=device, dtype=torch.bfloat16) \
-                .contiguous(memory_format=torch.channels_last)
+            # (memory_format in the factory: empty(...).contiguous(channels_last) would launch a copy of the whole slab)
+            self._slab = torch.empty((n, self._slab_channels, h, w), device=device, dtype=torch.bfloat16,
+                                     memory_format=torch.channels_last)
         c = self._slab_slices[offset]
         slab = self._slab
         # an ALIAS of the slice, not an autograd view of the slab: the producers' kernels write disjoint slices of one

@@ -58,6 +58,9 @@ class EmulatedKernels:
     def set_conv_pair(self, on):
         return None
 
+    def set_bulk_epilogue(self, on):
+        return None
+
     def set_max_stages(self, n):
         return None
 
@@ -434,6 +437,12 @@ class EmulatedKernels:
             g.zero_()                       # persistent accumulation buffer: left zeroed for the next step's wgrad
         if wb is not None:
             wb.view(-1).copy_(_storage_order_flat(w))
+
+    def fused_update_multi(self, ws, gs, hs, wbs, lrs, decays, rearms, momentum, rule, l1, delta, gscale, lr_dev):
+        """Many tensors, one launch (csrc/comm/fused_update.cu: fused_update_multi_kernel): per-tensor lr / decay / re-arm."""
+        for w, g, h, wb, lr, decay, rearm in zip(ws, gs, hs, wbs, lrs, decays, rearms):
+            self.fused_update(w, g, h, wb if wb.numel() else None, lr, momentum, decay, rule, l1, delta, gscale, lr_dev,
+                              bool(rearm))
 
     # ------------------------------------------------------------------------------------------ multi-rank peer memory
     # The kernels address other ranks' memory by raw pointer (NVLink peer mappings of one symmetric arena per rank).

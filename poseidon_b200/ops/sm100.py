@@ -60,6 +60,16 @@ def K():
         else:
             load_extension()
             _ops = CountingOps(torch.ops.poseidon)
+            # schedule switches (defaults are the measured best; see profiles/r2_conv_ncu_summary.md)
+            env = os.environ
+            if "POSEIDON_PAIR_CTA" in env:
+                torch.ops.poseidon.set_pair_cta(int(env["POSEIDON_PAIR_CTA"]))
+            if "POSEIDON_CONV_PAIR" in env:
+                torch.ops.poseidon.set_conv_pair(int(env["POSEIDON_CONV_PAIR"]))
+            if "POSEIDON_CONV_MCAST" in env:
+                torch.ops.poseidon.set_conv_mcast(int(env["POSEIDON_CONV_MCAST"]))
+            if "POSEIDON_BULK_EPI" in env:
+                torch.ops.poseidon.set_bulk_epilogue(int(env["POSEIDON_BULK_EPI"]))
     return _ops
 
 
@@ -372,8 +382,8 @@ class _ConvFn(torch.autograd.Function):
             # zero-padded output channels: mask (if any) on the logical slice, then widen dY to the padded layout
             if y is not None and not st.consumer_masks:
                 dy = torch.where(y > 0, dy, dy * float(ctx.relu_slope))
-            dyp = torch.zeros(dy.shape[0], st.Coutp, dy.shape[2], dy.shape[3], device=dy.device,
-                              dtype=torch.bfloat16).contiguous(memory_format=CL)
+            dyp = torch.empty((dy.shape[0], st.Coutp, dy.shape[2], dy.shape[3]), device=dy.device,
+                              dtype=torch.bfloat16, memory_format=CL).zero_()
             dyp[:, : st.Cout].copy_(dy)
             dy = dyp
         else:
@@ -428,7 +438,7 @@ def _strided_dgrad(k, st: "ConvState", layer, dy: torch.Tensor, xin: torch.Tenso
     ph, pw = layer.pad
     n, _, H, W = xin.shape
     cin = st.Cp
-    dx = torch.empty(n, cin, H, W, device=dy.device, dtype=torch.bfloat16).contiguous(memory_format=CL)
+    dx = torch.empty((n, cin, H, W), device=dy.device, dtype=torch.bfloat16, memory_format=CL)
     w4 = layer.weight.data.permute(0, 2, 3, 1)                       # [Cout, R, S, Cg] (physical order of the master)
     if st.pad8:
         w4 = torch.nn.functional.pad(w4, (0, st.Cp - st.cin_logical))

@@ -169,7 +169,9 @@ class FusedBackend(Backend):
         self.use_multimem = use_multimem and os.environ.get("POSEIDON_MULTIMEM", "1") != "0"
         # SFB reconstruct: optimizer step fused into the outer-product kernel's epilogue (1), or the two-pass form
         # "P-source outer product -> fp32 buffer (bulk row stores), then the streaming update kernel" (0)
-        self.fuse_sfb_sgd = os.environ.get("POSEIDON_SFB_FUSED_SGD", "1") != "0"
+        # Measured on 2 x B200 (profiles/r2_scale2_call56.log): two-pass 3.339 ms / step, fused epilogue 3.447 ms (1 GPU on the
+        # same box: 3.280 ms) — the epilogue's W/H stream runs at 37 % of the HBM copy rate, the update kernel at 96-100 %.
+        self.fuse_sfb_sgd = os.environ.get("POSEIDON_SFB_FUSED_SGD", "0") == "1"
         self.arena: Optional[SymmetricArena] = None
         self.epoch = 0
         self.dense_bytes = 0
@@ -219,6 +221,8 @@ class FusedBackend(Backend):
                 st = getattr(layer, "_sm100", None)
                 if isinstance(st, sm100.ConvState) and not st.row_mode and layer.weight.requires_grad:
                     layer._grad_sink = self
+        self.multi_update = self.world == 1 and os.environ.get("POSEIDON_MULTI_UPDATE", "1") != "0"
+        self._deferred = []
         self.per_worker_state = self.ssp and self.world > 1
         self.done_counter = torch.zeros(4, dtype=torch.int32, device=self.device)
         self.lr_t = torch.zeros(1, dtype=torch.float32, device=self.device)     # global lr, read by the kernels
@@ -406,9 +410,29 @@ class FusedBackend(Backend):
             st.mark_updated(keep_wb=fresh)
 
     def _launch_local(self, bucket) -> bool:
-        """Steps the bucket's parameters; returns True when the layer's bf16 weight operand is still in sync."""
+        """Steps the bucket's parameters; returns True when the layer's bf16 weight operand is still in sync.
+        One GPU has nothing to overlap the update with, so (default) the steps of all buckets are deferred to ONE
+        multi-tensor launch at the end of the iteration (`fused_update_multi`, POSEIDON_MULTI_UPDATE=0 restores one
+        launch per tensor)."""
         st = getattr(bucket.layer, "_sm100", None)
         fresh = st is not None and not st.dirty_wb
+        if self.multi_update:
+            for p, h, lm, dm in zip(bucket.params, bucket.history, bucket.lr_mult, bucket.decay_mult):
+                if p.grad is None:
+                    continue
+                wb = None
+                if st is not None and p is bucket.layer.weight and st.wb is not None and not getattr(st, "row_mode", False):
+                    wb = st.wb
+                g = p.grad
+                if not _same_order(g, p.data):
+                    g = torch.empty_like(p.data).copy_(g)
+                lr, mom, decay, rule, l1, delta, gscale = self._hyper_args(lm, dm)
+                gs = getattr(st, "_gsink", None) if p is getattr(bucket.layer, "weight", None) else None
+                rearm = gs is not None and g.data_ptr() == gs.data_ptr()
+                self._deferred.append((p.data, g, h, wb, lr, decay, rearm, st if rearm else None))
+                if p is getattr(bucket.layer, "weight", None):
+                    fresh = wb is not None
+            return fresh
         for p, h, lm, dm in zip(bucket.params, bucket.history, bucket.lr_mult, bucket.decay_mult):
             if p.grad is None:
                 continue                            # weight already stepped inside the fused SFB/wgrad kernel
@@ -561,11 +585,29 @@ class FusedBackend(Backend):
         gseg.zero_()
         gseg[lo:hi].copy_(shard)
 
+    def _flush_deferred(self):
+        if not self._deferred:
+            return
+        hy = self.sync.hyper
+        d = self._deferred
+        self._deferred = []
+        empty = torch.empty(0, dtype=torch.bfloat16, device=self.device)
+        self.k.fused_update_multi([e[0] for e in d], [e[1] for e in d], [e[2] for e in d],
+                                  [e[3] if e[3] is not None else empty for e in d], [e[4] for e in d], [e[5] for e in d],
+                                  [1 if e[6] else 0 for e in d], hy.momentum, hy.solver_type, hy.l1, hy.delta,
+                                  1.0 if self.reduce == "sum" else 1.0 / self.gworld, self.lr_t)
+        for e in d:
+            if e[7] is not None:
+                e[7]._gsink_dirty = False
+        self.launches += (len(d) + 47) // 48
+
     def finish_iteration(self):
         """Close the step: the device-resident epoch counter (read by every comm kernel of this step as
         ``epoch_t + 1``) is bumped on the comm stream, i.e. after all of them in stream order.  Keeping it on the
         device is what lets a captured CUDA graph of the whole step be replayed."""
         self.epoch += 1
+        if self.world == 1:
+            self._flush_deferred()
         if self.world > 1:
             cur = self.cu.current_stream()
             self.stream.wait_stream(cur)

@@ -36,7 +36,7 @@ def conv_mode(ext, request):
     ext.set_conv_pair(pair)
     yield request.param
     ext.set_conv_mcast(1)
-    ext.set_conv_pair(0)
+    ext.set_conv_pair(1)
 
 
 @pytest.mark.parametrize("M,N,K", [(256, 256, 64), (384, 256, 512), (1000, 320, 200), (4096, 1024, 1024), (640, 96, 576),

@@ -170,8 +170,9 @@ def test_shadows_are_not_rederived_every_step(emu):
     s.step(1)
     ops = counting.by_op()
     n_params = sum(len(l.blobs) for l in s.net.layers)
-    # every blob stepped by exactly one optimizer launch; IP weights take wgrad GEMM + update
-    assert ops["fused_update"] == n_params, ops
+    # every blob stepped exactly once: the two IP weights by their own wgrad GEMM + update pair, all other blobs (8 of
+    # the 10) by ONE multi-tensor launch at the end of the iteration
+    assert ops["fused_update"] == 2 and ops["fused_update_multi"] == 1 and n_params == 10, ops
     assert ops["gemm_f32"] == 2, ops
     assert ops["conv_wgrad"] == 3 and ops["conv_fprop"] == 3 and ops["conv_dgrad"] == 2, ops
     assert "relu_fwd" not in ops, ops        # all four ReLUs live in epilogues
