@@ -22,6 +22,8 @@ namespace psd {
 
 void encode_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner,
                          int box_outer);
+void encode_tmap_bf16_3d(CUtensorMap* map, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t stride1, int64_t stride2,
+                         int box0, int box1, int box2);
 void encode_tmap_im2col_bf16(CUtensorMap* map, const void* base, int64_t C, int64_t W, int64_t H, int64_t N, int64_t pitch,
                              int lower_w, int lower_h, int upper_w, int upper_h, int pixels, int stride_w, int stride_h);
 
@@ -31,6 +33,7 @@ static int g_conv_cluster = 1;     // CTAs per cluster sharing the TMA operand b
 
 int pair_cta_enabled();
 extern int g_max_stages;
+extern int g_no_bulk_epi;
 
 template <int BN, bool A_MN, bool B_MN, int EPI, int GATHER, int CG = 1>
 static void launch_conv(const TmapSet& tm, const GemmParams& p, const ConvGeom& cg, int grid, cudaStream_t stream) {
@@ -257,6 +260,7 @@ at::Tensor conv_fprop(const at::Tensor& x, const at::Tensor& wb, const c10::opti
     tm.a[0] = tm.b[0];
     GemmParams p{};
     p.max_stages = g_max_stages;
+    p.no_bulk_epi = g_no_bulk_epi;
     p.cluster = cl;
     p.M = static_cast<int>(cg.M);
     p.N = Cout_g;
@@ -336,6 +340,7 @@ at::Tensor conv_dgrad(const at::Tensor& dy, const at::Tensor& wt, at::IntArrayRe
     tm.a[0] = tm.b[0];
     GemmParams p{};
     p.max_stages = g_max_stages;
+    p.no_bulk_epi = g_no_bulk_epi;
     p.cluster = cl;
     p.M = static_cast<int>(cg.M);
     p.N = Cg;
@@ -377,6 +382,79 @@ at::Tensor conv_dgrad(const at::Tensor& dy, const at::Tensor& wt, at::IntArrayRe
   return dx;
 }
 
+// Data gradient of a stride-1 convolution read straight from the FPROP weight operand wb [Cout][R][S][Cg] (bf16): no
+// packed [Cin][R][S][Cout] copy, no pack kernel per step.  K = (tap, co) with Cok = round64(Cout_g) slots per tap; the
+// surplus slots are zero on both sides (im2col channel overrun on dY, row overrun of the 3-D weight map).  Any Cout_g,
+// C_g that are multiples of 8 take this (TMA) path; returns false if the geometry does not fit the im2col descriptor.
+bool conv_dgrad_w_impl(const at::Tensor& dy, const at::Tensor& wb, at::IntArrayRef kernel, at::IntArrayRef pad, int64_t groups,
+                       int64_t H, int64_t W, const c10::optional<at::Tensor>& mask, double slope, at::Tensor& dx) {
+  NhwcView dv = nhwc_view(dy);
+  ConvDesc d{static_cast<int>(kernel[0]), static_cast<int>(kernel[1]), 1, 1, static_cast<int>(pad[0]), static_cast<int>(pad[1]),
+             static_cast<int>(groups), 0};
+  const int Cout = wb.size(0), Cout_g = Cout / groups, RS = d.R * d.S;
+  const int Cg = static_cast<int>(wb.size(1) / RS), Cin = Cg * groups;
+  if (Cout_g % 8 != 0 || Cg % 8 != 0 || dv.C != Cout) return false;
+  const int Cok = (Cout_g + 63) / 64 * 64;
+  NhwcView xv = nhwc_view(dx);
+  auto stream = at::cuda::getCurrentCUDAStream();
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  for (int gidx = 0; gidx < groups; ++gidx) {
+    ConvGeom cg = make_geom(dy, dv, gidx * Cout_g, Cout_g, H, W, d, true, Cok);
+    TmapSet tm;
+    if (!try_im2col_map(&tm.a[0], cg, BLOCK_M)) return false;
+    const long m_blocks = (cg.M + BLOCK_M - 1) / BLOCK_M;
+    int bn = pick_conv_bn(Cg, m_blocks, sms);
+    if (bn == 192) bn = 256;                       // MN-major B: whole 64-column chunks per CTA (and per pair half)
+    const long n_blocks = (Cg + bn - 1) / bn;
+    const __nv_bfloat16* wptr = reinterpret_cast<const __nv_bfloat16*>(wb.data_ptr()) + static_cast<long>(gidx) * Cout_g * RS * Cg;
+    encode_tmap_bf16_3d(&tm.b[0], wptr, Cg, Cout_g, RS, static_cast<int64_t>(RS) * Cg, Cg, 64, 64, 1);
+    GemmParams p{};
+    p.max_stages = g_max_stages;
+    p.no_bulk_epi = g_no_bulk_epi;
+    p.cluster = 1;
+    p.M = static_cast<int>(cg.M);
+    p.N = Cg;
+    p.kb_per_src = (cg.K + BLOCK_K - 1) / BLOCK_K;
+    p.num_src = 1;
+    p.split_k = 1;
+    p.c_bf16 = reinterpret_cast<__nv_bfloat16*>(dx.data_ptr()) + gidx * Cg;
+    p.ldc = xv.pitch;
+    p.mask = mask.has_value() ? reinterpret_cast<const __nv_bfloat16*>(mask->data_ptr()) + gidx * Cg : nullptr;
+    p.relu_slope = static_cast<float>(slope);
+    p.alpha = 1.f;
+    const bool pair = g_conv_pair && pair_cta_enabled() && m_blocks >= 2 && bn >= 128;
+    if (pair) {
+      const int pgrid = pair_grid(m_blocks, n_blocks, 1, sms);
+      if (bn == 128) launch_conv<128, false, true, EPI_BF16, IM2COL_A, 2>(tm, p, cg, pgrid, stream);
+      else launch_conv<256, false, true, EPI_BF16, IM2COL_A, 2>(tm, p, cg, pgrid, stream);
+    } else {
+      const int grid = static_cast<int>(std::max<long>(1, std::min<long>(m_blocks * n_blocks, sms)));
+      if (bn == 64) launch_conv<64, false, true, EPI_BF16, IM2COL_A, 1>(tm, p, cg, grid, stream);
+      else if (bn == 128) launch_conv<128, false, true, EPI_BF16, IM2COL_A, 1>(tm, p, cg, grid, stream);
+      else launch_conv<256, false, true, EPI_BF16, IM2COL_A, 1>(tm, p, cg, grid, stream);
+    }
+  }
+  return true;
+}
+
+at::Tensor conv_dgrad_w(const at::Tensor& dy, const at::Tensor& wb, at::IntArrayRef kernel, at::IntArrayRef pad, int64_t groups,
+                        int64_t H, int64_t W, const c10::optional<at::Tensor>& mask, double slope) {
+  TORCH_CHECK(dy.is_cuda() && dy.scalar_type() == at::kBFloat16 && wb.scalar_type() == at::kBFloat16 && wb.dim() == 2 &&
+              wb.is_contiguous(), "conv_dgrad_w: bf16 dY and the contiguous fprop weight operand expected");
+  c10::cuda::CUDAGuard guard(dy.device());
+  NhwcView dv = nhwc_view(dy);
+  const int RS = static_cast<int>(kernel[0] * kernel[1]);
+  const int64_t Cin = wb.size(1) / RS * groups;
+  at::Tensor dx = empty_nhwc(dv.N, Cin, H, W, dy.options());
+  if (mask.has_value()) {
+    NhwcView mv = nhwc_view(*mask), xv = nhwc_view(dx);
+    TORCH_CHECK(mv.C == Cin && mv.H == H && mv.W == W && mv.pitch == xv.pitch, "conv_dgrad_w: mask must match dx layout");
+  }
+  TORCH_CHECK(conv_dgrad_w_impl(dy, wb, kernel, pad, groups, H, W, mask, slope, dx),
+              "conv_dgrad_w: geometry outside the im2col-TMA limits (use conv_dgrad with the packed operand)");
+  return dx;
+}
+
 // dw[Cout, Kw] fp32 += alpha * dYᵀ · im2col(x)   (atomic split-K over the N*OH*OW reduction; dw pre-zeroed
 // unless accumulating into an existing gradient).
 void conv_wgrad(const at::Tensor& x, const at::Tensor& dy, at::Tensor dw, at::IntArrayRef kernel, at::IntArrayRef stride,
@@ -404,6 +482,7 @@ void conv_wgrad(const at::Tensor& x, const at::Tensor& dy, at::Tensor dw, at::In
     const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(dy.data_ptr()) + gidx * Cout_g;
     GemmParams p{};
     p.max_stages = g_max_stages;
+    p.no_bulk_epi = g_no_bulk_epi;
     p.M = Cout_g;
     p.N = cg.K;
     p.kb_per_src = static_cast<int>((cg.M + BLOCK_K - 1) / BLOCK_K);
@@ -547,6 +626,8 @@ TORCH_LIBRARY_FRAGMENT(poseidon, m) {
         "int OH, int OW, bool relu, float slope, Tensor? out) -> Tensor", &psd::conv_fprop);
   m.def("conv_dgrad(Tensor dy, Tensor wt, int[] kernel, int[] pad, int groups, int H, int W, Tensor? mask, float slope) "
         "-> Tensor", &psd::conv_dgrad);
+  m.def("conv_dgrad_w(Tensor dy, Tensor wb, int[] kernel, int[] pad, int groups, int H, int W, Tensor? mask, float slope) "
+        "-> Tensor", &psd::conv_dgrad_w);
   m.def("conv_wgrad(Tensor x, Tensor dy, Tensor(a!) dw, int[] kernel, int[] stride, int[] pad, int groups, int mode, "
         "float alpha, int cgk) -> ()", &psd::conv_wgrad);
   m.def("conv_pack_dgrad(Tensor w, int Cout, int RS, int Cg, int groups, Tensor? out, int cop) -> Tensor", &psd::conv_pack_dgrad);

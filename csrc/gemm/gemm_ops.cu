@@ -45,6 +45,21 @@ void encode_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t inner, int6
               " outer=", outer, " ld=", ld);
 }
 
+// 3-D bf16 tensor map (innermost dimension contiguous), 128B swizzle; strides in elements for dims 1 and 2.
+void encode_tmap_bf16_3d(CUtensorMap* map, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t stride1, int64_t stride2,
+                         int box0, int box1, int box2) {
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (stride1 * 2) % 16 == 0 && (stride2 * 2) % 16 == 0,
+              "3-D TMA map: 16-byte alignment of base and strides");
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(d0), static_cast<cuuint64_t>(d1), static_cast<cuuint64_t>(d2)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(stride1) * 2, static_cast<cuuint64_t>(stride2) * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box0), static_cast<cuuint32_t>(box1), static_cast<cuuint32_t>(box2)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TORCH_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed: ", static_cast<int>(r));
+}
+
 // 4-D im2col-mode bf16 tensor map over an NHWC tensor (channels innermost, pixel pitch `pitch` elements).
 //   lower / upper : bounding-box corner offsets {w, h} (cuTensorMapEncodeIm2col semantics: base pixels run from
 //                   `lower` to `extent + upper - 1` in steps of the traversal stride)

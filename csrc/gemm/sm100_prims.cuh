@@ -89,6 +89,9 @@ __device__ __forceinline__ void bulk_commit_wait_read() {
   asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // (Measured: letting only lane 0 poll in the warp-uniform role loops and parking the other lanes on __syncwarp is much
 //  slower — AlexNet 80 k -> 62 k img/s — so all 32 lanes execute mbar_wait together.)
 
@@ -258,6 +261,19 @@ __device__ __forceinline__ void tma_load_2d_u32(uint32_t smem_dst, const CUtenso
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+// 3-D tiled loads (u32 addresses), plain and paired-CTA form
+__device__ __forceinline__ void tma_load_3d_u32(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int x, int y, int z) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_cg2(uint32_t smem_dst, const CUtensorMap* map, uint32_t leader_bar, int x, int y, int z) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(x), "r"(y), "r"(z)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_im2col_4d_cg2(uint32_t smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c,

@@ -502,7 +502,19 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
             else
               tma_load_im2col_4d(sa32, &tm.a[0], fbar, in_k ? c0 : 0, im_w, im_h, im_n,
                                  static_cast<uint16_t>(in_k ? offw : 0), static_cast<uint16_t>(in_k ? offh : 0));
-            TmaProducer<BN, A_MN, B_MN, CG>::load_b(tm, src, kb, n_blk, prank, sb32, fbar);
+            if constexpr (B_MN) {
+              // dgrad straight from the FPROP weight layout [co][tap][ci] (no packed copy): the B tile of k-block
+              // (tap, co0..co0+63) is BN/64 boxes {64 ci, 64 co, 1 tap} of a 3-D map — ci contiguous = MN-major B;
+              // output channels past Cout_g and input channels past C_g are zero-filled by the TMA
+              const int n0 = n_blk * BN + prank * (BN / CG);
+#pragma unroll
+              for (int c = 0; c < BN / CG / 64; ++c) {
+                if constexpr (CG == 2) tma_load_3d_cg2(sb32 + c * 8192, &tm.b[0], fbar, n0 + 64 * c, in_k ? c0 : 0, in_k ? tap : 0);
+                else tma_load_3d_u32(sb32 + c * 8192, &tm.b[0], fbar, n0 + 64 * c, in_k ? c0 : 0, in_k ? tap : 0);
+              }
+            } else {
+              TmaProducer<BN, A_MN, B_MN, CG>::load_b(tm, src, kb, n_blk, prank, sb32, fbar);
+            }
           } else if constexpr (GATHER == IM2COL_B) {
             // B tile = BN/64 chunks of [64 reduction pixels][64 channels of one tap]; the pixels advance with g.
             // Paired CTAs: this CTA fetches chunks [crank * BN/128, (crank + 1) * BN/128) of the tile.
@@ -707,6 +719,9 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
     if (kSgdPrefetch) prefetch_sgd_tile(tile0);
     [[maybe_unused]] const bool bulk_f32 = EPI == EPI_F32 && !p.atomic && !p.no_bulk_epi && p.col_cgk == 0 && (p.N & 3) == 0 && (p.ldc & 3) == 0 &&
                                            (reinterpret_cast<uintptr_t>(p.c_f32) & 15) == 0;
+    [[maybe_unused]] const bool bulk_bf16 = EPI == EPI_BF16 && !p.no_bulk_epi && (p.N & 7) == 0 && (p.ldc & 7) == 0 &&
+                                            (reinterpret_cast<uintptr_t>(p.c_bf16) & 15) == 0 &&
+                                            (p.mask == nullptr || (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0);
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
       const TileCoord tc = coord(tile);
       const int m_blk = tc.m_blk, n_blk = tc.n_blk;
@@ -780,6 +795,83 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
             stored = true;
           }
         }
+        if constexpr (EPI == EPI_BF16) {
+          // bf16 activations / data gradients: the same idea with TWO half-size slabs (32 rows x BN bf16, row pitch
+          // BN * 2 + 16 bytes: conflict-free 16-byte stores from the lane = row layout).  Bias, (leaky) ReLU and the
+          // producer's ReLU mask are applied in registers in that layout — the mask row segment of a lane is 64
+          // contiguous bytes.  Quadrant qq + 1 is converted into the other slab while the copy engine still reads
+          // quadrant qq; one CTA-wide barrier per quadrant, rows leave as up-to-512-byte bulk stores instead of the
+          // 64-byte pieces of the per-warp walk (GEMM with conv3's extent: fp32 output 79 us vs bf16 output 87 us
+          // with the walk although it writes twice the bytes — profiles/r2_conv_experiments.md).
+          if (bulk_bf16) {
+            constexpr int LDB = BN * 2 + 16;
+            static_assert(2 * 32 * LDB <= S::kEpiStageBytes, "two bf16 slabs must fit the epilogue staging buffer");
+            constexpr int RW = 32 / kEpiWarps;
+            uint8_t* slabs = reinterpret_cast<uint8_t*>(epi_stage);
+            const int col0 = n_blk * BN;
+            const int ncols = min(BN, p.N - col0);
+#pragma unroll 1
+            for (int qq = 0; qq < 4; ++qq) {
+              uint8_t* slab = slabs + (qq & 1) * (32 * LDB);
+              if (q == qq) {
+                const long grow = static_cast<long>(m_blk) * BLOCK_M + qq * 32 + lane;
+#pragma unroll 1
+                for (int c = half; c < BN / 32; c += kEpiWarps / 4) {
+                  const int cb = col0 + c * 32;
+                  if (cb >= p.N) break;                    // warp-uniform: no valid column in this chunk
+                  uint32_t r[32];
+                  tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, r);
+                  uint4 mk[4];
+                  const bool use_mask = p.mask != nullptr;
+                  if (use_mask) {
+                    // (1.0, 1.0) = keep; rows past M and 8-column groups past N are never stored
+                    const uint4* mrow = reinterpret_cast<const uint4*>(p.mask + (grow < p.M ? grow : 0) * p.ldc + cb);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      mk[k] = (cb + 8 * k < p.N) ? __ldg(mrow + k) : make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+                  }
+                  tmem_ld_wait();
+                  uint32_t out[16];
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    float x0 = __uint_as_float(r[2 * j]) * p.alpha, x1 = __uint_as_float(r[2 * j + 1]) * p.alpha;
+                    if (p.bias != nullptr) {               // warp-uniform addresses: one broadcast transaction each
+                      x0 += __ldg(p.bias + min(cb + 2 * j, p.N - 1));
+                      x1 += __ldg(p.bias + min(cb + 2 * j + 1, p.N - 1));
+                    }
+                    if (p.relu) {
+                      x0 = x0 > 0.f ? x0 : x0 * p.relu_slope;
+                      x1 = x1 > 0.f ? x1 : x1 * p.relu_slope;
+                    }
+                    if (use_mask) {
+                      const uint32_t m = reinterpret_cast<const uint32_t*>(mk)[j];
+                      if (!(__uint_as_float(m << 16) > 0.f)) x0 *= p.relu_slope;
+                      if (!(__uint_as_float(m & 0xffff0000u) > 0.f)) x1 *= p.relu_slope;
+                    }
+                    const __nv_bfloat162 v = __floats2bfloat162_rn(x0, x1);
+                    out[j] = *reinterpret_cast<const uint32_t*>(&v);
+                  }
+                  uint4* dst = reinterpret_cast<uint4*>(slab + lane * LDB + c * 64);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) dst[k] = make_uint4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
+                }
+                fence_proxy_async_smem();                 // generic-proxy writes -> visible to the bulk-copy engine
+              }
+              // every bulk group issued so far has been read (the other slab, quadrant qq - 1): after the barrier
+              // below that slab is free for quadrant qq + 1
+              if (lane < RW) bulk_wait_read_all();
+              epi_bar_sync();
+              if (lane < RW) {
+                const int rr = e * RW + lane;
+                const long row = static_cast<long>(m_blk) * BLOCK_M + qq * 32 + rr;
+                if (row < p.M && ncols > 0)
+                  bulk_store_row(p.c_bf16 + row * p.ldc + col0, slab + rr * LDB, static_cast<uint32_t>(ncols) * 2u);
+                bulk_commit();
+              }
+            }
+            stored = true;
+          }
+        }
         if (!stored) {
 #pragma unroll 1
           for (int c = half; c < BN / 32; c += kEpiWarps / 4) {
@@ -797,7 +889,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
         else mbar_arrive_remote(&tmem_empty[as], 0);      // the pair's accumulator buffer is released on the leader
       }
     }
-    if constexpr (EPI == EPI_F32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // bulk row stores have landed
+    if constexpr (EPI != EPI_SGD) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // bulk row stores have landed
   }
 
   tc_fence_before();

@@ -147,6 +147,20 @@ class EmulatedKernels:
             dx = torch.where(mask.float() > 0, dx, dx * slope)
         return _nhwc(dx.to(BF16))
 
+    def conv_dgrad_w(self, dy, wb, kernel, pad, groups, H, W, mask, slope):
+        """Stride-1 data gradient read from the FPROP operand wb [Cout, R*S*Cg] (no packed copy)
+        (csrc/gemm/conv_ops.cu conv_dgrad_w)."""
+        r, s = kernel
+        cout = wb.shape[0]
+        cg = wb.shape[1] // (r * s)
+        w4 = wb.float().reshape(cout, r, s, cg).permute(0, 3, 1, 2)             # [Cout, Cg, R, S]
+        full = F.conv_transpose2d(dy.float(), w4, None, 1, 0, 0, groups)
+        full = F.pad(full, (0, max(0, pad[1] + W - full.shape[3]), 0, max(0, pad[0] + H - full.shape[2])))
+        dx = full[:, :, pad[0]: pad[0] + H, pad[1]: pad[1] + W]
+        if mask is not None:
+            dx = torch.where(mask.float() > 0, dx, dx * slope)
+        return _nhwc(dx.to(BF16))
+
     def conv_wgrad(self, x, dy, dw, kernel, stride, pad, groups, mode, alpha, cgk):
         """dw[Cout, K] fp32 += alpha · (weight gradient in the operand's K order) (csrc/gemm/conv_ops.cu:304-365)."""
         r, s = kernel

@@ -418,11 +418,33 @@ class _ConvFn(torch.autograd.Function):
                 dx = _strided_dgrad(k, st, layer, dy, xin)
             else:
                 mask = xin if st.mask_input else None
-                dx = k.conv_dgrad(dy, st.dgrad_pack(), [st.R, st.S], list(layer.pad), st.groups, xin.shape[2],
-                                  xin.shape[3], mask, 0.0)
+                if _dgrad_reads_fprop_weights(st, layer, dy):
+                    # no packed [Cin][R][S][Cout] copy and no pack kernel per step: the kernel reads the fprop shadow
+                    # through a 3-D tensor map as an MN-major B operand
+                    dx = k.conv_dgrad_w(dy, st.shadow(), [st.R, st.S], list(layer.pad), st.groups, xin.shape[2],
+                                        xin.shape[3], mask, 0.0)
+                else:
+                    dx = k.conv_dgrad(dy, st.dgrad_pack(), [st.R, st.S], list(layer.pad), st.groups, xin.shape[2],
+                                      xin.shape[3], mask, 0.0)
             if st.pad8 and st.Cp != st.cin_logical:
                 dx = dx[:, : st.cin_logical]
         return dx, dw, db, None, None
+
+
+_DGRAD_PACK = os.environ.get("POSEIDON_DGRAD_PACK", "0") == "1"      # A/B switch: always use the packed dgrad operand
+
+
+def _dgrad_reads_fprop_weights(st: "ConvState", layer, dy: torch.Tensor) -> bool:
+    """Geometry the pack-free dgrad kernel covers (csrc/gemm/conv_ops.cu conv_dgrad_w): TAP-mode weights, channel counts
+    per group that are multiples of 8 (16-byte TMA strides), im2col-descriptor offsets within a signed byte."""
+    if _DGRAD_PACK or st.row_mode or st.pad8 or st.s2d or st.Coutp != st.Cout:
+        return False
+    if st.cg % 8 != 0 or (st.Cout // st.groups) % 8 != 0:
+        return False
+    if max(st.R, st.S, layer.pad[0], layer.pad[1]) > 64:
+        return False
+    pitch = dy.stride(3) if dy.shape[3] > 1 else (dy.stride(2) if dy.shape[2] > 1 else dy.stride(0))
+    return dy.stride(1) == 1 and pitch % 8 == 0 and dy.data_ptr() % 16 == 0
 
 
 def _strided_dgrad(k, st: "ConvState", layer, dy: torch.Tensor, xin: torch.Tensor) -> torch.Tensor:

@@ -123,6 +123,45 @@ def test_conv_im2col(ext, conv_mode, case):
     _close(layer.weight.grad, wref.grad, rel=3e-2, what="conv wgrad")
 
 
+DGRAD_W = [
+    # (N, Cin, H, W, Cout, k, pad, group): the pack-free data gradient (B = fprop weights through a 3-D map, MN-major)
+    (4, 256, 13, 13, 384, 3, 1, 1),        # AlexNet conv3: Cout_g 384 = 6 whole k-blocks per tap
+    (2, 384, 13, 13, 256, 3, 1, 2),        # conv5 grouped: Cout_g 128, C_g 192 -> BN 256 with 64 zero-filled columns
+    (2, 96, 28, 28, 208, 3, 1, 1),         # Cout_g 208: last k-block of every tap is 16 real + 48 zero-filled rows
+    (2, 16, 14, 14, 48, 5, 2, 1),          # GoogLeNet 5x5 reduce: C_g 16 (BN 64, 48 columns out of bounds), Cout_g 48
+    (3, 128, 7, 9, 24, 1, 0, 1),           # 1x1, Cout_g 24: a single, mostly empty k-block
+    (2, 64, 56, 56, 192, 3, 1, 1),         # many m-blocks: pairs and a full wave
+    (2, 40, 9, 9, 72, 3, 1, 1),            # C_g 40, Cout_g 72: neither a multiple of 64
+]
+
+
+@pytest.mark.parametrize("case", DGRAD_W)
+@pytest.mark.parametrize("masked", [False, True], ids=["plain", "relu_mask"])
+def test_conv_dgrad_from_fprop_weights(ext, conv_mode, case, masked):
+    """conv_dgrad_w against the fp32 transposed convolution AND against the packed-operand kernel it replaces."""
+    if conv_mode[0] != 1:
+        pytest.skip("the multicast schedules do not apply to the data gradient's weight operand")
+    from test_ops_gpu import _nhwc
+    n, cin, h, w, cout, k, pad, group = case
+    cg, cout_g = cin // group, cout // group
+    wf = (torch.randn(cout, k, k, cg, generator=torch.Generator().manual_seed(3)) * (cg * k * k) ** -0.5).cuda()
+    wb = wf.to(torch.bfloat16).reshape(cout, k * k * cg).contiguous()
+    oh, ow = h + 2 * pad - k + 1, w + 2 * pad - k + 1
+    dy = _nhwc((n, cout, oh, ow), 11)
+    mask = _nhwc((n, cin, h, w), 12) if masked else None
+    got = ext.conv_dgrad_w(dy, wb, [k, k], [pad, pad], group, h, w, mask, 0.0)
+    w4 = wb.float().reshape(cout, k, k, cg).permute(0, 3, 1, 2).contiguous()
+    ref = torch.nn.functional.conv_transpose2d(dy.float(), w4, None, 1, pad, 0, group)
+    if masked:
+        ref = ref * (mask.float() > 0)
+    assert got.shape == ref.shape and got.is_contiguous(memory_format=torch.channels_last)
+    _close(got, ref, rel=2e-2, what="dgrad from fprop weights")
+    wt = ext.conv_pack_dgrad(wf.reshape(-1), cout, k * k, cg, group, None, 0)
+    old = ext.conv_dgrad(dy, wt, [k, k], [pad, pad], group, h, w, mask, 0.0)
+    _close(got, old, rel=1e-2, what="pack-free vs packed dgrad")
+    assert cout_g % 8 == 0 and cg % 8 == 0
+
+
 def test_pair_gemm_throughput(ext):
     """8192^3 bf16: paired CTAs vs single-CTA vs cuBLAS on the same box (printed; asserts only a sanity floor)."""
     a, b = _rand((8192, 8192), 1.0, 1), _rand((8192, 8192), 1.0, 2)

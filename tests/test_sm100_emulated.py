@@ -174,7 +174,9 @@ def test_shadows_are_not_rederived_every_step(emu):
     # the 10) by ONE multi-tensor launch at the end of the iteration
     assert ops["fused_update"] == 2 and ops["fused_update_multi"] == 1 and n_params == 10, ops
     assert ops["gemm_f32"] == 2, ops
-    assert ops["conv_wgrad"] == 3 and ops["conv_fprop"] == 3 and ops["conv_dgrad"] == 2, ops
+    assert ops["conv_wgrad"] == 3 and ops["conv_fprop"] == 3, ops
+    # both data gradients read the fprop weights in place: no packed transposed copy, no pack launch per step
+    assert ops.get("conv_dgrad_w", 0) == 2 and "conv_dgrad" not in ops and "conv_pack_dgrad" not in ops, ops
     assert "relu_fwd" not in ops, ops        # all four ReLUs live in epilogues
     for name in ("conv2", "conv3", "fc4", "fc5"):
         assert not s.net.layer_by_name[name]._sm100.dirty_wb
