@@ -21,7 +21,8 @@ for line in text.splitlines():
         funcs[cur].append(line)
 print(f"# cuobjdump -sass {SO} (sm_100a): {len(funcs)} kernels")
 print("# PTX -> SASS: tcgen05.mma = UTCHMMA(.2CTA), tcgen05.commit = UTCBAR(.2CTA)(.MULTICAST), tcgen05.ld = LDTM, TMA load = UTMALDG"
-      "(.4D.IM2COL)(.2CTA)(.MULTICAST), bulk store = UBLKCP, multimem.ld_reduce = LDGMC..., multimem.st = STGMC..., cp.async = LDGSTS, HMMA = legacy mma.sync (none expected)")
+      "(.4D.IM2COL)(.2CTA)(.MULTICAST), bulk store = UBLKCP, multimem.ld_reduce = LDGMC..., multimem.st = STGMC..., "
+      "cp.async = LDGSTS, HMMA = legacy mma.sync (none expected)")
 print("\n## 1. mnemonic counts per kernel\n")
 for name, lines in funcs.items():
     c = collections.Counter()

@@ -416,7 +416,8 @@ __device__ __forceinline__ float dependent_zero(float v) {
 }
 
 __global__ void __launch_bounds__(512)
-allreduce_sgd_multi_kernel(const __grid_constant__ ArenaPtrs ap, const __grid_constant__ SegSet ss, int rank, int world, uint32_t epoch, UpdateHyper hp,
+allreduce_sgd_multi_kernel(const __grid_constant__ ArenaPtrs ap, const __grid_constant__ SegSet ss, int rank, int world, uint32_t epoch,
+                           UpdateHyper hp,
                            unsigned int* __restrict__ done_counter, const float* __restrict__ lr_dev,
                            const uint32_t* __restrict__ epoch_dev) {
   const float lr_glob = lr_dev != nullptr ? __ldg(lr_dev) : 1.f;

@@ -92,7 +92,7 @@ void encode_tmap_im2col_bf16(CUtensorMap* map, const void* base, int64_t C, int6
               " N=", N, " lower=", lower_w, ",", lower_h, " upper=", upper_w, ",", upper_h);
 }
 
-int g_no_bulk_epi = 0;
+int g_no_bulk_epi = 2;             // bit 0 / 1: fp32 / bf16 outputs NOT through the bulk-store epilogue (bf16: measured slower, off)
 int g_max_stages = 0;             // experiment knob (set_max_stages): ring stages actually used, 0 = all
 static int g_pair_cta = 1;        // cta_group::2 (paired CTAs) where the tile space allows it; 0 = single-CTA kernels only
 int pair_cta_enabled() { return g_pair_cta; }
@@ -423,7 +423,8 @@ void sfb_outer_f32(std::vector<int64_t> u_ptrs, std::vector<int64_t> v_ptrs, int
 
 void set_pair_cta(int64_t on) { g_pair_cta = on != 0; }
 void set_max_stages(int64_t n) { g_max_stages = static_cast<int>(n); }
-void set_bulk_epilogue(int64_t on) { g_no_bulk_epi = on ? 0 : 1; }
+// bit 0: fp32 outputs, bit 1: bf16 outputs leave through shared slabs + bulk row stores (default 1: fp32 only)
+void set_bulk_epilogue(int64_t on) { g_no_bulk_epi = static_cast<int>(~on & 3); }
 
 }  // namespace psd
 

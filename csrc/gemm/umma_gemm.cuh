@@ -52,7 +52,7 @@ struct GemmParams {
   int src_rot;           // first source to visit (own rank for SFB: local data needs no flag wait)
   int cluster;           // CTAs per cluster sharing the TMA operand by multicast (1 = no clusters); conv kernels only
   int max_stages;        // experiment knob: use only this many ring stages (0 = all that fit)
-  int no_bulk_epi;       // experiment knob: 1 = plain fp32 epilogue through the per-warp 32x32 walk instead of bulk row stores
+  int no_bulk_epi;       // experiment knob: bit 0 / bit 1 = fp32 / bf16 output through the per-warp 32x32 walk instead of bulk row stores
   // --- epilogue operands
   __nv_bfloat16* c_bf16; // EPI_BF16 output [M, ldc]
   float* c_f32;          // EPI_F32 output [M, ldc]
@@ -717,9 +717,9 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
       }
     };
     if (kSgdPrefetch) prefetch_sgd_tile(tile0);
-    [[maybe_unused]] const bool bulk_f32 = EPI == EPI_F32 && !p.atomic && !p.no_bulk_epi && p.col_cgk == 0 && (p.N & 3) == 0 && (p.ldc & 3) == 0 &&
+    [[maybe_unused]] const bool bulk_f32 = EPI == EPI_F32 && !p.atomic && !(p.no_bulk_epi & 1) && p.col_cgk == 0 && (p.N & 3) == 0 && (p.ldc & 3) == 0 &&
                                            (reinterpret_cast<uintptr_t>(p.c_f32) & 15) == 0;
-    [[maybe_unused]] const bool bulk_bf16 = EPI == EPI_BF16 && !p.no_bulk_epi && (p.N & 7) == 0 && (p.ldc & 7) == 0 &&
+    [[maybe_unused]] const bool bulk_bf16 = EPI == EPI_BF16 && !(p.no_bulk_epi & 2) && (p.N & 7) == 0 && (p.ldc & 7) == 0 &&
                                             (reinterpret_cast<uintptr_t>(p.c_bf16) & 15) == 0 &&
                                             (p.mask == nullptr || (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0);
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
@@ -801,8 +801,9 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
           // producer's ReLU mask are applied in registers in that layout — the mask row segment of a lane is 64
           // contiguous bytes.  Quadrant qq + 1 is converted into the other slab while the copy engine still reads
           // quadrant qq; one CTA-wide barrier per quadrant, rows leave as up-to-512-byte bulk stores instead of the
-          // 64-byte pieces of the per-warp walk (GEMM with conv3's extent: fp32 output 79 us vs bf16 output 87 us
-          // with the walk although it writes twice the bytes — profiles/r2_conv_experiments.md).
+          // 64-byte pieces of the per-warp walk.  MEASURED SLOWER than the walk in every network (AlexNet 3.65 vs
+          // 3.27 ms, VGG-16 12.7 vs 9.97 ms: only two of the eight epilogue warps convert at a time) — kept behind
+          // set_bulk_epilogue(3) with its numerics test, OFF by default (profiles/r2_conv_experiments.md, E7).
           if (bulk_bf16) {
             constexpr int LDB = BN * 2 + 16;
             static_assert(2 * 32 * LDB <= S::kEpiStageBytes, "two bf16 slabs must fit the epilogue staging buffer");

@@ -162,6 +162,29 @@ def test_conv_dgrad_from_fprop_weights(ext, conv_mode, case, masked):
     assert cout_g % 8 == 0 and cg % 8 == 0
 
 
+@pytest.mark.parametrize("M,N,K,ldc_pad", [(256, 256, 64, 0), (1000, 328, 200, 0), (130, 96, 256, 8), (4096, 1024, 512, 0),
+                                           (515, 40, 128, 24), (384, 200, 192, 0)])
+@pytest.mark.parametrize("bn", [0, 64, 128, 256])
+def test_bf16_bulk_epilogue_matches_walk(ext, mode, M, N, K, ldc_pad, bn):
+    """bf16 outputs through the two-slab bulk-store epilogue (bias + ReLU + mask applied in the lane = row layout) against
+    the per-warp walk and the fp32 reference; N a multiple of 8 with ragged last tiles, partial last chunk, padded ldc."""
+    a, b = _rand((M, K), 1.0, 1), _rand((N, K), K ** -0.5, 2)
+    bias = torch.randn(N, device="cuda")
+    ref = torch.nn.functional.leaky_relu(a.float() @ b.float().t() + bias, 0.1)
+    outs = []
+    for bits in (3, 1):
+        ext.set_bulk_epilogue(bits)
+        try:
+            out = torch.full((M, N + ldc_pad), 7.0, device="cuda", dtype=torch.bfloat16)
+            c = out[:, :N]
+            ext.gemm_bf16(a, False, b, False, bias, True, 0.1, None, c, bn)
+            outs.append(out)
+        finally:
+            ext.set_bulk_epilogue(1)
+    _close(outs[0][:, :N], ref, what="bulk epilogue")
+    assert torch.equal(outs[0], outs[1]), "bulk-store and walk epilogues must agree bit for bit (padding untouched)"
+
+
 def test_pair_gemm_throughput(ext):
     """8192^3 bf16: paired CTAs vs single-CTA vs cuBLAS on the same box (printed; asserts only a sanity floor)."""
     a, b = _rand((8192, 8192), 1.0, 1), _rand((8192, 8192), 1.0, 2)
