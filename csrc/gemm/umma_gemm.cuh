@@ -717,7 +717,8 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmParams p, const C
       }
     };
     if (kSgdPrefetch) prefetch_sgd_tile(tile0);
-    [[maybe_unused]] const bool bulk_f32 = EPI == EPI_F32 && !p.atomic && !(p.no_bulk_epi & 1) && p.col_cgk == 0 && (p.N & 3) == 0 && (p.ldc & 3) == 0 &&
+    [[maybe_unused]] const bool bulk_f32 = EPI == EPI_F32 && !p.atomic && !(p.no_bulk_epi & 1) && p.col_cgk == 0 && (p.N & 3) == 0 &&
+                                           (p.ldc & 3) == 0 &&
                                            (reinterpret_cast<uintptr_t>(p.c_f32) & 15) == 0;
     [[maybe_unused]] const bool bulk_bf16 = EPI == EPI_BF16 && !(p.no_bulk_epi & 2) && (p.N & 7) == 0 && (p.ldc & 7) == 0 &&
                                             (reinterpret_cast<uintptr_t>(p.c_bf16) & 15) == 0 &&

@@ -210,6 +210,8 @@ class Net(nn.Module):
             if sm100.active(self.ctx.device):
                 from .fusion import plan_sm100
                 plan_sm100(self)
+        from .lanes import default_lanes, plan_lanes
+        plan_lanes(self, default_lanes(self.ctx))
 
     def _consumed_later(self, blob: str) -> bool:
         last_prod = max(i for i, tn in enumerate(self.top_names) if blob in tn)
@@ -231,6 +233,10 @@ class Net(nn.Module):
                 raise ValueError(f"missing net input '{n}'")
         end = len(self.layers) - 1 if end is None else end
         loss = None
+        lanes = self._lane_runner(start, end)
+        if lanes is not None:
+            loss = self._forward_lanes(lanes, blobs, start, end)
+            start = end + 1
         for i in range(start, end + 1):
             if self.skip_layer[i]:
                 continue                      # fused into the producer's epilogue (in-place layer: blob unchanged)
@@ -247,6 +253,49 @@ class Net(nn.Module):
         self.blobs = blobs if keep_blobs else {}
         outputs = {n: blobs[n] for n in self.output_names if n in blobs}
         return loss, outputs
+
+    def _forward_lanes(self, lanes, blobs, start: int, end: int):
+        """Branch-parallel pass (net/lanes.py): every layer runs on its lane's stream, which first waits for bottoms
+        produced on other lanes; loss terms are summed on the caller's stream after all lanes have joined it."""
+        terms = []
+        cur_lane = 0
+        try:
+            for i in range(start, end + 1):
+                if self.skip_layer[i]:
+                    continue
+                lane = self.lane[i]
+                if lane != cur_lane:          # (switching only on a change: the context manager costs ~10 us per layer)
+                    torch.cuda.set_stream(lanes.streams[lane])
+                    cur_lane = lane
+                lanes.before(i)
+                outs = self.layers[i](*[blobs[b] for b in self.bottom_names[i]])
+                for t, o, w in zip(self.top_names[i], outs, self.loss_weights[i]):
+                    blobs[t] = o
+                    if w != 0.0:
+                        terms.append((o.float().sum() * w if o.numel() > 1 else o.float().reshape(()) * w, lane))
+                lanes.after(i, outs)
+        finally:
+            torch.cuda.set_stream(lanes.cur)
+        lanes.finish()                        # every lane has joined the caller's stream
+        loss = None
+        for term, lane in terms:
+            if lane != 0:
+                term.record_stream(lanes.cur)
+            loss = term if loss is None else loss + term
+        return loss
+
+    def _lane_runner(self, start: int, end: int):
+        """Stream bookkeeping of a branch-parallel pass, or None (CPU nets, single-lane plans, passes that stop early)."""
+        if getattr(self, "n_lanes", 1) <= 1 or self.debug_info or end != len(self.layers) - 1:
+            return None
+        if self.ctx.device is None or torch.device(self.ctx.device).type != "cuda":
+            return None
+        r = getattr(self, "_lanes", None)
+        if r is None:
+            from .lanes import LaneRunner
+            r = self._lanes = LaneRunner(self)
+        r.begin(start)
+        return r
 
     def _forward_debug(self, i, outs):
         """reference: src/caffe/net.cpp:787-812 (ForwardDebugInfo: mean |x| per top/param)."""

@@ -36,10 +36,18 @@ def main():
     ap.add_argument("--snapshot_prefix", default="", help="write <prefix>_iter_N.{caffemodel,solverstate} after the last step")
     ap.add_argument("--restore", default="", help="resume from this .solverstate; --steps counts the steps still to run")
     ap.add_argument("--total_steps", type=int, default=0, help="with --restore: length of the uninterrupted run (data order)")
+    ap.add_argument("--net", default="small", choices=["small", "inception"], help="inception: branchy net (lanes)")
+    ap.add_argument("--graph", type=int, default=0, help="capture the training step as a CUDA graph")
     args = ap.parse_args()
     rc = init_rank_context(args.device)
     M, W = args.batch, rc.world_size
-    net = small_net(batch=M, hw=args.hw)
+    classes = 16
+    if args.net == "inception":
+        from test_lanes import inception_net
+        args.hw, classes = 20, 10
+        net = inception_net(batch=M, classes=classes, hw=args.hw)
+    else:
+        net = small_net(batch=M, hw=args.hw)
     for l in net.layers:
         if l.name in args.freeze.split(","):
             l.blobs_lr = [0.0, 0.0]
@@ -53,7 +61,7 @@ def main():
                    dtype=torch.float32 if args.engine == "torch" else None)
     total = args.total_steps or args.steps
     first = total - args.steps if args.restore else 0
-    x, y = make_data(M * W * total, hw=args.hw)
+    x, y = make_data(M * W * total, classes=classes, hw=args.hw)
     # global batch t = samples [t*M*W, (t+1)*M*W); this rank takes the slice [r*M, (r+1)*M) of it
     idx = torch.cat([torch.arange(t * M * W + rc.rank * M, t * M * W + (rc.rank + 1) * M)
                      for t in range(first, first + args.steps)])
@@ -65,7 +73,11 @@ def main():
     if args.delay_rank == rc.rank and hasattr(s.sync.backend, "delay_hook"):
         import time
         s.sync.backend.delay_hook = lambda clock: time.sleep(0.05)
-    s.step(args.steps)
+    if args.graph:
+        s.enable_cuda_graph(warmup=1)               # 1 eager + 1 captured step
+        s.step(args.steps - 2)
+    else:
+        s.step(args.steps)
     s.sync.wait_all()
     if hasattr(s.sync.backend, "drain"):
         s.sync.backend.drain()

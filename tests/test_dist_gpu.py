@@ -85,3 +85,18 @@ def test_fused_ssp_straggler_stays_within_the_staleness_bound(tmp_path, monkeypa
     assert np.isfinite(res[0]["loss"])
     lib = launch(2, str(tmp_path / "l"), base + ["--comm", "ssp"], device=None)
     _close(res[0], lib[0], 0.3)
+
+
+@pytest.mark.parametrize("graph", ["0", "1"], ids=["eager", "cuda_graph"])
+def test_fused_branch_parallel_lanes_two_ranks(tmp_path, monkeypatch, graph):
+    """A branchy net (two inception modules + an auxiliary head) on 2 GPUs with the layers of independent branches on
+    separate streams: DWBP buckets are launched from hooks that fire on the lane streams, the fused all-reduce + SGD
+    kernels wait on those — the replicas must stay bit-close and follow one GPU on the concatenated batch."""
+    base = ["--engine", "sm100", "--net", "inception", "--steps", "4", "--graph", graph]
+    monkeypatch.setenv("POSEIDON_LANES", "1")
+    ref = launch(1, str(tmp_path / "s"), base + ["--batch", "16", "--base_lr", "0.02"], device=None)[0]
+    monkeypatch.setenv("POSEIDON_LANES", "4")
+    res = launch(2, str(tmp_path / "w"), base + ["--batch", "8", "--comm", "fused", "--svb", "1", "--sfb_mode", "all"],
+                 device=None)
+    _close(res[0], res[1], 1e-6)
+    _close(res[0], ref, 0.03)
