@@ -395,21 +395,44 @@ class _ConvFn(torch.autograd.Function):
                     dy = k.relu_bwd_nhwc(y, dy, float(ctx.relu_slope))
         stride = layer.stride
         dw = db = dx = None
-        if ctx.needs_input_grad[1]:
+        # The weight / bias gradient and the data gradient of one layer are independent: with a data gradient to compute,
+        # the former run on a side stream (forked here, joined before returning), so a layer costs max(dgrad, wgrad)
+        # instead of their sum on its lane — small convolutions (GoogLeNet at batch 32) do not fill the chip alone.
+        side = done = None
+        if dy.is_cuda and ctx.needs_input_grad[0] and ctx.needs_input_grad[1] and _wgrad_lane():
+            cur = torch.cuda.current_stream()
+            side = _wgrad_stream(cur)
+        dw2 = dbf = None
+        if ctx.needs_input_grad[1]:             # (outputs are allocated on the layer's own stream)
             sink = getattr(layer, "_grad_sink", None)
             dw2 = sink.weight_buffer(layer, st) if sink is not None else \
                 torch.zeros(st.Coutp, st.Kw, device=dy.device, dtype=torch.float32)
-            if st.s2d:
-                k.conv_wgrad(xin, dy, dw2, [st.Rq, st.Sq], [1, 1], [0, 0], 1, 0, 1.0, 0)
-            else:
-                k.conv_wgrad(xin, dy, dw2, [st.R, st.S], list(stride), list(ctx.conv_pad), st.groups,
-                             1 if (st.row_mode and not st.pad8) else 0, 1.0, st.cgk if not st.row_mode else 0)
-            dw = st.grad_from_dw(dw2)
         if layer.bias_term and ctx.needs_input_grad[2]:
-            db = torch.empty(st.Coutp, device=dy.device, dtype=torch.float32)
-            pitch = dy.stride(3) if dy.shape[3] > 1 else (dy.stride(2) if dy.shape[2] > 1 else dy.stride(0))
-            k.colsum(dy, dy.shape[0] * dy.shape[2] * dy.shape[3], st.Coutp, pitch, db, 1.0, False)
-            db = db[: st.Cout]
+            dbf = torch.empty(st.Coutp, device=dy.device, dtype=torch.float32)
+        if side is not None:
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            side.wait_event(fork)
+            dy.record_stream(side)
+            xin.record_stream(side)
+            torch.cuda.set_stream(side)
+        try:
+            if dw2 is not None:
+                if st.s2d:
+                    k.conv_wgrad(xin, dy, dw2, [st.Rq, st.Sq], [1, 1], [0, 0], 1, 0, 1.0, 0)
+                else:
+                    k.conv_wgrad(xin, dy, dw2, [st.R, st.S], list(stride), list(ctx.conv_pad), st.groups,
+                                 1 if (st.row_mode and not st.pad8) else 0, 1.0, st.cgk if not st.row_mode else 0)
+                dw = st.grad_from_dw(dw2)
+            if dbf is not None:
+                pitch = dy.stride(3) if dy.shape[3] > 1 else (dy.stride(2) if dy.shape[2] > 1 else dy.stride(0))
+                k.colsum(dy, dy.shape[0] * dy.shape[2] * dy.shape[3], st.Coutp, pitch, dbf, 1.0, False)
+                db = dbf[: st.Cout]
+        finally:
+            if side is not None:
+                done = torch.cuda.Event()
+                done.record(side)
+                torch.cuda.set_stream(cur)
         if ctx.needs_input_grad[0]:
             if st.row_mode and not st.pad8:
                 raise NotImplementedError(f"sm100 conv '{layer.layer_name}': ROW-mode (<= 4 channel) layers are image "
@@ -428,10 +451,28 @@ class _ConvFn(torch.autograd.Function):
                                       xin.shape[3], mask, 0.0)
             if st.pad8 and st.Cp != st.cin_logical:
                 dx = dx[:, : st.cin_logical]
+        if done is not None:
+            cur.wait_event(done)                # join: dw / db are complete for whoever consumes them on this stream
         return dx, dw, db, None, None
 
 
 _DGRAD_PACK = os.environ.get("POSEIDON_DGRAD_PACK", "0") == "1"      # A/B switch: always use the packed dgrad operand
+
+
+def _wgrad_lane() -> bool:
+    """Weight gradients on a side stream next to the data gradient (POSEIDON_WGRAD_LANE=0: same stream)."""
+    return os.environ.get("POSEIDON_WGRAD_LANE", "1") == "1"
+
+_wgrad_streams: dict = {}
+
+
+def _wgrad_stream(cur: "torch.cuda.Stream") -> "torch.cuda.Stream":
+    """The side stream paired with ``cur`` (one per stream a layer can run on: the caller's stream and every lane)."""
+    key = (cur.device.index, cur.cuda_stream)
+    s = _wgrad_streams.get(key)
+    if s is None:
+        s = _wgrad_streams[key] = torch.cuda.Stream(device=cur.device)
+    return s
 
 
 def _dgrad_reads_fprop_weights(st: "ConvState", layer, dy: torch.Tensor) -> bool:

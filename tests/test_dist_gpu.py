@@ -8,11 +8,11 @@ from test_dist_cpu import _weights, launch
 pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
 
 
-def _close(a, b, rel):
+def _close(a, b, rel, floor=2e-4):
     for k in _weights(a):
         d = np.abs(a[k] - b[k]).max()
         m = np.abs(b[k]).max() + 1e-6
-        assert d <= rel * m + 2e-4, (k, d, m)
+        assert d <= rel * m + floor, (k, d, m)
 
 
 @pytest.fixture(scope="module")
@@ -84,7 +84,9 @@ def test_fused_ssp_straggler_stays_within_the_staleness_bound(tmp_path, monkeypa
     assert all(int(r["max_lag"]) <= staleness for r in res)
     assert np.isfinite(res[0]["loss"])
     lib = launch(2, str(tmp_path / "l"), base + ["--comm", "ssp"], device=None)
-    _close(res[0], lib[0], 0.3)
+    # two asynchronous runs whose fold order depends on timing: same neighbourhood, not the same trajectory (the
+    # absolute floor covers the biases, which start at zero and are ~1e-2 after six steps)
+    _close(res[0], lib[0], 0.3, floor=1e-3)
 
 
 @pytest.mark.parametrize("graph", ["0", "1"], ids=["eager", "cuda_graph"])
