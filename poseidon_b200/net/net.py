@@ -318,6 +318,9 @@ class Net(nn.Module):
         loss, outputs = self.forward(inputs)
         if loss is not None and loss.requires_grad:
             loss.backward()
+            if self.ctx.engine == "sm100":
+                from ..ops import sm100
+                sm100.wait_pending_wgrad(clear=True)     # weight gradients forked to side streams join here
         return loss, outputs
 
     def zero_grad_(self):

@@ -398,17 +398,27 @@ class _ConvFn(torch.autograd.Function):
         # The weight / bias gradient and the data gradient of one layer are independent: with a data gradient to compute,
         # the former run on a side stream (forked here, joined before returning), so a layer costs max(dgrad, wgrad)
         # instead of their sum on its lane — small convolutions (GoogLeNet at batch 32) do not fill the chip alone.
+        # When the gradient lands in a sink whose owner (the fused backend) waits for it itself, the join is deferred: the
+        # weight gradients of all layers queue up on the side stream and fill whatever the main chain (data gradients,
+        # pooling / LRN backward) leaves idle; the update / communication launches wait on the recorded events.
         side = done = None
+        sink = getattr(layer, "_grad_sink", None) if ctx.needs_input_grad[1] else None
         if dy.is_cuda and ctx.needs_input_grad[0] and ctx.needs_input_grad[1] and _wgrad_lane():
             cur = torch.cuda.current_stream()
             side = _wgrad_stream(cur)
+        defer = side is not None and sink is not None and getattr(sink, "defers_wgrad_join", False) and _wgrad_defer()
         dw2 = dbf = None
         if ctx.needs_input_grad[1]:             # (outputs are allocated on the layer's own stream)
-            sink = getattr(layer, "_grad_sink", None)
             dw2 = sink.weight_buffer(layer, st) if sink is not None else \
                 torch.zeros(st.Coutp, st.Kw, device=dy.device, dtype=torch.float32)
         if layer.bias_term and ctx.needs_input_grad[2]:
             dbf = torch.empty(st.Coutp, device=dy.device, dtype=torch.float32)
+
+        def bias_grad():
+            pitch = dy.stride(3) if dy.shape[3] > 1 else (dy.stride(2) if dy.shape[2] > 1 else dy.stride(0))
+            k.colsum(dy, dy.shape[0] * dy.shape[2] * dy.shape[3], st.Coutp, pitch, dbf, 1.0, False)
+            return dbf[: st.Cout]
+
         if side is not None:
             fork = torch.cuda.Event()
             fork.record(cur)
@@ -424,15 +434,15 @@ class _ConvFn(torch.autograd.Function):
                     k.conv_wgrad(xin, dy, dw2, [st.R, st.S], list(stride), list(ctx.conv_pad), st.groups,
                                  1 if (st.row_mode and not st.pad8) else 0, 1.0, st.cgk if not st.row_mode else 0)
                 dw = st.grad_from_dw(dw2)
-            if dbf is not None:
-                pitch = dy.stride(3) if dy.shape[3] > 1 else (dy.stride(2) if dy.shape[2] > 1 else dy.stride(0))
-                k.colsum(dy, dy.shape[0] * dy.shape[2] * dy.shape[3], st.Coutp, pitch, dbf, 1.0, False)
-                db = dbf[: st.Cout]
+            if dbf is not None and not defer:
+                db = bias_grad()
         finally:
             if side is not None:
                 done = torch.cuda.Event()
                 done.record(side)
                 torch.cuda.set_stream(cur)
+        if dbf is not None and defer:
+            db = bias_grad()                    # (a fresh tensor autograd may copy on this stream: not deferred)
         if ctx.needs_input_grad[0]:
             if st.row_mode and not st.pad8:
                 raise NotImplementedError(f"sm100 conv '{layer.layer_name}': ROW-mode (<= 4 channel) layers are image "
@@ -452,7 +462,10 @@ class _ConvFn(torch.autograd.Function):
             if st.pad8 and st.Cp != st.cin_logical:
                 dx = dx[:, : st.cin_logical]
         if done is not None:
-            cur.wait_event(done)                # join: dw / db are complete for whoever consumes them on this stream
+            if defer:
+                _pending_wgrad.setdefault(cur.device.index, []).append(done)
+            else:
+                cur.wait_event(done)            # join: dw / db are complete for whoever consumes them on this stream
         return dx, dw, db, None, None
 
 
@@ -463,7 +476,31 @@ def _wgrad_lane() -> bool:
     """Weight gradients on a side stream next to the data gradient (POSEIDON_WGRAD_LANE=0: same stream)."""
     return os.environ.get("POSEIDON_WGRAD_LANE", "1") == "1"
 
+
+
+def _wgrad_defer() -> bool:
+    """Join the side streams at the update / communication launches instead of at the end of each layer's backward
+    (POSEIDON_WGRAD_DEFER=0: join per layer)."""
+    return os.environ.get("POSEIDON_WGRAD_DEFER", "1") == "1"
+
+
 _wgrad_streams: dict = {}
+_pending_wgrad: dict = {}          # device index -> events of weight-gradient kernels not yet joined
+
+
+def wait_pending_wgrad(stream=None, clear: bool = False) -> None:
+    """Make ``stream`` (default: the current one) wait for every weight-gradient kernel that was forked to a side stream
+    and not joined yet.  Called by whoever consumes the gradient sinks: the update launches at the end of the iteration
+    (``clear=True``) and the per-bucket communication launches."""
+    if not _pending_wgrad:
+        return
+    s = stream if stream is not None else torch.cuda.current_stream()
+    lst = _pending_wgrad.get(s.device.index)
+    if lst:
+        for ev in lst:
+            s.wait_event(ev)
+        if clear:
+            lst.clear()
 
 
 def _wgrad_stream(cur: "torch.cuda.Stream") -> "torch.cuda.Stream":

@@ -398,9 +398,13 @@ class FusedBackend(Backend):
         # lr here is only the per-blob multiplier; the kernels multiply by lr_t[0]
         return (lm, hy.momentum, decay, hy.solver_type, hy.l1, hy.delta, gscale)
 
+    defers_wgrad_join = True        # ops/sm100.py: convolution weight gradients may still be running on a side stream
+
     def launch(self, bucket: Bucket):
         st = getattr(bucket.layer, "_sm100", None)
         if self.world == 1:
+            if not self.multi_update:
+                sm100.wait_pending_wgrad()          # per-tensor updates read the sinks on this stream right now
             fresh = self._launch_local(bucket)
         else:
             self._launch_peer(bucket)
@@ -464,6 +468,7 @@ class FusedBackend(Backend):
             if p.grad.data_ptr() != gview.data_ptr():
                 gview.copy_(p.grad)
         self.stream.wait_stream(cur)
+        sm100.wait_pending_wgrad(self.stream)       # weight gradients forked to side streams (no-op on the CPU emulation)
         self.epoch_of_bucket = self.epoch + 1
         with self.cu.stream(self.stream):
             live = [(p, seg, lm, dm) for p, seg, lm, dm in zip(bucket.params, bucket.segs, bucket.lr_mult, bucket.decay_mult)
@@ -606,6 +611,7 @@ class FusedBackend(Backend):
         ``epoch_t + 1``) is bumped on the comm stream, i.e. after all of them in stream order.  Keeping it on the
         device is what lets a captured CUDA graph of the whole step be replayed."""
         self.epoch += 1
+        sm100.wait_pending_wgrad(clear=True)        # every side stream joins the caller's stream (capture-safe)
         if self.world == 1:
             self._flush_deferred()
         if self.world > 1:

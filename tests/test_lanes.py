@@ -75,10 +75,11 @@ def test_lane_plan_forks_the_inception_branches():
     assert chain.n_lanes == 1
 
 
-def _train(lanes, graph, monkeypatch, steps=6, wgrad_lane=1):
+def _train(lanes, graph, monkeypatch, steps=6, wgrad_lane=1, defer=1):
     from poseidon_b200 import get_solver
     monkeypatch.setenv("POSEIDON_LANES", str(lanes))
     monkeypatch.setenv("POSEIDON_WGRAD_LANE", str(wgrad_lane))
+    monkeypatch.setenv("POSEIDON_WGRAD_DEFER", str(defer))
     net = inception_net()
     sp = P.SolverParameter(base_lr=0.01, lr_policy="fixed", momentum=0.9, weight_decay=0.0005, display=0, max_iter=steps,
                            snapshot=0, snapshot_after_train=False, random_seed=11, solver_type="SGD", solver_mode="GPU")
@@ -113,9 +114,10 @@ def test_lanes_match_the_sequential_schedule(ext, monkeypatch, graph):
     """Same kernels, same order per stream: the branch-parallel step must reproduce the one-stream trajectory (weights
     after 6 momentum steps; the per-weight reductions are order-independent, so the match is tight)."""
     l1, w1 = _train(1, graph, monkeypatch, wgrad_lane=0)          # one stream for everything
-    for lanes, wl in ((4, 0), (4, 1), (1, 1)):                    # branch lanes, + weight gradients on side streams
-        l4, w4 = _train(lanes, graph, monkeypatch, wgrad_lane=wl)
-        assert np.allclose(l1, l4, rtol=2e-3, atol=2e-3), (lanes, wl, l1, l4)
+    # branch lanes; + weight gradients on side streams joined per layer; + joined at the update launches (default)
+    for lanes, wl, defer in ((4, 0, 0), (4, 1, 0), (4, 1, 1), (1, 1, 1)):
+        l4, w4 = _train(lanes, graph, monkeypatch, wgrad_lane=wl, defer=defer)
+        assert np.allclose(l1, l4, rtol=2e-3, atol=2e-3), (lanes, wl, defer, l1, l4)
         for n in w1:
             d = np.abs(w1[n] - w4[n]).max()
-            assert d <= 2e-3 * np.abs(w1[n]).max() + 1e-5, (lanes, wl, n, d)
+            assert d <= 2e-3 * np.abs(w1[n]).max() + 1e-5, (lanes, wl, defer, n, d)
