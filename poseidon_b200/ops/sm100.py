@@ -699,7 +699,27 @@ class _IPFn(torch.autograd.Function):
                 sink = getattr(layer, "_grad_sink", None)
                 dw = sink.weight_buffer(layer, st) if sink is not None else \
                     torch.empty(st.N, st.Kp, device=dy.device, dtype=torch.float32)
-                k.gemm_f32(dy, True, x2, True, dw, 1.0, False, 1, 0)
+                # output-bound GEMM (fc6: 151 MB of fp32 for 19 GFLOP): on the weight-gradient side stream when its
+                # consumer waits for it itself (see _ConvFn.backward), next to the convolutions' backward
+                defer = dy.is_cuda and sink is not None and getattr(sink, "defers_wgrad_join", False) and \
+                    _wgrad_lane() and _wgrad_defer() and os.environ.get("POSEIDON_IP_WGRAD_LANE", "1") == "1"
+                if defer:
+                    cur = torch.cuda.current_stream()
+                    side = _wgrad_stream(cur)
+                    fork = torch.cuda.Event()
+                    fork.record(cur)
+                    side.wait_event(fork)
+                    dy.record_stream(side)
+                    x2.record_stream(side)
+                    torch.cuda.set_stream(side)
+                try:
+                    k.gemm_f32(dy, True, x2, True, dw, 1.0, False, 1, 0)
+                finally:
+                    if defer:
+                        done = torch.cuda.Event()
+                        done.record(side)
+                        torch.cuda.set_stream(cur)
+                        _pending_wgrad.setdefault(cur.device.index, []).append(done)
                 if st.Kp != st.K:
                     dw = dw[:, : st.K]
         return dx, dw, db, None, None

@@ -85,7 +85,7 @@ def _train(lanes, graph, monkeypatch, steps=6, wgrad_lane=1, defer=1):
                            snapshot=0, snapshot_after_train=False, random_seed=11, solver_type="SGD", solver_mode="GPU")
     sp.net_param = net
     s = get_solver(sp, engine="sm100")
-    assert s.net.n_lanes == (4 if lanes > 1 else 1)
+    assert s.net.n_lanes == (lanes if lanes > 1 else 1)
     rng = np.random.RandomState(5)
     x = torch.from_numpy(rng.randn(8 * steps, 3, 20, 20).astype(np.float32))
     y = torch.from_numpy(rng.randint(0, 10, size=(8 * steps,)).astype(np.float32))
