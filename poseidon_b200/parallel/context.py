@@ -111,6 +111,15 @@ def init_rank_context(device: Optional[str] = None, hostfile: Optional[str] = No
         else:
             dev = torch.device("cuda", local_rank % torch.cuda.device_count())
         torch.cuda.set_device(dev)
+        # NumaMgr's role (ps/src/petuum_ps/thread/numa_mgr.hpp:28-203): the per-GPU process — and with it the first-touch
+        # placement of its pinned input buffers — stays on the CPUs of the GPU's NUMA node, so the per-step H2D copies do
+        # not cross sockets.  POSEIDON_NUMA=off | center (default) | even.
+        policy = os.environ.get("POSEIDON_NUMA", "center")
+        if policy != "off":
+            from ..utils.affinity import pin_to_gpu_numa
+            cpus = pin_to_gpu_numa(dev.index if dev.index is not None else 0, policy, local_rank,
+                                   int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
+            log.debug("rank %d: pinned to %d CPUs (%s)", rank, len(cpus), policy)
     else:
         dev = torch.device("cpu")
     backend = None

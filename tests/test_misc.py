@@ -254,3 +254,23 @@ def test_hostfile_node_layout(tmp_path, monkeypatch):
     hf.write_text("0 10.0.0.1 9000\n1 10.0.0.2 9000\n2 10.0.0.1 9001\n3 10.0.0.2 9001\n")       # interleaved hosts
     with pytest.raises(ValueError, match="consecutive lines"):
         context.init_rank_context("cpu", str(hf), client_id=0)
+
+
+def test_numa_affinity_policies(monkeypatch):
+    """utils/affinity.py (NumaMgr's role): cpulist parsing, the 'even' slice per local rank, and 'center' degrading to
+    the current CPU set when the GPU's NUMA node is unknown; the process affinity is restored afterwards."""
+    import os
+    from poseidon_b200.utils import affinity
+    assert affinity._parse_cpulist("0-3,8,10-11") == [0, 1, 2, 3, 8, 10, 11]
+    assert affinity.gpu_numa_node("ffff:ff:00.0") is None
+    before = sorted(os.sched_getaffinity(0))
+    try:
+        assert affinity.pin_to_gpu_numa(0, "center") == before          # no GPU here: unchanged
+        if len(before) >= 2:
+            a = affinity.pin_to_gpu_numa(0, "even", local_rank=0, local_world=2)
+            os.sched_setaffinity(0, before)
+            b = affinity.pin_to_gpu_numa(0, "even", local_rank=1, local_world=2)
+            assert a and b and not set(a) & set(b) and set(a) | set(b) <= set(before)
+    finally:
+        os.sched_setaffinity(0, before)
+    assert sorted(os.sched_getaffinity(0)) == before
