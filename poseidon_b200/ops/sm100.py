@@ -407,6 +407,9 @@ class _ConvFn(torch.autograd.Function):
             cur = torch.cuda.current_stream()
             side = _wgrad_stream(cur)
         defer = side is not None and sink is not None and getattr(sink, "defers_wgrad_join", False) and _wgrad_defer()
+        # one GPU: nothing touches the bias gradient before the end-of-iteration update (autograd adopts the tensor
+        # without a copy, the hook only queues it), so its column-sum kernel can ride the side stream as well
+        defer_bias = defer and getattr(sink, "world", 0) == 1 and getattr(sink, "multi_update", False)
         dw2 = dbf = None
         if ctx.needs_input_grad[1]:             # (outputs are allocated on the layer's own stream)
             dw2 = sink.weight_buffer(layer, st) if sink is not None else \
@@ -434,15 +437,15 @@ class _ConvFn(torch.autograd.Function):
                     k.conv_wgrad(xin, dy, dw2, [st.R, st.S], list(stride), list(ctx.conv_pad), st.groups,
                                  1 if (st.row_mode and not st.pad8) else 0, 1.0, st.cgk if not st.row_mode else 0)
                 dw = st.grad_from_dw(dw2)
-            if dbf is not None and not defer:
+            if dbf is not None and (not defer or defer_bias):
                 db = bias_grad()
         finally:
             if side is not None:
                 done = torch.cuda.Event()
                 done.record(side)
                 torch.cuda.set_stream(cur)
-        if dbf is not None and defer:
-            db = bias_grad()                    # (a fresh tensor autograd may copy on this stream: not deferred)
+        if dbf is not None and defer and not defer_bias:
+            db = bias_grad()                    # (multi-GPU: staged into the arena on this stream by the bucket launch)
         if ctx.needs_input_grad[0]:
             if st.row_mode and not st.pad8:
                 raise NotImplementedError(f"sm100 conv '{layer.layer_name}': ROW-mode (<= 4 channel) layers are image "
@@ -486,6 +489,11 @@ def _wgrad_defer() -> bool:
 
 _wgrad_streams: dict = {}
 _pending_wgrad: dict = {}          # device index -> events of weight-gradient kernels not yet joined
+
+
+def add_pending_wgrad(event, device_index: int) -> None:
+    """Register work queued behind a forked weight gradient (its optimizer step) for the same deferred join."""
+    _pending_wgrad.setdefault(device_index, []).append(event)
 
 
 def wait_pending_wgrad(stream=None, clear: bool = False) -> None:
@@ -703,9 +711,11 @@ class _IPFn(torch.autograd.Function):
                 # consumer waits for it itself (see _ConvFn.backward), next to the convolutions' backward
                 defer = dy.is_cuda and sink is not None and getattr(sink, "defers_wgrad_join", False) and \
                     _wgrad_lane() and _wgrad_defer() and os.environ.get("POSEIDON_IP_WGRAD_LANE", "1") == "1"
+                layer._wgrad_side = None
                 if defer:
                     cur = torch.cuda.current_stream()
                     side = _wgrad_stream(cur)
+                    layer._wgrad_side = side        # the one-GPU backend steps this weight on the same stream, right away
                     fork = torch.cuda.Event()
                     fork.record(cur)
                     side.wait_event(fork)

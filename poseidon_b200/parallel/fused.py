@@ -222,6 +222,7 @@ class FusedBackend(Backend):
                 if isinstance(st, sm100.ConvState) and not st.row_mode and layer.weight.requires_grad:
                     layer._grad_sink = self
         self.multi_update = self.world == 1 and os.environ.get("POSEIDON_MULTI_UPDATE", "1") != "0"
+        self._early_ip_update = os.environ.get("POSEIDON_EARLY_IP_UPDATE", "1") == "1"
         self._deferred = []
         self.per_worker_state = self.ssp and self.world > 1
         self.done_counter = torch.zeros(4, dtype=torch.int32, device=self.device)
@@ -433,6 +434,23 @@ class FusedBackend(Backend):
                 lr, mom, decay, rule, l1, delta, gscale = self._hyper_args(lm, dm)
                 gs = getattr(st, "_gsink", None) if p is getattr(bucket.layer, "weight", None) else None
                 rearm = gs is not None and g.data_ptr() == gs.data_ptr()
+                side = getattr(bucket.layer, "_wgrad_side", None) if p is getattr(bucket.layer, "weight", None) else None
+                if side is not None and rearm and self._early_ip_update:
+                    # inner-product weight whose gradient GEMM was forked to the side stream (ops/sm100.py): its HBM-bound
+                    # optimizer step follows on that stream at once and fills the tails of the convolution backward
+                    # kernels, instead of running alone at the end of the step.  (The layer's data gradient, which reads
+                    # the bf16 operand this step rewrites, completed before the fork.)
+                    bucket.layer._wgrad_side = None
+                    with self.cu.stream(side):
+                        self.k.fused_update(p.data, g, h, wb, lr, mom, decay, rule, l1, delta, gscale, self.lr_t, True)
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                    sm100.add_pending_wgrad(ev, side.device.index)
+                    st._gsink_dirty = False
+                    self.launches += 1
+                    if p is getattr(bucket.layer, "weight", None):
+                        fresh = wb is not None
+                    continue
                 self._deferred.append((p.data, g, h, wb, lr, decay, rearm, st if rearm else None))
                 if p is getattr(bucket.layer, "weight", None):
                     fresh = wb is not None
