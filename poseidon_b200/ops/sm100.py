@@ -409,12 +409,18 @@ class _ConvFn(torch.autograd.Function):
         defer = side is not None and sink is not None and getattr(sink, "defers_wgrad_join", False) and _wgrad_defer()
         # one GPU: nothing touches the bias gradient before the end-of-iteration update (autograd adopts the tensor
         # without a copy, the hook only queues it), so its column-sum kernel can ride the side stream as well
-        defer_bias = defer and getattr(sink, "world", 0) == 1 and getattr(sink, "multi_update", False)
-        dw2 = dbf = None
+        # several GPUs: the bias gradient lands in its arena segment directly (sink.bias_buffer) and the bucket launch
+        # waits for the side stream like it does for the weight gradient
+        dbf = None
+        if layer.bias_term and ctx.needs_input_grad[2] and sink is not None and st.Coutp == st.Cout and \
+                hasattr(sink, "bias_buffer"):
+            dbf = sink.bias_buffer(layer, st)
+        defer_bias = defer and (dbf is not None or (getattr(sink, "world", 0) == 1 and getattr(sink, "multi_update", False)))
+        dw2 = None
         if ctx.needs_input_grad[1]:             # (outputs are allocated on the layer's own stream)
             dw2 = sink.weight_buffer(layer, st) if sink is not None else \
                 torch.zeros(st.Coutp, st.Kw, device=dy.device, dtype=torch.float32)
-        if layer.bias_term and ctx.needs_input_grad[2]:
+        if layer.bias_term and ctx.needs_input_grad[2] and dbf is None:
             dbf = torch.empty(st.Coutp, device=dy.device, dtype=torch.float32)
 
         def bias_grad():

@@ -222,7 +222,8 @@ class FusedBackend(Backend):
                 if isinstance(st, sm100.ConvState) and not st.row_mode and layer.weight.requires_grad:
                     layer._grad_sink = self
         self.multi_update = self.world == 1 and os.environ.get("POSEIDON_MULTI_UPDATE", "1") != "0"
-        self._early_ip_update = os.environ.get("POSEIDON_EARLY_IP_UPDATE", "1") == "1"
+        # (measured neutral on AlexNet / VGG-16, profiles/r2_side_stream_call26.log: off by default)
+        self._early_ip_update = os.environ.get("POSEIDON_EARLY_IP_UPDATE", "0") == "1"
         self._deferred = []
         self.per_worker_state = self.ssp and self.world > 1
         self.done_counter = torch.zeros(4, dtype=torch.int32, device=self.device)
@@ -352,6 +353,16 @@ class FusedBackend(Backend):
         seg = self.seg_of[id(layer.weight)]
         shape = (st.Cout, st.Kw) if isinstance(st, sm100.ConvState) else (st.N, st.K)
         return self.arena.view(seg.g_off, (seg.numel,), torch.float32)[: layer.weight.numel()].view(*shape)
+
+    def bias_buffer(self, layer, st) -> Optional[torch.Tensor]:
+        """Bias-gradient sink (multi-GPU): the column-sum kernel writes straight into the bias segment of the G arena, so
+        the bucket launch has nothing to stage (one copy and its launch per layer and step less)."""
+        if self.world == 1 or getattr(layer, "bias", None) is None:
+            return None
+        seg = self.seg_of.get(id(layer.bias))
+        if seg is None:
+            return None
+        return self.arena.view(seg.g_off, (seg.numel,), torch.float32)[: layer.bias.numel()]
 
     def _alloc_flag_block(self) -> int:
         off = self.flag_off + self._next_flag * _ALIGN
