@@ -121,3 +121,31 @@ def test_lanes_match_the_sequential_schedule(ext, monkeypatch, graph):
         for n in w1:
             d = np.abs(w1[n] - w4[n]).max()
             assert d <= 2e-3 * np.abs(w1[n]).max() + 1e-5, (lanes, wl, defer, n, d)
+
+
+def test_lane_plan_of_the_zoo_nets():
+    """GoogLeNet (train phase): every inception module forks into four distinct lanes and its CONCAT waits for three
+    producers; the auxiliary classifier heads leave the trunk's lane; AlexNet / VGG-16 are chains and stay on one stream."""
+    from poseidon_b200.layers import NetContext
+    from poseidon_b200.models import zoo
+    from poseidon_b200.net.lanes import plan_lanes
+    from poseidon_b200.net.net import Net
+
+    def build(param):
+        return Net(param, phase=P.TRAIN, ctx=NetContext(phase=P.TRAIN, device="cpu", engine="torch",
+                                                        data_shape_hint=(3, 224, 224)))
+    g = build(zoo.googlenet(batch=2, test_batch=2))
+    plan_lanes(g, 8)
+    assert g.n_lanes == 8
+    lane = dict(zip(g.layer_names, g.lane))
+    for tag in ("3a", "3b", "4a", "4b", "4c", "4d", "4e", "5a", "5b"):
+        p = f"inception_{tag}/"
+        heads = {lane[p + "1x1"], lane[p + "3x3_reduce"], lane[p + "5x5_reduce"], lane[p + "pool"]}
+        assert len(heads) == 4, (tag, heads)
+        assert len(g.lane_wait[g.layer_names.index(p + "output")]) == 3
+    for idx, trunk in ((1, "inception_4b/1x1"), (2, "inception_4e/1x1")):
+        assert lane[f"loss{idx}/ave_pool"] != lane[trunk]
+    for name in ("alexnet", "vgg16"):
+        n = build(getattr(zoo, name)(batch=2, test_batch=2))
+        plan_lanes(n, 8)
+        assert n.n_lanes == 1, name
