@@ -78,26 +78,3 @@ def load_extension(build_if_missing: bool = True) -> bool:
 
 def is_loaded() -> bool:
     return _loaded
-
-
-# ---------------------------------------------------------------------------------------------------------------------
-# Experimental kernels (csrc_experimental/): opt-in, never loaded by the engine.
-EXP_DIR = os.path.join(_ROOT, "poseidon_b200", "_ext_exp")
-
-
-def build_experimental(verbose: bool = False) -> str:
-    """Compile csrc_experimental/*.cu into poseidon_b200/_ext_exp/poseidon_b200_exp.so (ops under torch.ops.poseidon_exp)."""
-    from torch.utils import cpp_extension
-    os.makedirs(EXP_DIR, exist_ok=True)
-    srcs = sorted(glob.glob(os.path.join(_ROOT, "csrc_experimental", "*.cu")))
-    cpp_extension.load(name="poseidon_b200_exp", sources=srcs, extra_cflags=["-O3", "-std=c++17"],
-                       extra_cuda_cflags=NVCC_FLAGS, extra_include_paths=[CSRC, os.path.join(CSRC, "gemm")],
-                       build_directory=EXP_DIR, verbose=verbose, is_python_module=False, with_cuda=True)
-    return os.path.join(EXP_DIR, "poseidon_b200_exp.so")
-
-
-def load_experimental() -> None:
-    so = os.path.join(EXP_DIR, "poseidon_b200_exp.so")
-    if not os.path.exists(so):
-        so = build_experimental()
-    torch.ops.load_library(so)

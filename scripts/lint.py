@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PY_DIRS = ["poseidon_b200", "tests", "benchmarks", "scripts", "bench.py", "__graft_entry__.py"]
-CC_DIRS = ["csrc", "csrc_host", "csrc_experimental"]
+CC_DIRS = ["csrc", "csrc_host"]
 SKIP = {"_ext", "_ext_exp", "__pycache__", "wt"}
 
 
