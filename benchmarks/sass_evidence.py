@@ -21,7 +21,8 @@ for line in text.splitlines():
         funcs[cur].append(line)
 print(f"# cuobjdump -sass {SO} (sm_100a): {len(funcs)} kernels")
 print("# PTX -> SASS: tcgen05.mma = UTCHMMA(.2CTA), tcgen05.commit = UTCBAR(.2CTA)(.MULTICAST), tcgen05.ld = LDTM, TMA load = UTMALDG"
-      "(.4D.IM2COL)(.2CTA)(.MULTICAST), bulk store = UBLKCP, multimem.ld_reduce = LDGMC..., multimem.st = STGMC..., "
+      "(.4D.IM2COL)(.2CTA)(.MULTICAST), bulk store = UBLKCP, multimem.ld_reduce = LDGMC.E.ADD..., "
+      "multimem.st = STG.E.128.STRONG.SYS to the multicast address (no mnemonic of its own), "
       "cp.async = LDGSTS, HMMA = legacy mma.sync (none expected)")
 print("\n## 1. mnemonic counts per kernel\n")
 for name, lines in funcs.items():
@@ -63,4 +64,4 @@ excerpt(lambda n: "umma_gemm_kernel<256, true, true, 2, 0, 2>" in n, r"UTCHMMA|L
 excerpt(lambda n: "allreduce_sgd_multi_kernel" in n, r"LDGMC|STGMC|REDGMC|MULTIMEM|LD\.E\..*SYS|ST\.E\..*SYS|MEMBAR",
         "fused all-reduce + SGD: multimem.ld_reduce / multimem.st (NVLS) and system-scope flags", ctx=0, limit=16)
 excerpt(lambda n: "ssp_fold_kernel" in n, r"ST\.E\..*SYS|LD\.E\..*SYS|MEMBAR|ATOMG", "SSP fold: peer loads + system-scope consumed flags", ctx=0, limit=8)
-excerpt(lambda n: "peer_push_kernel" in n, r"STGMC|MULTIMEM|ST\.E", "SFB factor publish: multimem.st", ctx=0, limit=6)
+excerpt(lambda n: "peer_push_kernel" in n, r"STG\.E[.\w]*STRONG\.SYS|STG\.E\.128", "SFB factor publish: stores to the multicast (or peer) address", ctx=0, limit=6)
