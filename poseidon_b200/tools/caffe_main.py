@@ -221,6 +221,9 @@ def cmd_time(args) -> int:
     _setup_logging(args.log_level, 0)
     if not args.model:
         raise SystemExit("Need a model definition to time.")
+    # per-layer times only mean something when layers run one after the other: no branch lanes, no side streams
+    os.environ["POSEIDON_LANES"] = "1"
+    os.environ["POSEIDON_WGRAD_LANE"] = "0"
     net, dev = _build_net(args, P.TRAIN)
     log.info("Performing Forward + Backward warm-up")
     loss, _ = net.forward()
